@@ -1,0 +1,374 @@
+"""Feeder repair (D4) and compilation to the structure-of-arrays the kernels read.
+
+Two host-side steps sit upstream of *both* the CPU oracle and the CUDA path, so
+that they solve the same network with the same bus / line numbering:
+
+``repair_topology(feeder)``
+    Turns a shipped feeder into a connected radial tree (deviation D4 in
+    DESIGN.md).  The reference's own Ybus treats ``abs(z) <= 1e-12`` as an open
+    line (reference ``grid_fed_rl/environments/power_flow.py:62-63``), which
+    islands three IEEE-13 buses, and its IEEE-34 / IEEE-123 generators produce
+    several components plus cycles.  Buses, loads and generators
+    are passed through untouched; only ``lines`` changes, kept lines preserve
+    their reference order and repair lines are appended at the end.
+
+``compile_feeder(feeder, ...)``
+    Bus order = ``feeder.buses`` order, line order = ``feeder.lines`` order
+    (these indices are what "topology ordering" means in the parity tests),
+    plus a breadth-first (level) permutation with ``parent[]`` used by the
+    leaf->root / root->leaf traversals on the device.
+"""
+
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Any, Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+# zero-length IEEE-13 entries keep their configured impedance, un-scaled, as pu
+# (reference ieee_feeders.py:64,67,79-80): XFM1 and SWITCH.
+IEEE13_ZERO_LENGTH_PU: Dict[str, Tuple[float, float]] = {
+    "line_633_634": (0.0, 0.06),
+    "line_671_692": (1e-4, 1e-4),
+}
+
+OPEN_Z = 1e-12  # reference power_flow.py:63
+
+
+class TopologyError(ValueError):
+    """The feeder cannot be compiled for the radial solvers."""
+
+
+class RepairedFeeder:
+    """Same buses / loads / generators objects as the source feeder, new ``lines``."""
+
+    def __init__(self, source, lines: List[Any], dropped: List[Any], added: List[Any]) -> None:
+        self.name = getattr(source, "name", type(source).__name__)
+        self.parameters = source.parameters
+        self.buses = source.buses
+        self.loads = source.loads
+        self.generators = source.generators
+        self.lines = lines
+        self.dropped_lines = dropped
+        self.added_lines = added
+        self.source = source
+
+
+def _slack_index(buses: Sequence[Any]) -> int:
+    idx = [i for i, b in enumerate(buses) if b.bus_type == "slack"]
+    if len(idx) != 1:
+        raise TopologyError(f"exactly one slack bus is required, found {len(idx)}")
+    return idx[0]
+
+
+def _new_line(proto, **kw):
+    """Build a line of the same class as the feeder's own lines (so a reference
+    feeder keeps reference ``Line`` objects with their ``update_state``)."""
+    return type(proto)(**kw)
+
+
+def repair_topology(feeder, zero_length_pu: Optional[Dict[str, Tuple[float, float]]] = None):
+    """Deviation D4 (ii)+(iii): see module docstring.  Returns a ``RepairedFeeder``."""
+    overrides = IEEE13_ZERO_LENGTH_PU if zero_length_pu is None else zero_length_pu
+    buses = list(feeder.buses)
+    n = len(buses)
+    index = {b.id: i for i, b in enumerate(buses)}
+    slack = _slack_index(buses)
+
+    # (ii) zero-impedance entries: configured pu value if known
+    lines: List[Any] = []
+    for ln in feeder.lines:
+        z = complex(ln.resistance, ln.reactance)
+        if abs(z) <= OPEN_Z and ln.id in overrides:
+            r, x = overrides[ln.id]
+            ln = _new_line(ln, id=ln.id, from_bus=ln.from_bus, to_bus=ln.to_bus,
+                           resistance=r, reactance=x, rating=ln.rating)
+        lines.append(ln)
+
+    live = [ln for ln in lines if abs(complex(ln.resistance, ln.reactance)) > OPEN_Z]
+    if not live:
+        raise TopologyError("feeder has no line with a non-zero impedance")
+    med_r = float(np.median([ln.resistance for ln in live]))
+    med_x = float(np.median([ln.reactance for ln in live]))
+    ratings = [ln.rating for ln in live]
+    modal_rating = max(sorted(set(ratings)), key=ratings.count)
+
+    # (iii) radialise: union-find in list order, cycle-closing (and open) lines are dropped
+    root = list(range(n))
+
+    def find(a: int) -> int:
+        while root[a] != a:
+            root[a] = root[root[a]]
+            a = root[a]
+        return a
+
+    kept: List[Any] = []
+    dropped: List[Any] = []
+    for ln in lines:
+        if ln.from_bus not in index or ln.to_bus not in index:
+            raise TopologyError(f"line {ln.id} references an unknown bus")
+        if abs(complex(ln.resistance, ln.reactance)) <= OPEN_Z:
+            dropped.append(ln)
+            continue
+        a, b = find(index[ln.from_bus]), find(index[ln.to_bus])
+        if a == b:
+            dropped.append(ln)
+        else:
+            root[a] = b
+            kept.append(ln)
+
+    added: List[Any] = []
+    for i in range(n):
+        if find(i) == find(slack):
+            continue
+        j = i - 1 if i > 0 else slack
+        ln = _new_line(lines[0], id=f"repair_{buses[j].id}_{buses[i].id}", from_bus=buses[j].id,
+                       to_bus=buses[i].id, resistance=med_r, reactance=med_x, rating=modal_rating)
+        root[find(i)] = find(j)
+        kept.append(ln)
+        added.append(ln)
+    # one pass can leave a component attached to a predecessor that was itself
+    # not yet on the slack's side only if i-1 was unreachable; chaining in list
+    # order makes that impossible for i>slack, but check anyway
+    if any(find(i) != find(slack) for i in range(n)):
+        raise TopologyError("repair failed to connect every bus to the slack bus")
+    if len(kept) != n - 1:
+        raise TopologyError("repair did not produce a spanning tree")
+    return RepairedFeeder(feeder, kept, dropped, added)
+
+
+# --------------------------------------------------------------------------- SoA
+
+GEN_SOLAR, GEN_WIND = 0, 1
+BUS_SLACK, BUS_PV, BUS_PQ = 0, 1, 2
+
+# reference dynamics.py:43-48 - the default 24-point residential load profile
+DEFAULT_LOAD_PROFILE = (0.5, 0.4, 0.4, 0.4, 0.4, 0.5, 0.7, 0.9, 0.8, 0.7, 0.6, 0.6,
+                        0.7, 0.7, 0.6, 0.6, 0.7, 0.9, 1.0, 0.9, 0.8, 0.7, 0.6, 0.5)
+
+
+@dataclass
+class FeederSoA:
+    """Compiled feeder.  "ref order" = position in ``feeder.buses`` / ``feeder.lines``;
+    "level order" = breadth-first position k (k=0 is the slack bus)."""
+    name: str
+    n_bus: int
+    n_line: int
+    s_base: float                      # VA
+    bus_ids: list                      # ref order
+    line_ids: list                     # ref order
+    # level order ---------------------------------------------------------
+    order: np.ndarray                  # int32[n]  level k -> ref bus index
+    rank: np.ndarray                   # int32[n]  ref bus index -> level k
+    parent: np.ndarray                 # int32[n]  parent level index, -1 for k=0
+    level_ptr: np.ndarray              # int32[n_levels+1]  level l = [ptr[l], ptr[l+1])
+    child_ptr: np.ndarray              # int32[n+1] children of k = [child_ptr[k], child_ptr[k+1]) (contiguous level indices)
+    bus_type: np.ndarray               # int32[n]  BUS_*
+    vm_set: np.ndarray                 # f64[n]   slack / pv magnitude (bus.voltage_magnitude)
+    g: np.ndarray                      # f64[n]   series conductance of the branch parent[k]-k (k>=1)
+    b: np.ndarray                      # f64[n]   series susceptance of that branch
+    gdiag: np.ndarray                  # f64[n]   Re Y_kk summed in line order (reference Ybus)
+    bdiag: np.ndarray                  # f64[n]   Im Y_kk
+    r: np.ndarray                      # f64[n]   branch resistance (pu)  - sweep
+    x: np.ndarray                      # f64[n]   branch reactance (pu)   - sweep
+    line_of: np.ndarray                # int32[n] ref line index of that branch (-1 for k=0)
+    from_is_parent: np.ndarray         # int32[n] 1 if line.from_bus is the parent end
+    rating: np.ndarray                 # f64[n]   VA
+    # components (ref order of feeder.loads / generators) ------------------
+    load_bus: np.ndarray               # int32[L] level index
+    load_base: np.ndarray              # f64[L]   W
+    load_p: np.ndarray                 # f64[L]   static active_power (obs, frequency model)
+    load_q: np.ndarray                 # f64[L]   static reactive_power (obs)
+    gen_ids: list
+    gen_type: np.ndarray               # int32[G] GEN_*
+    gen_bus: np.ndarray                # int32[G] level index
+    gen_cap: np.ndarray                # f64[G]   W
+    gen_p0: np.ndarray                 # f64[G]   solar: panel_area        wind: cut_in_speed
+    gen_p1: np.ndarray                 # f64[G]   solar: efficiency        wind: rated_speed
+    gen_p2: np.ndarray                 # f64[G]   solar: unused            wind: cut_out_speed
+    bat_ids: list
+    bat_bus: np.ndarray                # int32[Bt] level index
+    bat_cap: np.ndarray                # f64[Bt]
+    bat_rating: np.ndarray             # f64[Bt]
+    bat_eff: np.ndarray                # f64[Bt]
+    bat_soc0: np.ndarray               # f64[Bt]
+    load_profile: np.ndarray = field(default_factory=lambda: np.array(DEFAULT_LOAD_PROFILE))
+
+    @property
+    def n_load(self) -> int:
+        return int(self.load_bus.size)
+
+    @property
+    def n_gen(self) -> int:
+        return int(self.gen_bus.size)
+
+    @property
+    def n_bat(self) -> int:
+        return int(self.bat_bus.size)
+
+    @property
+    def n_levels(self) -> int:
+        return int(self.level_ptr.size - 1)
+
+    @property
+    def obs_dim(self) -> int:
+        # reference grid_env.py:307-314
+        return (2 * self.n_bus + 2 * self.n_line + 1 + 2 * self.n_load + self.n_gen
+                + 2 * self.n_bat)
+
+    @property
+    def act_dim(self) -> int:
+        # reference grid_env.py:351
+        return self.n_bat + self.n_gen
+
+
+def _series_admittance(r: float, x: float) -> complex:
+    # same expression, same Python complex division as reference power_flow.py:62-63
+    z = complex(r, x)
+    return 1.0 / z if abs(z) > OPEN_Z else 0.0
+
+
+def compile_feeder(feeder, renewable_sources: Optional[Sequence[str]] = None,
+                   with_components: bool = True) -> FeederSoA:
+    """Compile a *radial, connected* feeder (run ``repair_topology`` first if it is not).
+
+    ``renewable_sources`` has the reference meaning (grid_env.py:167,273,282): a
+    generator of type "solar"/"wind" becomes an environment generator only if
+    its type is listed.  Generators of type "battery" always become batteries; a
+    feeder without one gets the reference's template unit (grid_env.py:292-297)
+    at its first load bus (deviation D3).
+    """
+    buses, lines = list(feeder.buses), list(feeder.lines)
+    n, m = len(buses), len(lines)
+    if n < 1:
+        raise TopologyError("feeder has no buses")
+    if m != n - 1:
+        raise TopologyError(f"radial solver needs n-1 lines, feeder has {n} buses and {m} lines "
+                            "(run repair_topology first)")
+    index = {b.id: i for i, b in enumerate(buses)}
+    if len(index) != n:
+        raise TopologyError("duplicate bus ids")
+    slack = _slack_index(buses)
+
+    adj: List[List[Tuple[int, int]]] = [[] for _ in range(n)]
+    ydiag = np.zeros(n, dtype=complex)
+    ys: List[complex] = []
+    for k, ln in enumerate(lines):
+        if ln.from_bus not in index or ln.to_bus not in index:
+            raise TopologyError(f"line {ln.id} references an unknown bus")
+        i, j = index[ln.from_bus], index[ln.to_bus]
+        if i == j:
+            raise TopologyError(f"line {ln.id} is a self loop")
+        y = _series_admittance(ln.resistance, ln.reactance)
+        if y == 0.0:
+            raise TopologyError(f"line {ln.id} has zero impedance (open in the reference Ybus)")
+        ys.append(y)
+        ydiag[i] += y          # accumulation order = line order, as the reference Ybus
+        ydiag[j] += y
+        adj[i].append((j, k))
+        adj[j].append((i, k))
+
+    # breadth-first from the slack; neighbours visited in line order
+    order = [slack]
+    parent_ref = {slack: (-1, -1)}
+    level_of = {slack: 0}
+    for u in order:
+        for v, k in adj[u]:
+            if v not in parent_ref:
+                parent_ref[v] = (u, k)
+                level_of[v] = level_of[u] + 1
+                order.append(v)
+    if len(order) != n:
+        raise TopologyError("feeder is not connected (run repair_topology first)")
+    rank = np.empty(n, dtype=np.int32)
+    rank[np.array(order)] = np.arange(n, dtype=np.int32)
+
+    parent = np.full(n, -1, dtype=np.int32)
+    line_of = np.full(n, -1, dtype=np.int32)
+    from_is_parent = np.zeros(n, dtype=np.int32)
+    g = np.zeros(n); b = np.zeros(n); r = np.zeros(n); x = np.zeros(n); rating = np.zeros(n)
+    for k in range(1, n):
+        u, li = parent_ref[order[k]]
+        parent[k] = rank[u]
+        line_of[k] = li
+        ln = lines[li]
+        from_is_parent[k] = 1 if index[ln.from_bus] == u else 0
+        g[k], b[k] = ys[li].real, ys[li].imag
+        r[k], x[k] = ln.resistance, ln.reactance
+        rating[k] = ln.rating
+    levels = np.array([level_of[v] for v in order])
+    n_levels = int(levels.max()) + 1
+    level_ptr = np.searchsorted(levels, np.arange(n_levels + 1)).astype(np.int32)
+    child_cnt = np.bincount(parent[1:], minlength=n) if n > 1 else np.zeros(n, dtype=np.int64)
+    child_ptr = np.zeros(n + 1, dtype=np.int32)
+    # BFS enqueues the children of a node consecutively, so they are contiguous in level order
+    first = 1
+    for k in range(n):
+        child_ptr[k] = first
+        first += int(child_cnt[k])
+    child_ptr[n] = first
+    for k in range(1, n):
+        assert child_ptr[parent[k]] <= k < child_ptr[parent[k] + 1]
+
+    tmap = {"slack": BUS_SLACK, "pv": BUS_PV}
+    bus_type = np.array([tmap.get(buses[i].bus_type, BUS_PQ) for i in order], dtype=np.int32)
+    vm_set = np.array([float(buses[i].voltage_magnitude) for i in order])
+
+    soa = dict(
+        name=getattr(feeder, "name", type(feeder).__name__), n_bus=n, n_line=m,
+        s_base=float(feeder.parameters.base_power) * 1e6,
+        bus_ids=[b_.id for b_ in buses], line_ids=[l_.id for l_ in lines],
+        order=np.array(order, dtype=np.int32), rank=rank, parent=parent, level_ptr=level_ptr,
+        child_ptr=child_ptr, bus_type=bus_type, vm_set=vm_set, g=g, b=b,
+        gdiag=ydiag.real[order].copy(), bdiag=ydiag.imag[order].copy(), r=r, x=x,
+        line_of=line_of, from_is_parent=from_is_parent, rating=rating)
+
+    # ---- components -------------------------------------------------------
+    loads = list(feeder.loads) if with_components else []
+    for ld in loads:
+        if ld.bus not in index:
+            raise TopologyError(f"load {ld.id} references an unknown bus")
+    soa.update(
+        load_bus=np.array([rank[index[ld.bus]] for ld in loads], dtype=np.int32),
+        load_base=np.array([float(ld.base_power) for ld in loads]),
+        load_p=np.array([float(ld.active_power) for ld in loads]),
+        load_q=np.array([float(ld.reactive_power) for ld in loads]))
+
+    sources = list(renewable_sources or [])
+    gen_ids, gtype, gbus, gcap, p0, p1, p2 = [], [], [], [], [], [], []
+    bat_ids, bbus, bcap, brat, beff = [], [], [], [], []
+    gens = feeder.generators if with_components else {}
+    for gid, info in gens.items():
+        kind = info.get("type")
+        if kind == "battery":
+            bat_ids.append(gid)
+            bbus.append(rank[index[info["bus"]]])
+            bcap.append(float(info["capacity_kwh"]))
+            brat.append(float(info["power_rating_kw"]) * 1e3)
+            beff.append(float(info["efficiency"]))
+        elif kind == "solar" and "solar" in sources:
+            eff = float(info.get("efficiency", 0.18))
+            gen_ids.append(gid); gtype.append(GEN_SOLAR); gbus.append(rank[index[info["bus"]]])
+            gcap.append(float(info["capacity"]))
+            p0.append(float(info["capacity"]) / (eff * 1000)); p1.append(eff); p2.append(0.0)
+        elif kind == "wind" and "wind" in sources:
+            gen_ids.append(gid); gtype.append(GEN_WIND); gbus.append(rank[index[info["bus"]]])
+            gcap.append(float(info["capacity"]))
+            p0.append(float(info.get("cut_in_speed", 3.0)))
+            p1.append(float(info.get("rated_speed", 12.0)))
+            p2.append(float(info.get("cut_out_speed", 25.0)))
+    if with_components and not bat_ids:
+        home = loads[0].bus if loads else buses[slack].id
+        bat_ids.append(f"battery_{home}")
+        bbus.append(rank[index[home]])
+        bcap.append(1e3); brat.append(0.5e6); beff.append(0.95)
+    soa.update(
+        gen_ids=gen_ids, gen_type=np.array(gtype, dtype=np.int32),
+        gen_bus=np.array(gbus, dtype=np.int32), gen_cap=np.array(gcap, dtype=float),
+        gen_p0=np.array(p0, dtype=float), gen_p1=np.array(p1, dtype=float),
+        gen_p2=np.array(p2, dtype=float),
+        bat_ids=bat_ids, bat_bus=np.array(bbus, dtype=np.int32),
+        bat_cap=np.array(bcap, dtype=float), bat_rating=np.array(brat, dtype=float),
+        bat_eff=np.array(beff, dtype=float), bat_soc0=np.full(len(bat_ids), 0.5))
+    return FeederSoA(**soa)
