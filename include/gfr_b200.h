@@ -1,0 +1,195 @@
+/*
+ * gfr_b200.h - C ABI of the B200-native batched GridEnvironment.step path.
+ *
+ * The reference (danieleschmidt/grid-fed-rl-gym) is pure Python and has no FFI; these
+ * entry points are what a binding for its hot path would call.  Each one cites the
+ * reference interface it replaces (paths relative to /root/reference/grid_fed_rl/).
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative GFR_E_* code otherwise, never
+ *     throws; gfr_last_error() gives the thread-local message of the last failure
+ *   - all I/O buffers are CALLER-OWNED DEVICE pointers on the env's / feeder's device
+ *     (e.g. torch.Tensor.data_ptr()); NULL output pointers are skipped.  The library owns
+ *     only the compiled feeder and the persistent per-env state, released by *_destroy
+ *   - calls are asynchronous on the given cudaStream_t (passed as void*); a handle is
+ *     not thread-safe; there is no global mutable state
+ *   - "ref order" = position in feeder.buses / feeder.lines of the (repaired) feeder;
+ *     "level order" = breadth-first position from the slack bus (what the kernels use)
+ *   - there is NO CPU fallback: without a CUDA device every call fails with GFR_E_CUDA
+ */
+#ifndef GFR_B200_H
+#define GFR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GFR_ABI_VERSION 1
+
+enum {
+  GFR_OK = 0,
+  GFR_E_ARG = -1,      /* bad argument / inconsistent description */
+  GFR_E_CUDA = -2,     /* CUDA runtime failure (message has the cudaError string) */
+  GFR_E_LIMIT = -3     /* feeder too large for the compiled kernels' shared-memory plan */
+};
+
+enum { GFR_SOLVER_SWEEP = 0, GFR_SOLVER_NEWTON = 1 };
+enum { GFR_BUS_SLACK = 0, GFR_BUS_PV = 1, GFR_BUS_PQ = 2 };
+enum { GFR_GEN_SOLAR = 0, GFR_GEN_WIND = 1 };
+
+typedef struct gfr_feeder gfr_feeder;   /* compiled topology, device resident */
+typedef struct gfr_env gfr_env;         /* B environment instances on one device */
+
+/* Host-side description of a radial feeder, arrays in LEVEL order (k = 0 is the slack bus).
+ * Produced by grid_fed_rl_b200.topology.compile_feeder from feeder.buses / .lines / .loads /
+ * .generators (reference feeders/base.py:30-52; Bus/Line/Load environments/base.py:197-295). */
+typedef struct {
+  int32_t n_bus, n_levels, n_load, n_gen, n_bat;
+  double s_base;                    /* VA; feeder.parameters.base_power * 1e6 */
+  const int32_t* order;             /* [n]  level k -> ref bus index */
+  const int32_t* parent;            /* [n]  level index of the parent, -1 for k = 0 */
+  const int32_t* level_ptr;         /* [n_levels+1] */
+  const int32_t* child_ptr;         /* [n+1] children of k are the level indices [child_ptr[k], child_ptr[k+1]) */
+  const int32_t* bus_type;          /* [n]  GFR_BUS_* */
+  const double* vm_set;             /* [n]  slack / pv voltage magnitude */
+  const double* g;                  /* [n]  series conductance of branch (parent[k], k), k >= 1 */
+  const double* b;                  /* [n]  series susceptance */
+  const double* gdiag;              /* [n]  Re Y_kk (reference power_flow.py:48-73 accumulation order) */
+  const double* bdiag;              /* [n]  Im Y_kk */
+  const double* r;                  /* [n]  branch resistance, pu */
+  const double* x;                  /* [n]  branch reactance, pu */
+  const int32_t* line_of;           /* [n]  ref line index of branch k (-1 for k = 0) */
+  const int32_t* from_is_parent;    /* [n]  1 if line.from_bus is the parent end */
+  const double* rating;             /* [n]  line rating, VA */
+  const int32_t* load_bus;          /* [L]  level index */
+  const double* load_base;          /* [L]  W  (Load.base_power) */
+  const double* load_p;             /* [L]  W  static Load.active_power (obs, frequency model) */
+  const double* load_q;             /* [L]  var static Load.reactive_power (obs) */
+  const int32_t* gen_type;          /* [G]  GFR_GEN_* */
+  const int32_t* gen_bus;           /* [G] */
+  const double* gen_cap;            /* [G]  W */
+  const double* gen_p0;             /* [G]  solar panel_area | wind cut_in_speed */
+  const double* gen_p1;             /* [G]  solar efficiency | wind rated_speed */
+  const double* gen_p2;             /* [G]  -                | wind cut_out_speed */
+  const int32_t* bat_bus;           /* [Bt] */
+  const double* bat_cap;            /* [Bt] BatteryModel.capacity */
+  const double* bat_rating;         /* [Bt] BatteryModel.power_rating */
+  const double* bat_eff;            /* [Bt] BatteryModel.efficiency */
+  const double* bat_soc0;           /* [Bt] state of charge after reset (0.5) */
+  const double* load_profile;       /* [24] TimeVaryingLoadModel.daily_profile (dynamics.py:43-48) */
+} gfr_feeder_desc;
+
+/* Solver settings: PowerFlowSolver.__init__(tolerance, max_iterations) + NewtonRaphsonSolver's
+ * acceleration_factor (reference power_flow.py:28-35, :79-87). */
+typedef struct {
+  int32_t solver;                   /* GFR_SOLVER_* */
+  int32_t max_iterations;
+  double tolerance;                 /* newton: max |dP|,|dQ| (pu); sweep: max |dV| (pu) */
+  double acceleration;              /* newton only; reference default 1.0 */
+  int32_t lanes;                    /* 0 = auto; threads cooperating on one instance (4,8,16,32 or CTA size) */
+  int32_t reserved;
+} gfr_solver_cfg;
+
+/* GridEnvironment.__init__ kwargs (reference grid_env.py:161-174). */
+typedef struct {
+  double timestep;                  /* s */
+  int32_t episode_length;
+  int32_t stochastic_loads;         /* bool */
+  int32_t weather_variation;        /* bool */
+  int32_t reserved;
+  double v_min, v_max;              /* voltage_limits */
+  double f_min, f_max;              /* frequency_limits */
+  double safety_penalty;
+  double load_noise;                /* TimeVaryingLoadModel noise_factor, reference 0.1 */
+  gfr_solver_cfg solver;
+} gfr_env_cfg;
+
+/* Per-step results besides the observation (reference step() 5-tuple + info, grid_env.py:610-619). */
+typedef struct {
+  double* reward;                   /* [B] */
+  uint8_t* terminated;              /* [B] */
+  uint8_t* truncated;               /* [B] */
+  uint8_t* error;                   /* [B] action rejected (NaN/Inf): reward = -2*safety_penalty, terminated */
+  uint8_t* converged;               /* [B] info["power_flow_converged"] */
+  int32_t* iterations;              /* [B] PowerFlowSolution.iterations */
+  double* max_voltage;              /* [B] info["max_voltage"] */
+  double* min_voltage;              /* [B] info["min_voltage"] */
+  double* losses;                   /* [B] W, info["total_losses"] (= solution.losses) */
+  double* max_mismatch;             /* [B] PowerFlowSolution.max_mismatch */
+  uint8_t* violations;              /* [B,4] voltage_high, voltage_low, frequency_high, frequency_low */
+  int32_t* violation_count;         /* [B] env.constraint_violations */
+  int32_t* current_step;            /* [B] */
+  double* episode_reward;           /* [B] */
+  double* noise_used;               /* [B, 4+L] the noise row this step consumed (either mode) */
+} gfr_step_out;
+
+/* PowerFlowSolution fields (reference power_flow.py:12-22), batched, ref order. */
+typedef struct {
+  uint8_t* converged;               /* [B] */
+  int32_t* iterations;              /* [B] */
+  double* bus_voltages;             /* [B,n] */
+  double* bus_angles;               /* [B,n] rad */
+  double* line_flows;               /* [B,m] pu, from -> to */
+  double* line_loadings;            /* [B,m] |S_ij| * s_base / rating */
+  double* losses;                   /* [B] pu */
+  double* max_mismatch;             /* [B] */
+} gfr_sol_out;
+
+int gfr_abi_version(void);
+const char* gfr_last_error(void);
+
+/* Compile a feeder description onto `device`.  Replaces the per-call Ybus build of
+ * PowerFlowSolver.build_admittance_matrix (reference power_flow.py:48-73). */
+int gfr_feeder_create(const gfr_feeder_desc* desc, int device, gfr_feeder** out);
+void gfr_feeder_destroy(gfr_feeder* f);
+
+/* GridEnvironment(feeder, **cfg) for n_envs instances (reference grid_env.py:161-241).
+ * State after creation is the constructor's (wind 5, temperature 25, cloud 0.3, ...). */
+int gfr_env_create(const gfr_feeder* f, int64_t n_envs, const gfr_env_cfg* cfg, gfr_env** out);
+void gfr_env_destroy(gfr_env* e);
+int64_t gfr_env_num_envs(const gfr_env* e);
+int gfr_env_obs_dim(const gfr_env* e);      /* D = 2n + 2m + 1 + 2L + G + 2Bt (grid_env.py:307-314) */
+int gfr_env_act_dim(const gfr_env* e);      /* A = Bt + G (grid_env.py:351) */
+int gfr_env_noise_dim(const gfr_env* e);    /* 4 + L */
+/* Library-owned observation buffer [B, D] fp64 row-major (get_observation, grid_env.py:753-783);
+ * rewritten in place by reset and step (left untouched for instances whose action was rejected,
+ * whose observation is by definition unchanged). */
+double* gfr_env_obs(gfr_env* e);
+/* Size in bytes / copy of the persistent per-instance state (checkpoint / resume). */
+int64_t gfr_env_state_bytes(const gfr_env* e);
+int gfr_env_state_get(gfr_env* e, void* dst_device, void* stream);
+int gfr_env_state_set(gfr_env* e, const void* src_device, void* stream);
+
+/* GridEnvironment.reset(seed) (reference grid_env.py:360-408) for the instances with mask != 0
+ * (mask NULL = all).  seeds [B] (NULL = keep each instance's stream) re-key the in-kernel
+ * Philox stream.  noise [B,4] = the four weather draws reset consumes (NULL = Philox).
+ * start_time = time of day (s) the first step starts from (the reference always uses 0). */
+int gfr_env_reset(gfr_env* e, const uint64_t* seeds, const uint8_t* mask, const double* noise,
+                  double start_time, void* stream);
+
+/* GridEnvironment.step(action) (reference grid_env.py:410-619) for all B instances.
+ * actions [B,A].  noise [B,4+L] (u_irradiance, z_wind, z_temperature, z_cloud, z_load_0..)
+ * replays the reference's random.random / random.gauss / np.random.normal draws; NULL =
+ * in-kernel Philox4x32-10 keyed (seed, draw counter, slot). */
+int gfr_env_step(gfr_env* e, const double* actions, const double* noise, const gfr_step_out* out,
+                 void* stream);
+
+/* solver.solve(...) (reference power_flow.py:89-211) on B independent injection vectors.
+ * p_inj [B,n] pu in ref bus order (generation minus load; the slack entry is ignored). */
+int gfr_solve(const gfr_feeder* f, int64_t B, const double* p_inj, const gfr_solver_cfg* cfg,
+              const gfr_sol_out* out, void* stream);
+
+/* The noise rows the in-kernel generator yields: out [B, n_slots] for keys seeds[B] and draw
+ * counters draws[B] (slot 0 uniform, slots 1.. standard normal). */
+int gfr_noise_fill(int device, int64_t B, int32_t n_slots, const uint64_t* seeds,
+                   const uint64_t* draws, double* out, void* stream);
+
+/* Launch bookkeeping for benchmarks: kernels launched by this library since load. */
+int64_t gfr_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GFR_B200_H */
