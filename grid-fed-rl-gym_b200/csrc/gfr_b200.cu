@@ -1,0 +1,516 @@
+// gfr_b200.cu - kernels (sm_100a) and the C ABI declared in include/gfr_b200.h.
+//
+// Launch shape: persistent CTAs; a group of LANES threads takes instance after instance
+// (stride gridDim * groups-per-CTA) and never meets a CTA-wide barrier after the prologue,
+// so an instance whose solve converges early frees its group early.  The prologue stages
+// the compiled feeder ("image") into shared memory with ONE bulk async copy (TMA,
+// cp.async.bulk -> SASS UBLKCP) completed on an mbarrier.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/gfr_b200.h"
+#include "gfr_device.cuh"
+#include "gfr_image.hpp"
+
+using namespace gfr;
+
+// ----------------------------------------------------------------------------- device side
+
+namespace {
+
+constexpr int kSmemHeader = 16;   // the mbarrier, keeps the image 16-byte aligned
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+// One elected thread issues the bulk copy global -> shared; everyone waits on the mbarrier.
+__device__ __forceinline__ void stage_image(unsigned char* smem, const void* img, int bytes) {
+  const uint32_t bar = smem_u32(smem);
+  const uint32_t dst = smem_u32(smem + kSmemHeader);
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(1) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+                 : "memory");
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+        "l"(img), "r"(bytes), "r"(bar)
+        : "memory");
+  }
+  uint32_t ok = 0;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(0)
+        : "memory");
+  } while (!ok);
+}
+
+template <int LANES>
+__device__ __forceinline__ Grp<LANES> make_group(const Layout& lay, unsigned char* smem) {
+  Grp<LANES> g;
+  g.E = blockDim.x / LANES;
+  g.e = threadIdx.x / LANES;
+  g.lane = threadIdx.x % LANES;
+  g.FS = ((lay.n + LANES - 1) / LANES) * LANES * g.E;
+  g.st = (double*)(smem + kSmemHeader + lay.img_bytes);
+  g.mask = (LANES == 32) ? 0xffffffffu
+                         : (((1u << (LANES & 31)) - 1u) << (((threadIdx.x & 31) / LANES) * LANES));
+  return g;
+}
+
+template <int LANES, int SOLVER>
+__global__ void __launch_bounds__(128)
+step_kernel(const Layout lay, const EnvCfg cfg, const int nf, const void* __restrict__ img,
+            double* __restrict__ state, double* __restrict__ obs,
+            const double* __restrict__ actions, const double* __restrict__ noise, const StepOut o,
+            const long long B) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  stage_image(smem, img, lay.img_bytes);
+  const int* simg = (const int*)(smem + kSmemHeader);
+  const double* dimg = (const double*)(smem + kSmemHeader);
+  const Grp<LANES> g = make_group<LANES>(lay, smem);
+  for (long long env = (long long)blockIdx.x * g.E + g.e; env < B; env += (long long)gridDim.x * g.E)
+    step_instance<LANES, SOLVER>(g, lay, simg, dimg, cfg, nf, env, state, obs, actions, noise, o);
+}
+
+template <int LANES, int SOLVER>
+__global__ void __launch_bounds__(128)
+solve_kernel(const Layout lay, const EnvCfg cfg, const int nf, const void* __restrict__ img,
+             const double* __restrict__ p_inj, const SolOut o, const long long B) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  stage_image(smem, img, lay.img_bytes);
+  const int* simg = (const int*)(smem + kSmemHeader);
+  const double* dimg = (const double*)(smem + kSmemHeader);
+  const Grp<LANES> g = make_group<LANES>(lay, smem);
+  for (long long env = (long long)blockIdx.x * g.E + g.e; env < B; env += (long long)gridDim.x * g.E)
+    solve_instance<LANES, SOLVER>(g, lay, simg, dimg, cfg, nf, env, p_inj, o);
+}
+
+// reset: 4 lanes per instance, image read through L2 (touched once per instance)
+__global__ void __launch_bounds__(128)
+reset_kernel(const Layout lay, const EnvCfg cfg, const void* __restrict__ img,
+             double* __restrict__ state, double* __restrict__ obs,
+             const double* __restrict__ load_pq, const double* __restrict__ bat_soc0,
+             const uint64_t* __restrict__ seeds, const uint8_t* __restrict__ mask,
+             const double* __restrict__ noise, const double start_time, const int construct,
+             const long long B) {
+  constexpr int LANES = 4;
+  Grp<LANES> g;
+  g.E = blockDim.x / LANES; g.e = threadIdx.x / LANES; g.lane = threadIdx.x % LANES;
+  g.FS = 0; g.st = nullptr;
+  g.mask = ((1u << LANES) - 1u) << (((threadIdx.x & 31) / LANES) * LANES);
+  const int* simg = (const int*)img;
+  const double* dimg = (const double*)img;
+  for (long long env = (long long)blockIdx.x * g.E + g.e; env < B; env += (long long)gridDim.x * g.E) {
+    if (mask && !mask[env]) continue;
+    reset_instance<LANES>(g, lay, simg, dimg, cfg, env, state, obs, load_pq, bat_soc0, seeds, noise,
+                          start_time, construct != 0);
+  }
+}
+
+__global__ void noise_fill_kernel(const long long B, const int n_slots,
+                                  const uint64_t* __restrict__ seeds,
+                                  const uint64_t* __restrict__ draws, double* __restrict__ out) {
+  const long long total = B * (long long)n_slots;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long env = i / n_slots;
+    const int s = (int)(i - env * n_slots);
+    out[i] = noise_slot(seeds[env], draws[env], s);
+  }
+}
+
+}  // namespace
+
+// ----------------------------------------------------------------------------- host side
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<long long> g_launches{0};
+
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+int cuda_fail(cudaError_t e, const char* what) {
+  g_err = std::string(what) + ": " + cudaGetErrorString(e);
+  return GFR_E_CUDA;
+}
+#define GFR_CUDA(call)                                     \
+  do {                                                     \
+    cudaError_t e_ = (call);                               \
+    if (e_ != cudaSuccess) return cuda_fail(e_, #call);    \
+  } while (0)
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+    if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+    cur = dev;
+  }
+  ~DeviceGuard() { if (ok && prev >= 0 && prev != cur) cudaSetDevice(prev); }
+  int cur = -1;
+};
+
+}  // namespace
+
+struct gfr_feeder {
+  int device = 0;
+  int sm_count = 0;
+  int smem_optin = 0;
+  Layout lay{};
+  bool has_pv = false;
+  void* d_img = nullptr;         // image
+  double* d_load_pq = nullptr;   // [2L] static active / reactive power (observation)
+  double* d_bat_soc0 = nullptr;  // [Bt]
+};
+
+struct gfr_env {
+  const gfr_feeder* f = nullptr;
+  long long B = 0;
+  EnvCfg cfg{};
+  int solver = GFR_SOLVER_NEWTON;
+  int lanes = 0, threads = 0, nf = 0, grid = 0;
+  size_t smem = 0;
+  double* d_state = nullptr;
+  double* d_obs = nullptr;
+};
+
+namespace {
+
+struct LaunchPlan { int lanes, threads, nf, grid; size_t smem; };
+
+int fields_needed(const Layout& lay, int solver, int lanes) {
+  const int kbl = ((lay.n + lanes - 1) / lanes) * lanes;
+  int nf = solver == GFR_SOLVER_NEWTON ? NF_NEWTON : NF_SWEEP;
+  const int need = F_SCRATCH + (lay.n_src + kbl - 1) / kbl;
+  return need > nf ? need : nf;
+}
+
+int auto_lanes(const Layout& lay) {
+  if (lay.n <= 16) return 4;
+  if (lay.n <= 64) return 8;
+  return 16;
+}
+
+// threads per CTA: the candidate that keeps the most threads resident per SM
+int plan_launch(const gfr_feeder* f, int solver, int lanes, long long B, LaunchPlan* out) {
+  const Layout& lay = f->lay;
+  if (lanes == 0) lanes = auto_lanes(lay);
+  if (lanes != 1 && lanes != 2 && lanes != 4 && lanes != 8 && lanes != 16 && lanes != 32)
+    return fail(GFR_E_ARG, "lanes must be 0 (auto), 1, 2, 4, 8, 16 or 32");
+  const int nf = fields_needed(lay, solver, lanes);
+  const int kbl = ((lay.n + lanes - 1) / lanes) * lanes;
+  const size_t per_env = (size_t)nf * kbl * sizeof(double);
+  const size_t sm_budget = 227u * 1024u;
+  int best_threads = 0;
+  long long best_resident = 0;
+  size_t best_smem = 0;
+  for (int threads = 128; threads >= 32 && threads >= lanes; threads >>= 1) {
+    const size_t smem = kSmemHeader + (size_t)lay.img_bytes + per_env * (threads / lanes);
+    if (smem > (size_t)f->smem_optin) continue;
+    long long ctas = (long long)(sm_budget / (smem + 1024));
+    if (ctas > 32) ctas = 32;
+    if (ctas * threads > 2048) ctas = 2048 / threads;
+    if (ctas < 1) ctas = 1;
+    const long long resident = ctas * threads;
+    if (resident > best_resident) { best_resident = resident; best_threads = threads; best_smem = smem; }
+  }
+  if (!best_threads)
+    return fail(GFR_E_LIMIT, "feeder image + one instance's working set exceed the shared memory of an SM");
+  const int E = best_threads / lanes;
+  long long tiles = (B + E - 1) / E;
+  long long grid = (long long)f->sm_count * (best_resident / best_threads);
+  if (grid > tiles) grid = tiles;
+  if (grid < 1) grid = 1;
+  out->lanes = lanes; out->threads = best_threads; out->nf = nf; out->grid = (int)grid; out->smem = best_smem;
+  return GFR_OK;
+}
+
+template <int LANES, int SOLVER>
+int launch_step_t(const gfr_env* e, const double* actions, const double* noise, const StepOut& o,
+                  cudaStream_t s) {
+  auto kern = step_kernel<LANES, SOLVER>;
+  GFR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
+  kern<<<e->grid, e->threads, e->smem, s>>>(e->f->lay, e->cfg, e->nf, e->f->d_img, e->d_state, e->d_obs,
+                                           actions, noise, o, e->B);
+  g_launches.fetch_add(1);
+  GFR_CUDA(cudaGetLastError());
+  return GFR_OK;
+}
+
+template <int LANES, int SOLVER>
+int launch_solve_t(const gfr_feeder* f, const LaunchPlan& p, const EnvCfg& cfg, const double* p_inj,
+                   const SolOut& o, long long B, cudaStream_t s) {
+  auto kern = solve_kernel<LANES, SOLVER>;
+  GFR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+  kern<<<p.grid, p.threads, p.smem, s>>>(f->lay, cfg, p.nf, f->d_img, p_inj, o, B);
+  g_launches.fetch_add(1);
+  GFR_CUDA(cudaGetLastError());
+  return GFR_OK;
+}
+
+#define GFR_DISPATCH(LN, SV, CALL)                                                   \
+  switch ((LN) * 2 + ((SV) == GFR_SOLVER_NEWTON ? 1 : 0)) {                            \
+    case 1 * 2 + 0: return CALL(1, SOLVER_SWEEP);                                      \
+    case 1 * 2 + 1: return CALL(1, SOLVER_NEWTON);                                     \
+    case 2 * 2 + 0: return CALL(2, SOLVER_SWEEP);                                      \
+    case 2 * 2 + 1: return CALL(2, SOLVER_NEWTON);                                     \
+    case 4 * 2 + 0: return CALL(4, SOLVER_SWEEP);                                      \
+    case 4 * 2 + 1: return CALL(4, SOLVER_NEWTON);                                     \
+    case 8 * 2 + 0: return CALL(8, SOLVER_SWEEP);                                      \
+    case 8 * 2 + 1: return CALL(8, SOLVER_NEWTON);                                     \
+    case 16 * 2 + 0: return CALL(16, SOLVER_SWEEP);                                    \
+    case 16 * 2 + 1: return CALL(16, SOLVER_NEWTON);                                   \
+    case 32 * 2 + 0: return CALL(32, SOLVER_SWEEP);                                    \
+    case 32 * 2 + 1: return CALL(32, SOLVER_NEWTON);                                   \
+    default: return fail(GFR_E_ARG, "unsupported lanes / solver combination");         \
+  }
+
+int launch_step(const gfr_env* e, const double* actions, const double* noise, const StepOut& o,
+                cudaStream_t s) {
+#define GFR_CALL_STEP(L_, S_) launch_step_t<L_, S_>(e, actions, noise, o, s)
+  GFR_DISPATCH(e->lanes, e->solver, GFR_CALL_STEP)
+#undef GFR_CALL_STEP
+}
+
+int launch_solve(const gfr_feeder* f, const LaunchPlan& p, int solver, const EnvCfg& cfg,
+                 const double* p_inj, const SolOut& o, long long B, cudaStream_t s) {
+#define GFR_CALL_SOLVE(L_, S_) launch_solve_t<L_, S_>(f, p, cfg, p_inj, o, B, s)
+  GFR_DISPATCH(p.lanes, solver, GFR_CALL_SOLVE)
+#undef GFR_CALL_SOLVE
+}
+
+int check_solver_cfg(const gfr_feeder* f, const gfr_solver_cfg* c) {
+  if (c->solver != GFR_SOLVER_SWEEP && c->solver != GFR_SOLVER_NEWTON)
+    return fail(GFR_E_ARG, "solver must be GFR_SOLVER_SWEEP or GFR_SOLVER_NEWTON");
+  if (c->max_iterations < 1) return fail(GFR_E_ARG, "max_iterations must be >= 1");
+  if (!(c->tolerance > 0.0)) return fail(GFR_E_ARG, "tolerance must be > 0");
+  if (c->solver == GFR_SOLVER_SWEEP && f->has_pv)
+    return fail(GFR_E_ARG, "the sweep solver handles slack + PQ buses only; use GFR_SOLVER_NEWTON for PV buses");
+  return GFR_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int gfr_abi_version(void) { return GFR_ABI_VERSION; }
+const char* gfr_last_error(void) { return g_err.c_str(); }
+int64_t gfr_launch_count(void) { return g_launches.load(); }
+
+int gfr_feeder_create(const gfr_feeder_desc* d, int device, gfr_feeder** out) {
+  if (!d || !out) return fail(GFR_E_ARG, "null argument");
+  *out = nullptr;
+  FeederImage fi;
+  {
+    std::string complaint = build_feeder_image(d, &fi);
+    if (!complaint.empty()) return fail(GFR_E_ARG, complaint);
+  }
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail(GFR_E_CUDA, "no usable CUDA device (this library has no CPU fallback)");
+  cudaDeviceProp prop;
+  GFR_CUDA(cudaGetDeviceProperties(&prop, device));
+
+  auto* f = new gfr_feeder();
+  f->device = device;
+  f->sm_count = prop.multiProcessorCount;
+  f->smem_optin = (int)prop.sharedMemPerBlockOptin;
+  f->lay = fi.lay;
+  f->has_pv = fi.has_pv;
+  const Layout& lay = f->lay;
+  const int L = lay.L, Bt = lay.Bt;
+  const size_t img_bytes = fi.img.size();
+  const std::vector<unsigned char>& img = fi.img;
+  const std::vector<double>& load_pq = fi.load_pq;
+  cudaError_t e1 = cudaMalloc(&f->d_img, img_bytes);
+  cudaError_t e2 = cudaMalloc((void**)&f->d_load_pq, load_pq.size() * 8);
+  cudaError_t e3 = cudaMalloc((void**)&f->d_bat_soc0, ((size_t)Bt + 1) * 8);
+  if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
+    gfr_feeder_destroy(f);
+    return cuda_fail(e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3), "cudaMalloc(feeder)");
+  }
+  cudaError_t c1 = cudaMemcpy(f->d_img, img.data(), img_bytes, cudaMemcpyHostToDevice);
+  cudaError_t c2 = cudaMemcpy(f->d_load_pq, load_pq.data(), load_pq.size() * 8, cudaMemcpyHostToDevice);
+  cudaError_t c3 = Bt ? cudaMemcpy(f->d_bat_soc0, d->bat_soc0, (size_t)Bt * 8, cudaMemcpyHostToDevice) : cudaSuccess;
+  if (c1 != cudaSuccess || c2 != cudaSuccess || c3 != cudaSuccess) {
+    gfr_feeder_destroy(f);
+    return cuda_fail(c1 != cudaSuccess ? c1 : (c2 != cudaSuccess ? c2 : c3), "cudaMemcpy(feeder)");
+  }
+  *out = f;
+  return GFR_OK;
+}
+
+void gfr_feeder_destroy(gfr_feeder* f) {
+  if (!f) return;
+  DeviceGuard guard(f->device);
+  cudaFree(f->d_img);
+  cudaFree(f->d_load_pq);
+  cudaFree(f->d_bat_soc0);
+  delete f;
+}
+
+static int fill_env_cfg(const gfr_feeder* f, const gfr_env_cfg* c, EnvCfg* out) {
+  if (int rc = check_solver_cfg(f, &c->solver)) return rc;
+  if (!(c->timestep > 0.0)) return fail(GFR_E_ARG, "timestep must be > 0");
+  if (c->episode_length < 1) return fail(GFR_E_ARG, "episode_length must be >= 1");
+  out->dt = c->timestep; out->v_min = c->v_min; out->v_max = c->v_max; out->f_min = c->f_min;
+  out->f_max = c->f_max; out->penalty = c->safety_penalty; out->load_noise = c->load_noise;
+  out->tol = c->solver.tolerance;
+  out->accel = c->solver.solver == GFR_SOLVER_NEWTON ? (c->solver.acceleration != 0.0 ? c->solver.acceleration : 1.0) : 1.0;
+  out->episode_length = c->episode_length; out->stochastic_loads = c->stochastic_loads != 0;
+  out->weather_variation = c->weather_variation != 0; out->max_it = c->solver.max_iterations;
+  return GFR_OK;
+}
+
+static int launch_reset(gfr_env* e, const uint64_t* seeds, const uint8_t* mask, const double* noise,
+                        double start_time, int construct, cudaStream_t s) {
+  const int threads = 128, per_cta = threads / 4;
+  long long grid = (e->B + per_cta - 1) / per_cta;
+  const long long cap = (long long)e->f->sm_count * 16;
+  if (grid > cap) grid = cap;
+  reset_kernel<<<(int)grid, threads, 0, s>>>(e->f->lay, e->cfg, e->f->d_img, e->d_state, e->d_obs,
+                                            e->f->d_load_pq, e->f->d_bat_soc0, seeds, mask, noise,
+                                            start_time, construct, e->B);
+  g_launches.fetch_add(1);
+  GFR_CUDA(cudaGetLastError());
+  return GFR_OK;
+}
+
+int gfr_env_create(const gfr_feeder* f, int64_t n_envs, const gfr_env_cfg* cfg, gfr_env** out) {
+  if (!f || !cfg || !out) return fail(GFR_E_ARG, "null argument");
+  *out = nullptr;
+  if (n_envs < 1) return fail(GFR_E_ARG, "n_envs must be >= 1");
+  EnvCfg ec;
+  if (int rc = fill_env_cfg(f, cfg, &ec)) return rc;
+  LaunchPlan plan;
+  if (int rc = plan_launch(f, cfg->solver.solver, cfg->solver.lanes, n_envs, &plan)) return rc;
+  DeviceGuard guard(f->device);
+  if (!guard.ok) return fail(GFR_E_CUDA, "no usable CUDA device (this library has no CPU fallback)");
+  auto* e = new gfr_env();
+  e->f = f; e->B = n_envs; e->cfg = ec; e->solver = cfg->solver.solver;
+  e->lanes = plan.lanes; e->threads = plan.threads; e->nf = plan.nf; e->grid = plan.grid; e->smem = plan.smem;
+  cudaError_t e1 = cudaMalloc((void**)&e->d_state, (size_t)n_envs * f->lay.R * 8);
+  cudaError_t e2 = cudaMalloc((void**)&e->d_obs, (size_t)n_envs * f->lay.D * 8);
+  if (e1 != cudaSuccess || e2 != cudaSuccess) {
+    gfr_env_destroy(e);
+    return cuda_fail(e1 != cudaSuccess ? e1 : e2, "cudaMalloc(env)");
+  }
+  if (int rc = launch_reset(e, nullptr, nullptr, nullptr, 0.0, 1, 0)) { gfr_env_destroy(e); return rc; }
+  cudaError_t es = cudaStreamSynchronize(0);
+  if (es != cudaSuccess) { gfr_env_destroy(e); return cuda_fail(es, "reset at construction"); }
+  *out = e;
+  return GFR_OK;
+}
+
+void gfr_env_destroy(gfr_env* e) {
+  if (!e) return;
+  DeviceGuard guard(e->f->device);
+  cudaFree(e->d_state);
+  cudaFree(e->d_obs);
+  delete e;
+}
+
+int64_t gfr_env_num_envs(const gfr_env* e) { return e ? e->B : 0; }
+int gfr_env_obs_dim(const gfr_env* e) { return e ? e->f->lay.D : 0; }
+int gfr_env_act_dim(const gfr_env* e) { return e ? e->f->lay.A : 0; }
+int gfr_env_noise_dim(const gfr_env* e) { return e ? e->f->lay.n_noise : 0; }
+double* gfr_env_obs(gfr_env* e) { return e ? e->d_obs : nullptr; }
+int64_t gfr_env_state_bytes(const gfr_env* e) { return e ? (int64_t)e->B * e->f->lay.R * 8 : 0; }
+
+int gfr_env_launch_info(const gfr_env* e, int32_t* lanes, int32_t* threads, int32_t* grid, int64_t* smem_bytes) {
+  if (!e) return fail(GFR_E_ARG, "null env");
+  if (lanes) *lanes = e->lanes;
+  if (threads) *threads = e->threads;
+  if (grid) *grid = e->grid;
+  if (smem_bytes) *smem_bytes = (int64_t)e->smem;
+  return GFR_OK;
+}
+
+int gfr_env_state_get(gfr_env* e, void* dst, void* stream) {
+  if (!e || !dst) return fail(GFR_E_ARG, "null argument");
+  DeviceGuard guard(e->f->device);
+  GFR_CUDA(cudaMemcpyAsync(dst, e->d_state, (size_t)gfr_env_state_bytes(e), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return GFR_OK;
+}
+
+int gfr_env_state_set(gfr_env* e, const void* src, void* stream) {
+  if (!e || !src) return fail(GFR_E_ARG, "null argument");
+  DeviceGuard guard(e->f->device);
+  GFR_CUDA(cudaMemcpyAsync(e->d_state, src, (size_t)gfr_env_state_bytes(e), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return GFR_OK;
+}
+
+int gfr_env_reset(gfr_env* e, const uint64_t* seeds, const uint8_t* mask, const double* noise,
+                  double start_time, void* stream) {
+  if (!e) return fail(GFR_E_ARG, "null env");
+  if (!(start_time >= 0.0)) return fail(GFR_E_ARG, "start_time must be >= 0");
+  DeviceGuard guard(e->f->device);
+  return launch_reset(e, seeds, mask, noise, start_time, 0, (cudaStream_t)stream);
+}
+
+int gfr_env_step(gfr_env* e, const double* actions, const double* noise, const gfr_step_out* out,
+                 void* stream) {
+  if (!e || !actions) return fail(GFR_E_ARG, "null argument");
+  StepOut o{};
+  if (out) {
+    o.reward = out->reward; o.terminated = out->terminated; o.truncated = out->truncated;
+    o.error = out->error; o.converged = out->converged; o.iterations = out->iterations;
+    o.max_voltage = out->max_voltage; o.min_voltage = out->min_voltage; o.losses = out->losses;
+    o.max_mismatch = out->max_mismatch; o.violations = out->violations;
+    o.violation_count = out->violation_count; o.current_step = out->current_step;
+    o.episode_reward = out->episode_reward; o.noise_used = out->noise_used;
+  }
+  DeviceGuard guard(e->f->device);
+  return launch_step(e, actions, noise, o, (cudaStream_t)stream);
+}
+
+int gfr_solve(const gfr_feeder* f, int64_t B, const double* p_inj, const gfr_solver_cfg* cfg,
+              const gfr_sol_out* out, void* stream) {
+  if (!f || !p_inj || !cfg || !out) return fail(GFR_E_ARG, "null argument");
+  if (B < 1) return fail(GFR_E_ARG, "B must be >= 1");
+  if (int rc = check_solver_cfg(f, cfg)) return rc;
+  LaunchPlan plan;
+  if (int rc = plan_launch(f, cfg->solver, cfg->lanes, B, &plan)) return rc;
+  EnvCfg ec{};
+  ec.tol = cfg->tolerance; ec.max_it = cfg->max_iterations;
+  ec.accel = cfg->acceleration != 0.0 ? cfg->acceleration : 1.0;
+  SolOut o{};
+  o.converged = out->converged; o.iterations = out->iterations; o.bus_voltages = out->bus_voltages;
+  o.bus_angles = out->bus_angles; o.line_flows = out->line_flows; o.line_loadings = out->line_loadings;
+  o.losses = out->losses; o.max_mismatch = out->max_mismatch;
+  DeviceGuard guard(f->device);
+  return launch_solve(f, plan, cfg->solver, ec, p_inj, o, B, (cudaStream_t)stream);
+}
+
+int gfr_noise_fill(int device, int64_t B, int32_t n_slots, const uint64_t* seeds, const uint64_t* draws,
+                   double* out, void* stream) {
+  if (B < 1 || n_slots < 1 || !seeds || !draws || !out) return fail(GFR_E_ARG, "bad argument");
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail(GFR_E_CUDA, "no usable CUDA device (this library has no CPU fallback)");
+  long long total = B * (long long)n_slots;
+  long long grid = (total + 255) / 256;
+  if (grid > 148 * 8) grid = 148 * 8;
+  noise_fill_kernel<<<(int)grid, 256, 0, (cudaStream_t)stream>>>(B, n_slots, seeds, draws, out);
+  g_launches.fetch_add(1);
+  GFR_CUDA(cudaGetLastError());
+  return GFR_OK;
+}
+
+}  // extern "C"

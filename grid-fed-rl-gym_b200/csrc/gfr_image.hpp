@@ -1,0 +1,166 @@
+// gfr_image.hpp - host-side check of a gfr_feeder_desc and its packing into the "image" the
+// kernels read (ints first, then doubles; offsets recorded in gfr::Layout).
+#pragma once
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/gfr_b200.h"
+#include "gfr_device.cuh"
+
+namespace gfr {
+
+struct ImageBuilder {
+  std::vector<int32_t> ints;
+  std::vector<double> dbls;
+  int add_i(const int32_t* p, int count) {
+    int off = (int)ints.size();
+    if (count > 0) ints.insert(ints.end(), p, p + count);
+    return off;
+  }
+  int add_d(const double* p, int count) {
+    int off = (int)dbls.size();
+    if (count > 0) dbls.insert(dbls.end(), p, p + count);
+    return off;
+  }
+};
+
+struct FeederImage {
+  Layout lay{};
+  bool has_pv = false;
+  std::vector<unsigned char> img;
+  std::vector<double> load_pq;     // [2L] static active / reactive power (observation)
+};
+
+// returns an empty string on success, the complaint otherwise
+inline std::string build_feeder_image(const gfr_feeder_desc* d, FeederImage* out) {
+  const int n = d->n_bus, nl = d->n_levels, L = d->n_load, G = d->n_gen, Bt = d->n_bat;
+  if (n < 1 || nl < 1 || L < 0 || G < 0 || Bt < 0) return "bad feeder dimensions";
+  if (!(d->s_base > 0.0)) return "s_base must be > 0";
+  if (!d->order || !d->parent || !d->level_ptr || !d->child_ptr || !d->bus_type || !d->vm_set || !d->g ||
+      !d->b || !d->gdiag || !d->bdiag || !d->r || !d->x || !d->line_of || !d->from_is_parent ||
+      !d->rating || !d->load_profile)
+    return "missing topology array";
+  if ((L && (!d->load_bus || !d->load_base || !d->load_p || !d->load_q)) ||
+      (G && (!d->gen_type || !d->gen_bus || !d->gen_cap || !d->gen_p0 || !d->gen_p1 || !d->gen_p2)) ||
+      (Bt && (!d->bat_bus || !d->bat_cap || !d->bat_rating || !d->bat_eff || !d->bat_soc0)))
+    return "missing component array";
+  // ---- structure checks: level order, contiguous children, one slack at k = 0
+  if (d->parent[0] != -1 || d->bus_type[0] != GFR_BUS_SLACK) return "k = 0 must be the slack bus";
+  if (d->level_ptr[0] != 0 || d->level_ptr[nl] != n) return "level_ptr must span [0, n]";
+  if (nl >= 1 && n >= 1 && d->level_ptr[1] != 1) return "level 0 must hold the slack bus only";
+  std::vector<int32_t> seen_ref(n, 0), seen_line(n > 1 ? n - 1 : 0, 0);
+  for (int l = 0; l < nl; ++l)
+    if (d->level_ptr[l + 1] <= d->level_ptr[l]) return "empty level";
+  for (int k = 0; k < n; ++k) {
+    if (d->order[k] < 0 || d->order[k] >= n || seen_ref[d->order[k]]++) return "order is not a permutation";
+    if (d->child_ptr[k + 1] < d->child_ptr[k]) return "child_ptr must be non-decreasing";
+    if (k > 0) {
+      if (d->bus_type[k] == GFR_BUS_SLACK) return "more than one slack bus";
+      const int p = d->parent[k];
+      if (p < 0 || p >= k) return "parent must precede its child in level order";
+      if (k < d->child_ptr[p] || k >= d->child_ptr[p + 1]) return "child_ptr does not match parent";
+      const int li = d->line_of[k];
+      if (li < 0 || li >= n - 1 || seen_line[li]++) return "line_of is not a permutation of the lines";
+      if (!(d->g[k] == d->g[k]) || !(d->b[k] == d->b[k]) || (d->g[k] == 0.0 && d->b[k] == 0.0))
+        return "branch with zero / NaN admittance";
+    }
+  }
+  if (d->child_ptr[0] != 1 && n > 1) return "child_ptr[0] must be 1";
+  if (d->child_ptr[n] != n) return "child_ptr[n] must be n";
+  // level of a child = level of its parent + 1
+  {
+    std::vector<int> level(n, 0);
+    for (int l = 0; l < nl; ++l)
+      for (int k = d->level_ptr[l]; k < d->level_ptr[l + 1]; ++k) level[k] = l;
+    for (int k = 1; k < n; ++k)
+      if (level[k] != level[d->parent[k]] + 1) return "level_ptr does not match parent";
+  }
+  for (int l = 0; l < L; ++l) if (d->load_bus[l] < 0 || d->load_bus[l] >= n) return "load_bus out of range";
+  for (int g = 0; g < G; ++g) {
+    if (d->gen_bus[g] < 0 || d->gen_bus[g] >= n) return "gen_bus out of range";
+    if (d->gen_type[g] != GFR_GEN_SOLAR && d->gen_type[g] != GFR_GEN_WIND) return "unknown gen_type";
+  }
+  for (int b = 0; b < Bt; ++b) if (d->bat_bus[b] < 0 || d->bat_bus[b] >= n) return "bat_bus out of range";
+
+  FeederImage* f = out;
+  Layout& lay = f->lay;
+  lay.n = n; lay.nl = nl; lay.L = L; lay.G = G; lay.Bt = Bt; lay.A = Bt + G; lay.m = n - 1;
+  lay.D = 2 * n + 2 * (n - 1) + 1 + 2 * L + G + 2 * Bt;
+  lay.n_src = L + G + Bt; lay.R = R_BAT + 2 * Bt; lay.n_noise = 4 + L;
+  lay.s_base = d->s_base;
+  double lp = 0.0;
+  for (int l = 0; l < L; ++l) lp = lp + d->load_p[l];   // sequential, as grid_env.py:744
+  lay.load_p_sum = lp;
+
+  ImageBuilder ib;
+  std::vector<int32_t> flags(n), rank(n), bol(n > 1 ? n - 1 : 0), line_of(n);
+  for (int k = 0; k < n; ++k) {
+    int fl = 0;
+    if (d->bus_type[k] == GFR_BUS_PQ) fl |= FL_PQ;
+    else fl |= FL_FIXED_VM;
+    if (d->bus_type[k] == GFR_BUS_PV) f->has_pv = true;
+    if (d->from_is_parent[k]) fl |= FL_FROM_IS_PARENT;
+    flags[k] = fl;
+    rank[d->order[k]] = k;
+    line_of[k] = d->line_of[k];
+    if (k > 0) bol[d->line_of[k]] = k;
+  }
+  // injection sources per bus: loads, then generators, then batteries (reference accumulation order)
+  std::vector<int32_t> inj_ptr(n + 1, 0), inj_idx(lay.n_src);
+  {
+    std::vector<int> cnt(n, 0);
+    for (int l = 0; l < L; ++l) cnt[d->load_bus[l]]++;
+    for (int g = 0; g < G; ++g) cnt[d->gen_bus[g]]++;
+    for (int b = 0; b < Bt; ++b) cnt[d->bat_bus[b]]++;
+    for (int k = 0; k < n; ++k) inj_ptr[k + 1] = inj_ptr[k] + cnt[k];
+    std::vector<int> fill(inj_ptr.begin(), inj_ptr.end() - 1);
+    for (int l = 0; l < L; ++l) inj_idx[fill[d->load_bus[l]]++] = l;
+    for (int g = 0; g < G; ++g) inj_idx[fill[d->gen_bus[g]]++] = L + g;
+    for (int b = 0; b < Bt; ++b) inj_idx[fill[d->bat_bus[b]]++] = L + G + b;
+  }
+  lay.o_parent = ib.add_i(d->parent, n);
+  lay.o_child_ptr = ib.add_i(d->child_ptr, n + 1);
+  lay.o_level_ptr = ib.add_i(d->level_ptr, nl + 1);
+  lay.o_flags = ib.add_i(flags.data(), n);
+  lay.o_order = ib.add_i(d->order, n);
+  lay.o_rank = ib.add_i(rank.data(), n);
+  lay.o_line_of = ib.add_i(line_of.data(), n);
+  lay.o_branch_of_line = ib.add_i(bol.data(), n - 1);
+  lay.o_inj_ptr = ib.add_i(inj_ptr.data(), n + 1);
+  lay.o_inj_idx = ib.add_i(inj_idx.data(), lay.n_src);
+  lay.o_gen_type = ib.add_i(d->gen_type, G);
+  const int n_int_padded = ((int)ib.ints.size() + 3) / 4 * 4;      // keep the doubles 16-byte aligned
+  const int dbase = n_int_padded / 2;
+  lay.o_g = dbase + ib.add_d(d->g, n);
+  lay.o_b = dbase + ib.add_d(d->b, n);
+  lay.o_gdiag = dbase + ib.add_d(d->gdiag, n);
+  lay.o_bdiag = dbase + ib.add_d(d->bdiag, n);
+  lay.o_r = dbase + ib.add_d(d->r, n);
+  lay.o_x = dbase + ib.add_d(d->x, n);
+  lay.o_rating = dbase + ib.add_d(d->rating, n);
+  lay.o_vm_set = dbase + ib.add_d(d->vm_set, n);
+  lay.o_load_base = dbase + ib.add_d(d->load_base, L);
+  lay.o_gen_cap = dbase + ib.add_d(d->gen_cap, G);
+  lay.o_gen_p0 = dbase + ib.add_d(d->gen_p0, G);
+  lay.o_gen_p1 = dbase + ib.add_d(d->gen_p1, G);
+  lay.o_gen_p2 = dbase + ib.add_d(d->gen_p2, G);
+  lay.o_bat_cap = dbase + ib.add_d(d->bat_cap, Bt);
+  lay.o_bat_rating = dbase + ib.add_d(d->bat_rating, Bt);
+  lay.o_bat_eff = dbase + ib.add_d(d->bat_eff, Bt);
+  lay.o_profile = dbase + ib.add_d(d->load_profile, 24);
+  const size_t img_bytes = ((size_t)n_int_padded * 4 + ib.dbls.size() * 8 + 15) / 16 * 16;
+  lay.img_bytes = (int)img_bytes;
+  std::vector<unsigned char> img(img_bytes, 0);
+  std::memcpy(img.data(), ib.ints.data(), ib.ints.size() * 4);
+  std::memcpy(img.data() + (size_t)n_int_padded * 4, ib.dbls.data(), ib.dbls.size() * 8);
+
+  std::vector<double> load_pq(2 * (size_t)L + 1, 0.0);
+  for (int l = 0; l < L; ++l) { load_pq[2 * l] = d->load_p[l]; load_pq[2 * l + 1] = d->load_q[l]; }
+
+  f->img.swap(img);
+  f->load_pq.swap(load_pq);
+  return std::string();
+}
+
+}  // namespace gfr

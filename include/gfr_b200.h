@@ -157,6 +157,10 @@ int gfr_env_noise_dim(const gfr_env* e);    /* 4 + L */
  * rewritten in place by reset and step (left untouched for instances whose action was rejected,
  * whose observation is by definition unchanged). */
 double* gfr_env_obs(gfr_env* e);
+/* How the step kernel is launched for this env (for benchmarks / profiles): threads cooperating
+ * on one instance, threads per CTA, CTAs, dynamic shared memory per CTA. */
+int gfr_env_launch_info(const gfr_env* e, int32_t* lanes, int32_t* threads, int32_t* grid,
+                        int64_t* smem_bytes);
 /* Size in bytes / copy of the persistent per-instance state (checkpoint / resume). */
 int64_t gfr_env_state_bytes(const gfr_env* e);
 int gfr_env_state_get(gfr_env* e, void* dst_device, void* stream);

@@ -55,7 +55,7 @@ def obs_layout(n, m, L, G, Bt):
     return out
 
 
-def compare_step(got, g, t, lay, s_base, ctx=""):
+def compare_step(got, g, t, lay, s_base, ctx="", check_iterations=True):
     """got: dict of per-env arrays (env 0 compared) vs golden step t."""
     def chk(a, b, tol, what):
         a, b = np.asarray(a, dtype=float), np.asarray(b, dtype=float)
@@ -79,7 +79,8 @@ def compare_step(got, g, t, lay, s_base, ctx=""):
     assert bool(got["terminated"]) == bool(g["terminated"][t]), f"{ctx} step {t}: terminated"
     assert bool(got["error"]) == bool(g["error"][t]), f"{ctx} step {t}: error flag"
     assert bool(got["converged"]) == bool(g["converged"][t]), f"{ctx} step {t}: converged"
-    assert abs(int(got["iterations"]) - int(g["iterations"][t])) <= 1, f"{ctx} step {t}: iterations"
+    if check_iterations:
+        assert abs(int(got["iterations"]) - int(g["iterations"][t])) <= 1, f"{ctx} step {t}: iterations"
     assert int(got["current_step"]) == int(g["current_step"][t]), f"{ctx} step {t}: current_step"
     # threshold margins
     vm = ref[lay["vm"]]
@@ -94,7 +95,7 @@ def compare_step(got, g, t, lay, s_base, ctx=""):
     return False
 
 
-def replay_trace(env_factory, g, ctx=""):
+def replay_trace(env_factory, g, ctx="", check_iterations=True):
     """env_factory(feeder, kwargs) -> object with reset(noise4, start_time) -> obs[D] and
     step(action[A], noise[4+L]) -> dict of scalars/arrays for one env.  Returns #steps compared
     with exact flags."""
@@ -119,5 +120,44 @@ def replay_trace(env_factory, g, ctx=""):
             obs0 = env.reset(g["reset_noise"][ep], start_time)
             assert np.max(np.abs(np.asarray(obs0) - g["reset_obs"][ep])) <= 1e-9, f"{ctx}: reset obs {ep}"
         got = env.step(g["actions"][t], g["noise"][t])
-        exact += bool(compare_step(got, g, t, lay, s_base, ctx))
+        exact += bool(compare_step(got, g, t, lay, s_base, ctx, check_iterations))
     return exact
+
+
+def port_trace(g, tolerance=None, max_iterations=None):
+    """Re-run a golden trace's inputs (actions, noise, reset draws) through the numpy oracle,
+    optionally at another solver tolerance, and return a dict shaped like the golden file.
+    Used where the compared solver is a different algorithm (sweep), so both sides run tight."""
+    from oracle import port
+    f = feeder_for(g)
+    kw, start_time = trace_kwargs(g)
+    if tolerance is not None:
+        kw["tolerance"] = tolerance
+    if max_iterations is not None:
+        kw["max_iterations"] = max_iterations
+    env = port.PortEnv(f, 1, **kw)
+    T = g["obs"].shape[0]
+    keys = ("obs", "reward", "terminated", "truncated", "error", "converged", "iterations",
+            "max_voltage", "min_voltage", "losses", "violations", "viol_count", "current_step",
+            "episode_reward")
+    rec = {k: [] for k in keys}
+    rec["reset_before"], rec["reset_obs"] = [], []
+    ep = 0
+    rec["reset_obs"].append(env.reset(g["reset_noise"][ep][None, :], start_time=start_time)[0])
+    need = False
+    for t in range(T):
+        rec["reset_before"].append(need)
+        if need:
+            ep += 1
+            rec["reset_obs"].append(env.reset(g["reset_noise"][ep][None, :], start_time=start_time)[0])
+        out = env.step(g["actions"][t][None, :], g["noise"][t][None, :])
+        for k in keys:
+            rec[k].append(out[k][0])
+        need = bool(out["terminated"][0] or out["truncated"][0])
+    res = {k: np.array(v) for k, v in rec.items()}
+    for k in ("actions", "noise", "reset_noise", "meta", "renewable_sources", "spec"):
+        res[k] = g[k]
+    if tolerance is not None:
+        res["meta"] = g["meta"].copy()
+        res["meta"][5] = tolerance
+    return res

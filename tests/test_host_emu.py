@@ -1,0 +1,75 @@
+"""The device functions (csrc/gfr_device.cuh, LANES = 1 compiled for the host by tests/host_emu)
+against the frozen reference outputs and the numpy oracle.  This is the CPU-tier check of the
+kernels' arithmetic; the GPU tier (test_gpu_parity.py) runs the same cases through the C ABI."""
+import numpy as np
+import pytest
+
+from oracle import port
+from tests.golden_util import (TOL_PU, feeder_for, golden_names, load_golden, port_trace,
+                               replay_trace)
+from tests.host_emu import emu
+
+
+def _factory(solver, tol_override=None):
+    class _One:
+        def __init__(self, feeder, kw):
+            kw = dict(kw)
+            tol = kw.pop("tolerance")
+            self.env = emu.EmuEnv(feeder, 1, solver=solver, tolerance=tol_override or tol, **kw)
+
+        def reset(self, noise4, start_time):
+            return self.env.reset(np.asarray(noise4)[None, :], start_time=start_time)[0]
+
+        def step(self, action, noise):
+            out = self.env.step(action[None, :], noise[None, :])
+            return {k: v[0] for k, v in out.items()}
+    return _One
+
+
+@pytest.mark.parametrize("name", golden_names("trace_"))
+def test_emu_newton_matches_reference_trace(name):
+    g = load_golden(name)
+    exact = replay_trace(_factory("newton"), g, ctx=name)
+    assert exact >= 0.9 * g["obs"].shape[0]
+
+
+@pytest.mark.parametrize("name", golden_names("trace_"))
+def test_emu_sweep_matches_reference_trace(name):
+    # a different algorithm: both sides run tight, the oracle at NR tol 1e-10
+    g = port_trace(load_golden(name), tolerance=1e-10)
+    exact = replay_trace(_factory("sweep", 1e-11), g, ctx=name, check_iterations=False)
+    assert exact >= 0.9 * g["obs"].shape[0]
+
+
+@pytest.mark.parametrize("name", golden_names("solve_"))
+@pytest.mark.parametrize("solver", ["newton", "sweep"])
+def test_emu_solver_matches_reference(name, solver):
+    g = load_golden(name)
+    f = feeder_for(g)
+    tol, max_it = float(g["meta"][0]), int(g["meta"][1])
+    if solver == "sweep":
+        # both sides tight: the oracle's NR at 1e-10 instead of the frozen (looser) reference run
+        net = port.DenseNetwork(f.buses, f.lines)
+        ref = port.newton_raphson(net, g["p_spec"], 1e-10, 50)
+        g = dict(g); g.update({k: ref[k] for k in ("bus_voltages", "bus_angles", "line_flows", "losses")})
+        tol, max_it = 1e-11, 200
+    sol = emu.emu_solve(f, g["p_spec"], solver, tol, max_it)
+    conv = g["converged"]
+    if solver == "newton":
+        assert np.array_equal(sol["converged"].astype(bool), conv)
+        assert np.all(np.abs(sol["iterations"].astype(int) - g["iterations"]) <= 1)
+    else:
+        assert np.all(sol["converged"].astype(bool)[conv])
+    if conv.any():
+        for k in ("bus_voltages", "bus_angles", "line_flows", "losses"):
+            assert np.max(np.abs(sol[k][conv] - g[k][conv])) <= TOL_PU, k
+
+
+def test_emu_philox_matches_oracle():
+    rs = np.random.RandomState(0)
+    seeds = rs.randint(0, 2**63 - 1, size=64, dtype=np.int64).astype(np.uint64)
+    draws = rs.randint(0, 2**40, size=64, dtype=np.int64).astype(np.uint64)
+    for n_slots in (4, 5, 12, 99):
+        a = emu.emu_noise(seeds, draws, n_slots)
+        b = port.philox_noise(seeds, draws, n_slots)
+        assert np.max(np.abs(a - b)) < 1e-13
