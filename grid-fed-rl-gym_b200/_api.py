@@ -1,5 +1,8 @@
 """Public names of the package (what ``import grid_fed_rl_b200`` exposes)."""
 from .components import Box, Bus, FeederParameters, Line, Load, PowerFlowSolution
+from .errors import (GridEnvironmentError, GridLimitError, InvalidActionError,
+                     InvalidConfigurationError, NativeRuntimeError, NetworkTopologyError,
+                     PowerFlowError)
 from .feeders import (BaseFeeder, CustomFeeder, IEEE13Bus, IEEE34Bus, IEEE123Bus, NetworkConfig,
                       ScalableFeeder, SimpleRadialFeeder, SyntheticFeeder)
 from .topology import (FeederSoA, RepairedFeeder, TopologyError, compile_feeder,
@@ -10,4 +13,18 @@ __all__ = [
     "Box", "Bus", "FeederParameters", "Line", "Load", "PowerFlowSolution",
     "BaseFeeder", "CustomFeeder", "IEEE13Bus", "IEEE34Bus", "IEEE123Bus", "NetworkConfig",
     "ScalableFeeder", "SimpleRadialFeeder", "SyntheticFeeder",
+    "GridEnvironmentError", "GridLimitError", "InvalidActionError", "InvalidConfigurationError",
+    "NativeRuntimeError", "NetworkTopologyError", "PowerFlowError",
+    "BatchedGridEnvironment", "B200PowerFlowSolver", "shard_range",
 ]
+
+
+def __getattr__(name):
+    # the torch-backed classes load lazily so that feeder / topology tooling imports stay light
+    if name in ("BatchedGridEnvironment", "shard_range"):
+        from . import env
+        return getattr(env, name)
+    if name == "B200PowerFlowSolver":
+        from .solver import B200PowerFlowSolver
+        return B200PowerFlowSolver
+    raise AttributeError(name)

@@ -190,6 +190,7 @@ struct gfr_env {
   size_t smem = 0;
   double* d_state = nullptr;
   double* d_obs = nullptr;
+  bool obs_external = false;   // bound by gfr_env_bind_obs: caller-owned
 };
 
 namespace {
@@ -423,7 +424,7 @@ void gfr_env_destroy(gfr_env* e) {
   if (!e) return;
   DeviceGuard guard(e->f->device);
   cudaFree(e->d_state);
-  cudaFree(e->d_obs);
+  if (!e->obs_external) cudaFree(e->d_obs);
   delete e;
 }
 
@@ -433,6 +434,18 @@ int gfr_env_act_dim(const gfr_env* e) { return e ? e->f->lay.A : 0; }
 int gfr_env_noise_dim(const gfr_env* e) { return e ? e->f->lay.n_noise : 0; }
 double* gfr_env_obs(gfr_env* e) { return e ? e->d_obs : nullptr; }
 int64_t gfr_env_state_bytes(const gfr_env* e) { return e ? (int64_t)e->B * e->f->lay.R * 8 : 0; }
+
+int gfr_env_bind_obs(gfr_env* e, double* obs, void* stream) {
+  if (!e || !obs) return fail(GFR_E_ARG, "null argument");
+  DeviceGuard guard(e->f->device);
+  cudaStream_t s = (cudaStream_t)stream;
+  GFR_CUDA(cudaMemcpyAsync(obs, e->d_obs, (size_t)e->B * e->f->lay.D * 8, cudaMemcpyDeviceToDevice, s));
+  GFR_CUDA(cudaStreamSynchronize(s));
+  if (!e->obs_external) cudaFree(e->d_obs);
+  e->d_obs = obs;
+  e->obs_external = true;
+  return GFR_OK;
+}
 
 int gfr_env_launch_info(const gfr_env* e, int32_t* lanes, int32_t* threads, int32_t* grid, int64_t* smem_bytes) {
   if (!e) return fail(GFR_E_ARG, "null env");

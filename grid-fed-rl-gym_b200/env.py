@@ -1,0 +1,348 @@
+"""``BatchedGridEnvironment`` - the reference's ``GridEnvironment`` reset / step / observation /
+info contract for B independent feeder instances on one GPU, one fused kernel per step.
+
+Reference surface mirrored here (paths under /root/reference/grid_fed_rl/):
+  * constructor kwargs             environments/grid_env.py:161-174
+  * ``reset(seed, options)``       environments/grid_env.py:360-408   -> (obs, info)
+  * ``step(action)``               environments/grid_env.py:410-619   -> (obs, reward, terminated, truncated, info)
+  * ``observation_space`` / ``action_space`` / ``current_step`` / ``episode_reward`` /
+    ``constraint_violations``      environments/grid_env.py:300-358, environments/base.py:71-176
+  * list-of-envs batching          utils/parallel_environment.py:283-355 (``VectorizedEnvironment``)
+
+All arithmetic happens in ``libgfr_b200.so`` (hand-written sm_100a CUDA behind the C ABI of
+``include/gfr_b200.h``); this module only owns tensors and argument checking.  There is no
+CPU path: without the library or without a CUDA device construction fails.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from typing import Any, Dict, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _native as nat
+from .components import Box
+from .errors import InvalidActionError, InvalidConfigurationError, NetworkTopologyError
+from .topology import FeederSoA, TopologyError, compile_feeder, repair_topology
+
+
+def _compile(feeder, renewable_sources, repair) -> Tuple[FeederSoA, Any]:
+    if isinstance(feeder, FeederSoA):
+        return feeder, None
+    try:
+        if repair is True:
+            feeder = repair_topology(feeder)
+        return compile_feeder(feeder, renewable_sources=renewable_sources), feeder
+    except TopologyError as exc:
+        if repair == "auto":
+            fixed = repair_topology(feeder)
+            return compile_feeder(fixed, renewable_sources=renewable_sources), fixed
+        raise NetworkTopologyError(str(exc)) from exc
+
+
+class NativeFeeder:
+    """A compiled feeder resident on one device (``gfr_feeder``)."""
+
+    def __init__(self, soa: FeederSoA, device: torch.device) -> None:
+        self.lib = nat.load_library()
+        self.soa = soa
+        self.device = device
+        desc, keep = nat.make_feeder_desc(soa)
+        h = C.c_void_p()
+        nat.check(self.lib, self.lib.gfr_feeder_create(C.byref(desc), device.index, C.byref(h)))
+        self.handle = h
+
+    def close(self) -> None:
+        if getattr(self, "handle", None):
+            self.lib.gfr_feeder_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self) -> None:
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _cuda_device(device) -> torch.device:
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise InvalidConfigurationError("grid_fed_rl_b200 runs on CUDA devices only (no CPU fallback)")
+    if not torch.cuda.is_available():
+        raise nat.NativeLibraryMissing("no CUDA device is visible; grid_fed_rl_b200 has no CPU fallback")
+    if dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
+    return dev
+
+
+class BatchedGridEnvironment:
+    """B instances of one feeder; tensors in, tensors out.
+
+    ``step`` returns views of buffers that the next ``step`` / ``reset`` overwrites (the observation
+    buffer is owned by the native library); ``clone()`` what must survive, or pass
+    ``copy_outputs=True``.
+    """
+
+    INFO_KEYS = ("power_flow_converged", "max_voltage", "min_voltage", "total_losses",
+                 "constraint_violations", "constraint_violation_count", "iterations", "current_step",
+                 "episode_reward", "error", "max_mismatch")
+
+    def __init__(self, feeder, num_envs: int = 1, device="cuda", *, timestep: float = 1.0,
+                 episode_length: int = 86400, stochastic_loads: bool = True,
+                 renewable_sources: Optional[Sequence[str]] = None, weather_variation: bool = True,
+                 safety_penalty: float = 100.0, voltage_limits: Tuple[float, float] = (0.95, 1.05),
+                 frequency_limits: Tuple[float, float] = (59.5, 60.5), power_flow_solver=None,
+                 solver: str = "newton", tolerance: float = 1e-6, max_iterations: int = 50,
+                 acceleration: float = 1.0, lanes: int = 0, load_noise: float = 0.1, repair="auto",
+                 start_time: float = 0.0, env_id_offset: int = 0, auto_reset: bool = False,
+                 copy_outputs: bool = False, record_noise: bool = False, **kwargs) -> None:
+        # **kwargs are accepted and ignored, as the reference constructor does (base.py:84)
+        if int(num_envs) < 1:
+            raise InvalidConfigurationError("num_envs must be >= 1")
+        if power_flow_solver is not None:
+            # reference: GridEnvironment(power_flow_solver=<PowerFlowSolver>) (grid_env.py:169,198-206)
+            solver = getattr(power_flow_solver, "method", solver)
+            tolerance = getattr(power_flow_solver, "tolerance", tolerance)
+            max_iterations = getattr(power_flow_solver, "max_iterations", max_iterations)
+        self.device = _cuda_device(device)
+        self.num_envs = int(num_envs)
+        self.renewable_sources = list(renewable_sources or [])
+        self.soa, self.feeder = _compile(feeder, self.renewable_sources, repair)
+        self.timestep, self.episode_length = float(timestep), int(episode_length)
+        self.stochastic_loads, self.weather_variation = bool(stochastic_loads), bool(weather_variation)
+        self.safety_penalty = float(safety_penalty)
+        self.voltage_limits, self.frequency_limits = tuple(voltage_limits), tuple(frequency_limits)
+        self.solver, self.tolerance, self.max_iterations = solver, float(tolerance), int(max_iterations)
+        self.start_time, self.env_id_offset = float(start_time), int(env_id_offset)
+        self.auto_reset, self.copy_outputs = bool(auto_reset), bool(copy_outputs)
+
+        self._native_feeder = NativeFeeder(self.soa, self.device)
+        self.lib = self._native_feeder.lib
+        scfg = nat.make_solver_cfg(solver, tolerance, max_iterations, acceleration, lanes)
+        self._cfg = nat.make_env_cfg(timestep=timestep, episode_length=episode_length,
+                                     stochastic_loads=stochastic_loads,
+                                     weather_variation=weather_variation,
+                                     voltage_limits=voltage_limits, frequency_limits=frequency_limits,
+                                     safety_penalty=safety_penalty, load_noise=load_noise,
+                                     solver_cfg=scfg)
+        h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            nat.check(self.lib, self.lib.gfr_env_create(self._native_feeder.handle, self.num_envs,
+                                                        C.byref(self._cfg), C.byref(h)))
+        self._h = h
+        B = self.num_envs
+        self.obs_dim = self.lib.gfr_env_obs_dim(h)
+        self.act_dim = self.lib.gfr_env_act_dim(h)
+        self.noise_dim = self.lib.gfr_env_noise_dim(h)
+        # reference spaces (grid_env.py:300-358): obs bounds are +-inf placeholders there too
+        self.observation_space = Box(low=-np.inf, high=np.inf, shape=(self.obs_dim,), dtype=np.float64)
+        self.action_space = Box(low=-1.0, high=1.0, shape=(self.act_dim,), dtype=np.float64)
+
+        dev = self.device
+        f64 = dict(dtype=torch.float64, device=dev)
+        # the observation buffer is a torch tensor the library writes into (gfr_env_bind_obs)
+        self._obs = torch.empty(B, self.obs_dim, **f64)
+        nat.check(self.lib, self.lib.gfr_env_bind_obs(h, self._obs.data_ptr(), self._stream()))
+        u8 = dict(dtype=torch.uint8, device=dev)
+        i32 = dict(dtype=torch.int32, device=dev)
+        self._out = dict(
+            reward=torch.zeros(B, **f64), terminated=torch.zeros(B, **u8), truncated=torch.zeros(B, **u8),
+            error=torch.zeros(B, **u8), converged=torch.zeros(B, **u8), iterations=torch.zeros(B, **i32),
+            max_voltage=torch.ones(B, **f64), min_voltage=torch.ones(B, **f64), losses=torch.zeros(B, **f64),
+            max_mismatch=torch.zeros(B, **f64), violations=torch.zeros(B, 4, **u8),
+            violation_count=torch.zeros(B, **i32), current_step=torch.zeros(B, **i32),
+            episode_reward=torch.zeros(B, **f64),
+            noise_used=torch.zeros(B, self.noise_dim, **f64) if record_noise else None)
+        self._step_out = nat.StepOut(*[(self._out[k].data_ptr() if self._out[k] is not None else None)
+                                       for k, _ in nat.StepOut._fields_])
+        self._bool = {k: self._out[k].view(torch.bool) for k in
+                      ("terminated", "truncated", "error", "converged", "violations")}
+        self._done = torch.zeros(B, **u8)
+        self._seeds = None
+
+    # ------------------------------------------------------------------ plumbing
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self.lib.gfr_env_destroy(self._h)
+            self._h = None
+        if getattr(self, "_native_feeder", None) is not None:
+            self._native_feeder.close()
+
+    def __del__(self) -> None:
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def launch_info(self) -> Dict[str, int]:
+        lanes, threads, grid, smem = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int64()
+        nat.check(self.lib, self.lib.gfr_env_launch_info(self._h, C.byref(lanes), C.byref(threads),
+                                                         C.byref(grid), C.byref(smem)))
+        return dict(lanes=lanes.value, threads=threads.value, grid=grid.value, smem_bytes=smem.value)
+
+    def _as_device(self, x, shape, dtype, what) -> Optional[torch.Tensor]:
+        if x is None:
+            return None
+        t = torch.as_tensor(x) if not isinstance(x, torch.Tensor) else x
+        if tuple(t.shape) != tuple(shape):
+            if t.numel() == int(np.prod(shape)):
+                t = t.reshape(shape)
+            else:
+                raise InvalidActionError(f"{what} must have shape {tuple(shape)}, got {tuple(t.shape)}")
+        if t.dtype != dtype or t.device != self.device or not t.is_contiguous():
+            t = t.to(device=self.device, dtype=dtype, non_blocking=True).contiguous()
+        return t
+
+    # ------------------------------------------------------------------ API
+    def reset(self, seed: Optional[int] = None, options: Optional[Dict[str, Any]] = None, *,
+              seeds=None, mask=None, noise=None):
+        """``seed``: instance i gets ``seed + env_id_offset + i`` (results do not depend on how the
+        instances are sharded).  ``seeds`` [B] uint64 overrides.  ``mask`` [B] selects instances.
+        ``noise`` [B,4] replays the four weather draws instead of the in-kernel Philox stream."""
+        B = self.num_envs
+        if seeds is None and seed is not None:
+            seeds = (torch.arange(B, dtype=torch.int64, device=self.device)
+                     + int(seed) + self.env_id_offset)
+        if seeds is not None:
+            seeds = torch.as_tensor(seeds)
+            if seeds.dtype == torch.uint64:
+                seeds = seeds.view(torch.int64)
+            seeds = self._as_device(seeds, (B,), torch.int64, "seeds")
+        mask_t = None
+        if mask is not None:
+            mask_t = torch.as_tensor(mask)
+            if mask_t.dtype == torch.bool:
+                mask_t = mask_t.to(torch.uint8)
+            mask_t = self._as_device(mask_t, (B,), torch.uint8, "mask")
+        noise_t = self._as_device(noise, (B, 4), torch.float64, "reset noise")
+        start = float((options or {}).get("start_time", self.start_time))
+        nat.check(self.lib, self.lib.gfr_env_reset(
+            self._h, seeds.data_ptr() if seeds is not None else None,
+            mask_t.data_ptr() if mask_t is not None else None,
+            noise_t.data_ptr() if noise_t is not None else None, start, self._stream()))
+        # info of the instances that were reset
+        o = self._out
+        if mask_t is None:
+            for k in ("reward", "losses", "max_mismatch", "episode_reward"):
+                o[k].zero_()
+            for k in ("terminated", "truncated", "error", "converged", "iterations", "violations",
+                      "violation_count", "current_step"):
+                o[k].zero_()
+            o["max_voltage"].fill_(1.0); o["min_voltage"].fill_(1.0)
+        else:
+            sel = mask_t.bool()
+            for k in ("reward", "losses", "max_mismatch", "episode_reward", "terminated", "truncated",
+                      "error", "converged", "iterations", "violation_count", "current_step"):
+                o[k].masked_fill_(sel, 0)
+            o["violations"].masked_fill_(sel[:, None], 0)
+            o["max_voltage"].masked_fill_(sel, 1.0); o["min_voltage"].masked_fill_(sel, 1.0)
+        obs = self._obs.clone() if self.copy_outputs else self._obs
+        return obs, self._info()
+
+    def step(self, actions, noise=None):
+        """``actions`` [B, A] float64 (any device / dtype is converted; a host array costs one
+        H2D copy).  ``noise`` [B, 4 + L] replays the reference's random draws (parity mode)."""
+        B = self.num_envs
+        act = self._as_device(actions, (B, self.act_dim), torch.float64, "actions")
+        noise_t = self._as_device(noise, (B, self.noise_dim), torch.float64, "noise")
+        nat.check(self.lib, self.lib.gfr_env_step(
+            self._h, act.data_ptr(), noise_t.data_ptr() if noise_t is not None else None,
+            C.byref(self._step_out), self._stream()))
+        o, b = self._out, self._bool
+        reward, terminated, truncated = o["reward"], b["terminated"], b["truncated"]
+        info = self._info()
+        obs = self._obs
+        if self.copy_outputs or self.auto_reset:
+            obs = obs.clone()
+            reward, terminated, truncated = reward.clone(), terminated.clone(), truncated.clone()
+            info = {k: v.clone() for k, v in info.items()}
+        if self.auto_reset:
+            torch.bitwise_or(o["terminated"], o["truncated"], out=self._done)
+            info["final_observation"] = obs
+            nat.check(self.lib, self.lib.gfr_env_reset(self._h, None, self._done.data_ptr(), None,
+                                                       self.start_time, self._stream()))
+            obs = torch.where(self._done.bool()[:, None], self._obs, obs)
+        return obs, reward, terminated, truncated, info
+
+    def _info(self) -> Dict[str, torch.Tensor]:
+        # same keys as the reference's info (grid_env.py:610-617, base.py:169-176); its
+        # ``constraint_violations`` dict of four bools becomes a [B, 4] tensor
+        o, b = self._out, self._bool
+        return {"power_flow_converged": b["converged"], "max_voltage": o["max_voltage"],
+                "min_voltage": o["min_voltage"], "total_losses": o["losses"],
+                "constraint_violations": b["violations"],
+                "constraint_violation_count": o["violation_count"], "iterations": o["iterations"],
+                "current_step": o["current_step"], "episode_reward": o["episode_reward"],
+                "error": b["error"], "max_mismatch": o["max_mismatch"],
+                "timestep": self.timestep}
+
+    def get_observation(self) -> torch.Tensor:
+        return self._obs
+
+    @property
+    def noise_used(self) -> Optional[torch.Tensor]:
+        return self._out["noise_used"]
+
+    @property
+    def current_step(self) -> torch.Tensor:
+        return self._out["current_step"]
+
+    @property
+    def episode_reward(self) -> torch.Tensor:
+        return self._out["episode_reward"]
+
+    @property
+    def constraint_violations(self) -> torch.Tensor:
+        return self._out["violation_count"]
+
+    def sample_actions(self, generator: Optional[torch.Generator] = None) -> torch.Tensor:
+        """U(-1, 1) actions on the device (the batched form of ``action_space.sample()``)."""
+        return torch.rand(self.num_envs, self.act_dim, dtype=torch.float64, device=self.device,
+                          generator=generator) * 2.0 - 1.0
+
+    # ------------------------------------------------------------------ checkpoint / resume
+    def state_dict(self) -> Dict[str, torch.Tensor]:
+        n = self.lib.gfr_env_state_bytes(self._h)
+        rec = torch.empty(n // 8, dtype=torch.float64, device=self.device)
+        nat.check(self.lib, self.lib.gfr_env_state_get(self._h, rec.data_ptr(), self._stream()))
+        sd = {"records": rec, "observation": self._obs.clone()}
+        sd.update({k: v.clone() for k, v in self._out.items() if v is not None})
+        return sd
+
+    def load_state_dict(self, sd: Dict[str, torch.Tensor]) -> None:
+        rec = self._as_device(sd["records"], (self.lib.gfr_env_state_bytes(self._h) // 8,),
+                              torch.float64, "records")
+        nat.check(self.lib, self.lib.gfr_env_state_set(self._h, rec.data_ptr(), self._stream()))
+        self._obs.copy_(sd["observation"])
+        for k, v in self._out.items():
+            if v is not None and k in sd:
+                v.copy_(sd[k])
+
+    # ------------------------------------------------------------------ episode statistics
+    def episode_stats(self, reduce: bool = False) -> Dict[str, float]:
+        """Sums over this rank's instances; ``reduce=True`` adds one NCCL all-reduce of an fp64[8]
+        vector over the default process group (the only collective anywhere near this path)."""
+        o = self._out
+        v = torch.stack([o["reward"].sum(), o["episode_reward"].sum(),
+                         o["converged"].sum(dtype=torch.float64), o["iterations"].sum(dtype=torch.float64),
+                         o["violation_count"].sum(dtype=torch.float64),
+                         (o["terminated"] | o["truncated"]).sum(dtype=torch.float64),
+                         o["error"].sum(dtype=torch.float64),
+                         torch.tensor(float(self.num_envs), dtype=torch.float64, device=self.device)])
+        if reduce and torch.distributed.is_available() and torch.distributed.is_initialized():
+            torch.distributed.all_reduce(v)
+        keys = ("reward_sum", "episode_reward_sum", "converged", "iterations_sum", "violation_steps",
+                "done", "errors", "num_envs")
+        return dict(zip(keys, v.tolist()))
+
+
+def shard_range(total_envs: int, rank: int, world_size: int) -> Tuple[int, int]:
+    """Contiguous instance range [start, stop) of ``rank``: no data-path collective."""
+    base, rem = divmod(int(total_envs), int(world_size))
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)

@@ -1,0 +1,155 @@
+"""``B200PowerFlowSolver`` - the reference's solver plugin surface on the CUDA path.
+
+Reference (paths under /root/reference/grid_fed_rl/):
+  * ``PowerFlowSolver.__init__(tolerance, max_iterations)`` + abstract
+    ``solve(buses, lines, loads, generation) -> PowerFlowSolution``   environments/power_flow.py:28-46
+  * ``NewtonRaphsonSolver`` defaults 1e-6 / 50, ``acceleration_factor``  environments/power_flow.py:79-87
+  * the documented two-argument form ``solver.solve(feeder, loading_conditions)``
+    (README.md:200, API_REFERENCE.md:407,429; never implemented upstream)
+
+Both call shapes are accepted.  Quantities are taken in the units the caller uses, exactly
+like the reference solver (which never converts): pass per-unit injections with per-unit
+impedances.  The two-argument form with a ``{'loads': {bus: W}, 'generation': {bus: W}}`` dict
+divides by the feeder's base power first (deviation D1).
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from typing import Any, Dict, Optional
+
+import numpy as np
+import torch
+
+from . import _native as nat
+from .components import FeederParameters, PowerFlowSolution
+from .env import NativeFeeder, _cuda_device
+from .errors import InvalidConfigurationError, NetworkTopologyError
+from .topology import FeederSoA, TopologyError, compile_feeder
+
+
+class _Topology:
+    """Just enough of a feeder for ``compile_feeder`` when only buses + lines are given."""
+
+    def __init__(self, buses, lines, base_power_mva: float) -> None:
+        self.name = "adhoc"
+        self.buses, self.lines, self.loads, self.generators = list(buses), list(lines), [], {}
+        self.parameters = FeederParameters(base_voltage=1.0, base_power=base_power_mva, frequency=60.0)
+
+
+def _signature(buses, lines):
+    return (tuple((b.id, b.bus_type, float(b.voltage_magnitude)) for b in buses),
+            tuple((l.id, l.from_bus, l.to_bus, float(l.resistance), float(l.reactance), float(l.rating))
+                  for l in lines))
+
+
+class B200PowerFlowSolver:
+    """Batched radial load flow on one GPU.  ``method`` is "newton" (the reference's polar
+    Newton-Raphson iterates, solved by tree-ordered block elimination) or "sweep"
+    (backward / forward sweep)."""
+
+    def __init__(self, tolerance: float = 1e-6, max_iterations: int = 50, method: str = "newton",
+                 acceleration_factor: float = 1.0, device="cuda", lanes: int = 0, **kwargs) -> None:
+        if method not in nat.SOLVERS:
+            raise InvalidConfigurationError(f"method must be one of {sorted(nat.SOLVERS)}")
+        self.tolerance, self.max_iterations = float(tolerance), int(max_iterations)
+        self.method, self.acceleration_factor = method, float(acceleration_factor)
+        self.lanes = int(lanes)
+        self._device_arg = device
+        self._cache: Dict[Any, NativeFeeder] = {}
+        self.last: Optional[PowerFlowSolution] = None
+
+    # -- compiled topologies ------------------------------------------------------
+    def _native(self, key, make_soa) -> NativeFeeder:
+        nf = self._cache.get(key)
+        if nf is None:
+            try:
+                soa = make_soa()
+            except TopologyError as exc:
+                raise NetworkTopologyError(str(exc)) from exc
+            nf = NativeFeeder(soa, _cuda_device(self._device_arg))
+            if len(self._cache) >= 8:
+                self._cache.pop(next(iter(self._cache))).close()
+            self._cache[key] = nf
+        return nf
+
+    def solve_batch(self, feeder, p_inj) -> PowerFlowSolution:
+        """``p_inj`` [B, n] per-unit injections (generation minus load) in ``feeder.buses`` order;
+        returns a ``PowerFlowSolution`` of tensors with a leading B axis."""
+        if isinstance(feeder, NativeFeeder):
+            nf = feeder
+        elif isinstance(feeder, FeederSoA):
+            nf = self._native(("soa", id(feeder)), lambda: feeder)
+        else:
+            nf = self._native(("feeder", id(feeder), _signature(feeder.buses, feeder.lines)),
+                              lambda: compile_feeder(feeder, with_components=False))
+        dev, soa, lib = nf.device, nf.soa, nf.lib
+        p = torch.as_tensor(p_inj)
+        if p.dim() == 1:
+            p = p[None, :]
+        if p.shape[1] != soa.n_bus:
+            raise InvalidConfigurationError(f"p_inj must be [B, {soa.n_bus}], got {tuple(p.shape)}")
+        p = p.to(device=dev, dtype=torch.float64).contiguous()
+        B, n, m = p.shape[0], soa.n_bus, soa.n_line
+        f64 = dict(dtype=torch.float64, device=dev)
+        out = dict(converged=torch.zeros(B, dtype=torch.uint8, device=dev),
+                   iterations=torch.zeros(B, dtype=torch.int32, device=dev),
+                   bus_voltages=torch.empty(B, n, **f64), bus_angles=torch.empty(B, n, **f64),
+                   line_flows=torch.empty(B, m, **f64), line_loadings=torch.empty(B, m, **f64),
+                   losses=torch.empty(B, **f64), max_mismatch=torch.empty(B, **f64))
+        so = nat.SolOut(*[out[k].data_ptr() for k, _ in nat.SolOut._fields_])
+        cfg = nat.make_solver_cfg(self.method, self.tolerance, self.max_iterations,
+                                  self.acceleration_factor, self.lanes)
+        nat.check(lib, lib.gfr_solve(nf.handle, B, p.data_ptr(), C.byref(cfg), C.byref(so),
+                                     torch.cuda.current_stream(dev).cuda_stream))
+        out["converged"] = out["converged"].view(torch.bool)
+        return PowerFlowSolution(**out)
+
+    # -- the reference's two call shapes ----------------------------------------------
+    def solve(self, *args):
+        if len(args) == 4:
+            return self._solve_reference_form(*args)
+        if len(args) == 2:
+            return self._solve_feeder_form(*args)
+        raise TypeError("solve(buses, lines, loads, generation) or solve(feeder, loading_conditions)")
+
+    def _solve_reference_form(self, buses, lines, loads: Dict[Any, float],
+                              generation: Dict[Any, float]) -> PowerFlowSolution:
+        # power_flow.py:105-121: P_spec = generation - load at each bus id; Q_spec = 0
+        nf = self._native(("lists", _signature(buses, lines)),
+                          lambda: compile_feeder(_Topology(buses, lines, 1e-6), with_components=False))
+        index = {b.id: i for i, b in enumerate(buses)}
+        p = np.zeros((1, len(buses)))
+        for bus, v in loads.items():
+            if bus in index:
+                p[0, index[bus]] -= v
+        for bus, v in generation.items():
+            if bus in index:
+                p[0, index[bus]] += v
+        return self._unwrap(self.solve_batch(nf, p))
+
+    def _solve_feeder_form(self, feeder, loading_conditions):
+        if isinstance(loading_conditions, dict):
+            s_base = float(feeder.parameters.base_power) * 1e6
+            index = {b.id: i for i, b in enumerate(feeder.buses)}
+            p = np.zeros((1, len(feeder.buses)))
+            for bus, v in loading_conditions.get("loads", {}).items():
+                p[0, index[bus]] -= v / s_base
+            for bus, v in loading_conditions.get("generation", {}).items():
+                p[0, index[bus]] += v / s_base
+            return self._unwrap(self.solve_batch(feeder, p))
+        return self.solve_batch(feeder, loading_conditions)
+
+    def _unwrap(self, sol: PowerFlowSolution) -> PowerFlowSolution:
+        one = PowerFlowSolution(
+            converged=bool(sol.converged[0].item()), iterations=int(sol.iterations[0].item()),
+            bus_voltages=sol.bus_voltages[0].cpu().numpy(), bus_angles=sol.bus_angles[0].cpu().numpy(),
+            line_flows=sol.line_flows[0].cpu().numpy(), line_loadings=sol.line_loadings[0].cpu().numpy(),
+            losses=float(sol.losses[0].item()), max_mismatch=float(sol.max_mismatch[0].item()))
+        self.last = one
+        return one
+
+    def close(self) -> None:
+        for nf in self._cache.values():
+            nf.close()
+        self._cache.clear()

@@ -10,5 +10,13 @@ _SRC = _os.path.join(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__
                      "grid-fed-rl-gym_b200")
 __path__.insert(0, _SRC)  # submodules resolve inside the product directory
 
-from ._api import *  # noqa: E402,F401,F403
+from . import _api  # noqa: E402
 from ._api import __all__  # noqa: E402,F401
+
+for _n in __all__:
+    if _n in _api.__dict__:
+        globals()[_n] = _api.__dict__[_n]
+
+
+def __getattr__(name):
+    return _api.__getattr__(name)

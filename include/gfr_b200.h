@@ -157,6 +157,10 @@ int gfr_env_noise_dim(const gfr_env* e);    /* 4 + L */
  * rewritten in place by reset and step (left untouched for instances whose action was rejected,
  * whose observation is by definition unchanged). */
 double* gfr_env_obs(gfr_env* e);
+/* Make the env write its observations into a CALLER-OWNED device buffer [B, D] instead (the
+ * current contents are copied over, the library's own buffer is released).  This is how a host
+ * framework gets the observation as one of its own tensors without a copy per step. */
+int gfr_env_bind_obs(gfr_env* e, double* obs, void* stream);
 /* How the step kernel is launched for this env (for benchmarks / profiles): threads cooperating
  * on one instance, threads per CTA, CTAs, dynamic shared memory per CTA. */
 int gfr_env_launch_info(const gfr_env* e, int32_t* lanes, int32_t* threads, int32_t* grid,

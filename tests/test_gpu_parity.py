@@ -1,0 +1,347 @@
+"""GPU tier: the CUDA path, called through the C ABI (ctypes) exactly as a user would, against
+ (a) the frozen outputs of the reference itself (tests/golden, written by oracle/ref_harness.py),
+ (b) the numpy oracle (oracle/port.py) on seeded batches,
+ (c) size-independent properties at BASELINE.json's full sizes.
+Tolerances (BASELINE.json north_star): |V|, angle, line flow, losses within 1e-8 pu in fp64;
+flags and counters bit-exact; Newton iteration counts within +-1."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import port
+from tests.golden_util import (TOL_PU, feeder_for, golden_names, load_golden, obs_layout, port_trace,
+                               replay_trace)
+
+pytestmark = pytest.mark.gpu
+
+LANES = (1, 4, 8, 16, 32)
+REPL = 3      # replicas of the golden instance per batch: all must agree bit for bit
+
+
+def _factory(solver, lanes, tol_override=None):
+    import grid_fed_rl_b200 as m
+
+    class _One:
+        def __init__(self, feeder, kw):
+            kw = dict(kw)
+            tol = kw.pop("tolerance")
+            self.env = m.BatchedGridEnvironment(feeder, REPL, solver=solver, lanes=lanes,
+                                                tolerance=tol_override or tol, repair=False, **kw)
+
+        def reset(self, noise4, start_time):
+            nz = np.tile(np.asarray(noise4)[None, :4], (REPL, 1))
+            obs, _ = self.env.reset(noise=nz, options={"start_time": start_time})
+            obs = obs.cpu().numpy()
+            assert np.array_equal(obs[0], obs[1]) and np.array_equal(obs[0], obs[2])
+            return obs[0]
+
+        def step(self, action, noise):
+            obs, reward, term, trunc, info = self.env.step(np.tile(action[None, :], (REPL, 1)),
+                                                           np.tile(noise[None, :], (REPL, 1)))
+            out = dict(obs=obs, reward=reward, terminated=term, truncated=trunc,
+                       error=info["error"], converged=info["power_flow_converged"],
+                       iterations=info["iterations"], losses=info["total_losses"],
+                       violations=info["constraint_violations"],
+                       viol_count=info["constraint_violation_count"],
+                       current_step=info["current_step"], episode_reward=info["episode_reward"])
+            out = {k: v.cpu().numpy() for k, v in out.items()}
+            for k, v in out.items():
+                assert np.array_equal(v[0], v[1], equal_nan=True) and np.array_equal(v[0], v[2], equal_nan=True), k
+            return {k: v[0] for k, v in out.items()}
+    return _One
+
+
+@pytest.mark.parametrize("lanes", LANES)
+@pytest.mark.parametrize("name", golden_names("trace_"))
+def test_newton_step_matches_reference_trace(name, lanes):
+    g = load_golden(name)
+    exact = replay_trace(_factory("newton", lanes), g, ctx=f"{name}/lanes{lanes}")
+    assert exact >= 0.9 * g["obs"].shape[0]
+
+
+@pytest.mark.parametrize("lanes", (1, 8, 32))
+@pytest.mark.parametrize("name", golden_names("trace_"))
+def test_sweep_step_matches_oracle_trace(name, lanes):
+    g = port_trace(load_golden(name), tolerance=1e-10)
+    exact = replay_trace(_factory("sweep", lanes, 1e-11), g, ctx=f"{name}/sweep/lanes{lanes}",
+                         check_iterations=False)
+    assert exact >= 0.9 * g["obs"].shape[0]
+
+
+@pytest.mark.parametrize("lanes", LANES)
+@pytest.mark.parametrize("name", golden_names("solve_"))
+def test_solver_matches_reference(name, lanes):
+    import grid_fed_rl_b200 as m
+    g = load_golden(name)
+    f = feeder_for(g)
+    tol, max_it = float(g["meta"][0]), int(g["meta"][1])
+    s = m.B200PowerFlowSolver(tolerance=tol, max_iterations=max_it, method="newton", lanes=lanes)
+    sol = s.solve_batch(f, g["p_spec"])
+    conv = g["converged"]
+    assert np.array_equal(sol.converged.cpu().numpy(), conv)
+    assert np.all(np.abs(sol.iterations.cpu().numpy().astype(int) - g["iterations"]) <= 1)
+    for k in ("bus_voltages", "bus_angles", "line_flows", "losses"):
+        if conv.any():
+            assert np.max(np.abs(getattr(sol, k).cpu().numpy()[conv] - g[k][conv])) <= TOL_PU, k
+    # |S| s_base / rating against the reference's |S| / rating
+    s_base = f.parameters.base_power * 1e6
+    if conv.any():
+        assert np.allclose(sol.line_loadings.cpu().numpy()[conv], g["line_loadings"][conv] * s_base,
+                           rtol=1e-7, atol=1e-12)
+    # sweep, both sides tight
+    net = port.DenseNetwork(f.buses, f.lines)
+    ref = port.newton_raphson(net, g["p_spec"], 1e-10, 50)
+    sw = m.B200PowerFlowSolver(tolerance=1e-11, max_iterations=200, method="sweep", lanes=lanes)
+    sol = sw.solve_batch(f, g["p_spec"])
+    ok = ref["converged"]
+    assert np.all(sol.converged.cpu().numpy()[ok])
+    for k in ("bus_voltages", "bus_angles", "line_flows", "losses"):
+        if ok.any():
+            assert np.max(np.abs(getattr(sol, k).cpu().numpy()[ok] - ref[k][ok])) <= TOL_PU, k
+
+
+def test_reference_call_shapes_appendix_a():
+    """SURVEY Appendix A through solve(buses, lines, loads, generation) and solve(feeder, dict)."""
+    import grid_fed_rl_b200 as m
+    from oracle.ref_harness import make_feeder
+    f = make_feeder(None, "fixture3", use_reference_classes=False)
+    s = m.B200PowerFlowSolver(tolerance=1e-10, max_iterations=50)
+    sol = s.solve(f.buses, f.lines, {2: 0.1, 3: 0.05}, {})
+    assert sol.converged and sol.iterations == 4
+    assert np.allclose(sol.bus_voltages, [1, 0.998491585126075, 0.997739099627788], atol=1e-11)
+    assert np.allclose(sol.bus_angles, [0, -0.003004662358732, -0.004259387863609], atol=1e-11)
+    assert np.allclose(sol.line_flows, [0.15026346387586, 0.05003767014433], atol=1e-11)
+    assert abs(sol.losses - 2.6346387586110437e-04) < 1e-12
+    s6 = m.B200PowerFlowSolver(tolerance=1e-6, max_iterations=50)
+    assert s6.solve(f.buses, f.lines, {2: 0.1, 3: 0.05}, {}).iterations == 3
+    sol2 = s.solve(f, {"loads": {2: 0.1 * 1e7, 3: 0.05 * 1e7}, "generation": {}})
+    assert np.allclose(sol2.bus_voltages, sol.bus_voltages, atol=1e-13)
+
+
+def _batch_against_port(spec, B, steps, solver, lanes, seed, tol=1e-8, **kw):
+    import grid_fed_rl_b200 as m
+    from oracle.ref_harness import make_feeder
+    f = make_feeder(None, spec, use_reference_classes=False)
+    kw = dict(dict(timestep=60.0, episode_length=steps - 3, renewable_sources=["solar", "wind"]), **kw)
+    start = 11.5 * 3600.0
+    env = m.BatchedGridEnvironment(f, B, solver=solver, lanes=lanes, tolerance=tol, repair=False, **kw)
+    ptol = 1e-10 if solver == "sweep" else tol
+    ref = port.PortEnv(f, B, tolerance=ptol, **kw)
+    rs = np.random.RandomState(seed)
+    L, A = ref.L, ref.A
+    nz0 = np.concatenate([rs.random_sample((B, 1)), rs.standard_normal((B, 3))], axis=1)
+    obs, _ = env.reset(noise=nz0, options={"start_time": start})
+    robs = ref.reset(nz0, start_time=start)
+    assert np.max(np.abs(obs.cpu().numpy() - robs)) < 1e-9
+    lay = obs_layout(ref.n, ref.m, L, ref.G, ref.Bt)
+    s_base = ref.s_base
+    for t in range(steps):
+        act = rs.uniform(-1, 1, size=(B, A))
+        if t == 2 and A > 1:
+            act[1, 0] = np.nan
+        nz = np.concatenate([rs.random_sample((B, 1)), rs.standard_normal((B, 3 + L))], axis=1)
+        obs, reward, term, trunc, info = env.step(act, nz)
+        r = ref.step(act, nz)
+        o = obs.cpu().numpy()
+        ok = r["converged"] | r["error"]
+        assert np.array_equal(info["power_flow_converged"].cpu().numpy(), r["converged"])
+        assert np.array_equal(info["error"].cpu().numpy(), r["error"])
+        assert np.max(np.abs(o[ok][:, lay["vm"]] - r["obs"][ok][:, lay["vm"]])) <= TOL_PU
+        assert np.max(np.abs(o[ok][:, lay["va"]] - r["obs"][ok][:, lay["va"]])) <= TOL_PU
+        assert np.max(np.abs(o[ok][:, lay["p"]] - r["obs"][ok][:, lay["p"]])) / s_base <= TOL_PU
+        assert np.max(np.abs(info["total_losses"].cpu().numpy()[ok] - r["losses"][ok])) / s_base <= TOL_PU
+        assert np.max(np.abs(o[ok][:, lay["freq"]] - r["obs"][ok][:, lay["freq"]])) <= 1e-9
+        assert np.max(np.abs(o[ok][:, lay["soc"]] - r["obs"][ok][:, lay["soc"]])) <= 1e-12
+        assert np.allclose(o[ok][:, lay["gen"]], r["obs"][ok][:, lay["gen"]], rtol=1e-12, atol=1e-6)
+        assert np.allclose(reward.cpu().numpy()[ok], r["reward"][ok], rtol=1e-9, atol=1e-6)
+        assert np.array_equal(term.cpu().numpy(), r["terminated"])
+        assert np.array_equal(info["current_step"].cpu().numpy(), r["current_step"])
+        if solver == "newton":
+            assert np.all(np.abs(info["iterations"].cpu().numpy().astype(int) - r["iterations"]) <= 1)
+        # flags: exact wherever no voltage / frequency sits within 1e-9 of a limit
+        vm, fr = r["obs"][:, lay["vm"]], r["obs"][:, lay["freq"]]
+        margin = np.minimum(np.min(np.abs(vm - 0.95), axis=1), np.min(np.abs(vm - 1.05), axis=1))
+        margin = np.minimum(margin, np.minimum(np.abs(fr - 59.5), np.abs(fr - 60.5)))
+        clear = ok & (margin > 1e-9)
+        assert clear.mean() > 0.9
+        assert np.array_equal(info["constraint_violations"].cpu().numpy()[clear], r["violations"][clear])
+        assert np.array_equal(info["constraint_violation_count"].cpu().numpy()[clear], r["viol_count"][clear])
+        assert np.array_equal(trunc.cpu().numpy()[clear], r["truncated"][clear])
+        done = r["terminated"] | r["truncated"]
+        if done.any():
+            nzr = np.concatenate([rs.random_sample((B, 1)), rs.standard_normal((B, 3))], axis=1)
+            env.reset(noise=nzr, mask=done, options={"start_time": start})
+            ref.reset(nzr, mask=done, start_time=start)
+    env.close()
+
+
+@pytest.mark.parametrize("lanes", LANES)
+def test_batch_ieee13_newton_vs_oracle(lanes):
+    _batch_against_port("ieee13", 333, 16, "newton", lanes, seed=lanes)
+
+
+@pytest.mark.parametrize("lanes", (1, 4, 32))
+def test_batch_ieee13_sweep_vs_oracle(lanes):
+    _batch_against_port("ieee13", 257, 14, "sweep", lanes, seed=10 + lanes, tol=1e-11)
+
+
+@pytest.mark.parametrize("lanes", (4, 8, 32))
+def test_batch_ieee34_vs_oracle(lanes):
+    _batch_against_port("ieee34", 130, 10, "newton", lanes, seed=20 + lanes, renewable_sources=["solar"])
+    _batch_against_port("ieee34", 130, 10, "sweep", lanes, seed=30 + lanes, tol=1e-11, renewable_sources=["solar"])
+
+
+@pytest.mark.parametrize("lanes", (8, 16, 32))
+def test_batch_ieee123_newton_vs_oracle(lanes):
+    _batch_against_port("ieee123", 40, 5, "newton", lanes, seed=40 + lanes, tol=1e-6)
+
+
+def test_pv_bus_feeder_vs_oracle():
+    """PV buses (none in the shipped feeders): |V| held, no Q equation - against the oracle port."""
+    import grid_fed_rl_b200 as m
+    f = m.SimpleRadialFeeder(9)
+    f.buses[4].bus_type = "pv"; f.buses[4].voltage_magnitude = 1.01
+    f.buses[7].bus_type = "pv"; f.buses[7].voltage_magnitude = 0.99
+    rs = np.random.RandomState(5)
+    p = rs.uniform(-0.08, 0.02, size=(64, 9)); p[:, 0] = 0
+    net = port.DenseNetwork(f.buses, f.lines)
+    ref = port.newton_raphson(net, p, 1e-10, 50)
+    for lanes in (1, 4, 32):
+        sol = m.B200PowerFlowSolver(tolerance=1e-10, lanes=lanes).solve_batch(f, p)
+        assert np.array_equal(sol.converged.cpu().numpy(), ref["converged"]) and ref["converged"].all()
+        assert np.max(np.abs(sol.bus_voltages.cpu().numpy() - ref["bus_voltages"])) <= TOL_PU
+        assert np.max(np.abs(sol.bus_angles.cpu().numpy() - ref["bus_angles"])) <= TOL_PU
+        assert np.max(np.abs(sol.line_flows.cpu().numpy() - ref["line_flows"])) <= TOL_PU
+        assert np.all(np.abs(sol.iterations.cpu().numpy().astype(int) - ref["iterations"]) <= 1)
+    with pytest.raises(m.InvalidConfigurationError):
+        m.B200PowerFlowSolver(method="sweep").solve_batch(f, p)
+
+
+def test_philox_noise_matches_oracle_and_replays():
+    import ctypes as C
+    import grid_fed_rl_b200 as m
+    from grid_fed_rl_b200 import _native as nat
+    lib = nat.load_library()
+    rs = np.random.RandomState(0)
+    seeds = rs.randint(0, 2**63 - 1, size=300, dtype=np.int64)
+    draws = rs.randint(0, 2**40, size=300, dtype=np.int64)
+    for n_slots in (4, 5, 12, 99):
+        out = torch.empty(300, n_slots, dtype=torch.float64, device="cuda")
+        nat.check(lib, lib.gfr_noise_fill(0, 300, n_slots, torch.as_tensor(seeds).cuda().data_ptr(),
+                                          torch.as_tensor(draws).cuda().data_ptr(), out.data_ptr(), None))
+        ref = port.philox_noise(seeds.astype(np.uint64), draws.astype(np.uint64), n_slots)
+        assert np.max(np.abs(out.cpu().numpy() - ref)) < 1e-12
+    # throughput mode: the env's own stream == the oracle's Philox row, and replaying the recorded
+    # row through the oracle reproduces the step
+    from oracle.ref_harness import make_feeder
+    f = make_feeder(None, "ieee13", use_reference_classes=False)
+    kw = dict(timestep=30.0, renewable_sources=["solar", "wind"])
+    B = 100
+    env = m.BatchedGridEnvironment(f, B, solver="newton", tolerance=1e-8, repair=False, record_noise=True,
+                                   env_id_offset=1000, **kw)
+    ref = port.PortEnv(f, B, tolerance=1e-8, **kw)
+    env.reset(seed=7, options={"start_time": 12 * 3600.0})
+    sd = np.arange(B, dtype=np.uint64) + np.uint64(1007)
+    nz0 = port.philox_noise(sd, np.zeros(B, dtype=np.uint64), 4)
+    ref.reset(nz0, start_time=12 * 3600.0)
+    lay = obs_layout(ref.n, ref.m, ref.L, ref.G, ref.Bt)
+    for t in range(6):
+        act = rs.uniform(-1, 1, size=(B, ref.A))
+        obs, reward, _, _, info = env.step(act)
+        used = env.noise_used.cpu().numpy()
+        expect = port.philox_noise(sd, np.full(B, t + 1, dtype=np.uint64), 4 + ref.L)
+        assert np.max(np.abs(used - expect)) < 1e-12
+        r = ref.step(act, used)
+        assert np.max(np.abs(obs.cpu().numpy()[:, lay["vm"]] - r["obs"][:, lay["vm"]])) <= TOL_PU
+        assert np.allclose(reward.cpu().numpy(), r["reward"], rtol=1e-9, atol=1e-6)
+
+
+def test_reset_mask_autoreset_and_checkpoint():
+    import grid_fed_rl_b200 as m
+    f = m.repair_topology(m.IEEE13Bus())
+    kw = dict(renewable_sources=["solar", "wind"], episode_length=5, timestep=60.0, repair=False)
+    a = m.BatchedGridEnvironment(f, 64, **kw)
+    a.reset(seed=3)
+    g = torch.Generator(device="cuda"); g.manual_seed(1)
+    for _ in range(3):
+        a.step(a.sample_actions(g))
+    sd = a.state_dict()
+    b = m.BatchedGridEnvironment(f, 64, **kw)
+    b.load_state_dict(sd)
+    act = a.sample_actions(g)
+    oa, ra, ta, _, ia = a.step(act)
+    ob, rb, tb, _, ib = b.step(act)
+    assert torch.equal(oa, ob) and torch.equal(ra, rb) and torch.equal(ia["current_step"], ib["current_step"])
+    # masked reset touches only the selected instances
+    before = a.get_observation().clone()
+    mask = torch.zeros(64, dtype=torch.bool, device="cuda"); mask[::4] = True
+    obs, info = a.reset(mask=mask)
+    assert torch.equal(obs[~mask], before[~mask])
+    assert torch.all(obs[mask][:, 0] == 1.0) and torch.all(info["current_step"][mask] == 0)
+    assert torch.all(info["current_step"][~mask] == 4)
+    # auto-reset: instances that terminate come back at step 0 with the initial observation
+    c = m.BatchedGridEnvironment(f, 32, auto_reset=True, **kw)
+    c.reset(seed=5)
+    for t in range(5):
+        obs, rew, term, trunc, info = c.step(c.sample_actions(g))
+    assert bool(term.all())
+    assert torch.all(obs[:, 0] == 1.0) and "final_observation" in info
+    obs, rew, term, trunc, info = c.step(c.sample_actions(g))
+    assert torch.all(info["current_step"] == 1) and not bool(term.any())
+
+
+def test_full_size_properties_ieee123():
+    """BASELINE config 4 per-GPU size: 131,072 IEEE-123 instances, Newton, Philox noise."""
+    import grid_fed_rl_b200 as m
+    f = m.repair_topology(m.IEEE123Bus(seed=0))
+    B = 131072
+    kw = dict(renewable_sources=["solar", "wind"], solver="newton", tolerance=1e-6, repair=False)
+    env = m.BatchedGridEnvironment(f, B, start_time=12 * 3600.0, **kw)
+    env.reset(seed=11)
+    g = torch.Generator(device="cuda"); g.manual_seed(2)
+    act = env.sample_actions(g)
+    obs, reward, term, trunc, info = env.step(act)
+    assert bool(info["power_flow_converged"].all())
+    assert int(info["iterations"].min()) >= 2 and int(info["iterations"].max()) <= 6
+    assert torch.isfinite(obs).all() and torch.isfinite(reward).all()
+    n, mlines = env.soa.n_bus, env.soa.n_line
+    lay = obs_layout(n, mlines, env.soa.n_load, env.soa.n_gen, env.soa.n_bat)
+    vm = obs[:, lay["vm"]]
+    assert torch.all(vm[:, 0] == 1.0)                                  # slack magnitude
+    assert torch.equal(info["max_voltage"], vm.max(dim=1).values)
+    assert torch.equal(info["min_voltage"], vm.min(dim=1).values)
+    assert torch.equal(info["constraint_violations"][:, 1], (vm < 0.95).any(dim=1))
+    # power balance: the slack line flow(s) carry load - generation + losses; losses > 0 and small
+    assert torch.all(info["total_losses"] > 0) and torch.all(info["total_losses"] < 0.05 * env.soa.s_base)
+    # determinism + independence from the thread mapping
+    first = obs.clone(); r1 = reward.clone()
+    for lanes in (8, 32):
+        e2 = m.BatchedGridEnvironment(f, 4096, start_time=12 * 3600.0, lanes=lanes, **kw)
+        e2.reset(seed=11)
+        o2, r2, _, _, i2 = e2.step(act[:4096])
+        assert torch.max(torch.abs(o2[:, lay["vm"]] - first[:4096, lay["vm"]])) < 1e-12
+        assert torch.allclose(r2, r1[:4096], rtol=1e-12, atol=1e-9)
+        e2.close()
+    env2 = m.BatchedGridEnvironment(f, B, start_time=12 * 3600.0, **kw)
+    env2.reset(seed=11)
+    o3, r3, _, _, _ = env2.step(act)
+    assert torch.equal(o3, first) and torch.equal(r3, r1)
+
+
+def test_sharding_is_seed_stable():
+    """Results do not depend on how instances are split over ranks."""
+    import grid_fed_rl_b200 as m
+    f = m.repair_topology(m.IEEE13Bus())
+    kw = dict(renewable_sources=["solar", "wind"], solver="sweep", tolerance=1e-10, repair=False,
+              start_time=9 * 3600.0)
+    whole = m.BatchedGridEnvironment(f, 1000, **kw)
+    whole.reset(seed=42)
+    g = torch.Generator(device="cuda"); g.manual_seed(3)
+    act = whole.sample_actions(g)
+    ow = whole.step(act)[0].clone()
+    for rank in range(3):
+        lo, hi = m.shard_range(1000, rank, 3)
+        part = m.BatchedGridEnvironment(f, hi - lo, env_id_offset=lo, **kw)
+        part.reset(seed=42)
+        op = part.step(act[lo:hi])[0]
+        assert torch.equal(op, ow[lo:hi])
