@@ -58,14 +58,12 @@ __device__ __forceinline__ void stage_image(unsigned char* smem, const void* img
   } while (!ok);
 }
 
-template <int LANES>
-__device__ __forceinline__ Grp<LANES> make_group(const Layout& lay, unsigned char* smem) {
-  Grp<LANES> g;
-  g.E = blockDim.x / LANES;
-  g.e = threadIdx.x / LANES;
+template <int LANES, int NF>
+__device__ __forceinline__ Grp<LANES, NF> make_group(const Layout& lay, unsigned char* smem) {
+  Grp<LANES, NF> g;
   g.lane = threadIdx.x % LANES;
-  g.FS = ((lay.n + LANES - 1) / LANES) * LANES * g.E;
-  g.st = (double*)(smem + kSmemHeader + lay.img_bytes);
+  g.n = lay.n;
+  g.rec = (double*)(smem + kSmemHeader + lay.img_bytes) + (size_t)(threadIdx.x / LANES) * lay.n * NF;
   g.mask = (LANES == 32) ? 0xffffffffu
                          : (((1u << (LANES & 31)) - 1u) << (((threadIdx.x & 31) / LANES) * LANES));
   return g;
@@ -73,7 +71,7 @@ __device__ __forceinline__ Grp<LANES> make_group(const Layout& lay, unsigned cha
 
 template <int LANES, int SOLVER>
 __global__ void __launch_bounds__(128)
-step_kernel(const Layout lay, const EnvCfg cfg, const int nf, const void* __restrict__ img,
+step_kernel(const Layout lay, const EnvCfg cfg, const void* __restrict__ img,
             double* __restrict__ state, double* __restrict__ obs,
             const double* __restrict__ actions, const double* __restrict__ noise, const StepOut o,
             const long long B) {
@@ -81,22 +79,24 @@ step_kernel(const Layout lay, const EnvCfg cfg, const int nf, const void* __rest
   stage_image(smem, img, lay.img_bytes);
   const int* simg = (const int*)(smem + kSmemHeader);
   const double* dimg = (const double*)(smem + kSmemHeader);
-  const Grp<LANES> g = make_group<LANES>(lay, smem);
-  for (long long env = (long long)blockIdx.x * g.E + g.e; env < B; env += (long long)gridDim.x * g.E)
-    step_instance<LANES, SOLVER>(g, lay, simg, dimg, cfg, nf, env, state, obs, actions, noise, o);
+  const auto g = make_group<LANES, RecOf<SOLVER>::NF>(lay, smem);
+  const int E = blockDim.x / LANES;
+  for (long long env = (long long)blockIdx.x * E + threadIdx.x / LANES; env < B; env += (long long)gridDim.x * E)
+    step_instance<LANES, SOLVER>(g, lay, simg, dimg, cfg, env, state, obs, actions, noise, o);
 }
 
 template <int LANES, int SOLVER>
 __global__ void __launch_bounds__(128)
-solve_kernel(const Layout lay, const EnvCfg cfg, const int nf, const void* __restrict__ img,
+solve_kernel(const Layout lay, const EnvCfg cfg, const void* __restrict__ img,
              const double* __restrict__ p_inj, const SolOut o, const long long B) {
   extern __shared__ __align__(16) unsigned char smem[];
   stage_image(smem, img, lay.img_bytes);
   const int* simg = (const int*)(smem + kSmemHeader);
   const double* dimg = (const double*)(smem + kSmemHeader);
-  const Grp<LANES> g = make_group<LANES>(lay, smem);
-  for (long long env = (long long)blockIdx.x * g.E + g.e; env < B; env += (long long)gridDim.x * g.E)
-    solve_instance<LANES, SOLVER>(g, lay, simg, dimg, cfg, nf, env, p_inj, o);
+  const auto g = make_group<LANES, RecOf<SOLVER>::NF>(lay, smem);
+  const int E = blockDim.x / LANES;
+  for (long long env = (long long)blockIdx.x * E + threadIdx.x / LANES; env < B; env += (long long)gridDim.x * E)
+    solve_instance<LANES, SOLVER>(g, lay, simg, dimg, cfg, env, p_inj, o);
 }
 
 // reset: 4 lanes per instance, image read through L2 (touched once per instance)
@@ -108,13 +108,14 @@ reset_kernel(const Layout lay, const EnvCfg cfg, const void* __restrict__ img,
              const double* __restrict__ noise, const double start_time, const int construct,
              const long long B) {
   constexpr int LANES = 4;
-  Grp<LANES> g;
-  g.E = blockDim.x / LANES; g.e = threadIdx.x / LANES; g.lane = threadIdx.x % LANES;
-  g.FS = 0; g.st = nullptr;
+  Grp<LANES, 1> g;
+  g.lane = threadIdx.x % LANES;
+  g.n = lay.n; g.rec = nullptr;
   g.mask = ((1u << LANES) - 1u) << (((threadIdx.x & 31) / LANES) * LANES);
   const int* simg = (const int*)img;
   const double* dimg = (const double*)img;
-  for (long long env = (long long)blockIdx.x * g.E + g.e; env < B; env += (long long)gridDim.x * g.E) {
+  const int E = blockDim.x / LANES;
+  for (long long env = (long long)blockIdx.x * E + threadIdx.x / LANES; env < B; env += (long long)gridDim.x * E) {
     if (mask && !mask[env]) continue;
     reset_instance<LANES>(g, lay, simg, dimg, cfg, env, state, obs, load_pq, bat_soc0, seeds, noise,
                           start_time, construct != 0);
@@ -197,11 +198,12 @@ namespace {
 
 struct LaunchPlan { int lanes, threads, nf, grid; size_t smem; };
 
-int fields_needed(const Layout& lay, int solver, int lanes) {
-  const int kbl = ((lay.n + lanes - 1) / lanes) * lanes;
-  int nf = solver == GFR_SOLVER_NEWTON ? NF_NEWTON : NF_SWEEP;
-  const int need = F_SCRATCH + (lay.n_src + kbl - 1) / kbl;
-  return need > nf ? need : nf;
+// shared memory of one instance slot; 0 if the scratch carried in the records cannot hold the sources
+size_t slot_bytes(const Layout& lay, int solver) {
+  const int nf = solver == GFR_SOLVER_NEWTON ? NF_NEWTON : NF_SWEEP;
+  const int cap = (solver == GFR_SOLVER_NEWTON ? SCRATCH_FIELDS_NEWTON : SCRATCH_FIELDS_SWEEP) * lay.n;
+  if (lay.n_src > cap) return 0;
+  return (size_t)nf * lay.n * sizeof(double);
 }
 
 int auto_lanes(const Layout& lay) {
@@ -216,9 +218,11 @@ int plan_launch(const gfr_feeder* f, int solver, int lanes, long long B, LaunchP
   if (lanes == 0) lanes = auto_lanes(lay);
   if (lanes != 1 && lanes != 2 && lanes != 4 && lanes != 8 && lanes != 16 && lanes != 32)
     return fail(GFR_E_ARG, "lanes must be 0 (auto), 1, 2, 4, 8, 16 or 32");
-  const int nf = fields_needed(lay, solver, lanes);
-  const int kbl = ((lay.n + lanes - 1) / lanes) * lanes;
-  const size_t per_env = (size_t)nf * kbl * sizeof(double);
+  const int nf = solver == GFR_SOLVER_NEWTON ? NF_NEWTON : NF_SWEEP;
+  const size_t per_env = slot_bytes(lay, solver);
+  if (!per_env)
+    return fail(GFR_E_LIMIT, "more loads + generators + batteries than the solver's per-bus scratch holds "
+                             "(newton: 6 per bus on average, sweep: 2)");
   const size_t sm_budget = 227u * 1024u;
   int best_threads = 0;
   long long best_resident = 0;
@@ -249,7 +253,7 @@ int launch_step_t(const gfr_env* e, const double* actions, const double* noise, 
                   cudaStream_t s) {
   auto kern = step_kernel<LANES, SOLVER>;
   GFR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
-  kern<<<e->grid, e->threads, e->smem, s>>>(e->f->lay, e->cfg, e->nf, e->f->d_img, e->d_state, e->d_obs,
+  kern<<<e->grid, e->threads, e->smem, s>>>(e->f->lay, e->cfg, e->f->d_img, e->d_state, e->d_obs,
                                            actions, noise, o, e->B);
   g_launches.fetch_add(1);
   GFR_CUDA(cudaGetLastError());
@@ -261,7 +265,7 @@ int launch_solve_t(const gfr_feeder* f, const LaunchPlan& p, const EnvCfg& cfg, 
                    const SolOut& o, long long B, cudaStream_t s) {
   auto kern = solve_kernel<LANES, SOLVER>;
   GFR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
-  kern<<<p.grid, p.threads, p.smem, s>>>(f->lay, cfg, p.nf, f->d_img, p_inj, o, B);
+  kern<<<p.grid, p.threads, p.smem, s>>>(f->lay, cfg, f->d_img, p_inj, o, B);
   g_launches.fetch_add(1);
   GFR_CUDA(cudaGetLastError());
   return GFR_OK;

@@ -32,23 +32,35 @@ namespace gfr {
 enum { SOLVER_SWEEP = 0, SOLVER_NEWTON = 1 };
 enum { BUS_SLACK = 0, BUS_PV = 1, BUS_PQ = 2 };
 enum { GEN_SOLAR = 0, GEN_WIND = 1 };
-// per-bus slots of an instance's working set (field index)
-enum { F_E = 0, F_F = 1, F_P = 2, F_M0 = 3, F_M1 = 4, F_M2 = 5, F_M3 = 6, F_V0 = 7, F_V1 = 8 };
-enum { NF_NEWTON = 9, NF_SWEEP = 5, F_SCRATCH = 3 };
+// An instance's working set is one RECORD per bus (level order), NF doubles each, so that a
+// field is an immediate offset from the bus's address and pairs load as one 128-bit access:
+//   Newton (NF = 10): e f | M0 M1 | M2 M3 | V0 V1 | P pad
+//   sweep  (NF = 6):  e f | Jr Ji | P pad
+// e + jf is the bus voltage, P the specified injection; M*, V* hold the 2x2 diagonal block and
+// the right-hand side during assembly, D^-1 U and D^-1 r after elimination, the correction
+// after back-substitution; Jr + jJi is the branch current.  Fields F_SCRATCH.. double as the
+// scratch that carries the load / generator / battery powers into the injection sums.
+enum { F_E = 0, F_F = 1, F_SCRATCH = 2 };
+enum { NF_NEWTON = 10, N_M0 = 2, N_M1 = 3, N_M2 = 4, N_M3 = 5, N_V0 = 6, N_V1 = 7, N_P = 8 };
+enum { NF_SWEEP = 6, S_JR = 2, S_JI = 3, S_P = 4 };
+enum { SCRATCH_FIELDS_NEWTON = 6, SCRATCH_FIELDS_SWEEP = 2 };
 // bus flag bits
 enum { FL_PQ = 1, FL_FROM_IS_PARENT = 2, FL_FIXED_VM = 4 };
 // record (persistent per-instance state) slots, in doubles
 enum { R_TIME = 0, R_FREQ, R_WIND, R_TEMP, R_CLOUD, R_TOTAL_LOSSES, R_EPISODE_REWARD, R_SEED,
        R_DRAWS, R_COUNTS, R_BAT };   // soc[Bt] then bpow[Bt] from R_BAT on
 
+struct alignas(16) D2 { double x, y; };
+struct alignas(16) I4 { int x, y, z, w; };   // per-bus topology: parent, first child, end child, flags
+
 // Where everything is inside the feeder image (ints / doubles counted from the image base)
 // plus the sizes; passed as a kernel parameter (constant bank).
 struct Layout {
   int n, nl, L, G, Bt, A, D, m, n_src, R, img_bytes, n_noise;
-  int o_parent, o_child_ptr, o_level_ptr, o_flags, o_order, o_rank, o_line_of,
-      o_branch_of_line, o_inj_ptr, o_inj_idx, o_gen_type;
-  int o_g, o_b, o_gdiag, o_bdiag, o_r, o_x, o_rating, o_vm_set, o_load_base, o_gen_cap,
-      o_gen_p0, o_gen_p1, o_gen_p2, o_bat_cap, o_bat_rating, o_bat_eff, o_profile;
+  int o_topo, o_level_ptr, o_order, o_rank, o_line_of, o_branch_of_line, o_inj_ptr, o_inj_idx,
+      o_gen_type;
+  int o_gb, o_gbd, o_rx, o_rating, o_vm_set, o_load_base, o_gen_cap, o_gen_p0, o_gen_p1, o_gen_p2,
+      o_bat_cap, o_bat_rating, o_bat_eff, o_profile;
   double s_base, load_p_sum;
 };
 
@@ -65,21 +77,20 @@ struct SolveStat {
 
 // ----------------------------------------------------------------------------- group ops
 
-template <int LANES>
+template <int LANES, int NF>
 struct Grp {
   int lane;        // lane inside the group
-  int e;           // instance slot inside the CTA
-  int E;           // instance slots per CTA
-  int FS;          // field stride in doubles = ceil(n / LANES) * LANES * E
   unsigned mask;   // the group's lanes inside its warp
-  double* st;      // CTA working set (shared memory)
+  double* rec;     // this instance slot's records (shared memory): bus k at rec + k * NF
+  int n;           // buses
 
-  GFR_HD int sidx(int k) const {
-    unsigned u = (unsigned)k;
-    return (int)(((u / LANES) * (unsigned)E + (unsigned)e) * LANES + (u % LANES));
+  GFR_HD double& at(int field, int k) const { return rec[k * NF + field]; }
+  GFR_HD D2& at2(int field, int k) const { return *reinterpret_cast<D2*>(rec + k * NF + field); }
+  GFR_HD double& scr(int j) const {     // source j -> field F_SCRATCH + j / n of bus j % n
+    int f = F_SCRATCH;
+    while (j >= n) { j -= n; ++f; }
+    return rec[j * NF + f];
   }
-  GFR_HD double& at(int field, int k) const { return st[field * FS + sidx(k)]; }
-  GFR_HD double& scr(int j) const { return st[F_SCRATCH * FS + sidx(j)]; }
   // first index >= k0 owned by this lane
   GFR_HD int first(int k0) const { return k0 + ((lane - k0) & (LANES - 1)); }
 
@@ -215,19 +226,17 @@ GFR_HD double noise_slot(uint64_t seed, uint64_t draw, int s) {
 
 // ----------------------------------------------------------------------------- solvers
 
-#define GFR_II(name) (simg[lay.name])          /* int array base inside the image */
-#define GFR_DI(name) (dimg[lay.name])          /* double array base */
-
 // Flat start (power_flow.py:103, :131): 1.0 at 0 rad, slack / PV buses at their set magnitude.
-template <int LANES>
-GFR_HD void flat_start(const Grp<LANES>& g, const Layout& lay, const int* simg, const double* dimg,
-                       int nf) {
+template <int LANES, int NF>
+GFR_HD void flat_start(const Grp<LANES, NF>& g, const Layout& lay, const int* simg, const double* dimg) {
+  const I4* topo = reinterpret_cast<const I4*>(simg + lay.o_topo);
   for (int k = g.lane; k < lay.n; k += LANES) {
-    int fl = simg[lay.o_flags + k];
-    g.at(F_E, k) = (fl & FL_FIXED_VM) ? dimg[lay.o_vm_set + k] : 1.0;
-    g.at(F_F, k) = 0.0;
+    D2 v;
+    v.x = (topo[k].w & FL_FIXED_VM) ? dimg[lay.o_vm_set + k] : 1.0;
+    v.y = 0.0;
+    g.at2(F_E, k) = v;
   }
-  if (g.lane == 0 && nf > F_V1) { g.at(F_V0, 0) = 0.0; g.at(F_V1, 0) = 0.0; }   // slack correction = 0
+  if (NF == NF_NEWTON && g.lane == 0) { D2 z; z.x = 0.0; z.y = 0.0; g.at2(N_V0, 0) = z; }   // slack correction = 0
   g.sync();
 }
 
@@ -241,18 +250,14 @@ GFR_HD void flat_start(const Grp<LANES>& g, const Layout& lay, const int* simg, 
 // with G_ij + jB_ij = -(g + jb) of the branch and everything written on e + jf = |V| e^{j theta}:
 //   |Vi||Vj| cos th_ij = ei ej + fi fj,  |Vi||Vj| sin th_ij = fi ej - ei fj   (no trigonometry).
 template <int LANES>
-GFR_HD void newton_solve(const Grp<LANES>& g, const Layout& lay, const int* simg,
+GFR_HD void newton_solve(const Grp<LANES, NF_NEWTON>& g, const Layout& lay, const int* simg,
                          const double* dimg, double tol, int max_it, double accel,
                          SolveStat* out) {
   const int n = lay.n, nl = lay.nl;
-  const int* parent = simg + lay.o_parent;
-  const int* child_ptr = simg + lay.o_child_ptr;
+  const I4* topo = reinterpret_cast<const I4*>(simg + lay.o_topo);
   const int* level_ptr = simg + lay.o_level_ptr;
-  const int* flags = simg + lay.o_flags;
-  const double* bg = dimg + lay.o_g;
-  const double* bb = dimg + lay.o_b;
-  const double* gdiag = dimg + lay.o_gdiag;
-  const double* bdiag = dimg + lay.o_bdiag;
+  const D2* gb = reinterpret_cast<const D2*>(dimg + lay.o_gb);      // branch series g, b
+  const D2* gbd = reinterpret_cast<const D2*>(dimg + lay.o_gbd);    // Re, Im of Y_kk
 
   out->converged = 0;
   out->iterations = max_it;
@@ -262,35 +267,40 @@ GFR_HD void newton_solve(const Grp<LANES>& g, const Layout& lay, const int* simg
     // ---- mismatch + diagonal blocks, every bus independently (power_flow.py:150-166, 213-295)
     double mm = 0.0;
     for (int k = g.first(1); k < n; k += LANES) {
-      double ek = g.at(F_E, k), fk = g.at(F_F, k);
-      double v2 = ek * ek + fk * fk;
-      double gd = gdiag[k], bd = bdiag[k];
-      double P = gd * v2, Q = -bd * v2;
+      const I4 t = topo[k];
+      const D2 vk = g.at2(F_E, k);
+      const D2 yd = gbd[k];
+      const double v2 = vk.x * vk.x + vk.y * vk.y;
+      double P = yd.x * v2, Q = -yd.y * v2;
       {
-        int p = parent[k];
-        double ep = g.at(F_E, p), fp = g.at(F_F, p);
-        double a = ek * ep + fk * fp, s = fk * ep - ek * fp;
-        P += -bg[k] * a - bb[k] * s;
-        Q += -bg[k] * s + bb[k] * a;
+        const D2 vp = g.at2(F_E, t.x);
+        const D2 y = gb[k];
+        const double a = vk.x * vp.x + vk.y * vp.y, s = vk.y * vp.x - vk.x * vp.y;
+        P += -y.x * a - y.y * s;
+        Q += -y.x * s + y.y * a;
       }
-      for (int c = child_ptr[k]; c < child_ptr[k + 1]; ++c) {
-        double ec = g.at(F_E, c), fc = g.at(F_F, c);
-        double a = ek * ec + fk * fc, s = fk * ec - ek * fc;
-        P += -bg[c] * a - bb[c] * s;
-        Q += -bg[c] * s + bb[c] * a;
+      for (int c = t.y; c < t.z; ++c) {
+        const D2 vc = g.at2(F_E, c);
+        const D2 y = gb[c];
+        const double a = vk.x * vc.x + vk.y * vc.y, s = vk.y * vc.x - vk.x * vc.y;
+        P += -y.x * a - y.y * s;
+        Q += -y.x * s + y.y * a;
       }
-      int pq = flags[k] & FL_PQ;
-      double dP = g.at(F_P, k) - P;
-      double dQ = pq ? (0.0 - Q) : 0.0;
-      double aP = fabs(dP), aQ = fabs(dQ);
-      double loc = (aQ > aP || aQ != aQ) ? aQ : aP;
+      const int pq = t.w & FL_PQ;
+      const double dP = g.at(N_P, k) - P;
+      const double dQ = pq ? (0.0 - Q) : 0.0;
+      const double aP = fabs(dP), aQ = fabs(dQ);
+      const double loc = (aQ > aP || aQ != aQ) ? aQ : aP;
       mm = (loc > mm || loc != loc) ? loc : mm;
-      g.at(F_M0, k) = -Q - bd * v2;
-      g.at(F_M1, k) = P + gd * v2;
-      g.at(F_M2, k) = pq ? (P - gd * v2) : 0.0;
-      g.at(F_M3, k) = pq ? (Q - bd * v2) : 1.0;
-      g.at(F_V0, k) = dP;
-      g.at(F_V1, k) = dQ;
+      D2 r0, r1, rr;
+      r0.x = -Q - yd.y * v2;
+      r0.y = P + yd.x * v2;
+      r1.x = pq ? (P - yd.x * v2) : 0.0;
+      r1.y = pq ? (Q - yd.y * v2) : 1.0;
+      rr.x = dP; rr.y = dQ;
+      g.at2(N_M0, k) = r0;
+      g.at2(N_M2, k) = r1;
+      g.at2(N_V0, k) = rr;
     }
     mm = g.gmax_nan(mm);
     out->max_mismatch = mm;
@@ -304,40 +314,44 @@ GFR_HD void newton_solve(const Grp<LANES>& g, const Layout& lay, const int* simg
     for (int l = nl - 1; l >= 1; --l) {
       const int k1 = level_ptr[l + 1];
       for (int k = g.first(level_ptr[l]); k < k1; k += LANES) {
-        double ek = g.at(F_E, k), fk = g.at(F_F, k);
-        double d00 = g.at(F_M0, k), d01 = g.at(F_M1, k), d10 = g.at(F_M2, k), d11 = g.at(F_M3, k);
-        double r0 = g.at(F_V0, k), r1 = g.at(F_V1, k);
-        int pq = flags[k] & FL_PQ;
-        for (int c = child_ptr[k]; c < child_ptr[k + 1]; ++c) {
-          double ec = g.at(F_E, c), fc = g.at(F_F, c);
-          double a = ek * ec + fk * fc, s = fk * ec - ek * fc;
-          double ga = -bg[c] * a - bb[c] * s, al = -bg[c] * s + bb[c] * a;   // J[k,c]
-          double m00 = g.at(F_M0, c), m01 = g.at(F_M1, c), m10 = g.at(F_M2, c), m11 = g.at(F_M3, c);
-          double v0 = g.at(F_V0, c), v1 = g.at(F_V1, c);
-          d00 -= al * m00 + ga * m10;
-          d01 -= al * m01 + ga * m11;
-          r0 -= al * v0 + ga * v1;
+        const I4 t = topo[k];
+        const D2 vk = g.at2(F_E, k);
+        D2 d0 = g.at2(N_M0, k), d1 = g.at2(N_M2, k), r = g.at2(N_V0, k);
+        const int pq = t.w & FL_PQ;
+        for (int c = t.y; c < t.z; ++c) {
+          const D2 vc = g.at2(F_E, c);
+          const D2 y = gb[c];
+          const double a = vk.x * vc.x + vk.y * vc.y, s = vk.y * vc.x - vk.x * vc.y;
+          const double ga = -y.x * a - y.y * s, al = -y.x * s + y.y * a;   // J[k,c]
+          const D2 m0 = g.at2(N_M0, c), m1 = g.at2(N_M2, c), v = g.at2(N_V0, c);
+          d0.x -= al * m0.x + ga * m1.x;
+          d0.y -= al * m0.y + ga * m1.y;
+          r.x -= al * v.x + ga * v.y;
           if (pq) {
-            d10 -= -ga * m00 + al * m10;
-            d11 -= -ga * m01 + al * m11;
-            r1 -= -ga * v0 + al * v1;
+            d1.x -= -ga * m0.x + al * m1.x;
+            d1.y -= -ga * m0.y + al * m1.y;
+            r.y -= -ga * v.x + al * v.y;
           }
         }
-        int p = parent[k];
-        double ep = g.at(F_E, p), fp = g.at(F_F, p);
-        double a = ek * ep + fk * fp, s = fk * ep - ek * fp;
-        double ga = -bg[k] * a - bb[k] * s, al = -bg[k] * s + bb[k] * a;     // J[k,p]
-        double u00 = al, u01 = ga, u10 = pq ? -ga : 0.0, u11 = pq ? al : 0.0;
-        double det = d00 * d11 - d01 * d10;
+        const D2 vp = g.at2(F_E, t.x);
+        const D2 y = gb[k];
+        const double a = vk.x * vp.x + vk.y * vp.y, s = vk.y * vp.x - vk.x * vp.y;
+        const double ga = -y.x * a - y.y * s, al = -y.x * s + y.y * a;     // J[k,p]
+        const double u00 = al, u01 = ga, u10 = pq ? -ga : 0.0, u11 = pq ? al : 0.0;
+        const double det = d0.x * d1.y - d0.y * d1.x;
         if (det == 0.0) singular = 1;                 // dgesv's exact-zero pivot (:188-190)
-        double inv = 1.0 / det;
-        double i00 = d11 * inv, i01 = -d01 * inv, i10 = -d10 * inv, i11 = d00 * inv;
-        g.at(F_M0, k) = i00 * u00 + i01 * u10;
-        g.at(F_M1, k) = i00 * u01 + i01 * u11;
-        g.at(F_M2, k) = i10 * u00 + i11 * u10;
-        g.at(F_M3, k) = i10 * u01 + i11 * u11;
-        g.at(F_V0, k) = i00 * r0 + i01 * r1;
-        g.at(F_V1, k) = i10 * r0 + i11 * r1;
+        const double inv = 1.0 / det;
+        const double i00 = d1.y * inv, i01 = -d0.y * inv, i10 = -d1.x * inv, i11 = d0.x * inv;
+        D2 o0, o1, ov;
+        o0.x = i00 * u00 + i01 * u10;
+        o0.y = i00 * u01 + i01 * u11;
+        o1.x = i10 * u00 + i11 * u10;
+        o1.y = i10 * u01 + i11 * u11;
+        ov.x = i00 * r.x + i01 * r.y;
+        ov.y = i10 * r.x + i11 * r.y;
+        g.at2(N_M0, k) = o0;
+        g.at2(N_M2, k) = o1;
+        g.at2(N_V0, k) = ov;
       }
       g.sync();
     }
@@ -349,22 +363,27 @@ GFR_HD void newton_solve(const Grp<LANES>& g, const Layout& lay, const int* simg
     for (int l = 1; l < nl; ++l) {
       const int k1 = level_ptr[l + 1];
       for (int k = g.first(level_ptr[l]); k < k1; k += LANES) {
-        int p = parent[k];
-        double x0 = g.at(F_V0, p), x1 = g.at(F_V1, p);
-        g.at(F_V0, k) -= g.at(F_M0, k) * x0 + g.at(F_M1, k) * x1;
-        g.at(F_V1, k) -= g.at(F_M2, k) * x0 + g.at(F_M3, k) * x1;
+        const D2 x = g.at2(N_V0, topo[k].x);
+        const D2 m0 = g.at2(N_M0, k), m1 = g.at2(N_M2, k);
+        D2 v = g.at2(N_V0, k);
+        v.x -= m0.x * x.x + m0.y * x.y;
+        v.y -= m1.x * x.x + m1.y * x.y;
+        g.at2(N_V0, k) = v;
       }
       g.sync();
     }
     // ---- polar update, every bus independently (:297-327):
     //      theta += a dtheta, |V| += a d|V|  <=>  V *= (1 + a x1) e^{j a x0}
     for (int k = g.first(1); k < n; k += LANES) {
+      const D2 x = g.at2(N_V0, k);
       double sn, cs;
-      sincos_small(accel * g.at(F_V0, k), &sn, &cs);
-      double sc = 1.0 + accel * g.at(F_V1, k);
-      double ek = g.at(F_E, k), fk = g.at(F_F, k);
-      g.at(F_E, k) = sc * (ek * cs - fk * sn);
-      g.at(F_F, k) = sc * (ek * sn + fk * cs);
+      sincos_small(accel * x.x, &sn, &cs);
+      const double sc = 1.0 + accel * x.y;
+      const D2 v = g.at2(F_E, k);
+      D2 w;
+      w.x = sc * (v.x * cs - v.y * sn);
+      w.y = sc * (v.x * sn + v.y * cs);
+      g.at2(F_E, k) = w;
     }
     g.sync();
   }
@@ -374,15 +393,12 @@ GFR_HD void newton_solve(const Grp<LANES>& g, const Layout& lay, const int* simg
 // compared with the reference's Newton-Raphson at tight tolerance).  Constant-power
 // injections P + j0; convergence on max(|de|, |df|) over buses.
 template <int LANES>
-GFR_HD void sweep_solve(const Grp<LANES>& g, const Layout& lay, const int* simg,
+GFR_HD void sweep_solve(const Grp<LANES, NF_SWEEP>& g, const Layout& lay, const int* simg,
                         const double* dimg, double tol, int max_it, SolveStat* out) {
-  const int n = lay.n, nl = lay.nl;
-  const int* parent = simg + lay.o_parent;
-  const int* child_ptr = simg + lay.o_child_ptr;
+  const int nl = lay.nl;
+  const I4* topo = reinterpret_cast<const I4*>(simg + lay.o_topo);
   const int* level_ptr = simg + lay.o_level_ptr;
-  const double* br = dimg + lay.o_r;
-  const double* bx = dimg + lay.o_x;
-  (void)n;
+  const D2* rx = reinterpret_cast<const D2*>(dimg + lay.o_rx);
   out->converged = 0;
   out->iterations = max_it;
   out->max_mismatch = INFINITY;
@@ -391,15 +407,16 @@ GFR_HD void sweep_solve(const Grp<LANES>& g, const Layout& lay, const int* simg,
     for (int l = nl - 1; l >= 1; --l) {
       const int k1 = level_ptr[l + 1];
       for (int k = g.first(level_ptr[l]); k < k1; k += LANES) {
-        double ek = g.at(F_E, k), fk = g.at(F_F, k);
-        double w = g.at(F_P, k) / (ek * ek + fk * fk);      // injected current = conj(S / V) = P V / |V|^2
-        double jr = -w * ek, ji = -w * fk;
-        for (int c = child_ptr[k]; c < child_ptr[k + 1]; ++c) {
-          jr += g.at(F_M0, c);
-          ji += g.at(F_M1, c);
+        const I4 t = topo[k];
+        const D2 v = g.at2(F_E, k);
+        const double w = g.at(S_P, k) / (v.x * v.x + v.y * v.y);   // injected current = conj(S / V) = P V / |V|^2
+        D2 j;
+        j.x = -w * v.x; j.y = -w * v.y;
+        for (int c = t.y; c < t.z; ++c) {
+          const D2 jc = g.at2(S_JR, c);
+          j.x += jc.x; j.y += jc.y;
         }
-        g.at(F_M0, k) = jr;
-        g.at(F_M1, k) = ji;
+        g.at2(S_JR, k) = j;
       }
       g.sync();
     }
@@ -408,15 +425,17 @@ GFR_HD void sweep_solve(const Grp<LANES>& g, const Layout& lay, const int* simg,
     for (int l = 1; l < nl; ++l) {
       const int k1 = level_ptr[l + 1];
       for (int k = g.first(level_ptr[l]); k < k1; k += LANES) {
-        int p = parent[k];
-        double jr = g.at(F_M0, k), ji = g.at(F_M1, k);
-        double en = g.at(F_E, p) - (br[k] * jr - bx[k] * ji);
-        double fn = g.at(F_F, p) - (br[k] * ji + bx[k] * jr);
-        double de = fabs(en - g.at(F_E, k)), df = fabs(fn - g.at(F_F, k));
-        double loc = (df > de || df != df) ? df : de;
+        const D2 vp = g.at2(F_E, topo[k].x);
+        const D2 j = g.at2(S_JR, k);
+        const D2 z = rx[k];
+        const D2 vo = g.at2(F_E, k);
+        D2 vn;
+        vn.x = vp.x - (z.x * j.x - z.y * j.y);
+        vn.y = vp.y - (z.x * j.y + z.y * j.x);
+        const double de = fabs(vn.x - vo.x), df = fabs(vn.y - vo.y);
+        const double loc = (df > de || df != df) ? df : de;
         mm = (loc > mm || loc != loc) ? loc : mm;
-        g.at(F_E, k) = en;
-        g.at(F_F, k) = fn;
+        g.at2(F_E, k) = vn;
       }
       g.sync();
     }
@@ -431,23 +450,23 @@ GFR_HD void sweep_solve(const Grp<LANES>& g, const Layout& lay, const int* simg,
 }
 
 // From -> to flow of the branch above bus k (power_flow.py:329-358): P (pu), |S| (pu), series loss (pu)
-template <int LANES>
-GFR_HD void branch_flow(const Grp<LANES>& g, const Layout& lay, const int* simg, const double* dimg,
+template <int LANES, int NF>
+GFR_HD void branch_flow(const Grp<LANES, NF>& g, const Layout& lay, const int* simg, const double* dimg,
                         int k, double* p_ft, double* s_abs, double* loss) {
-  int p = simg[lay.o_parent + k];
-  double ek = g.at(F_E, k), fk = g.at(F_F, k), ep = g.at(F_E, p), fp = g.at(F_F, p);
-  double gg = dimg[lay.o_g + k], bb = dimg[lay.o_b + k];
-  double de = ep - ek, df = fp - fk;                 // V_parent - V_k
-  double ir = gg * de - bb * df, ii = gg * df + bb * de;   // current parent -> k
+  const I4 t = reinterpret_cast<const I4*>(simg + lay.o_topo)[k];
+  const D2 vk = g.at2(F_E, k), vp = g.at2(F_E, t.x);
+  const D2 y = reinterpret_cast<const D2*>(dimg + lay.o_gb)[k];
+  const double de = vp.x - vk.x, df = vp.y - vk.y;                 // V_parent - V_k
+  const double ir = y.x * de - y.y * df, ii = y.x * df + y.y * de;   // current parent -> k
   double P, Q;
-  if (simg[lay.o_flags + k] & FL_FROM_IS_PARENT) {
-    P = ep * ir + fp * ii; Q = fp * ir - ep * ii;    // V_p conj(I)
+  if (t.w & FL_FROM_IS_PARENT) {
+    P = vp.x * ir + vp.y * ii; Q = vp.y * ir - vp.x * ii;    // V_p conj(I)
   } else {
-    P = -(ek * ir + fk * ii); Q = -(fk * ir - ek * ii);    // V_k conj(-I)
+    P = -(vk.x * ir + vk.y * ii); Q = -(vk.y * ir - vk.x * ii);    // V_k conj(-I)
   }
   *p_ft = P;
   *s_abs = sqrt(P * P + Q * Q);
-  *loss = gg * (de * de + df * df);                  // Re sum_i V_i conj((YV)_i), branch by branch
+  *loss = y.x * (de * de + df * df);                 // Re sum_i V_i conj((YV)_i), branch by branch
 }
 
 // ----------------------------------------------------------------------------- solver entry (gfr_solve)
@@ -457,18 +476,37 @@ struct SolOut {
   double* line_flows; double* line_loadings; double* losses; double* max_mismatch;
 };
 
+template <int LANES>
+GFR_HD void run_solver_impl(const Grp<LANES, NF_NEWTON>& g, const Layout& lay, const int* simg,
+                            const double* dimg, const EnvCfg& cfg, SolveStat* st) {
+  newton_solve(g, lay, simg, dimg, cfg.tol, cfg.max_it, cfg.accel, st);
+}
+template <int LANES>
+GFR_HD void run_solver_impl(const Grp<LANES, NF_SWEEP>& g, const Layout& lay, const int* simg,
+                            const double* dimg, const EnvCfg& cfg, SolveStat* st) {
+  sweep_solve(g, lay, simg, dimg, cfg.tol, cfg.max_it, st);
+}
+template <int LANES, int SOLVER, int NF>
+GFR_HD void run_solver(const Grp<LANES, NF>& g, const Layout& lay, const int* simg, const double* dimg,
+                       const EnvCfg& cfg, SolveStat* st) {
+  run_solver_impl(g, lay, simg, dimg, cfg, st);
+}
+
+template <int SOLVER> struct RecOf { enum { NF = SOLVER == SOLVER_NEWTON ? NF_NEWTON : NF_SWEEP,
+                                              F_PSPEC = SOLVER == SOLVER_NEWTON ? N_P : S_P }; };
+
 template <int LANES, int SOLVER>
-GFR_HD void solve_instance(const Grp<LANES>& g, const Layout& lay, const int* simg,
-                           const double* dimg, const EnvCfg& cfg, int nf, long long env,
+GFR_HD void solve_instance(const Grp<LANES, RecOf<SOLVER>::NF>& g, const Layout& lay, const int* simg,
+                           const double* dimg, const EnvCfg& cfg, long long env,
                            const double* p_inj, const SolOut& o) {
+  constexpr int F_P = RecOf<SOLVER>::F_PSPEC;
   const int n = lay.n, m = lay.m;
   const int* rank = simg + lay.o_rank;
   const double* pin = p_inj + env * n;
   for (int i = g.lane; i < n; i += LANES) g.at(F_P, rank[i]) = pin[i];
-  flat_start(g, lay, simg, dimg, nf);
+  flat_start(g, lay, simg, dimg);
   SolveStat st;
-  if (SOLVER == SOLVER_NEWTON) newton_solve(g, lay, simg, dimg, cfg.tol, cfg.max_it, cfg.accel, &st);
-  else sweep_solve(g, lay, simg, dimg, cfg.tol, cfg.max_it, &st);
+  run_solver<LANES, SOLVER>(g, lay, simg, dimg, cfg, &st);
   for (int i = g.lane; i < n; i += LANES) {
     int k = rank[i];
     double e = g.at(F_E, k), f = g.at(F_F, k);
@@ -547,10 +585,11 @@ GFR_HD void update_weather(double hour, double u, double z1, double z2, double z
 }
 
 template <int LANES, int SOLVER>
-GFR_HD void step_instance(const Grp<LANES>& g, const Layout& lay, const int* simg,
-                          const double* dimg, const EnvCfg& cfg, int nf, long long env,
+GFR_HD void step_instance(const Grp<LANES, RecOf<SOLVER>::NF>& g, const Layout& lay, const int* simg,
+                          const double* dimg, const EnvCfg& cfg, long long env,
                           double* state, double* obs, const double* actions, const double* noise,
                           const StepOut& o) {
+  constexpr int F_P = RecOf<SOLVER>::F_PSPEC;
   const int n = lay.n, m = lay.m, L = lay.L, G = lay.G, Bt = lay.Bt, A = lay.A, D = lay.D;
   double* rec = state + env * lay.R;
   double* ob = obs + env * D;
@@ -728,10 +767,9 @@ GFR_HD void step_instance(const Grp<LANES>& g, const Layout& lay, const int* sim
     }
   }
   g.sync();
-  flat_start(g, lay, simg, dimg, nf);
+  flat_start(g, lay, simg, dimg);
   SolveStat st;
-  if (SOLVER == SOLVER_NEWTON) newton_solve(g, lay, simg, dimg, cfg.tol, cfg.max_it, cfg.accel, &st);
-  else sweep_solve(g, lay, simg, dimg, cfg.tol, cfg.max_it, &st);
+  run_solver<LANES, SOLVER>(g, lay, simg, dimg, cfg, &st);
 
   // ---- bus state -> observation (grid_env.py:722-731, 753-765), reductions for reward / constraints
   double dev = 0.0, vmax = -INFINITY, vmin = INFINITY;
@@ -843,7 +881,7 @@ GFR_HD void step_instance(const Grp<LANES>& g, const Layout& lay, const int* sim
 // GridEnvironment.reset (grid_env.py:360-408): counters to zero, buses at 1.0 / 0, lines idle,
 // 60 Hz, batteries at their initial state of charge, one weather update at t = 0, full observation.
 template <int LANES>
-GFR_HD void reset_instance(const Grp<LANES>& g, const Layout& lay, const int* simg,
+GFR_HD void reset_instance(const Grp<LANES, 1>& g, const Layout& lay, const int* simg,
                            const double* dimg, const EnvCfg& cfg, long long env, double* state,
                            double* obs, const double* load_pq, const double* bat_soc0,
                            const uint64_t* seeds, const double* noise, double start_time,

@@ -119,10 +119,16 @@ inline std::string build_feeder_image(const gfr_feeder_desc* d, FeederImage* out
     for (int g = 0; g < G; ++g) inj_idx[fill[d->gen_bus[g]]++] = L + g;
     for (int b = 0; b < Bt; ++b) inj_idx[fill[d->bat_bus[b]]++] = L + G + b;
   }
-  lay.o_parent = ib.add_i(d->parent, n);
-  lay.o_child_ptr = ib.add_i(d->child_ptr, n + 1);
+  // per-bus topology records first (16-byte aligned at the image base)
+  std::vector<int32_t> topo(4 * (size_t)n);
+  for (int k = 0; k < n; ++k) {
+    topo[4 * k + 0] = k > 0 ? d->parent[k] : 0;
+    topo[4 * k + 1] = d->child_ptr[k];
+    topo[4 * k + 2] = d->child_ptr[k + 1];
+    topo[4 * k + 3] = flags[k];
+  }
+  lay.o_topo = ib.add_i(topo.data(), 4 * n);
   lay.o_level_ptr = ib.add_i(d->level_ptr, nl + 1);
-  lay.o_flags = ib.add_i(flags.data(), n);
   lay.o_order = ib.add_i(d->order, n);
   lay.o_rank = ib.add_i(rank.data(), n);
   lay.o_line_of = ib.add_i(line_of.data(), n);
@@ -132,12 +138,16 @@ inline std::string build_feeder_image(const gfr_feeder_desc* d, FeederImage* out
   lay.o_gen_type = ib.add_i(d->gen_type, G);
   const int n_int_padded = ((int)ib.ints.size() + 3) / 4 * 4;      // keep the doubles 16-byte aligned
   const int dbase = n_int_padded / 2;
-  lay.o_g = dbase + ib.add_d(d->g, n);
-  lay.o_b = dbase + ib.add_d(d->b, n);
-  lay.o_gdiag = dbase + ib.add_d(d->gdiag, n);
-  lay.o_bdiag = dbase + ib.add_d(d->bdiag, n);
-  lay.o_r = dbase + ib.add_d(d->r, n);
-  lay.o_x = dbase + ib.add_d(d->x, n);
+  // paired arrays (one 128-bit load each): branch (g, b), diagonal (Re, Im Y_kk), branch (r, x)
+  std::vector<double> gb(2 * (size_t)n), gbd(2 * (size_t)n), rx(2 * (size_t)n);
+  for (int k = 0; k < n; ++k) {
+    gb[2 * k] = d->g[k]; gb[2 * k + 1] = d->b[k];
+    gbd[2 * k] = d->gdiag[k]; gbd[2 * k + 1] = d->bdiag[k];
+    rx[2 * k] = d->r[k]; rx[2 * k + 1] = d->x[k];
+  }
+  lay.o_gb = dbase + ib.add_d(gb.data(), 2 * n);
+  lay.o_gbd = dbase + ib.add_d(gbd.data(), 2 * n);
+  lay.o_rx = dbase + ib.add_d(rx.data(), 2 * n);
   lay.o_rating = dbase + ib.add_d(d->rating, n);
   lay.o_vm_set = dbase + ib.add_d(d->vm_set, n);
   lay.o_load_base = dbase + ib.add_d(d->load_base, L);

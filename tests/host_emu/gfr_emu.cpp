@@ -21,16 +21,16 @@ struct emu_env {
   std::vector<double> state, obs, work, bat_soc0;
 };
 
-static Grp<1> make_grp(const Layout& lay, double* work) {
-  Grp<1> g;
-  g.lane = 0; g.e = 0; g.E = 1; g.FS = lay.n; g.mask = 1u; g.st = work;
+template <int NF>
+static Grp<1, NF> make_grp(const Layout& lay, double* work) {
+  Grp<1, NF> g;
+  g.lane = 0; g.mask = 1u; g.rec = work; g.n = lay.n;
   return g;
 }
 
 static int fields(const Layout& lay, int solver) {
-  int nf = solver == SOLVER_NEWTON ? NF_NEWTON : NF_SWEEP;
-  int need = F_SCRATCH + (lay.n_src + lay.n - 1) / lay.n;
-  return need > nf ? need : nf;
+  (void)lay;
+  return solver == SOLVER_NEWTON ? NF_NEWTON : NF_SWEEP;
 }
 
 extern "C" {
@@ -53,9 +53,9 @@ emu_env* emu_create(const gfr_feeder_desc* d, long long B, const gfr_env_cfg* c)
   k.weather_variation = c->weather_variation != 0; k.max_it = c->solver.max_iterations;
   e->state.assign((size_t)B * lay.R, 0.0);
   e->obs.assign((size_t)B * lay.D, 0.0);
-  e->work.assign((size_t)e->nf * lay.n, 0.0);
+  e->work.assign((size_t)e->nf * lay.n + 2, 0.0);
   e->bat_soc0.assign(d->bat_soc0, d->bat_soc0 + lay.Bt);
-  Grp<1> g = make_grp(lay, e->work.data());
+  Grp<1, 1> g = make_grp<1>(lay, e->work.data());
   for (long long i = 0; i < B; ++i)
     reset_instance<1>(g, lay, (const int*)e->fi.img.data(), (const double*)e->fi.img.data(), k, i,
                       e->state.data(), e->obs.data(), e->fi.load_pq.data(), e->bat_soc0.data(),
@@ -70,7 +70,7 @@ int emu_obs_dim(emu_env* e) { return e->fi.lay.D; }
 void emu_reset(emu_env* e, const uint64_t* seeds, const uint8_t* mask, const double* noise,
                double start_time) {
   const Layout& lay = e->fi.lay;
-  Grp<1> g = make_grp(lay, e->work.data());
+  Grp<1, 1> g = make_grp<1>(lay, e->work.data());
   for (long long i = 0; i < e->B; ++i) {
     if (mask && !mask[i]) continue;
     reset_instance<1>(g, lay, (const int*)e->fi.img.data(), (const double*)e->fi.img.data(), e->cfg, i,
@@ -81,7 +81,6 @@ void emu_reset(emu_env* e, const uint64_t* seeds, const uint8_t* mask, const dou
 
 void emu_step(emu_env* e, const double* actions, const double* noise, const gfr_step_out* out) {
   const Layout& lay = e->fi.lay;
-  Grp<1> g = make_grp(lay, e->work.data());
   StepOut o{};
   o.reward = out->reward; o.terminated = out->terminated; o.truncated = out->truncated;
   o.error = out->error; o.converged = out->converged; o.iterations = out->iterations;
@@ -93,11 +92,11 @@ void emu_step(emu_env* e, const double* actions, const double* noise, const gfr_
   const double* dimg = (const double*)e->fi.img.data();
   for (long long i = 0; i < e->B; ++i) {
     if (e->solver == SOLVER_NEWTON)
-      step_instance<1, SOLVER_NEWTON>(g, lay, simg, dimg, e->cfg, e->nf, i, e->state.data(),
-                                      e->obs.data(), actions, noise, o);
+      step_instance<1, SOLVER_NEWTON>(make_grp<NF_NEWTON>(lay, e->work.data()), lay, simg, dimg, e->cfg, i,
+                                      e->state.data(), e->obs.data(), actions, noise, o);
     else
-      step_instance<1, SOLVER_SWEEP>(g, lay, simg, dimg, e->cfg, e->nf, i, e->state.data(),
-                                     e->obs.data(), actions, noise, o);
+      step_instance<1, SOLVER_SWEEP>(make_grp<NF_SWEEP>(lay, e->work.data()), lay, simg, dimg, e->cfg, i,
+                                     e->state.data(), e->obs.data(), actions, noise, o);
   }
 }
 
@@ -109,8 +108,7 @@ int emu_solve(const gfr_feeder_desc* d, long long B, const double* p_inj, const 
   const Layout& lay = fi.lay;
   const int solver = c->solver == GFR_SOLVER_NEWTON ? SOLVER_NEWTON : SOLVER_SWEEP;
   const int nf = fields(lay, solver);
-  std::vector<double> work((size_t)nf * lay.n, 0.0);
-  Grp<1> g = make_grp(lay, work.data());
+  std::vector<double> work((size_t)nf * lay.n + 2, 0.0);
   EnvCfg k{};
   k.tol = c->tolerance; k.max_it = c->max_iterations; k.accel = c->acceleration != 0.0 ? c->acceleration : 1.0;
   SolOut o{};
@@ -120,8 +118,10 @@ int emu_solve(const gfr_feeder_desc* d, long long B, const double* p_inj, const 
   const int* simg = (const int*)fi.img.data();
   const double* dimg = (const double*)fi.img.data();
   for (long long i = 0; i < B; ++i) {
-    if (solver == SOLVER_NEWTON) solve_instance<1, SOLVER_NEWTON>(g, lay, simg, dimg, k, nf, i, p_inj, o);
-    else solve_instance<1, SOLVER_SWEEP>(g, lay, simg, dimg, k, nf, i, p_inj, o);
+    if (solver == SOLVER_NEWTON)
+      solve_instance<1, SOLVER_NEWTON>(make_grp<NF_NEWTON>(lay, work.data()), lay, simg, dimg, k, i, p_inj, o);
+    else
+      solve_instance<1, SOLVER_SWEEP>(make_grp<NF_SWEEP>(lay, work.data()), lay, simg, dimg, k, i, p_inj, o);
   }
   return 0;
 }
