@@ -5,11 +5,12 @@ from .errors import (GridEnvironmentError, GridLimitError, InvalidActionError,
                      PowerFlowError)
 from .feeders import (BaseFeeder, CustomFeeder, IEEE13Bus, IEEE34Bus, IEEE123Bus, NetworkConfig,
                       ScalableFeeder, SimpleRadialFeeder, SyntheticFeeder)
-from .topology import (FeederSoA, RepairedFeeder, TopologyError, compile_feeder,
-                       repair_topology)
+from .topology import (FeederSoA, RepairedFeeder, TopologyError, auto_lanes, compile_feeder,
+                       compile_for_solver, repair_topology)
 
 __all__ = [
-    "FeederSoA", "RepairedFeeder", "TopologyError", "compile_feeder", "repair_topology",
+    "FeederSoA", "RepairedFeeder", "TopologyError", "auto_lanes", "compile_feeder",
+    "compile_for_solver", "repair_topology",
     "Box", "Bus", "FeederParameters", "Line", "Load", "PowerFlowSolution",
     "BaseFeeder", "CustomFeeder", "IEEE13Bus", "IEEE34Bus", "IEEE123Bus", "NetworkConfig",
     "ScalableFeeder", "SimpleRadialFeeder", "SyntheticFeeder",

@@ -24,6 +24,7 @@ using namespace gfr;
 namespace {
 
 constexpr int kSmemHeader = 16;   // the mbarrier, keeps the image 16-byte aligned
+constexpr int kMaxThreads = 512;  // per CTA: leaves 128 registers per thread
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
@@ -70,7 +71,7 @@ __device__ __forceinline__ Grp<LANES, NF> make_group(const Layout& lay, unsigned
 }
 
 template <int LANES, int SOLVER>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(kMaxThreads)
 step_kernel(const Layout lay, const EnvCfg cfg, const void* __restrict__ img,
             double* __restrict__ state, double* __restrict__ obs,
             const double* __restrict__ actions, const double* __restrict__ noise, const StepOut o,
@@ -86,7 +87,7 @@ step_kernel(const Layout lay, const EnvCfg cfg, const void* __restrict__ img,
 }
 
 template <int LANES, int SOLVER>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(kMaxThreads)
 solve_kernel(const Layout lay, const EnvCfg cfg, const void* __restrict__ img,
              const double* __restrict__ p_inj, const SolOut o, const long long B) {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -175,8 +176,10 @@ struct gfr_feeder {
   int device = 0;
   int sm_count = 0;
   int smem_optin = 0;
+  int smem_per_sm = 0;
   Layout lay{};
   bool has_pv = false;
+  bool root_is_slack = true;
   void* d_img = nullptr;         // image
   double* d_load_pq = nullptr;   // [2L] static active / reactive power (observation)
   double* d_bat_soc0 = nullptr;  // [Bt]
@@ -187,8 +190,9 @@ struct gfr_env {
   long long B = 0;
   EnvCfg cfg{};
   int solver = GFR_SOLVER_NEWTON;
-  int lanes = 0, threads = 0, nf = 0, grid = 0;
+  int lanes = 0, threads = 0, grid = 0;
   size_t smem = 0;
+  const void* fn = nullptr;
   double* d_state = nullptr;
   double* d_obs = nullptr;
   bool obs_external = false;   // bound by gfr_env_bind_obs: caller-owned
@@ -196,7 +200,7 @@ struct gfr_env {
 
 namespace {
 
-struct LaunchPlan { int lanes, threads, nf, grid; size_t smem; };
+struct LaunchPlan { int lanes, threads, grid; size_t smem; int ctas_per_sm; };
 
 // shared memory of one instance slot; 0 if the scratch carried in the records cannot hold the sources
 size_t slot_bytes(const Layout& lay, int solver) {
@@ -206,100 +210,117 @@ size_t slot_bytes(const Layout& lay, int solver) {
   return (size_t)nf * lay.n * sizeof(double);
 }
 
-int auto_lanes(const Layout& lay) {
-  if (lay.n <= 16) return 4;
-  if (lay.n <= 64) return 8;
+int auto_lanes(const Layout& lay, int solver) {
+  if (lay.n <= 20) return solver == GFR_SOLVER_SWEEP ? 1 : 4;
+  if (lay.n <= 64) return 4;
   return 16;
 }
 
-// threads per CTA: the candidate that keeps the most threads resident per SM
-int plan_launch(const gfr_feeder* f, int solver, int lanes, long long B, LaunchPlan* out) {
+template <int SOLVER>
+const void* step_fn(int lanes) {
+  switch (lanes) {
+    case 1: return (const void*)step_kernel<1, SOLVER>;
+    case 2: return (const void*)step_kernel<2, SOLVER>;
+    case 4: return (const void*)step_kernel<4, SOLVER>;
+    case 8: return (const void*)step_kernel<8, SOLVER>;
+    case 16: return (const void*)step_kernel<16, SOLVER>;
+    case 32: return (const void*)step_kernel<32, SOLVER>;
+  }
+  return nullptr;
+}
+template <int SOLVER>
+const void* solve_fn(int lanes) {
+  switch (lanes) {
+    case 1: return (const void*)solve_kernel<1, SOLVER>;
+    case 2: return (const void*)solve_kernel<2, SOLVER>;
+    case 4: return (const void*)solve_kernel<4, SOLVER>;
+    case 8: return (const void*)solve_kernel<8, SOLVER>;
+    case 16: return (const void*)solve_kernel<16, SOLVER>;
+    case 32: return (const void*)solve_kernel<32, SOLVER>;
+  }
+  return nullptr;
+}
+const void* kernel_fn(bool step, int solver, int lanes) {
+  if (step) return solver == GFR_SOLVER_NEWTON ? step_fn<SOLVER_NEWTON>(lanes) : step_fn<SOLVER_SWEEP>(lanes);
+  return solver == GFR_SOLVER_NEWTON ? solve_fn<SOLVER_NEWTON>(lanes) : solve_fn<SOLVER_SWEEP>(lanes);
+}
+
+// Instance slots per CTA and CTAs per SM: the split of an SM's shared memory (each CTA carries one
+// copy of the feeder image) that keeps the most instances resident, checked against the kernel's
+// real register use through the occupancy API.
+int plan_launch(const gfr_feeder* f, bool step, int solver, int lanes, long long B, LaunchPlan* out,
+                const void** fn_out) {
   const Layout& lay = f->lay;
-  if (lanes == 0) lanes = auto_lanes(lay);
+  if (lanes == 0) lanes = auto_lanes(lay, solver);
   if (lanes != 1 && lanes != 2 && lanes != 4 && lanes != 8 && lanes != 16 && lanes != 32)
     return fail(GFR_E_ARG, "lanes must be 0 (auto), 1, 2, 4, 8, 16 or 32");
-  const int nf = solver == GFR_SOLVER_NEWTON ? NF_NEWTON : NF_SWEEP;
+  const void* fn = kernel_fn(step, solver, lanes);
   const size_t per_env = slot_bytes(lay, solver);
   if (!per_env)
     return fail(GFR_E_LIMIT, "more loads + generators + batteries than the solver's per-bus scratch holds "
                              "(newton: 6 per bus on average, sweep: 2)");
-  const size_t sm_budget = 227u * 1024u;
-  int best_threads = 0;
+  GFR_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, f->smem_optin));
+  const size_t fixed = kSmemHeader + (size_t)lay.img_bytes;
+  const size_t sm_total = (size_t)f->smem_per_sm;
+  const int gran = lanes >= 32 ? 1 : 32 / lanes;         // whole warps
   long long best_resident = 0;
-  size_t best_smem = 0;
-  for (int threads = 128; threads >= 32 && threads >= lanes; threads >>= 1) {
-    const size_t smem = kSmemHeader + (size_t)lay.img_bytes + per_env * (threads / lanes);
-    if (smem > (size_t)f->smem_optin) continue;
-    long long ctas = (long long)(sm_budget / (smem + 1024));
-    if (ctas > 32) ctas = 32;
-    if (ctas * threads > 2048) ctas = 2048 / threads;
-    if (ctas < 1) ctas = 1;
-    const long long resident = ctas * threads;
-    if (resident > best_resident) { best_resident = resident; best_threads = threads; best_smem = smem; }
+  LaunchPlan best{};
+  // pass 0: whole warps only; pass 1 (only if nothing fits): a partial warp
+  for (int pass = 0; pass < 2 && !best_resident; ++pass) {
+    for (int c = 1; c <= 16; ++c) {
+      const size_t share = sm_total / c;
+      if (share < fixed + per_env + 1024) break;
+      long long E = (long long)((share - 1024 - fixed) / per_env);
+      if (E * lanes > kMaxThreads) E = kMaxThreads / lanes;
+      if (pass == 0) E -= E % gran;
+      if (E < 1) continue;
+      const int threads = (int)(E * lanes);
+      const size_t smem = fixed + per_env * (size_t)E;
+      if (smem > (size_t)f->smem_optin) continue;
+      int nb = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, threads, smem) != cudaSuccess) { cudaGetLastError(); continue; }
+      if (nb > c) nb = c;
+      const long long resident = (long long)nb * E;
+      // more resident instances win; on a tie more, smaller CTAs (they even out the last wave)
+      if (resident > best_resident || (resident == best_resident && resident > 0 && nb > best.ctas_per_sm)) {
+        best_resident = resident;
+        best.lanes = lanes; best.threads = threads; best.smem = smem; best.ctas_per_sm = nb;
+      }
+    }
   }
-  if (!best_threads)
+  if (!best_resident)
     return fail(GFR_E_LIMIT, "feeder image + one instance's working set exceed the shared memory of an SM");
-  const int E = best_threads / lanes;
+  const long long E = best.threads / lanes;
   long long tiles = (B + E - 1) / E;
-  long long grid = (long long)f->sm_count * (best_resident / best_threads);
+  long long grid = (long long)f->sm_count * best.ctas_per_sm;
   if (grid > tiles) grid = tiles;
   if (grid < 1) grid = 1;
-  out->lanes = lanes; out->threads = best_threads; out->nf = nf; out->grid = (int)grid; out->smem = best_smem;
+  best.grid = (int)grid;
+  *out = best;
+  *fn_out = fn;
   return GFR_OK;
 }
-
-template <int LANES, int SOLVER>
-int launch_step_t(const gfr_env* e, const double* actions, const double* noise, const StepOut& o,
-                  cudaStream_t s) {
-  auto kern = step_kernel<LANES, SOLVER>;
-  GFR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
-  kern<<<e->grid, e->threads, e->smem, s>>>(e->f->lay, e->cfg, e->f->d_img, e->d_state, e->d_obs,
-                                           actions, noise, o, e->B);
-  g_launches.fetch_add(1);
-  GFR_CUDA(cudaGetLastError());
-  return GFR_OK;
-}
-
-template <int LANES, int SOLVER>
-int launch_solve_t(const gfr_feeder* f, const LaunchPlan& p, const EnvCfg& cfg, const double* p_inj,
-                   const SolOut& o, long long B, cudaStream_t s) {
-  auto kern = solve_kernel<LANES, SOLVER>;
-  GFR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
-  kern<<<p.grid, p.threads, p.smem, s>>>(f->lay, cfg, f->d_img, p_inj, o, B);
-  g_launches.fetch_add(1);
-  GFR_CUDA(cudaGetLastError());
-  return GFR_OK;
-}
-
-#define GFR_DISPATCH(LN, SV, CALL)                                                   \
-  switch ((LN) * 2 + ((SV) == GFR_SOLVER_NEWTON ? 1 : 0)) {                            \
-    case 1 * 2 + 0: return CALL(1, SOLVER_SWEEP);                                      \
-    case 1 * 2 + 1: return CALL(1, SOLVER_NEWTON);                                     \
-    case 2 * 2 + 0: return CALL(2, SOLVER_SWEEP);                                      \
-    case 2 * 2 + 1: return CALL(2, SOLVER_NEWTON);                                     \
-    case 4 * 2 + 0: return CALL(4, SOLVER_SWEEP);                                      \
-    case 4 * 2 + 1: return CALL(4, SOLVER_NEWTON);                                     \
-    case 8 * 2 + 0: return CALL(8, SOLVER_SWEEP);                                      \
-    case 8 * 2 + 1: return CALL(8, SOLVER_NEWTON);                                     \
-    case 16 * 2 + 0: return CALL(16, SOLVER_SWEEP);                                    \
-    case 16 * 2 + 1: return CALL(16, SOLVER_NEWTON);                                   \
-    case 32 * 2 + 0: return CALL(32, SOLVER_SWEEP);                                    \
-    case 32 * 2 + 1: return CALL(32, SOLVER_NEWTON);                                   \
-    default: return fail(GFR_E_ARG, "unsupported lanes / solver combination");         \
-  }
 
 int launch_step(const gfr_env* e, const double* actions, const double* noise, const StepOut& o,
                 cudaStream_t s) {
-#define GFR_CALL_STEP(L_, S_) launch_step_t<L_, S_>(e, actions, noise, o, s)
-  GFR_DISPATCH(e->lanes, e->solver, GFR_CALL_STEP)
-#undef GFR_CALL_STEP
+  const void* img = e->f->d_img;
+  double* state = e->d_state;
+  double* obs = e->d_obs;
+  long long B = e->B;
+  void* args[] = {(void*)&e->f->lay, (void*)&e->cfg, (void*)&img, (void*)&state, (void*)&obs,
+                  (void*)&actions, (void*)&noise, (void*)&o, (void*)&B};
+  GFR_CUDA(cudaLaunchKernel(e->fn, dim3(e->grid), dim3(e->threads), args, e->smem, s));
+  g_launches.fetch_add(1);
+  return GFR_OK;
 }
 
-int launch_solve(const gfr_feeder* f, const LaunchPlan& p, int solver, const EnvCfg& cfg,
+int launch_solve(const gfr_feeder* f, const LaunchPlan& p, const void* fn, const EnvCfg& cfg,
                  const double* p_inj, const SolOut& o, long long B, cudaStream_t s) {
-#define GFR_CALL_SOLVE(L_, S_) launch_solve_t<L_, S_>(f, p, cfg, p_inj, o, B, s)
-  GFR_DISPATCH(p.lanes, solver, GFR_CALL_SOLVE)
-#undef GFR_CALL_SOLVE
+  const void* img = f->d_img;
+  void* args[] = {(void*)&f->lay, (void*)&cfg, (void*)&img, (void*)&p_inj, (void*)&o, (void*)&B};
+  GFR_CUDA(cudaLaunchKernel(fn, dim3(p.grid), dim3(p.threads), args, p.smem, s));
+  g_launches.fetch_add(1);
+  return GFR_OK;
 }
 
 int check_solver_cfg(const gfr_feeder* f, const gfr_solver_cfg* c) {
@@ -307,6 +328,8 @@ int check_solver_cfg(const gfr_feeder* f, const gfr_solver_cfg* c) {
     return fail(GFR_E_ARG, "solver must be GFR_SOLVER_SWEEP or GFR_SOLVER_NEWTON");
   if (c->max_iterations < 1) return fail(GFR_E_ARG, "max_iterations must be >= 1");
   if (!(c->tolerance > 0.0)) return fail(GFR_E_ARG, "tolerance must be > 0");
+  if (c->solver == GFR_SOLVER_SWEEP && !f->root_is_slack)
+    return fail(GFR_E_ARG, "the sweep solver needs the slack bus at the root (k = 0) of the level order");
   if (c->solver == GFR_SOLVER_SWEEP && f->has_pv)
     return fail(GFR_E_ARG, "the sweep solver handles slack + PQ buses only; use GFR_SOLVER_NEWTON for PV buses");
   return GFR_OK;
@@ -337,8 +360,10 @@ int gfr_feeder_create(const gfr_feeder_desc* d, int device, gfr_feeder** out) {
   f->device = device;
   f->sm_count = prop.multiProcessorCount;
   f->smem_optin = (int)prop.sharedMemPerBlockOptin;
+  f->smem_per_sm = (int)prop.sharedMemPerMultiprocessor;
   f->lay = fi.lay;
   f->has_pv = fi.has_pv;
+  f->root_is_slack = fi.root_is_slack;
   const Layout& lay = f->lay;
   const int L = lay.L, Bt = lay.Bt;
   const size_t img_bytes = fi.img.size();
@@ -404,13 +429,14 @@ int gfr_env_create(const gfr_feeder* f, int64_t n_envs, const gfr_env_cfg* cfg, 
   if (n_envs < 1) return fail(GFR_E_ARG, "n_envs must be >= 1");
   EnvCfg ec;
   if (int rc = fill_env_cfg(f, cfg, &ec)) return rc;
-  LaunchPlan plan;
-  if (int rc = plan_launch(f, cfg->solver.solver, cfg->solver.lanes, n_envs, &plan)) return rc;
   DeviceGuard guard(f->device);
   if (!guard.ok) return fail(GFR_E_CUDA, "no usable CUDA device (this library has no CPU fallback)");
+  LaunchPlan plan;
+  const void* fn = nullptr;
+  if (int rc = plan_launch(f, true, cfg->solver.solver, cfg->solver.lanes, n_envs, &plan, &fn)) return rc;
   auto* e = new gfr_env();
   e->f = f; e->B = n_envs; e->cfg = ec; e->solver = cfg->solver.solver;
-  e->lanes = plan.lanes; e->threads = plan.threads; e->nf = plan.nf; e->grid = plan.grid; e->smem = plan.smem;
+  e->lanes = plan.lanes; e->threads = plan.threads; e->grid = plan.grid; e->smem = plan.smem; e->fn = fn;
   cudaError_t e1 = cudaMalloc((void**)&e->d_state, (size_t)n_envs * f->lay.R * 8);
   cudaError_t e2 = cudaMalloc((void**)&e->d_obs, (size_t)n_envs * f->lay.D * 8);
   if (e1 != cudaSuccess || e2 != cudaSuccess) {
@@ -503,8 +529,11 @@ int gfr_solve(const gfr_feeder* f, int64_t B, const double* p_inj, const gfr_sol
   if (!f || !p_inj || !cfg || !out) return fail(GFR_E_ARG, "null argument");
   if (B < 1) return fail(GFR_E_ARG, "B must be >= 1");
   if (int rc = check_solver_cfg(f, cfg)) return rc;
+  DeviceGuard guard(f->device);
+  if (!guard.ok) return fail(GFR_E_CUDA, "no usable CUDA device (this library has no CPU fallback)");
   LaunchPlan plan;
-  if (int rc = plan_launch(f, cfg->solver, cfg->lanes, B, &plan)) return rc;
+  const void* fn = nullptr;
+  if (int rc = plan_launch(f, false, cfg->solver, cfg->lanes, B, &plan, &fn)) return rc;
   EnvCfg ec{};
   ec.tol = cfg->tolerance; ec.max_it = cfg->max_iterations;
   ec.accel = cfg->acceleration != 0.0 ? cfg->acceleration : 1.0;
@@ -512,8 +541,7 @@ int gfr_solve(const gfr_feeder* f, int64_t B, const double* p_inj, const gfr_sol
   o.converged = out->converged; o.iterations = out->iterations; o.bus_voltages = out->bus_voltages;
   o.bus_angles = out->bus_angles; o.line_flows = out->line_flows; o.line_loadings = out->line_loadings;
   o.losses = out->losses; o.max_mismatch = out->max_mismatch;
-  DeviceGuard guard(f->device);
-  return launch_solve(f, plan, cfg->solver, ec, p_inj, o, B, (cudaStream_t)stream);
+  return launch_solve(f, plan, fn, ec, p_inj, o, B, (cudaStream_t)stream);
 }
 
 int gfr_noise_fill(int device, int64_t B, int32_t n_slots, const uint64_t* seeds, const uint64_t* draws,

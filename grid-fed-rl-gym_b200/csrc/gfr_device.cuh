@@ -45,19 +45,19 @@ enum { NF_NEWTON = 10, N_M0 = 2, N_M1 = 3, N_M2 = 4, N_M3 = 5, N_V0 = 6, N_V1 = 
 enum { NF_SWEEP = 6, S_JR = 2, S_JI = 3, S_P = 4 };
 enum { SCRATCH_FIELDS_NEWTON = 6, SCRATCH_FIELDS_SWEEP = 2 };
 // bus flag bits
-enum { FL_PQ = 1, FL_FROM_IS_PARENT = 2, FL_FIXED_VM = 4 };
+enum { FL_PQ = 1, FL_FROM_IS_PARENT = 2, FL_FIXED_VM = 4, FL_THETA = 8 };   // PQ: |V| unknown; THETA: angle unknown
 // record (persistent per-instance state) slots, in doubles
 enum { R_TIME = 0, R_FREQ, R_WIND, R_TEMP, R_CLOUD, R_TOTAL_LOSSES, R_EPISODE_REWARD, R_SEED,
        R_DRAWS, R_COUNTS, R_BAT };   // soc[Bt] then bpow[Bt] from R_BAT on
 
 struct alignas(16) D2 { double x, y; };
-struct alignas(16) I4 { int x, y, z, w; };   // per-bus topology: parent, first child, end child, flags
+struct alignas(16) I4 { int x, y, z, w; };   // per-bus topology: parent, child list begin, end, flags
 
 // Where everything is inside the feeder image (ints / doubles counted from the image base)
 // plus the sizes; passed as a kernel parameter (constant bank).
 struct Layout {
   int n, nl, L, G, Bt, A, D, m, n_src, R, img_bytes, n_noise;
-  int o_topo, o_level_ptr, o_order, o_rank, o_line_of, o_branch_of_line, o_inj_ptr, o_inj_idx,
+  int o_topo, o_child_idx, o_level_ptr, o_order, o_rank, o_line_of, o_branch_of_line, o_inj_ptr, o_inj_idx,
       o_gen_type;
   int o_gb, o_gbd, o_rx, o_rating, o_vm_set, o_load_base, o_gen_cap, o_gen_p0, o_gen_p1, o_gen_p2,
       o_bat_cap, o_bat_rating, o_bat_eff, o_profile;
@@ -236,7 +236,6 @@ GFR_HD void flat_start(const Grp<LANES, NF>& g, const Layout& lay, const int* si
     v.y = 0.0;
     g.at2(F_E, k) = v;
   }
-  if (NF == NF_NEWTON && g.lane == 0) { D2 z; z.x = 0.0; z.y = 0.0; g.at2(N_V0, 0) = z; }   // slack correction = 0
   g.sync();
 }
 
@@ -256,7 +255,8 @@ GFR_HD void newton_solve(const Grp<LANES, NF_NEWTON>& g, const Layout& lay, cons
   const int n = lay.n, nl = lay.nl;
   const I4* topo = reinterpret_cast<const I4*>(simg + lay.o_topo);
   const int* level_ptr = simg + lay.o_level_ptr;
-  const D2* gb = reinterpret_cast<const D2*>(dimg + lay.o_gb);      // branch series g, b
+  const int* child_idx = simg + lay.o_child_idx;
+  const D2* gb = reinterpret_cast<const D2*>(dimg + lay.o_gb);      // branch series g, b (0 for the root)
   const D2* gbd = reinterpret_cast<const D2*>(dimg + lay.o_gbd);    // Re, Im of Y_kk
 
   out->converged = 0;
@@ -266,7 +266,7 @@ GFR_HD void newton_solve(const Grp<LANES, NF_NEWTON>& g, const Layout& lay, cons
   for (int it = 0; it < max_it; ++it) {
     // ---- mismatch + diagonal blocks, every bus independently (power_flow.py:150-166, 213-295)
     double mm = 0.0;
-    for (int k = g.first(1); k < n; k += LANES) {
+    for (int k = g.lane; k < n; k += LANES) {
       const I4 t = topo[k];
       const D2 vk = g.at2(F_E, k);
       const D2 yd = gbd[k];
@@ -279,22 +279,23 @@ GFR_HD void newton_solve(const Grp<LANES, NF_NEWTON>& g, const Layout& lay, cons
         P += -y.x * a - y.y * s;
         Q += -y.x * s + y.y * a;
       }
-      for (int c = t.y; c < t.z; ++c) {
+      for (int q = t.y; q < t.z; ++q) {
+        const int c = child_idx[q];
         const D2 vc = g.at2(F_E, c);
         const D2 y = gb[c];
         const double a = vk.x * vc.x + vk.y * vc.y, s = vk.y * vc.x - vk.x * vc.y;
         P += -y.x * a - y.y * s;
         Q += -y.x * s + y.y * a;
       }
-      const int pq = t.w & FL_PQ;
-      const double dP = g.at(N_P, k) - P;
+      const int pq = t.w & FL_PQ, th = t.w & FL_THETA;
+      const double dP = th ? (g.at(N_P, k) - P) : 0.0;      // the slack bus has no equations
       const double dQ = pq ? (0.0 - Q) : 0.0;
       const double aP = fabs(dP), aQ = fabs(dQ);
       const double loc = (aQ > aP || aQ != aQ) ? aQ : aP;
       mm = (loc > mm || loc != loc) ? loc : mm;
       D2 r0, r1, rr;
-      r0.x = -Q - yd.y * v2;
-      r0.y = P + yd.x * v2;
+      r0.x = th ? (-Q - yd.y * v2) : 1.0;
+      r0.y = th ? (P + yd.x * v2) : 0.0;
       r1.x = pq ? (P - yd.x * v2) : 0.0;
       r1.y = pq ? (Q - yd.y * v2) : 1.0;
       rr.x = dP; rr.y = dQ;
@@ -311,22 +312,25 @@ GFR_HD void newton_solve(const Grp<LANES, NF_NEWTON>& g, const Layout& lay, cons
     }
     // ---- eliminate leaf -> root
     int singular = 0;
-    for (int l = nl - 1; l >= 1; --l) {
+    for (int l = nl - 1; l >= 0; --l) {
       const int k1 = level_ptr[l + 1];
       for (int k = g.first(level_ptr[l]); k < k1; k += LANES) {
         const I4 t = topo[k];
         const D2 vk = g.at2(F_E, k);
         D2 d0 = g.at2(N_M0, k), d1 = g.at2(N_M2, k), r = g.at2(N_V0, k);
-        const int pq = t.w & FL_PQ;
-        for (int c = t.y; c < t.z; ++c) {
+        const int pq = t.w & FL_PQ, th = t.w & FL_THETA;
+        for (int q = t.y; q < t.z; ++q) {
+          const int c = child_idx[q];
           const D2 vc = g.at2(F_E, c);
           const D2 y = gb[c];
           const double a = vk.x * vc.x + vk.y * vc.y, s = vk.y * vc.x - vk.x * vc.y;
           const double ga = -y.x * a - y.y * s, al = -y.x * s + y.y * a;   // J[k,c]
           const D2 m0 = g.at2(N_M0, c), m1 = g.at2(N_M2, c), v = g.at2(N_V0, c);
-          d0.x -= al * m0.x + ga * m1.x;
-          d0.y -= al * m0.y + ga * m1.y;
-          r.x -= al * v.x + ga * v.y;
+          if (th) {
+            d0.x -= al * m0.x + ga * m1.x;
+            d0.y -= al * m0.y + ga * m1.y;
+            r.x -= al * v.x + ga * v.y;
+          }
           if (pq) {
             d1.x -= -ga * m0.x + al * m1.x;
             d1.y -= -ga * m0.y + al * m1.y;
@@ -337,7 +341,7 @@ GFR_HD void newton_solve(const Grp<LANES, NF_NEWTON>& g, const Layout& lay, cons
         const D2 y = gb[k];
         const double a = vk.x * vp.x + vk.y * vp.y, s = vk.y * vp.x - vk.x * vp.y;
         const double ga = -y.x * a - y.y * s, al = -y.x * s + y.y * a;     // J[k,p]
-        const double u00 = al, u01 = ga, u10 = pq ? -ga : 0.0, u11 = pq ? al : 0.0;
+        const double u00 = th ? al : 0.0, u01 = th ? ga : 0.0, u10 = pq ? -ga : 0.0, u11 = pq ? al : 0.0;
         const double det = d0.x * d1.y - d0.y * d1.x;
         if (det == 0.0) singular = 1;                 // dgesv's exact-zero pivot (:188-190)
         const double inv = 1.0 / det;
@@ -359,8 +363,8 @@ GFR_HD void newton_solve(const Grp<LANES, NF_NEWTON>& g, const Layout& lay, cons
       out->iterations = it + 1;
       break;
     }
-    // ---- back-substitute root -> leaf: x_k = v_k - M_k x_parent  (x_slack = 0)
-    for (int l = 1; l < nl; ++l) {
+    // ---- back-substitute root -> leaf: x_k = v_k - M_k x_parent  (the root's M is 0: it has no branch)
+    for (int l = 0; l < nl; ++l) {
       const int k1 = level_ptr[l + 1];
       for (int k = g.first(level_ptr[l]); k < k1; k += LANES) {
         const D2 x = g.at2(N_V0, topo[k].x);
@@ -374,7 +378,7 @@ GFR_HD void newton_solve(const Grp<LANES, NF_NEWTON>& g, const Layout& lay, cons
     }
     // ---- polar update, every bus independently (:297-327):
     //      theta += a dtheta, |V| += a d|V|  <=>  V *= (1 + a x1) e^{j a x0}
-    for (int k = g.first(1); k < n; k += LANES) {
+    for (int k = g.lane; k < n; k += LANES) {
       const D2 x = g.at2(N_V0, k);
       double sn, cs;
       sincos_small(accel * x.x, &sn, &cs);
@@ -398,6 +402,7 @@ GFR_HD void sweep_solve(const Grp<LANES, NF_SWEEP>& g, const Layout& lay, const 
   const int nl = lay.nl;
   const I4* topo = reinterpret_cast<const I4*>(simg + lay.o_topo);
   const int* level_ptr = simg + lay.o_level_ptr;
+  const int* child_idx = simg + lay.o_child_idx;
   const D2* rx = reinterpret_cast<const D2*>(dimg + lay.o_rx);
   out->converged = 0;
   out->iterations = max_it;
@@ -412,8 +417,8 @@ GFR_HD void sweep_solve(const Grp<LANES, NF_SWEEP>& g, const Layout& lay, const 
         const double w = g.at(S_P, k) / (v.x * v.x + v.y * v.y);   // injected current = conj(S / V) = P V / |V|^2
         D2 j;
         j.x = -w * v.x; j.y = -w * v.y;
-        for (int c = t.y; c < t.z; ++c) {
-          const D2 jc = g.at2(S_JR, c);
+        for (int q = t.y; q < t.z; ++q) {
+          const D2 jc = g.at2(S_JR, child_idx[q]);
           j.x += jc.x; j.y += jc.y;
         }
         g.at2(S_JR, k) = j;

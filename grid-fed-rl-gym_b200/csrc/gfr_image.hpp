@@ -28,6 +28,7 @@ struct ImageBuilder {
 struct FeederImage {
   Layout lay{};
   bool has_pv = false;
+  bool root_is_slack = false;
   std::vector<unsigned char> img;
   std::vector<double> load_pq;     // [2L] static active / reactive power (observation)
 };
@@ -37,7 +38,7 @@ inline std::string build_feeder_image(const gfr_feeder_desc* d, FeederImage* out
   const int n = d->n_bus, nl = d->n_levels, L = d->n_load, G = d->n_gen, Bt = d->n_bat;
   if (n < 1 || nl < 1 || L < 0 || G < 0 || Bt < 0) return "bad feeder dimensions";
   if (!(d->s_base > 0.0)) return "s_base must be > 0";
-  if (!d->order || !d->parent || !d->level_ptr || !d->child_ptr || !d->bus_type || !d->vm_set || !d->g ||
+  if (!d->order || !d->parent || !d->level_ptr || !d->child_ptr || (n > 1 && !d->child_idx) || !d->bus_type || !d->vm_set || !d->g ||
       !d->b || !d->gdiag || !d->bdiag || !d->r || !d->x || !d->line_of || !d->from_is_parent ||
       !d->rating || !d->load_profile)
     return "missing topology array";
@@ -45,37 +46,40 @@ inline std::string build_feeder_image(const gfr_feeder_desc* d, FeederImage* out
       (G && (!d->gen_type || !d->gen_bus || !d->gen_cap || !d->gen_p0 || !d->gen_p1 || !d->gen_p2)) ||
       (Bt && (!d->bat_bus || !d->bat_cap || !d->bat_rating || !d->bat_eff || !d->bat_soc0)))
     return "missing component array";
-  // ---- structure checks: level order, contiguous children, one slack at k = 0
-  if (d->parent[0] != -1 || d->bus_type[0] != GFR_BUS_SLACK) return "k = 0 must be the slack bus";
+  // ---- structure checks: root at k = 0, parents before children, one slack bus, child lists
+  if (d->parent[0] != -1) return "k = 0 must be the root (parent -1)";
   if (d->level_ptr[0] != 0 || d->level_ptr[nl] != n) return "level_ptr must span [0, n]";
-  if (nl >= 1 && n >= 1 && d->level_ptr[1] != 1) return "level 0 must hold the slack bus only";
-  std::vector<int32_t> seen_ref(n, 0), seen_line(n > 1 ? n - 1 : 0, 0);
-  for (int l = 0; l < nl; ++l)
+  if (d->level_ptr[1] != 1) return "level 0 must hold the root only";
+  std::vector<int32_t> seen_ref(n, 0), seen_line(n > 1 ? n - 1 : 0, 0), seen_child(n, 0);
+  std::vector<int> level(n, 0);
+  for (int l = 0; l < nl; ++l) {
     if (d->level_ptr[l + 1] <= d->level_ptr[l]) return "empty level";
+    for (int k = d->level_ptr[l]; k < d->level_ptr[l + 1]; ++k) level[k] = l;
+  }
+  int n_slack = 0;
+  if (d->child_ptr[0] != 0 || d->child_ptr[n] != n - 1) return "child_ptr must span [0, n-1]";
   for (int k = 0; k < n; ++k) {
     if (d->order[k] < 0 || d->order[k] >= n || seen_ref[d->order[k]]++) return "order is not a permutation";
     if (d->child_ptr[k + 1] < d->child_ptr[k]) return "child_ptr must be non-decreasing";
+    if (d->bus_type[k] != GFR_BUS_SLACK && d->bus_type[k] != GFR_BUS_PV && d->bus_type[k] != GFR_BUS_PQ)
+      return "unknown bus_type";
+    n_slack += d->bus_type[k] == GFR_BUS_SLACK;
+    for (int q = d->child_ptr[k]; q < d->child_ptr[k + 1]; ++q) {
+      const int c = d->child_idx[q];
+      if (c <= k || c >= n || d->parent[c] != k || seen_child[c]++) return "child_idx does not match parent";
+    }
     if (k > 0) {
-      if (d->bus_type[k] == GFR_BUS_SLACK) return "more than one slack bus";
       const int p = d->parent[k];
       if (p < 0 || p >= k) return "parent must precede its child in level order";
-      if (k < d->child_ptr[p] || k >= d->child_ptr[p + 1]) return "child_ptr does not match parent";
+      if (level[p] >= level[k]) return "a bus must sit in a later level than its parent";
       const int li = d->line_of[k];
       if (li < 0 || li >= n - 1 || seen_line[li]++) return "line_of is not a permutation of the lines";
       if (!(d->g[k] == d->g[k]) || !(d->b[k] == d->b[k]) || (d->g[k] == 0.0 && d->b[k] == 0.0))
         return "branch with zero / NaN admittance";
     }
   }
-  if (d->child_ptr[0] != 1 && n > 1) return "child_ptr[0] must be 1";
-  if (d->child_ptr[n] != n) return "child_ptr[n] must be n";
-  // level of a child = level of its parent + 1
-  {
-    std::vector<int> level(n, 0);
-    for (int l = 0; l < nl; ++l)
-      for (int k = d->level_ptr[l]; k < d->level_ptr[l + 1]; ++k) level[k] = l;
-    for (int k = 1; k < n; ++k)
-      if (level[k] != level[d->parent[k]] + 1) return "level_ptr does not match parent";
-  }
+  for (int k = 1; k < n; ++k) if (!seen_child[k]) return "child_idx does not list every bus";
+  if (n_slack != 1) return "exactly one slack bus is required";
   for (int l = 0; l < L; ++l) if (d->load_bus[l] < 0 || d->load_bus[l] >= n) return "load_bus out of range";
   for (int g = 0; g < G; ++g) {
     if (d->gen_bus[g] < 0 || d->gen_bus[g] >= n) return "gen_bus out of range";
@@ -99,6 +103,7 @@ inline std::string build_feeder_image(const gfr_feeder_desc* d, FeederImage* out
     int fl = 0;
     if (d->bus_type[k] == GFR_BUS_PQ) fl |= FL_PQ;
     else fl |= FL_FIXED_VM;
+    if (d->bus_type[k] != GFR_BUS_SLACK) fl |= FL_THETA;
     if (d->bus_type[k] == GFR_BUS_PV) f->has_pv = true;
     if (d->from_is_parent[k]) fl |= FL_FROM_IS_PARENT;
     flags[k] = fl;
@@ -128,6 +133,7 @@ inline std::string build_feeder_image(const gfr_feeder_desc* d, FeederImage* out
     topo[4 * k + 3] = flags[k];
   }
   lay.o_topo = ib.add_i(topo.data(), 4 * n);
+  lay.o_child_idx = ib.add_i(d->child_idx, n - 1);
   lay.o_level_ptr = ib.add_i(d->level_ptr, nl + 1);
   lay.o_order = ib.add_i(d->order, n);
   lay.o_rank = ib.add_i(rank.data(), n);
@@ -141,7 +147,7 @@ inline std::string build_feeder_image(const gfr_feeder_desc* d, FeederImage* out
   // paired arrays (one 128-bit load each): branch (g, b), diagonal (Re, Im Y_kk), branch (r, x)
   std::vector<double> gb(2 * (size_t)n), gbd(2 * (size_t)n), rx(2 * (size_t)n);
   for (int k = 0; k < n; ++k) {
-    gb[2 * k] = d->g[k]; gb[2 * k + 1] = d->b[k];
+    gb[2 * k] = k > 0 ? d->g[k] : 0.0; gb[2 * k + 1] = k > 0 ? d->b[k] : 0.0;   // the root has no branch
     gbd[2 * k] = d->gdiag[k]; gbd[2 * k + 1] = d->bdiag[k];
     rx[2 * k] = d->r[k]; rx[2 * k + 1] = d->x[k];
   }
@@ -168,6 +174,7 @@ inline std::string build_feeder_image(const gfr_feeder_desc* d, FeederImage* out
   std::vector<double> load_pq(2 * (size_t)L + 1, 0.0);
   for (int l = 0; l < L; ++l) { load_pq[2 * l] = d->load_p[l]; load_pq[2 * l + 1] = d->load_q[l]; }
 
+  f->root_is_slack = d->bus_type[0] == GFR_BUS_SLACK;
   f->img.swap(img);
   f->load_pq.swap(load_pq);
   return std::string();

@@ -25,20 +25,22 @@ import torch
 from . import _native as nat
 from .components import Box
 from .errors import InvalidActionError, InvalidConfigurationError, NetworkTopologyError
-from .topology import FeederSoA, TopologyError, compile_feeder, repair_topology
+from .topology import FeederSoA, TopologyError, compile_for_solver, repair_topology
 
 
-def _compile(feeder, renewable_sources, repair) -> Tuple[FeederSoA, Any]:
+def _compile(feeder, renewable_sources, repair, solver, lanes) -> Tuple[FeederSoA, Any, int]:
     if isinstance(feeder, FeederSoA):
-        return feeder, None
+        return feeder, None, int(lanes)
     try:
         if repair is True:
             feeder = repair_topology(feeder)
-        return compile_feeder(feeder, renewable_sources=renewable_sources), feeder
+        soa, lanes = compile_for_solver(feeder, solver, lanes, renewable_sources=renewable_sources)
+        return soa, feeder, lanes
     except TopologyError as exc:
         if repair == "auto":
             fixed = repair_topology(feeder)
-            return compile_feeder(fixed, renewable_sources=renewable_sources), fixed
+            soa, lanes = compile_for_solver(fixed, solver, lanes, renewable_sources=renewable_sources)
+            return soa, fixed, lanes
         raise NetworkTopologyError(str(exc)) from exc
 
 
@@ -109,7 +111,9 @@ class BatchedGridEnvironment:
         self.device = _cuda_device(device)
         self.num_envs = int(num_envs)
         self.renewable_sources = list(renewable_sources or [])
-        self.soa, self.feeder = _compile(feeder, self.renewable_sources, repair)
+        if solver not in nat.SOLVERS:
+            raise InvalidConfigurationError(f"solver must be one of {sorted(nat.SOLVERS)}, got {solver!r}")
+        self.soa, self.feeder, lanes = _compile(feeder, self.renewable_sources, repair, solver, lanes)
         self.timestep, self.episode_length = float(timestep), int(episode_length)
         self.stochastic_loads, self.weather_variation = bool(stochastic_loads), bool(weather_variation)
         self.safety_penalty = float(safety_penalty)

@@ -25,7 +25,7 @@ from . import _native as nat
 from .components import FeederParameters, PowerFlowSolution
 from .env import NativeFeeder, _cuda_device
 from .errors import InvalidConfigurationError, NetworkTopologyError
-from .topology import FeederSoA, TopologyError, compile_feeder
+from .topology import FeederSoA, TopologyError, auto_lanes, compile_for_solver
 
 
 class _Topology:
@@ -60,6 +60,10 @@ class B200PowerFlowSolver:
         self.last: Optional[PowerFlowSolution] = None
 
     # -- compiled topologies ------------------------------------------------------
+    def _compile(self, feeder) -> FeederSoA:
+        soa, self._lanes_used = compile_for_solver(feeder, self.method, self.lanes, with_components=False)
+        return soa
+
     def _native(self, key, make_soa) -> NativeFeeder:
         nf = self._cache.get(key)
         if nf is None:
@@ -82,7 +86,7 @@ class B200PowerFlowSolver:
             nf = self._native(("soa", id(feeder)), lambda: feeder)
         else:
             nf = self._native(("feeder", id(feeder), _signature(feeder.buses, feeder.lines)),
-                              lambda: compile_feeder(feeder, with_components=False))
+                              lambda: self._compile(feeder))
         dev, soa, lib = nf.device, nf.soa, nf.lib
         p = torch.as_tensor(p_inj)
         if p.dim() == 1:
@@ -99,7 +103,8 @@ class B200PowerFlowSolver:
                    losses=torch.empty(B, **f64), max_mismatch=torch.empty(B, **f64))
         so = nat.SolOut(*[out[k].data_ptr() for k, _ in nat.SolOut._fields_])
         cfg = nat.make_solver_cfg(self.method, self.tolerance, self.max_iterations,
-                                  self.acceleration_factor, self.lanes)
+                                  self.acceleration_factor,
+                                  self.lanes or auto_lanes(soa.n_bus, self.method))
         nat.check(lib, lib.gfr_solve(nf.handle, B, p.data_ptr(), C.byref(cfg), C.byref(so),
                                      torch.cuda.current_stream(dev).cuda_stream))
         out["converged"] = out["converged"].view(torch.bool)
@@ -117,7 +122,7 @@ class B200PowerFlowSolver:
                               generation: Dict[Any, float]) -> PowerFlowSolution:
         # power_flow.py:105-121: P_spec = generation - load at each bus id; Q_spec = 0
         nf = self._native(("lists", _signature(buses, lines)),
-                          lambda: compile_feeder(_Topology(buses, lines, 1e-6), with_components=False))
+                          lambda: self._compile(_Topology(buses, lines, 1e-6)))
         index = {b.id: i for i, b in enumerate(buses)}
         p = np.zeros((1, len(buses)))
         for bus, v in loads.items():

@@ -159,11 +159,12 @@ class FeederSoA:
     bus_ids: list                      # ref order
     line_ids: list                     # ref order
     # level order ---------------------------------------------------------
-    order: np.ndarray                  # int32[n]  level k -> ref bus index
+    order: np.ndarray                  # int32[n]  level k -> ref bus index (k = 0 is the ROOT of the elimination tree)
     rank: np.ndarray                   # int32[n]  ref bus index -> level k
     parent: np.ndarray                 # int32[n]  parent level index, -1 for k=0
     level_ptr: np.ndarray              # int32[n_levels+1]  level l = [ptr[l], ptr[l+1])
-    child_ptr: np.ndarray              # int32[n+1] children of k = [child_ptr[k], child_ptr[k+1]) (contiguous level indices)
+    child_ptr: np.ndarray              # int32[n+1] children of k = child_idx[child_ptr[k] : child_ptr[k+1]]
+    child_idx: np.ndarray              # int32[n-1] level indices of the children, parent by parent
     bus_type: np.ndarray               # int32[n]  BUS_*
     vm_set: np.ndarray                 # f64[n]   slack / pv magnitude (bus.voltage_magnitude)
     g: np.ndarray                      # f64[n]   series conductance of the branch parent[k]-k (k>=1)
@@ -229,8 +230,81 @@ def _series_admittance(r: float, x: float) -> complex:
     return 1.0 / z if abs(z) > OPEN_Z else 0.0
 
 
+def _schedule(n: int, root: int, adj, width: Optional[int]):
+    """Order the buses for leaf -> root elimination on ``width`` lanes.
+
+    Returns (order, parent_ref, level_of): ``order`` lists ref bus indices level by level,
+    level 0 = {root}; every bus sits in a later level than its parent, and each level holds at
+    most ``width`` buses when a width is given.  Levels are the time steps (reversed) of Hu's
+    highest-level-first list schedule, which is optimal for unit tasks on an in-tree: with
+    unbounded width it is the plain height-from-the-leaves layering.
+    """
+    parent_ref = {root: (-1, -1)}
+    depth = {root: 0}
+    bfs = [root]
+    for u in bfs:
+        for v, k in adj[u]:
+            if v not in parent_ref:
+                parent_ref[v] = (u, k)
+                depth[v] = depth[u] + 1
+                bfs.append(v)
+    if len(bfs) != n:
+        raise TopologyError("feeder is not connected (run repair_topology first)")
+    pending = [0] * n
+    for v in bfs[1:]:
+        pending[parent_ref[v][0]] += 1
+    ready = [v for v in bfs if pending[v] == 0]
+    steps = []
+    while ready:
+        ready.sort(key=lambda v: (-depth[v], v))
+        take = ready if width is None else ready[:width]
+        rest = [] if width is None else ready[width:]
+        steps.append(take)
+        for v in take:
+            u = parent_ref[v][0]
+            if u >= 0:
+                pending[u] -= 1
+                if pending[u] == 0:
+                    rest.append(u)
+        ready = rest
+    steps.reverse()                      # level 0 = last eliminated = root
+    assert steps[0] == [root]
+    order, level_of = [], {}
+    for l, members in enumerate(steps):
+        for v in sorted(members, key=lambda v: (parent_ref[v][0], v)):
+            level_of[v] = l
+            order.append(v)
+    return order, parent_ref, level_of
+
+
+def tree_center(n: int, adj, fallback: int) -> int:
+    """A bus of minimum eccentricity (the middle of a longest path): rooting the elimination
+    there halves the number of sequential levels of a feeder whose slack bus sits at one end."""
+    def far(s):
+        dist = {s: 0}
+        q = [s]
+        for u in q:
+            for v, _ in adj[u]:
+                if v not in dist:
+                    dist[v] = dist[u] + 1
+                    q.append(v)
+        t = max(dist, key=lambda v: (dist[v], -v))
+        return t, dist
+    if n == 1:
+        return fallback
+    a, _ = far(fallback)
+    b, da = far(a)
+    # walk back from b towards a
+    path = [b]
+    while path[-1] != a:
+        u = path[-1]
+        path.append(next(v for v, _ in adj[u] if da[v] == da[u] - 1))
+    return path[len(path) // 2]
+
+
 def compile_feeder(feeder, renewable_sources: Optional[Sequence[str]] = None,
-                   with_components: bool = True) -> FeederSoA:
+                   with_components: bool = True, root: str = "slack",
+                   width: Optional[int] = None) -> FeederSoA:
     """Compile a *radial, connected* feeder (run ``repair_topology`` first if it is not).
 
     ``renewable_sources`` has the reference meaning (grid_env.py:167,273,282): a
@@ -238,6 +312,11 @@ def compile_feeder(feeder, renewable_sources: Optional[Sequence[str]] = None,
     its type is listed.  Generators of type "battery" always become batteries; a
     feeder without one gets the reference's template unit (grid_env.py:292-297)
     at its first load bus (deviation D3).
+
+    ``root`` / ``width`` shape the device-side traversal only (never the bus / line numbering of
+    the results): ``root="center"`` roots the elimination tree at the tree's center instead of
+    the slack bus (Newton only; the sweep needs the slack at the root), ``width`` caps the buses
+    per level at the number of lanes that will cooperate on one instance.
     """
     buses, lines = list(feeder.buses), list(feeder.lines)
     n, m = len(buses), len(lines)
@@ -269,18 +348,12 @@ def compile_feeder(feeder, renewable_sources: Optional[Sequence[str]] = None,
         adj[i].append((j, k))
         adj[j].append((i, k))
 
-    # breadth-first from the slack; neighbours visited in line order
-    order = [slack]
-    parent_ref = {slack: (-1, -1)}
-    level_of = {slack: 0}
-    for u in order:
-        for v, k in adj[u]:
-            if v not in parent_ref:
-                parent_ref[v] = (u, k)
-                level_of[v] = level_of[u] + 1
-                order.append(v)
-    if len(order) != n:
-        raise TopologyError("feeder is not connected (run repair_topology first)")
+    if root not in ("slack", "center"):
+        raise TopologyError("root must be 'slack' or 'center'")
+    if width is not None and int(width) < 1:
+        raise TopologyError("width must be >= 1")
+    root_ref = slack if root == "slack" else tree_center(n, adj, slack)
+    order, parent_ref, level_of = _schedule(n, root_ref, adj, None if width is None else int(width))
     rank = np.empty(n, dtype=np.int32)
     rank[np.array(order)] = np.arange(n, dtype=np.int32)
 
@@ -302,14 +375,14 @@ def compile_feeder(feeder, renewable_sources: Optional[Sequence[str]] = None,
     level_ptr = np.searchsorted(levels, np.arange(n_levels + 1)).astype(np.int32)
     child_cnt = np.bincount(parent[1:], minlength=n) if n > 1 else np.zeros(n, dtype=np.int64)
     child_ptr = np.zeros(n + 1, dtype=np.int32)
-    # BFS enqueues the children of a node consecutively, so they are contiguous in level order
-    first = 1
-    for k in range(n):
-        child_ptr[k] = first
-        first += int(child_cnt[k])
-    child_ptr[n] = first
+    child_ptr[1:] = np.cumsum(child_cnt)
+    child_idx = np.zeros(max(n - 1, 0), dtype=np.int32)
+    fill = child_ptr[:-1].copy()
     for k in range(1, n):
-        assert child_ptr[parent[k]] <= k < child_ptr[parent[k] + 1]
+        child_idx[fill[parent[k]]] = k
+        fill[parent[k]] += 1
+    for k in range(1, n):
+        assert parent[k] < k and levels[parent[k]] < levels[k]
 
     tmap = {"slack": BUS_SLACK, "pv": BUS_PV}
     bus_type = np.array([tmap.get(buses[i].bus_type, BUS_PQ) for i in order], dtype=np.int32)
@@ -320,7 +393,7 @@ def compile_feeder(feeder, renewable_sources: Optional[Sequence[str]] = None,
         s_base=float(feeder.parameters.base_power) * 1e6,
         bus_ids=[b_.id for b_ in buses], line_ids=[l_.id for l_ in lines],
         order=np.array(order, dtype=np.int32), rank=rank, parent=parent, level_ptr=level_ptr,
-        child_ptr=child_ptr, bus_type=bus_type, vm_set=vm_set, g=g, b=b,
+        child_ptr=child_ptr, child_idx=child_idx, bus_type=bus_type, vm_set=vm_set, g=g, b=b,
         gdiag=ydiag.real[order].copy(), bdiag=ydiag.imag[order].copy(), r=r, x=x,
         line_of=line_of, from_is_parent=from_is_parent, rating=rating)
 
@@ -372,3 +445,26 @@ def compile_feeder(feeder, renewable_sources: Optional[Sequence[str]] = None,
         bat_cap=np.array(bcap, dtype=float), bat_rating=np.array(brat, dtype=float),
         bat_eff=np.array(beff, dtype=float), bat_soc0=np.full(len(bat_ids), 0.5))
     return FeederSoA(**soa)
+
+
+def auto_lanes(n_bus: int, solver: str = "newton") -> int:
+    """Threads cooperating on one instance when the caller does not say (tuned on B200, see
+    profiles/): one thread per instance for the smallest feeders, part of a warp otherwise."""
+    if n_bus <= 20:
+        return 1 if solver == "sweep" else 4
+    if n_bus <= 64:
+        return 4
+    return 16
+
+
+def compile_for_solver(feeder, solver: str = "newton", lanes: int = 0,
+                       renewable_sources: Optional[Sequence[str]] = None,
+                       with_components: bool = True):
+    """``compile_feeder`` with the traversal the given solver / lane count wants: Newton
+    eliminates towards the tree's center, the sweep towards the slack bus; levels are capped at
+    the lane count (Hu's schedule).  Returns (FeederSoA, lanes)."""
+    lanes = int(lanes) or auto_lanes(len(feeder.buses), solver)
+    soa = compile_feeder(feeder, renewable_sources=renewable_sources, with_components=with_components,
+                         root="center" if solver in ("newton", "newton_raphson") else "slack",
+                         width=lanes if lanes > 1 else None)
+    return soa, lanes

@@ -14,7 +14,7 @@
  *   - calls are asynchronous on the given cudaStream_t (passed as void*); a handle is
  *     not thread-safe; there is no global mutable state
  *   - "ref order" = position in feeder.buses / feeder.lines of the (repaired) feeder;
- *     "level order" = breadth-first position from the slack bus (what the kernels use)
+ *     "level order" = position in the leaf -> root elimination schedule (what the kernels use)
  *   - there is NO CPU fallback: without a CUDA device every call fails with GFR_E_CUDA
  */
 #ifndef GFR_B200_H
@@ -42,7 +42,11 @@ enum { GFR_GEN_SOLAR = 0, GFR_GEN_WIND = 1 };
 typedef struct gfr_feeder gfr_feeder;   /* compiled topology, device resident */
 typedef struct gfr_env gfr_env;         /* B environment instances on one device */
 
-/* Host-side description of a radial feeder, arrays in LEVEL order (k = 0 is the slack bus).
+/* Host-side description of a radial feeder, arrays in LEVEL order: k = 0 is the ROOT of the
+ * elimination tree (the slack bus for the sweep solver; any bus, e.g. the tree's center, for
+ * Newton), every bus sits in a later level than its parent, levels may be capped to the number
+ * of cooperating lanes.  The order only shapes the device-side traversal: results are always
+ * reported in ref order.
  * Produced by grid_fed_rl_b200.topology.compile_feeder from feeder.buses / .lines / .loads /
  * .generators (reference feeders/base.py:30-52; Bus/Line/Load environments/base.py:197-295). */
 typedef struct {
@@ -51,7 +55,8 @@ typedef struct {
   const int32_t* order;             /* [n]  level k -> ref bus index */
   const int32_t* parent;            /* [n]  level index of the parent, -1 for k = 0 */
   const int32_t* level_ptr;         /* [n_levels+1] */
-  const int32_t* child_ptr;         /* [n+1] children of k are the level indices [child_ptr[k], child_ptr[k+1]) */
+  const int32_t* child_ptr;         /* [n+1] children of k are child_idx[child_ptr[k] .. child_ptr[k+1]) */
+  const int32_t* child_idx;         /* [n-1] level indices of the children, parent by parent */
   const int32_t* bus_type;          /* [n]  GFR_BUS_* */
   const double* vm_set;             /* [n]  slack / pv voltage magnitude */
   const double* g;                  /* [n]  series conductance of branch (parent[k], k), k >= 1 */

@@ -5,7 +5,7 @@ import ctypes as C
 import numpy as np
 
 from grid_fed_rl_b200 import _native as nat
-from grid_fed_rl_b200.topology import compile_feeder
+from grid_fed_rl_b200.topology import compile_feeder, compile_for_solver
 
 from .build import build
 
@@ -40,8 +40,8 @@ STEP_FIELDS = dict(reward=np.float64, terminated=np.uint8, truncated=np.uint8, e
 
 class EmuEnv:
     def __init__(self, feeder, num_envs=1, solver="newton", tolerance=1e-6, max_iterations=50,
-                 renewable_sources=None, **kw):
-        self.soa = compile_feeder(feeder, renewable_sources=renewable_sources)
+                 renewable_sources=None, lanes=0, **kw):
+        self.soa, _ = compile_for_solver(feeder, solver, lanes, renewable_sources=renewable_sources)
         self.desc, self._keep = nat.make_feeder_desc(self.soa)
         scfg = nat.make_solver_cfg(solver, tolerance, max_iterations)
         self.cfg = nat.make_env_cfg(solver_cfg=scfg, **kw)
@@ -79,8 +79,8 @@ class EmuEnv:
         return out
 
 
-def emu_solve(feeder, p_inj, solver="newton", tolerance=1e-6, max_iterations=50):
-    soa = compile_feeder(feeder, with_components=False)
+def emu_solve(feeder, p_inj, solver="newton", tolerance=1e-6, max_iterations=50, lanes=0):
+    soa, _ = compile_for_solver(feeder, solver, lanes, with_components=False)
     desc, keep = nat.make_feeder_desc(soa)
     p = np.ascontiguousarray(np.atleast_2d(p_inj), dtype=np.float64)
     B, n, m = p.shape[0], soa.n_bus, soa.n_line

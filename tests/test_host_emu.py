@@ -41,9 +41,10 @@ def test_emu_sweep_matches_reference_trace(name):
     assert exact >= 0.9 * g["obs"].shape[0]
 
 
+@pytest.mark.parametrize("lanes", [0, 1, 8, 32])
 @pytest.mark.parametrize("name", golden_names("solve_"))
 @pytest.mark.parametrize("solver", ["newton", "sweep"])
-def test_emu_solver_matches_reference(name, solver):
+def test_emu_solver_matches_reference(name, solver, lanes):
     g = load_golden(name)
     f = feeder_for(g)
     tol, max_it = float(g["meta"][0]), int(g["meta"][1])
@@ -53,7 +54,7 @@ def test_emu_solver_matches_reference(name, solver):
         ref = port.newton_raphson(net, g["p_spec"], 1e-10, 50)
         g = dict(g); g.update({k: ref[k] for k in ("bus_voltages", "bus_angles", "line_flows", "losses")})
         tol, max_it = 1e-11, 200
-    sol = emu.emu_solve(f, g["p_spec"], solver, tol, max_it)
+    sol = emu.emu_solve(f, g["p_spec"], solver, tol, max_it, lanes=lanes)   # lanes shapes the level schedule
     conv = g["converged"]
     if solver == "newton":
         assert np.array_equal(sol["converged"].astype(bool), conv)
