@@ -238,6 +238,7 @@ def run_gpu(args):
     import torch.distributed as dist
     import grid_fed_rl_b200 as m
     from grid_fed_rl_b200 import _native
+    from grid_fed_rl_b200.distributed import max_over_ranks
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -277,12 +278,7 @@ def run_gpu(args):
             step_fn(i)
         ev1.record()
         barrier()
-        ms = ev0.elapsed_time(ev1)
-        if world > 1:
-            t = torch.tensor([ms], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms
+        return max_over_ranks(ev0.elapsed_time(ev1), dev)     # a timed region counts as its slowest rank
 
     # ---- device-resident arm
     conv_acc = torch.zeros((), dtype=torch.float64, device=dev)

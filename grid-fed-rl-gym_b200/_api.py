@@ -22,9 +22,12 @@ __all__ = [
 
 def __getattr__(name):
     # the torch-backed classes load lazily so that feeder / topology tooling imports stay light
-    if name in ("BatchedGridEnvironment", "shard_range"):
+    if name == "BatchedGridEnvironment":
         from . import env
         return getattr(env, name)
+    if name == "shard_range":
+        from .distributed import shard_range
+        return shard_range
     if name == "B200PowerFlowSolver":
         from .solver import B200PowerFlowSolver
         return B200PowerFlowSolver

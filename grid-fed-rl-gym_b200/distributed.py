@@ -1,0 +1,58 @@
+"""Multi-GPU plumbing of the batched step path.
+
+Instances shard trivially: rank r owns a contiguous range of global instance ids and keys its
+Philox streams with ``seed + global id``, so results do not depend on the number of ranks and the
+step path carries **no collective**.  The only communication is the optional episode-statistics
+reduction (one all-reduce of a short fp64 vector: NCCL over NVLink on GPUs, gloo in the CPU tests)
+and the max-over-ranks of a timed region in ``bench.py``.
+"""
+
+from __future__ import annotations
+
+from typing import Dict, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+STAT_KEYS = ("reward_sum", "episode_reward_sum", "converged", "iterations_sum", "violation_steps",
+             "done", "errors", "num_envs")
+
+
+def shard_range(total_envs: int, rank: int, world_size: int) -> Tuple[int, int]:
+    """Contiguous instance range [start, stop) of ``rank``; sizes differ by at most one."""
+    if not 0 <= rank < world_size:
+        raise ValueError("rank must be in [0, world_size)")
+    base, rem = divmod(int(total_envs), int(world_size))
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+def is_distributed() -> bool:
+    return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+
+def all_reduce_stats(local: torch.Tensor, group=None) -> torch.Tensor:
+    """Sum of the per-rank statistics vectors (fp64[len(STAT_KEYS)]), in place."""
+    if local.dtype != torch.float64 or local.numel() != len(STAT_KEYS):
+        raise ValueError(f"expected an fp64 vector of {len(STAT_KEYS)} statistics")
+    if is_distributed():
+        dist.all_reduce(local, op=dist.ReduceOp.SUM, group=group)
+    return local
+
+
+def stats_dict(vec: torch.Tensor) -> Dict[str, float]:
+    return dict(zip(STAT_KEYS, vec.tolist()))
+
+
+def max_over_ranks(value: float, device=None) -> float:
+    """A timed region counts as its slowest rank."""
+    if not is_distributed():
+        return float(value)
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def global_seeds(seed: int, start: int, count: int, device=None) -> torch.Tensor:
+    """Philox keys of the instances [start, start + count): ``seed + global id``."""
+    return torch.arange(count, dtype=torch.int64, device=device) + int(seed) + int(start)

@@ -23,6 +23,7 @@ import numpy as np
 import torch
 
 from . import _native as nat
+from .distributed import all_reduce_stats, global_seeds, shard_range, stats_dict  # noqa: F401
 from .components import Box
 from .errors import InvalidActionError, InvalidConfigurationError, NetworkTopologyError
 from .topology import FeederSoA, TopologyError, compile_for_solver, repair_topology
@@ -210,8 +211,7 @@ class BatchedGridEnvironment:
         ``noise`` [B,4] replays the four weather draws instead of the in-kernel Philox stream."""
         B = self.num_envs
         if seeds is None and seed is not None:
-            seeds = (torch.arange(B, dtype=torch.int64, device=self.device)
-                     + int(seed) + self.env_id_offset)
+            seeds = global_seeds(seed, self.env_id_offset, B, self.device)
         if seeds is not None:
             seeds = torch.as_tensor(seeds)
             if seeds.dtype == torch.uint64:
@@ -338,15 +338,6 @@ class BatchedGridEnvironment:
                          (o["terminated"] | o["truncated"]).sum(dtype=torch.float64),
                          o["error"].sum(dtype=torch.float64),
                          torch.tensor(float(self.num_envs), dtype=torch.float64, device=self.device)])
-        if reduce and torch.distributed.is_available() and torch.distributed.is_initialized():
-            torch.distributed.all_reduce(v)
-        keys = ("reward_sum", "episode_reward_sum", "converged", "iterations_sum", "violation_steps",
-                "done", "errors", "num_envs")
-        return dict(zip(keys, v.tolist()))
-
-
-def shard_range(total_envs: int, rank: int, world_size: int) -> Tuple[int, int]:
-    """Contiguous instance range [start, stop) of ``rank``: no data-path collective."""
-    base, rem = divmod(int(total_envs), int(world_size))
-    start = rank * base + min(rank, rem)
-    return start, start + base + (1 if rank < rem else 0)
+        if reduce:
+            all_reduce_stats(v)
+        return stats_dict(v)

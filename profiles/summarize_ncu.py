@@ -1,0 +1,68 @@
+#!/usr/bin/env python
+"""Summarise an .ncu-rep (read here, no GPU needed): key raw metrics + the hottest source lines.
+usage: python profiles/summarize_ncu.py gpurun_out/prof.ncu-rep [--lines N]"""
+import csv
+import io
+import subprocess
+import sys
+
+WANT = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum',
+        'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed',
+        'lts__t_bytes.sum', 'sm__warps_active.avg.pct_of_peak_sustained_active',
+        'launch__registers_per_thread', 'launch__occupancy_limit_registers',
+        'launch__occupancy_limit_shared_mem', 'launch__grid_size', 'launch__block_size',
+        'launch__shared_mem_per_block_dynamic',
+        'sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active',
+        'sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active',
+        'sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active',
+        'sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active',
+        'sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active',
+        'smsp__inst_executed.sum', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
+        'smsp__thread_inst_executed_per_inst_executed.ratio',
+        'smsp__warps_eligible.avg.per_cycle_active',
+        'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum', 'sm__cycles_elapsed.max']
+
+
+def run(args):
+    return subprocess.run(["ncu", "-i", *args], capture_output=True, text=True).stdout
+
+
+def main():
+    rep = sys.argv[1]
+    nlines = int(sys.argv[sys.argv.index("--lines") + 1]) if "--lines" in sys.argv else 25
+    rows = list(csv.reader(io.StringIO(run([rep, "--page", "raw", "--csv"]))))
+    hdr, units = rows[0], rows[1]
+    print(f"# {rep}")
+    for r in rows[2:]:
+        print("kernel:", r[hdr.index('Kernel Name')][:100])
+        for w in WANT:
+            if w in hdr:
+                i = hdr.index(w)
+                print(f"  {w:72s} {units[i]:16s} {r[i]:>20s}")
+    src = run([rep, "--page", "source", "--csv", "--print-source", "sass,cuda"])
+    per, fname = [], ""
+    stall_cols = None
+    for r in csv.reader(io.StringIO(src)):
+        if not r:
+            continue
+        if r[0] == "File Path":
+            fname = r[1].split('/')[-1]
+            continue
+        if r[0] == "Line No":
+            stall_cols = {h: i for i, h in enumerate(r)}
+            continue
+        if r[0].isdigit() and stall_cols:
+            try:
+                per.append((int(r[stall_cols["Instructions Executed"]]), int(r[stall_cols["# Samples"]]),
+                            fname, int(r[0]), r[1].strip()[:100]))
+            except ValueError:
+                pass
+    tot = sum(p[0] for p in per) or 1
+    tots = sum(p[1] for p in per) or 1
+    print(f"\nhottest source lines (share of warp instructions executed / of stall samples):")
+    for ie, smp, f, l, s in sorted(per, key=lambda x: -x[0])[:nlines]:
+        print(f"  {100 * ie / tot:5.2f}% inst {100 * smp / tots:5.2f}% smp  {f}:{l:<4d} {s}")
+
+
+if __name__ == "__main__":
+    main()
