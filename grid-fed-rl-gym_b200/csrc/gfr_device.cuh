@@ -146,31 +146,51 @@ struct Grp {
   }
 };
 
+// 1 / x for a normal, finite x: hardware seed + two Newton steps (~1 ulp), no slow-path call.
+GFR_HD double rcp_fast(double x) {
+#if defined(__CUDA_ARCH__)
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  r = fma(r, fma(-x, r, 1.0), r);
+  r = fma(r, fma(-x, r, 1.0), r);
+  return r;
+#else
+  return 1.0 / x;
+#endif
+}
+
+// sin / cos of a Newton angle correction.  Corrections are small: a Taylor pair is exact to
+// < 1 ulp of 1.0 for |x| <= 0.25 (next terms x^17/17! < 2e-25, x^18/18! < 1e-26).  Larger steps
+// (a diverging solve) are halved first and doubled back; nothing here calls a library slow path.
 GFR_HD void sincos_small(double x, double* s, double* c) {
-  // Newton corrections are small angles; a short Taylor pair is exact to < 1 ulp of 1.0
-  // for |x| <= 0.25 (next terms: x^17/17! < 2e-25, x^18/18! < 1e-26)
-  if (fabs(x) <= 0.25) {
-    double x2 = x * x;
-    double ps = -1.0 / 1307674368000.0;                 // -1/15!
-    ps = ps * x2 + 1.0 / 6227020800.0;                  //  1/13!
-    ps = ps * x2 - 1.0 / 39916800.0;                    // -1/11!
-    ps = ps * x2 + 1.0 / 362880.0;                      //  1/9!
-    ps = ps * x2 - 1.0 / 5040.0;                        // -1/7!
-    ps = ps * x2 + 1.0 / 120.0;                         //  1/5!
-    ps = ps * x2 - 1.0 / 6.0;                           // -1/3!
-    *s = x + x * x2 * ps;
-    double pc = 1.0 / 20922789888000.0;                 //  1/16!
-    pc = pc * x2 - 1.0 / 87178291200.0;                 // -1/14!
-    pc = pc * x2 + 1.0 / 479001600.0;                   //  1/12!
-    pc = pc * x2 - 1.0 / 3628800.0;                     // -1/10!
-    pc = pc * x2 + 1.0 / 40320.0;                       //  1/8!
-    pc = pc * x2 - 1.0 / 720.0;                         // -1/6!
-    pc = pc * x2 + 1.0 / 24.0;                          //  1/4!
-    pc = pc * x2 - 0.5;
-    *c = 1.0 + x2 * pc;
-  } else {
-    sincos(x, s, c);
+  int halvings = 0;
+  if (fabs(x) > 0.25) {
+    if (!(fabs(x) <= 64.0)) x -= 6.283185307179586 * rint(x * 0.15915494309189535);   // garbage in, bounded out
+    while (fabs(x) > 0.25 && halvings < 6) { x *= 0.5; ++halvings; }
   }
+  const double x2 = x * x;
+  double ps = -1.0 / 1307674368000.0;                 // -1/15!
+  ps = fma(ps, x2, 1.0 / 6227020800.0);               //  1/13!
+  ps = fma(ps, x2, -1.0 / 39916800.0);                // -1/11!
+  ps = fma(ps, x2, 1.0 / 362880.0);                   //  1/9!
+  ps = fma(ps, x2, -1.0 / 5040.0);                    // -1/7!
+  ps = fma(ps, x2, 1.0 / 120.0);                      //  1/5!
+  ps = fma(ps, x2, -1.0 / 6.0);                       // -1/3!
+  double sn = fma(x * x2, ps, x);
+  double pc = 1.0 / 20922789888000.0;                 //  1/16!
+  pc = fma(pc, x2, -1.0 / 87178291200.0);             // -1/14!
+  pc = fma(pc, x2, 1.0 / 479001600.0);                //  1/12!
+  pc = fma(pc, x2, -1.0 / 3628800.0);                 // -1/10!
+  pc = fma(pc, x2, 1.0 / 40320.0);                    //  1/8!
+  pc = fma(pc, x2, -1.0 / 720.0);                     // -1/6!
+  pc = fma(pc, x2, 1.0 / 24.0);                       //  1/4!
+  pc = fma(pc, x2, -0.5);
+  double cs = fma(x2, pc, 1.0);
+  for (; halvings > 0; --halvings) {                  // double-angle back up
+    const double s2 = 2.0 * sn * cs, c2 = fma(-2.0 * sn, sn, 1.0);
+    sn = s2; cs = c2;
+  }
+  *s = sn; *c = cs;
 }
 
 // ----------------------------------------------------------------------------- Philox4x32-10
@@ -270,22 +290,22 @@ GFR_HD void newton_solve(const Grp<LANES, NF_NEWTON>& g, const Layout& lay, cons
       const I4 t = topo[k];
       const D2 vk = g.at2(F_E, k);
       const D2 yd = gbd[k];
-      const double v2 = vk.x * vk.x + vk.y * vk.y;
+      const double v2 = fma(vk.x, vk.x, vk.y * vk.y);
       double P = yd.x * v2, Q = -yd.y * v2;
       {
         const D2 vp = g.at2(F_E, t.x);
         const D2 y = gb[k];
-        const double a = vk.x * vp.x + vk.y * vp.y, s = vk.y * vp.x - vk.x * vp.y;
-        P += -y.x * a - y.y * s;
-        Q += -y.x * s + y.y * a;
+        const double a = fma(vk.x, vp.x, vk.y * vp.y), s = fma(vk.y, vp.x, -vk.x * vp.y);
+        P = fma(-y.x, a, fma(-y.y, s, P));
+        Q = fma(-y.x, s, fma(y.y, a, Q));
       }
       for (int q = t.y; q < t.z; ++q) {
         const int c = child_idx[q];
         const D2 vc = g.at2(F_E, c);
         const D2 y = gb[c];
-        const double a = vk.x * vc.x + vk.y * vc.y, s = vk.y * vc.x - vk.x * vc.y;
-        P += -y.x * a - y.y * s;
-        Q += -y.x * s + y.y * a;
+        const double a = fma(vk.x, vc.x, vk.y * vc.y), s = fma(vk.y, vc.x, -vk.x * vc.y);
+        P = fma(-y.x, a, fma(-y.y, s, P));
+        Q = fma(-y.x, s, fma(y.y, a, Q));
       }
       const int pq = t.w & FL_PQ, th = t.w & FL_THETA;
       const double dP = th ? (g.at(N_P, k) - P) : 0.0;      // the slack bus has no equations
@@ -323,36 +343,36 @@ GFR_HD void newton_solve(const Grp<LANES, NF_NEWTON>& g, const Layout& lay, cons
           const int c = child_idx[q];
           const D2 vc = g.at2(F_E, c);
           const D2 y = gb[c];
-          const double a = vk.x * vc.x + vk.y * vc.y, s = vk.y * vc.x - vk.x * vc.y;
-          const double ga = -y.x * a - y.y * s, al = -y.x * s + y.y * a;   // J[k,c]
+          const double a = fma(vk.x, vc.x, vk.y * vc.y), s = fma(vk.y, vc.x, -vk.x * vc.y);
+          const double ga = fma(-y.x, a, -y.y * s), al = fma(-y.x, s, y.y * a);   // J[k,c]
           const D2 m0 = g.at2(N_M0, c), m1 = g.at2(N_M2, c), v = g.at2(N_V0, c);
           if (th) {
-            d0.x -= al * m0.x + ga * m1.x;
-            d0.y -= al * m0.y + ga * m1.y;
-            r.x -= al * v.x + ga * v.y;
+            d0.x = fma(-al, m0.x, fma(-ga, m1.x, d0.x));
+            d0.y = fma(-al, m0.y, fma(-ga, m1.y, d0.y));
+            r.x = fma(-al, v.x, fma(-ga, v.y, r.x));
           }
           if (pq) {
-            d1.x -= -ga * m0.x + al * m1.x;
-            d1.y -= -ga * m0.y + al * m1.y;
-            r.y -= -ga * v.x + al * v.y;
+            d1.x = fma(ga, m0.x, fma(-al, m1.x, d1.x));
+            d1.y = fma(ga, m0.y, fma(-al, m1.y, d1.y));
+            r.y = fma(ga, v.x, fma(-al, v.y, r.y));
           }
         }
         const D2 vp = g.at2(F_E, t.x);
         const D2 y = gb[k];
-        const double a = vk.x * vp.x + vk.y * vp.y, s = vk.y * vp.x - vk.x * vp.y;
-        const double ga = -y.x * a - y.y * s, al = -y.x * s + y.y * a;     // J[k,p]
+        const double a = fma(vk.x, vp.x, vk.y * vp.y), s = fma(vk.y, vp.x, -vk.x * vp.y);
+        const double ga = fma(-y.x, a, -y.y * s), al = fma(-y.x, s, y.y * a);     // J[k,p]
         const double u00 = th ? al : 0.0, u01 = th ? ga : 0.0, u10 = pq ? -ga : 0.0, u11 = pq ? al : 0.0;
-        const double det = d0.x * d1.y - d0.y * d1.x;
+        const double det = fma(d0.x, d1.y, -d0.y * d1.x);
         if (det == 0.0) singular = 1;                 // dgesv's exact-zero pivot (:188-190)
-        const double inv = 1.0 / det;
+        const double inv = rcp_fast(det);
         const double i00 = d1.y * inv, i01 = -d0.y * inv, i10 = -d1.x * inv, i11 = d0.x * inv;
         D2 o0, o1, ov;
-        o0.x = i00 * u00 + i01 * u10;
-        o0.y = i00 * u01 + i01 * u11;
-        o1.x = i10 * u00 + i11 * u10;
-        o1.y = i10 * u01 + i11 * u11;
-        ov.x = i00 * r.x + i01 * r.y;
-        ov.y = i10 * r.x + i11 * r.y;
+        o0.x = fma(i00, u00, i01 * u10);
+        o0.y = fma(i00, u01, i01 * u11);
+        o1.x = fma(i10, u00, i11 * u10);
+        o1.y = fma(i10, u01, i11 * u11);
+        ov.x = fma(i00, r.x, i01 * r.y);
+        ov.y = fma(i10, r.x, i11 * r.y);
         g.at2(N_M0, k) = o0;
         g.at2(N_M2, k) = o1;
         g.at2(N_V0, k) = ov;
@@ -370,8 +390,8 @@ GFR_HD void newton_solve(const Grp<LANES, NF_NEWTON>& g, const Layout& lay, cons
         const D2 x = g.at2(N_V0, topo[k].x);
         const D2 m0 = g.at2(N_M0, k), m1 = g.at2(N_M2, k);
         D2 v = g.at2(N_V0, k);
-        v.x -= m0.x * x.x + m0.y * x.y;
-        v.y -= m1.x * x.x + m1.y * x.y;
+        v.x = fma(-m0.x, x.x, fma(-m0.y, x.y, v.x));
+        v.y = fma(-m1.x, x.x, fma(-m1.y, x.y, v.y));
         g.at2(N_V0, k) = v;
       }
       g.sync();
