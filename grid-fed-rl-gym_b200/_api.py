@@ -17,6 +17,7 @@ __all__ = [
     "GridEnvironmentError", "GridLimitError", "InvalidActionError", "InvalidConfigurationError",
     "NativeRuntimeError", "NetworkTopologyError", "PowerFlowError",
     "BatchedGridEnvironment", "B200PowerFlowSolver", "shard_range",
+    "GridEnvironment", "VectorizedEnvironment", "RolloutBuffer", "collect_random_data",
 ]
 
 
@@ -31,4 +32,7 @@ def __getattr__(name):
     if name == "B200PowerFlowSolver":
         from .solver import B200PowerFlowSolver
         return B200PowerFlowSolver
+    if name in ("GridEnvironment", "VectorizedEnvironment", "RolloutBuffer", "collect_random_data"):
+        from . import compat
+        return getattr(compat, name)
     raise AttributeError(name)
