@@ -28,9 +28,9 @@ _i32p, _f64p, _u8p, _u64p = C.POINTER(C.c_int32), C.POINTER(C.c_double), C.POINT
 class FeederDesc(C.Structure):
     _fields_ = [
         ("n_bus", C.c_int32), ("n_levels", C.c_int32), ("n_load", C.c_int32), ("n_gen", C.c_int32),
-        ("n_bat", C.c_int32), ("s_base", C.c_double),
+        ("n_bat", C.c_int32), ("n_pool", C.c_int32), ("s_base", C.c_double),
         ("order", _i32p), ("parent", _i32p), ("level_ptr", _i32p), ("child_ptr", _i32p),
-        ("child_idx", _i32p),
+        ("child_idx", _i32p), ("pool_slot", _i32p),
         ("bus_type", _i32p), ("vm_set", _f64p), ("g", _f64p), ("b", _f64p), ("gdiag", _f64p),
         ("bdiag", _f64p), ("r", _f64p), ("x", _f64p), ("line_of", _i32p), ("from_is_parent", _i32p),
         ("rating", _f64p), ("load_bus", _i32p), ("load_base", _f64p), ("load_p", _f64p),
@@ -155,8 +155,9 @@ def make_feeder_desc(soa: FeederSoA):
     d = FeederDesc()
     d.n_bus, d.n_levels, d.n_load, d.n_gen, d.n_bat = (soa.n_bus, soa.n_levels, soa.n_load,
                                                       soa.n_gen, soa.n_bat)
+    d.n_pool = int(soa.n_pool)
     d.s_base = float(soa.s_base)
-    for name in ("order", "parent", "level_ptr", "child_ptr", "child_idx", "bus_type", "line_of", "from_is_parent",
+    for name in ("order", "parent", "level_ptr", "child_ptr", "child_idx", "pool_slot", "bus_type", "line_of", "from_is_parent",
                  "load_bus", "gen_type", "gen_bus", "bat_bus"):
         setattr(d, name, i32(name))
     for name in ("vm_set", "g", "b", "gdiag", "bdiag", "r", "x", "rating", "load_base", "load_p",

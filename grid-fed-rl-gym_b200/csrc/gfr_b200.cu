@@ -59,28 +59,31 @@ __device__ __forceinline__ void stage_image(unsigned char* smem, const void* img
   } while (!ok);
 }
 
-template <int LANES, int NF>
-__device__ __forceinline__ Grp<LANES, NF> make_group(const Layout& lay, unsigned char* smem) {
-  Grp<LANES, NF> g;
+template <int LANES, int SOLVER>
+__device__ __forceinline__ typename GroupOf<LANES, SOLVER>::type
+make_group(const Layout& lay, unsigned char* smem, int slot_bytes, D2* mscratch) {
+  typename GroupOf<LANES, SOLVER>::type g;
   g.lane = threadIdx.x % LANES;
-  g.n = lay.n;
-  g.rec = (double*)(smem + kSmemHeader + lay.img_bytes) + (size_t)(threadIdx.x / LANES) * lay.n * NF;
   g.mask = (LANES == 32) ? 0xffffffffu
                          : (((1u << (LANES & 31)) - 1u) << (((threadIdx.x & 31) / LANES) * LANES));
+  const int slot = threadIdx.x / LANES;
+  const int E = blockDim.x / LANES;
+  D2* mg = mscratch ? mscratch + ((size_t)blockIdx.x * E + slot) * 2 * (size_t)lay.n : nullptr;
+  bind_slot(g, smem + kSmemHeader + lay.img_bytes + (size_t)slot * slot_bytes, lay.n, lay.n_pool, mg);
   return g;
 }
 
 template <int LANES, int SOLVER>
 __global__ void __launch_bounds__(kMaxThreads)
-step_kernel(const Layout lay, const EnvCfg cfg, const void* __restrict__ img,
-            double* __restrict__ state, double* __restrict__ obs,
+step_kernel(const Layout lay, const EnvCfg cfg, const void* __restrict__ img, const int slot_bytes,
+            D2* __restrict__ mscratch, double* __restrict__ state, double* __restrict__ obs,
             const double* __restrict__ actions, const double* __restrict__ noise, const StepOut o,
             const long long B) {
   extern __shared__ __align__(16) unsigned char smem[];
   stage_image(smem, img, lay.img_bytes);
   const int* simg = (const int*)(smem + kSmemHeader);
   const double* dimg = (const double*)(smem + kSmemHeader);
-  const auto g = make_group<LANES, RecOf<SOLVER>::NF>(lay, smem);
+  const auto g = make_group<LANES, SOLVER>(lay, smem, slot_bytes, mscratch);
   const int E = blockDim.x / LANES;
   for (long long env = (long long)blockIdx.x * E + threadIdx.x / LANES; env < B; env += (long long)gridDim.x * E)
     step_instance<LANES, SOLVER>(g, lay, simg, dimg, cfg, env, state, obs, actions, noise, o);
@@ -88,13 +91,13 @@ step_kernel(const Layout lay, const EnvCfg cfg, const void* __restrict__ img,
 
 template <int LANES, int SOLVER>
 __global__ void __launch_bounds__(kMaxThreads)
-solve_kernel(const Layout lay, const EnvCfg cfg, const void* __restrict__ img,
-             const double* __restrict__ p_inj, const SolOut o, const long long B) {
+solve_kernel(const Layout lay, const EnvCfg cfg, const void* __restrict__ img, const int slot_bytes,
+             D2* __restrict__ mscratch, const double* __restrict__ p_inj, const SolOut o, const long long B) {
   extern __shared__ __align__(16) unsigned char smem[];
   stage_image(smem, img, lay.img_bytes);
   const int* simg = (const int*)(smem + kSmemHeader);
   const double* dimg = (const double*)(smem + kSmemHeader);
-  const auto g = make_group<LANES, RecOf<SOLVER>::NF>(lay, smem);
+  const auto g = make_group<LANES, SOLVER>(lay, smem, slot_bytes, mscratch);
   const int E = blockDim.x / LANES;
   for (long long env = (long long)blockIdx.x * E + threadIdx.x / LANES; env < B; env += (long long)gridDim.x * E)
     solve_instance<LANES, SOLVER>(g, lay, simg, dimg, cfg, env, p_inj, o);
@@ -109,9 +112,8 @@ reset_kernel(const Layout lay, const EnvCfg cfg, const void* __restrict__ img,
              const double* __restrict__ noise, const double start_time, const int construct,
              const long long B) {
   constexpr int LANES = 4;
-  Grp<LANES, 1> g;
+  Lanes<LANES> g;
   g.lane = threadIdx.x % LANES;
-  g.n = lay.n; g.rec = nullptr;
   g.mask = ((1u << LANES) - 1u) << (((threadIdx.x & 31) / LANES) * LANES);
   const int* simg = (const int*)img;
   const double* dimg = (const double*)img;
@@ -195,19 +197,19 @@ struct gfr_env {
   const void* fn = nullptr;
   double* d_state = nullptr;
   double* d_obs = nullptr;
+  D2* d_mscratch = nullptr;    // Newton: D^-1 U of every resident instance slot (L2 resident)
+  int slot_bytes = 0;
   bool obs_external = false;   // bound by gfr_env_bind_obs: caller-owned
 };
 
 namespace {
 
-struct LaunchPlan { int lanes, threads, grid; size_t smem; int ctas_per_sm; };
+struct LaunchPlan { int lanes, threads, grid; size_t smem; int ctas_per_sm; int slot_bytes; size_t mscratch_bytes; };
 
-// shared memory of one instance slot; 0 if the scratch carried in the records cannot hold the sources
+// shared memory of one instance slot; 0 if the scratch it doubles as cannot hold the sources
 size_t slot_bytes(const Layout& lay, int solver) {
-  const int nf = solver == GFR_SOLVER_NEWTON ? NF_NEWTON : NF_SWEEP;
-  const int cap = (solver == GFR_SOLVER_NEWTON ? SCRATCH_FIELDS_NEWTON : SCRATCH_FIELDS_SWEEP) * lay.n;
-  if (lay.n_src > cap) return 0;
-  return (size_t)nf * lay.n * sizeof(double);
+  return solver == GFR_SOLVER_NEWTON ? newton_slot_bytes(lay.n, lay.n_pool, lay.n_src)
+                                     : sweep_slot_bytes(lay.n, lay.n_src);
 }
 
 int auto_lanes(const Layout& lay, int solver) {
@@ -257,8 +259,8 @@ int plan_launch(const gfr_feeder* f, bool step, int solver, int lanes, long long
   const void* fn = kernel_fn(step, solver, lanes);
   const size_t per_env = slot_bytes(lay, solver);
   if (!per_env)
-    return fail(GFR_E_LIMIT, "more loads + generators + batteries than the solver's per-bus scratch holds "
-                             "(newton: 6 per bus on average, sweep: 2)");
+    return fail(GFR_E_LIMIT, "more loads + generators + batteries than the solver's working set can stage "
+                             "(sweep: 2 per bus on average)");
   GFR_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, f->smem_optin));
   const size_t fixed = kSmemHeader + (size_t)lay.img_bytes;
   const size_t sm_total = (size_t)f->smem_per_sm;
@@ -296,6 +298,9 @@ int plan_launch(const gfr_feeder* f, bool step, int solver, int lanes, long long
   if (grid > tiles) grid = tiles;
   if (grid < 1) grid = 1;
   best.grid = (int)grid;
+  best.slot_bytes = (int)per_env;
+  // Newton spills D^-1 U (32 B per bus) of every resident instance slot to global memory
+  best.mscratch_bytes = solver == GFR_SOLVER_NEWTON ? (size_t)grid * E * lay.n * 32 : 0;
   *out = best;
   *fn_out = fn;
   return GFR_OK;
@@ -307,8 +312,10 @@ int launch_step(const gfr_env* e, const double* actions, const double* noise, co
   double* state = e->d_state;
   double* obs = e->d_obs;
   long long B = e->B;
-  void* args[] = {(void*)&e->f->lay, (void*)&e->cfg, (void*)&img, (void*)&state, (void*)&obs,
-                  (void*)&actions, (void*)&noise, (void*)&o, (void*)&B};
+  int slot = e->slot_bytes;
+  D2* ms = e->d_mscratch;
+  void* args[] = {(void*)&e->f->lay, (void*)&e->cfg, (void*)&img, (void*)&slot, (void*)&ms, (void*)&state,
+                  (void*)&obs, (void*)&actions, (void*)&noise, (void*)&o, (void*)&B};
   GFR_CUDA(cudaLaunchKernel(e->fn, dim3(e->grid), dim3(e->threads), args, e->smem, s));
   g_launches.fetch_add(1);
   return GFR_OK;
@@ -317,8 +324,14 @@ int launch_step(const gfr_env* e, const double* actions, const double* noise, co
 int launch_solve(const gfr_feeder* f, const LaunchPlan& p, const void* fn, const EnvCfg& cfg,
                  const double* p_inj, const SolOut& o, long long B, cudaStream_t s) {
   const void* img = f->d_img;
-  void* args[] = {(void*)&f->lay, (void*)&cfg, (void*)&img, (void*)&p_inj, (void*)&o, (void*)&B};
-  GFR_CUDA(cudaLaunchKernel(fn, dim3(p.grid), dim3(p.threads), args, p.smem, s));
+  int slot = p.slot_bytes;
+  D2* ms = nullptr;
+  if (p.mscratch_bytes) GFR_CUDA(cudaMallocAsync((void**)&ms, p.mscratch_bytes, s));   // stream-ordered scratch
+  void* args[] = {(void*)&f->lay, (void*)&cfg, (void*)&img, (void*)&slot, (void*)&ms, (void*)&p_inj, (void*)&o,
+                  (void*)&B};
+  cudaError_t le = cudaLaunchKernel(fn, dim3(p.grid), dim3(p.threads), args, p.smem, s);
+  if (ms) cudaFreeAsync(ms, s);
+  if (le != cudaSuccess) return cuda_fail(le, "cudaLaunchKernel(solve)");
   g_launches.fetch_add(1);
   return GFR_OK;
 }
@@ -437,8 +450,11 @@ int gfr_env_create(const gfr_feeder* f, int64_t n_envs, const gfr_env_cfg* cfg, 
   auto* e = new gfr_env();
   e->f = f; e->B = n_envs; e->cfg = ec; e->solver = cfg->solver.solver;
   e->lanes = plan.lanes; e->threads = plan.threads; e->grid = plan.grid; e->smem = plan.smem; e->fn = fn;
+  e->slot_bytes = plan.slot_bytes;
   cudaError_t e1 = cudaMalloc((void**)&e->d_state, (size_t)n_envs * f->lay.R * 8);
   cudaError_t e2 = cudaMalloc((void**)&e->d_obs, (size_t)n_envs * f->lay.D * 8);
+  if (e1 == cudaSuccess && e2 == cudaSuccess && plan.mscratch_bytes)
+    e2 = cudaMalloc((void**)&e->d_mscratch, plan.mscratch_bytes);
   if (e1 != cudaSuccess || e2 != cudaSuccess) {
     gfr_env_destroy(e);
     return cuda_fail(e1 != cudaSuccess ? e1 : e2, "cudaMalloc(env)");
@@ -454,6 +470,7 @@ void gfr_env_destroy(gfr_env* e) {
   if (!e) return;
   DeviceGuard guard(e->f->device);
   cudaFree(e->d_state);
+  cudaFree(e->d_mscratch);
   if (!e->obs_external) cudaFree(e->d_obs);
   delete e;
 }

@@ -32,18 +32,19 @@ namespace gfr {
 enum { SOLVER_SWEEP = 0, SOLVER_NEWTON = 1 };
 enum { BUS_SLACK = 0, BUS_PV = 1, BUS_PQ = 2 };
 enum { GEN_SOLAR = 0, GEN_WIND = 1 };
-// An instance's working set is one RECORD per bus (level order), NF doubles each, so that a
-// field is an immediate offset from the bus's address and pairs load as one 128-bit access:
-//   Newton (NF = 10): e f | M0 M1 | M2 M3 | V0 V1 | P pad
-//   sweep  (NF = 6):  e f | Jr Ji | P pad
-// e + jf is the bus voltage, P the specified injection; M*, V* hold the 2x2 diagonal block and
-// the right-hand side during assembly, D^-1 U and D^-1 r after elimination, the correction
-// after back-substitution; Jr + jJi is the branch current.  Fields F_SCRATCH.. double as the
-// scratch that carries the load / generator / battery powers into the injection sums.
+// An instance's working set in shared memory (buses in level order):
+//   Newton:  ef[n] (e + jf, 16 B) | vx[n] (16 B) | pool[n_pool] (48 B) | P[n] (8 B)
+//            vx holds (P_calc, Q_calc) after the mismatch pass, D^-1 r after elimination and the
+//            correction after back-substitution; a pool entry holds one bus's Schur contribution
+//            to its parent (L D^-1 U, L D^-1 r) from the moment it is eliminated until the parent
+//            is - the host plans the slots (pool_slot[k]); D^-1 U itself, only needed again in the
+//            back-substitution, is spilled to an L2-resident scratch (global memory).
+//   sweep:   one record per bus, 6 doubles: e f | Jr Ji | P pad  (Jr + jJi = branch current)
+// Before the solve the same space (Newton: vx + pool; sweep: the J fields) carries the load /
+// generator / battery powers into the per-bus injection sums.
 enum { F_E = 0, F_F = 1, F_SCRATCH = 2 };
-enum { NF_NEWTON = 10, N_M0 = 2, N_M1 = 3, N_M2 = 4, N_M3 = 5, N_V0 = 6, N_V1 = 7, N_P = 8 };
 enum { NF_SWEEP = 6, S_JR = 2, S_JI = 3, S_P = 4 };
-enum { SCRATCH_FIELDS_NEWTON = 6, SCRATCH_FIELDS_SWEEP = 2 };
+enum { SCRATCH_FIELDS_SWEEP = 2 };
 // bus flag bits
 enum { FL_PQ = 1, FL_FROM_IS_PARENT = 2, FL_FIXED_VM = 4, FL_THETA = 8 };   // PQ: |V| unknown; THETA: angle unknown
 // record (persistent per-instance state) slots, in doubles
@@ -56,8 +57,8 @@ struct alignas(16) I4 { int x, y, z, w; };   // per-bus topology: parent, child 
 // Where everything is inside the feeder image (ints / doubles counted from the image base)
 // plus the sizes; passed as a kernel parameter (constant bank).
 struct Layout {
-  int n, nl, L, G, Bt, A, D, m, n_src, R, img_bytes, n_noise;
-  int o_topo, o_child_idx, o_level_ptr, o_order, o_rank, o_line_of, o_branch_of_line, o_inj_ptr, o_inj_idx,
+  int n, nl, L, G, Bt, A, D, m, n_src, R, img_bytes, n_noise, n_pool;
+  int o_topo, o_child_idx, o_pool_slot, o_level_ptr, o_order, o_rank, o_line_of, o_branch_of_line, o_inj_ptr, o_inj_idx,
       o_gen_type;
   int o_gb, o_gbd, o_rx, o_rating, o_vm_set, o_load_base, o_gen_cap, o_gen_p0, o_gen_p1, o_gen_p2,
       o_bat_cap, o_bat_rating, o_bat_eff, o_profile;
@@ -77,21 +78,11 @@ struct SolveStat {
 
 // ----------------------------------------------------------------------------- group ops
 
-template <int LANES, int NF>
-struct Grp {
+template <int LANES>
+struct Lanes {
   int lane;        // lane inside the group
   unsigned mask;   // the group's lanes inside its warp
-  double* rec;     // this instance slot's records (shared memory): bus k at rec + k * NF
-  int n;           // buses
-
-  GFR_HD double& at(int field, int k) const { return rec[k * NF + field]; }
-  GFR_HD D2& at2(int field, int k) const { return *reinterpret_cast<D2*>(rec + k * NF + field); }
-  GFR_HD double& scr(int j) const {     // source j -> field F_SCRATCH + j / n of bus j % n
-    int f = F_SCRATCH;
-    while (j >= n) { j -= n; ++f; }
-    return rec[j * NF + f];
-  }
-  // first index >= k0 owned by this lane
+  // first index >= k0 owned by this lane (lane k % LANES owns bus k in every phase)
   GFR_HD int first(int k0) const { return k0 + ((lane - k0) & (LANES - 1)); }
 
   GFR_HD void sync() const {
@@ -145,6 +136,63 @@ struct Grp {
     return v;
   }
 };
+
+// sweep working set: one record of NF_SWEEP doubles per bus
+template <int LANES>
+struct SGrp : Lanes<LANES> {
+  double* rec;
+  int n;
+  GFR_HD double& at(int field, int k) const { return rec[k * NF_SWEEP + field]; }
+  GFR_HD D2& at2(int field, int k) const { return *reinterpret_cast<D2*>(rec + k * NF_SWEEP + field); }
+  GFR_HD D2& ef(int k) const { return at2(F_E, k); }
+  GFR_HD double& pspec(int k) const { return at(S_P, k); }
+  GFR_HD double& scr(int j) const {     // source j -> field F_SCRATCH + j / n of bus j % n
+    int f = F_SCRATCH;
+    while (j >= n) { j -= n; ++f; }
+    return rec[j * NF_SWEEP + f];
+  }
+};
+
+// Newton working set (see the layout note above)
+template <int LANES>
+struct NGrp : Lanes<LANES> {
+  D2* efp;        // [n]      shared
+  D2* vxp;        // [n]      shared, followed directly by the pool
+  D2* poolp;      // [3 * n_pool] shared
+  double* pp;     // [n]      shared
+  D2* mg;         // [2 * n]  GLOBAL scratch of this instance slot: D^-1 U per bus
+  GFR_HD D2& ef(int k) const { return efp[k]; }
+  GFR_HD D2& vx(int k) const { return vxp[k]; }
+  GFR_HD double& pspec(int k) const { return pp[k]; }
+  GFR_HD double& scr(int j) const { return reinterpret_cast<double*>(vxp)[j]; }   // vx + pool, flat
+};
+
+template <int LANES, int SOLVER> struct GroupOf { typedef NGrp<LANES> type; };
+template <int LANES> struct GroupOf<LANES, SOLVER_SWEEP> { typedef SGrp<LANES> type; };
+
+// bytes of shared memory one instance slot needs (0 if the sources do not fit the scratch)
+GFR_HD size_t newton_slot_bytes(int n, int n_pool, int n_src) {
+  if (n_src > 2 * n + 6 * n_pool) return 0;
+  return (size_t)n * 32 + (size_t)n_pool * 48 + (((size_t)n * 8 + 15) / 16) * 16;
+}
+GFR_HD size_t sweep_slot_bytes(int n, int n_src) {
+  if (n_src > SCRATCH_FIELDS_SWEEP * n) return 0;
+  return (size_t)n * NF_SWEEP * 8;
+}
+template <int LANES>
+GFR_HD void bind_slot(NGrp<LANES>& g, unsigned char* slot, int n, int n_pool, D2* mg) {
+  g.efp = reinterpret_cast<D2*>(slot);
+  g.vxp = g.efp + n;
+  g.poolp = g.vxp + n;
+  g.pp = reinterpret_cast<double*>(g.poolp + 3 * (size_t)n_pool);
+  g.mg = mg;
+}
+template <int LANES>
+GFR_HD void bind_slot(SGrp<LANES>& g, unsigned char* slot, int n, int, D2*) {
+  g.rec = reinterpret_cast<double*>(slot);
+  g.n = n;
+}
+
 
 // 1 / x for a normal, finite x: hardware seed + two Newton steps (~1 ulp), no slow-path call.
 GFR_HD double rcp_fast(double x) {
@@ -247,16 +295,21 @@ GFR_HD double noise_slot(uint64_t seed, uint64_t draw, int s) {
 // ----------------------------------------------------------------------------- solvers
 
 // Flat start (power_flow.py:103, :131): 1.0 at 0 rad, slack / PV buses at their set magnitude.
-template <int LANES, int NF>
-GFR_HD void flat_start(const Grp<LANES, NF>& g, const Layout& lay, const int* simg, const double* dimg) {
+template <class G, int LANES>
+GFR_HD void flat_start_t(const G& g, const Lanes<LANES>&, const Layout& lay, const int* simg,
+                         const double* dimg) {
   const I4* topo = reinterpret_cast<const I4*>(simg + lay.o_topo);
   for (int k = g.lane; k < lay.n; k += LANES) {
     D2 v;
     v.x = (topo[k].w & FL_FIXED_VM) ? dimg[lay.o_vm_set + k] : 1.0;
     v.y = 0.0;
-    g.at2(F_E, k) = v;
+    g.ef(k) = v;
   }
   g.sync();
+}
+template <class G>
+GFR_HD void flat_start(const G& g, const Layout& lay, const int* simg, const double* dimg) {
+  flat_start_t(g, g, lay, simg, dimg);
 }
 
 // Polar Newton-Raphson on a radial feeder.  Same iterates as the reference's dense solve:
@@ -268,14 +321,18 @@ GFR_HD void flat_start(const Grp<LANES, NF>& g, const Layout& lay, const int* si
 //   diagonal block  J[i,i]   = [[ -Q_i - B_ii |Vi|^2, P_i + G_ii |Vi|^2 ], [ P_i - G_ii |Vi|^2, Q_i - B_ii |Vi|^2 ]]
 // with G_ij + jB_ij = -(g + jb) of the branch and everything written on e + jf = |V| e^{j theta}:
 //   |Vi||Vj| cos th_ij = ei ej + fi fj,  |Vi||Vj| sin th_ij = fi ej - ei fj   (no trigonometry).
+// Elimination of bus k (all its children done): D_k = J[k,k] - sum_c C_c, r_k = mismatch_k - sum_c cc_c,
+//   M_k = D_k^-1 J[k,p], v_k = D_k^-1 r_k, and its contribution to the parent p:
+//   C_k = J[p,k] M_k, cc_k = J[p,k] v_k.   Back-substitution: x_k = v_k - M_k x_p.
 template <int LANES>
-GFR_HD void newton_solve(const Grp<LANES, NF_NEWTON>& g, const Layout& lay, const int* simg,
+GFR_HD void newton_solve(const NGrp<LANES>& g, const Layout& lay, const int* simg,
                          const double* dimg, double tol, int max_it, double accel,
                          SolveStat* out) {
   const int n = lay.n, nl = lay.nl;
   const I4* topo = reinterpret_cast<const I4*>(simg + lay.o_topo);
   const int* level_ptr = simg + lay.o_level_ptr;
   const int* child_idx = simg + lay.o_child_idx;
+  const int* pool_slot = simg + lay.o_pool_slot;
   const D2* gb = reinterpret_cast<const D2*>(dimg + lay.o_gb);      // branch series g, b (0 for the root)
   const D2* gbd = reinterpret_cast<const D2*>(dimg + lay.o_gbd);    // Re, Im of Y_kk
 
@@ -284,16 +341,16 @@ GFR_HD void newton_solve(const Grp<LANES, NF_NEWTON>& g, const Layout& lay, cons
   out->max_mismatch = INFINITY;
 
   for (int it = 0; it < max_it; ++it) {
-    // ---- mismatch + diagonal blocks, every bus independently (power_flow.py:150-166, 213-295)
+    // ---- calculated injections + mismatch, every bus independently (power_flow.py:150-166)
     double mm = 0.0;
     for (int k = g.lane; k < n; k += LANES) {
       const I4 t = topo[k];
-      const D2 vk = g.at2(F_E, k);
+      const D2 vk = g.ef(k);
       const D2 yd = gbd[k];
       const double v2 = fma(vk.x, vk.x, vk.y * vk.y);
       double P = yd.x * v2, Q = -yd.y * v2;
       {
-        const D2 vp = g.at2(F_E, t.x);
+        const D2 vp = g.ef(t.x);
         const D2 y = gb[k];
         const double a = fma(vk.x, vp.x, vk.y * vp.y), s = fma(vk.y, vp.x, -vk.x * vp.y);
         P = fma(-y.x, a, fma(-y.y, s, P));
@@ -301,27 +358,19 @@ GFR_HD void newton_solve(const Grp<LANES, NF_NEWTON>& g, const Layout& lay, cons
       }
       for (int q = t.y; q < t.z; ++q) {
         const int c = child_idx[q];
-        const D2 vc = g.at2(F_E, c);
+        const D2 vc = g.ef(c);
         const D2 y = gb[c];
         const double a = fma(vk.x, vc.x, vk.y * vc.y), s = fma(vk.y, vc.x, -vk.x * vc.y);
         P = fma(-y.x, a, fma(-y.y, s, P));
         Q = fma(-y.x, s, fma(y.y, a, Q));
       }
       const int pq = t.w & FL_PQ, th = t.w & FL_THETA;
-      const double dP = th ? (g.at(N_P, k) - P) : 0.0;      // the slack bus has no equations
-      const double dQ = pq ? (0.0 - Q) : 0.0;
-      const double aP = fabs(dP), aQ = fabs(dQ);
+      const double aP = th ? fabs(g.pspec(k) - P) : 0.0;      // the slack bus has no equations
+      const double aQ = pq ? fabs(Q) : 0.0;
       const double loc = (aQ > aP || aQ != aQ) ? aQ : aP;
       mm = (loc > mm || loc != loc) ? loc : mm;
-      D2 r0, r1, rr;
-      r0.x = th ? (-Q - yd.y * v2) : 1.0;
-      r0.y = th ? (P + yd.x * v2) : 0.0;
-      r1.x = pq ? (P - yd.x * v2) : 0.0;
-      r1.y = pq ? (Q - yd.y * v2) : 1.0;
-      rr.x = dP; rr.y = dQ;
-      g.at2(N_M0, k) = r0;
-      g.at2(N_M2, k) = r1;
-      g.at2(N_V0, k) = rr;
+      D2 pc; pc.x = P; pc.y = Q;
+      g.vx(k) = pc;
     }
     mm = g.gmax_nan(mm);
     out->max_mismatch = mm;
@@ -330,52 +379,57 @@ GFR_HD void newton_solve(const Grp<LANES, NF_NEWTON>& g, const Layout& lay, cons
       out->iterations = it + 1;
       break;
     }
-    // ---- eliminate leaf -> root
+    // ---- assemble + eliminate leaf -> root (power_flow.py:213-295 with D2, then the solve of :187)
     int singular = 0;
     for (int l = nl - 1; l >= 0; --l) {
       const int k1 = level_ptr[l + 1];
       for (int k = g.first(level_ptr[l]); k < k1; k += LANES) {
         const I4 t = topo[k];
-        const D2 vk = g.at2(F_E, k);
-        D2 d0 = g.at2(N_M0, k), d1 = g.at2(N_M2, k), r = g.at2(N_V0, k);
+        const D2 vk = g.ef(k), vp = g.ef(t.x);
+        const D2 y = gb[k], yd = gbd[k];
+        const D2 pc = g.vx(k);
         const int pq = t.w & FL_PQ, th = t.w & FL_THETA;
+        const double v2 = fma(vk.x, vk.x, vk.y * vk.y);
+        D2 d0, d1, r;
+        d0.x = th ? fma(-yd.y, v2, -pc.y) : 1.0;          // -Q - B v2
+        d0.y = th ? fma(yd.x, v2, pc.x) : 0.0;            //  P + G v2
+        d1.x = pq ? fma(-yd.x, v2, pc.x) : 0.0;           //  P - G v2
+        d1.y = pq ? fma(-yd.y, v2, pc.y) : 1.0;           //  Q - B v2
+        r.x = th ? (g.pspec(k) - pc.x) : 0.0;
+        r.y = pq ? (0.0 - pc.y) : 0.0;
         for (int q = t.y; q < t.z; ++q) {
-          const int c = child_idx[q];
-          const D2 vc = g.at2(F_E, c);
-          const D2 y = gb[c];
-          const double a = fma(vk.x, vc.x, vk.y * vc.y), s = fma(vk.y, vc.x, -vk.x * vc.y);
-          const double ga = fma(-y.x, a, -y.y * s), al = fma(-y.x, s, y.y * a);   // J[k,c]
-          const D2 m0 = g.at2(N_M0, c), m1 = g.at2(N_M2, c), v = g.at2(N_V0, c);
-          if (th) {
-            d0.x = fma(-al, m0.x, fma(-ga, m1.x, d0.x));
-            d0.y = fma(-al, m0.y, fma(-ga, m1.y, d0.y));
-            r.x = fma(-al, v.x, fma(-ga, v.y, r.x));
-          }
-          if (pq) {
-            d1.x = fma(ga, m0.x, fma(-al, m1.x, d1.x));
-            d1.y = fma(ga, m0.y, fma(-al, m1.y, d1.y));
-            r.y = fma(ga, v.x, fma(-al, v.y, r.y));
-          }
+          const D2* e = g.poolp + 3 * pool_slot[child_idx[q]];
+          const D2 c0 = e[0], c1 = e[1], cc = e[2];
+          if (th) { d0.x -= c0.x; d0.y -= c0.y; r.x -= cc.x; }
+          if (pq) { d1.x -= c1.x; d1.y -= c1.y; r.y -= cc.y; }
         }
-        const D2 vp = g.at2(F_E, t.x);
-        const D2 y = gb[k];
         const double a = fma(vk.x, vp.x, vk.y * vp.y), s = fma(vk.y, vp.x, -vk.x * vp.y);
         const double ga = fma(-y.x, a, -y.y * s), al = fma(-y.x, s, y.y * a);     // J[k,p]
+        const double gl = fma(-y.x, a, y.y * s), ll = fma(y.x, s, y.y * a);      // J[p,k] (th_pk = -th_kp)
         const double u00 = th ? al : 0.0, u01 = th ? ga : 0.0, u10 = pq ? -ga : 0.0, u11 = pq ? al : 0.0;
         const double det = fma(d0.x, d1.y, -d0.y * d1.x);
         if (det == 0.0) singular = 1;                 // dgesv's exact-zero pivot (:188-190)
         const double inv = rcp_fast(det);
         const double i00 = d1.y * inv, i01 = -d0.y * inv, i10 = -d1.x * inv, i11 = d0.x * inv;
-        D2 o0, o1, ov;
-        o0.x = fma(i00, u00, i01 * u10);
-        o0.y = fma(i00, u01, i01 * u11);
-        o1.x = fma(i10, u00, i11 * u10);
-        o1.y = fma(i10, u01, i11 * u11);
-        ov.x = fma(i00, r.x, i01 * r.y);
-        ov.y = fma(i10, r.x, i11 * r.y);
-        g.at2(N_M0, k) = o0;
-        g.at2(N_M2, k) = o1;
-        g.at2(N_V0, k) = ov;
+        D2 m0, m1, v;
+        m0.x = fma(i00, u00, i01 * u10);
+        m0.y = fma(i00, u01, i01 * u11);
+        m1.x = fma(i10, u00, i11 * u10);
+        m1.y = fma(i10, u01, i11 * u11);
+        v.x = fma(i00, r.x, i01 * r.y);
+        v.y = fma(i10, r.x, i11 * r.y);
+        g.mg[2 * k] = m0;                              // D^-1 U: needed again in the back-substitution only
+        g.mg[2 * k + 1] = m1;
+        g.vx(k) = v;
+        D2 c0, c1, cc;                                 // contribution to the parent: L M, L v
+        c0.x = fma(ll, m0.x, gl * m1.x);
+        c0.y = fma(ll, m0.y, gl * m1.y);
+        c1.x = fma(-gl, m0.x, ll * m1.x);
+        c1.y = fma(-gl, m0.y, ll * m1.y);
+        cc.x = fma(ll, v.x, gl * v.y);
+        cc.y = fma(-gl, v.x, ll * v.y);
+        D2* e = g.poolp + 3 * pool_slot[k];
+        e[0] = c0; e[1] = c1; e[2] = cc;
       }
       g.sync();
     }
@@ -387,27 +441,27 @@ GFR_HD void newton_solve(const Grp<LANES, NF_NEWTON>& g, const Layout& lay, cons
     for (int l = 0; l < nl; ++l) {
       const int k1 = level_ptr[l + 1];
       for (int k = g.first(level_ptr[l]); k < k1; k += LANES) {
-        const D2 x = g.at2(N_V0, topo[k].x);
-        const D2 m0 = g.at2(N_M0, k), m1 = g.at2(N_M2, k);
-        D2 v = g.at2(N_V0, k);
+        const D2 m0 = g.mg[2 * k], m1 = g.mg[2 * k + 1];
+        const D2 x = g.vx(topo[k].x);
+        D2 v = g.vx(k);
         v.x = fma(-m0.x, x.x, fma(-m0.y, x.y, v.x));
         v.y = fma(-m1.x, x.x, fma(-m1.y, x.y, v.y));
-        g.at2(N_V0, k) = v;
+        g.vx(k) = v;
       }
       g.sync();
     }
     // ---- polar update, every bus independently (:297-327):
     //      theta += a dtheta, |V| += a d|V|  <=>  V *= (1 + a x1) e^{j a x0}
     for (int k = g.lane; k < n; k += LANES) {
-      const D2 x = g.at2(N_V0, k);
+      const D2 x = g.vx(k);
       double sn, cs;
       sincos_small(accel * x.x, &sn, &cs);
-      const double sc = 1.0 + accel * x.y;
-      const D2 v = g.at2(F_E, k);
+      const double sc = fma(accel, x.y, 1.0);
+      const D2 v = g.ef(k);
       D2 w;
-      w.x = sc * (v.x * cs - v.y * sn);
-      w.y = sc * (v.x * sn + v.y * cs);
-      g.at2(F_E, k) = w;
+      w.x = sc * fma(v.x, cs, -v.y * sn);
+      w.y = sc * fma(v.x, sn, v.y * cs);
+      g.ef(k) = w;
     }
     g.sync();
   }
@@ -417,7 +471,7 @@ GFR_HD void newton_solve(const Grp<LANES, NF_NEWTON>& g, const Layout& lay, cons
 // compared with the reference's Newton-Raphson at tight tolerance).  Constant-power
 // injections P + j0; convergence on max(|de|, |df|) over buses.
 template <int LANES>
-GFR_HD void sweep_solve(const Grp<LANES, NF_SWEEP>& g, const Layout& lay, const int* simg,
+GFR_HD void sweep_solve(const SGrp<LANES>& g, const Layout& lay, const int* simg,
                         const double* dimg, double tol, int max_it, SolveStat* out) {
   const int nl = lay.nl;
   const I4* topo = reinterpret_cast<const I4*>(simg + lay.o_topo);
@@ -475,11 +529,11 @@ GFR_HD void sweep_solve(const Grp<LANES, NF_SWEEP>& g, const Layout& lay, const 
 }
 
 // From -> to flow of the branch above bus k (power_flow.py:329-358): P (pu), |S| (pu), series loss (pu)
-template <int LANES, int NF>
-GFR_HD void branch_flow(const Grp<LANES, NF>& g, const Layout& lay, const int* simg, const double* dimg,
+template <class G>
+GFR_HD void branch_flow(const G& g, const Layout& lay, const int* simg, const double* dimg,
                         int k, double* p_ft, double* s_abs, double* loss) {
   const I4 t = reinterpret_cast<const I4*>(simg + lay.o_topo)[k];
-  const D2 vk = g.at2(F_E, k), vp = g.at2(F_E, t.x);
+  const D2 vk = g.ef(k), vp = g.ef(t.x);
   const D2 y = reinterpret_cast<const D2*>(dimg + lay.o_gb)[k];
   const double de = vp.x - vk.x, df = vp.y - vk.y;                 // V_parent - V_k
   const double ir = y.x * de - y.y * df, ii = y.x * df + y.y * de;   // current parent -> k
@@ -502,39 +556,31 @@ struct SolOut {
 };
 
 template <int LANES>
-GFR_HD void run_solver_impl(const Grp<LANES, NF_NEWTON>& g, const Layout& lay, const int* simg,
-                            const double* dimg, const EnvCfg& cfg, SolveStat* st) {
+GFR_HD void run_solver(const NGrp<LANES>& g, const Layout& lay, const int* simg, const double* dimg,
+                       const EnvCfg& cfg, SolveStat* st) {
   newton_solve(g, lay, simg, dimg, cfg.tol, cfg.max_it, cfg.accel, st);
 }
 template <int LANES>
-GFR_HD void run_solver_impl(const Grp<LANES, NF_SWEEP>& g, const Layout& lay, const int* simg,
-                            const double* dimg, const EnvCfg& cfg, SolveStat* st) {
+GFR_HD void run_solver(const SGrp<LANES>& g, const Layout& lay, const int* simg, const double* dimg,
+                       const EnvCfg& cfg, SolveStat* st) {
   sweep_solve(g, lay, simg, dimg, cfg.tol, cfg.max_it, st);
 }
-template <int LANES, int SOLVER, int NF>
-GFR_HD void run_solver(const Grp<LANES, NF>& g, const Layout& lay, const int* simg, const double* dimg,
-                       const EnvCfg& cfg, SolveStat* st) {
-  run_solver_impl(g, lay, simg, dimg, cfg, st);
-}
-
-template <int SOLVER> struct RecOf { enum { NF = SOLVER == SOLVER_NEWTON ? NF_NEWTON : NF_SWEEP,
-                                              F_PSPEC = SOLVER == SOLVER_NEWTON ? N_P : S_P }; };
 
 template <int LANES, int SOLVER>
-GFR_HD void solve_instance(const Grp<LANES, RecOf<SOLVER>::NF>& g, const Layout& lay, const int* simg,
-                           const double* dimg, const EnvCfg& cfg, long long env,
+GFR_HD void solve_instance(const typename GroupOf<LANES, SOLVER>::type& g, const Layout& lay,
+                           const int* simg, const double* dimg, const EnvCfg& cfg, long long env,
                            const double* p_inj, const SolOut& o) {
-  constexpr int F_P = RecOf<SOLVER>::F_PSPEC;
   const int n = lay.n, m = lay.m;
   const int* rank = simg + lay.o_rank;
   const double* pin = p_inj + env * n;
-  for (int i = g.lane; i < n; i += LANES) g.at(F_P, rank[i]) = pin[i];
+  for (int i = g.lane; i < n; i += LANES) g.pspec(rank[i]) = pin[i];
   flat_start(g, lay, simg, dimg);
   SolveStat st;
-  run_solver<LANES, SOLVER>(g, lay, simg, dimg, cfg, &st);
+  run_solver(g, lay, simg, dimg, cfg, &st);
   for (int i = g.lane; i < n; i += LANES) {
     int k = rank[i];
-    double e = g.at(F_E, k), f = g.at(F_F, k);
+    const D2 vv = g.ef(k);
+    double e = vv.x, f = vv.y;
     if (o.bus_voltages) o.bus_voltages[env * n + i] = sqrt(e * e + f * f);
     if (o.bus_angles) o.bus_angles[env * n + i] = atan2(f, e);
   }
@@ -610,11 +656,10 @@ GFR_HD void update_weather(double hour, double u, double z1, double z2, double z
 }
 
 template <int LANES, int SOLVER>
-GFR_HD void step_instance(const Grp<LANES, RecOf<SOLVER>::NF>& g, const Layout& lay, const int* simg,
-                          const double* dimg, const EnvCfg& cfg, long long env,
+GFR_HD void step_instance(const typename GroupOf<LANES, SOLVER>::type& g, const Layout& lay,
+                          const int* simg, const double* dimg, const EnvCfg& cfg, long long env,
                           double* state, double* obs, const double* actions, const double* noise,
                           const StepOut& o) {
-  constexpr int F_P = RecOf<SOLVER>::F_PSPEC;
   const int n = lay.n, m = lay.m, L = lay.L, G = lay.G, Bt = lay.Bt, A = lay.A, D = lay.D;
   double* rec = state + env * lay.R;
   double* ob = obs + env * D;
@@ -788,13 +833,13 @@ GFR_HD void step_instance(const Grp<LANES, RecOf<SOLVER>::NF>& g, const Layout& 
         else if (v < 0.0) ld += fabs(v);
       }
       // write after every lane has read its sources: F_P is not part of the scratch region
-      g.at(F_P, k) = (0.0 - ld / lay.s_base) + gn / lay.s_base;
+      g.pspec(k) = (0.0 - ld / lay.s_base) + gn / lay.s_base;
     }
   }
   g.sync();
   flat_start(g, lay, simg, dimg);
   SolveStat st;
-  run_solver<LANES, SOLVER>(g, lay, simg, dimg, cfg, &st);
+  run_solver(g, lay, simg, dimg, cfg, &st);
 
   // ---- bus state -> observation (grid_env.py:722-731, 753-765), reductions for reward / constraints
   double dev = 0.0, vmax = -INFINITY, vmin = INFINITY;
@@ -803,7 +848,8 @@ GFR_HD void step_instance(const Grp<LANES, RecOf<SOLVER>::NF>& g, const Layout& 
     const int* rank = simg + lay.o_rank;
     for (int i = g.lane; i < n; i += LANES) {
       int k = rank[i];
-      double e = g.at(F_E, k), f = g.at(F_F, k);
+      const D2 vv = g.ef(k);
+      double e = vv.x, f = vv.y;
       double vm = sqrt(e * e + f * f);
       ob[2 * i] = vm;
       ob[2 * i + 1] = atan2(f, e);
@@ -906,7 +952,7 @@ GFR_HD void step_instance(const Grp<LANES, RecOf<SOLVER>::NF>& g, const Layout& 
 // GridEnvironment.reset (grid_env.py:360-408): counters to zero, buses at 1.0 / 0, lines idle,
 // 60 Hz, batteries at their initial state of charge, one weather update at t = 0, full observation.
 template <int LANES>
-GFR_HD void reset_instance(const Grp<LANES, 1>& g, const Layout& lay, const int* simg,
+GFR_HD void reset_instance(const Lanes<LANES>& g, const Layout& lay, const int* simg,
                            const double* dimg, const EnvCfg& cfg, long long env, double* state,
                            double* obs, const double* load_pq, const double* bat_soc0,
                            const uint64_t* seeds, const double* noise, double start_time,

@@ -134,6 +134,28 @@ inline std::string build_feeder_image(const gfr_feeder_desc* d, FeederImage* out
   }
   lay.o_topo = ib.add_i(topo.data(), 4 * n);
   lay.o_child_idx = ib.add_i(d->child_idx, n - 1);
+  // pool plan: given by the caller (checked by replaying the schedule) or one slot per bus
+  std::vector<int32_t> pool_slot(n);
+  if (d->pool_slot) {
+    if (d->n_pool < 1 || d->n_pool > n) return "n_pool must be in [1, n]";
+    std::vector<int> owner(d->n_pool, -1);        // which bus's contribution a slot holds
+    for (int l = nl - 1; l >= 0; --l) {
+      for (int k = d->level_ptr[l]; k < d->level_ptr[l + 1]; ++k) {
+        const int sl = d->pool_slot[k];
+        if (sl < 0 || sl >= d->n_pool) return "pool_slot out of range";
+        if (owner[sl] >= 0) return "pool_slot reuses a slot that is still live";
+        owner[sl] = k;
+        pool_slot[k] = sl;
+      }
+      for (int k = d->level_ptr[l]; k < d->level_ptr[l + 1]; ++k)
+        for (int q = d->child_ptr[k]; q < d->child_ptr[k + 1]; ++q) owner[d->pool_slot[d->child_idx[q]]] = -1;
+    }
+    lay.n_pool = d->n_pool;
+  } else {
+    for (int k = 0; k < n; ++k) pool_slot[k] = k;
+    lay.n_pool = n;
+  }
+  lay.o_pool_slot = ib.add_i(pool_slot.data(), n);
   lay.o_level_ptr = ib.add_i(d->level_ptr, nl + 1);
   lay.o_order = ib.add_i(d->order, n);
   lay.o_rank = ib.add_i(rank.data(), n);

@@ -165,6 +165,8 @@ class FeederSoA:
     level_ptr: np.ndarray              # int32[n_levels+1]  level l = [ptr[l], ptr[l+1])
     child_ptr: np.ndarray              # int32[n+1] children of k = child_idx[child_ptr[k] : child_ptr[k+1]]
     child_idx: np.ndarray              # int32[n-1] level indices of the children, parent by parent
+    pool_slot: np.ndarray              # int32[n]  where bus k parks its Schur contribution until its parent is eliminated
+    n_pool: int                        # slots needed (max contributions alive at once)
     bus_type: np.ndarray               # int32[n]  BUS_*
     vm_set: np.ndarray                 # f64[n]   slack / pv magnitude (bus.voltage_magnitude)
     g: np.ndarray                      # f64[n]   series conductance of the branch parent[k]-k (k>=1)
@@ -277,6 +279,31 @@ def _schedule(n: int, root: int, adj, width: Optional[int]):
     return order, parent_ref, level_of
 
 
+def plan_pool(parent: np.ndarray, level_ptr: np.ndarray):
+    """Slot of every bus's contribution to its parent.  A contribution is written when its bus is
+    eliminated (levels run last -> first) and read when the parent is; the slot is free again once
+    the parent's level is done.  Slots released by a level are only handed out to later levels, so
+    a level never writes a slot another lane of the same level still reads."""
+    n = parent.size
+    slot = np.zeros(n, dtype=np.int32)
+    free: List[int] = []
+    n_pool = 0
+    kids: List[List[int]] = [[] for _ in range(n)]
+    for k in range(1, n):
+        kids[parent[k]].append(k)
+    for l in range(level_ptr.size - 2, -1, -1):
+        members = range(int(level_ptr[l]), int(level_ptr[l + 1]))
+        for k in members:
+            if free:
+                slot[k] = free.pop()
+            else:
+                slot[k] = n_pool
+                n_pool += 1
+        for k in members:                      # their children's contributions have been consumed
+            free.extend(int(slot[c]) for c in kids[k])
+    return slot, max(n_pool, 1)
+
+
 def tree_center(n: int, adj, fallback: int) -> int:
     """A bus of minimum eccentricity (the middle of a longest path): rooting the elimination
     there halves the number of sequential levels of a feeder whose slack bus sits at one end."""
@@ -383,6 +410,7 @@ def compile_feeder(feeder, renewable_sources: Optional[Sequence[str]] = None,
         fill[parent[k]] += 1
     for k in range(1, n):
         assert parent[k] < k and levels[parent[k]] < levels[k]
+    pool_slot, n_pool = plan_pool(parent, level_ptr)
 
     tmap = {"slack": BUS_SLACK, "pv": BUS_PV}
     bus_type = np.array([tmap.get(buses[i].bus_type, BUS_PQ) for i in order], dtype=np.int32)
@@ -393,7 +421,7 @@ def compile_feeder(feeder, renewable_sources: Optional[Sequence[str]] = None,
         s_base=float(feeder.parameters.base_power) * 1e6,
         bus_ids=[b_.id for b_ in buses], line_ids=[l_.id for l_ in lines],
         order=np.array(order, dtype=np.int32), rank=rank, parent=parent, level_ptr=level_ptr,
-        child_ptr=child_ptr, child_idx=child_idx, bus_type=bus_type, vm_set=vm_set, g=g, b=b,
+        child_ptr=child_ptr, child_idx=child_idx, pool_slot=pool_slot, n_pool=n_pool, bus_type=bus_type, vm_set=vm_set, g=g, b=b,
         gdiag=ydiag.real[order].copy(), bdiag=ydiag.imag[order].copy(), r=r, x=x,
         line_of=line_of, from_is_parent=from_is_parent, rating=rating)
 

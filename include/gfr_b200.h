@@ -50,13 +50,15 @@ typedef struct gfr_env gfr_env;         /* B environment instances on one device
  * Produced by grid_fed_rl_b200.topology.compile_feeder from feeder.buses / .lines / .loads /
  * .generators (reference feeders/base.py:30-52; Bus/Line/Load environments/base.py:197-295). */
 typedef struct {
-  int32_t n_bus, n_levels, n_load, n_gen, n_bat;
+  int32_t n_bus, n_levels, n_load, n_gen, n_bat, n_pool;
   double s_base;                    /* VA; feeder.parameters.base_power * 1e6 */
   const int32_t* order;             /* [n]  level k -> ref bus index */
   const int32_t* parent;            /* [n]  level index of the parent, -1 for k = 0 */
   const int32_t* level_ptr;         /* [n_levels+1] */
   const int32_t* child_ptr;         /* [n+1] children of k are child_idx[child_ptr[k] .. child_ptr[k+1]) */
   const int32_t* child_idx;         /* [n-1] level indices of the children, parent by parent */
+  const int32_t* pool_slot;         /* [n]  Newton: slot (< n_pool) where bus k parks its Schur contribution from
+                                            its own elimination until its parent's; NULL = one slot per bus */
   const int32_t* bus_type;          /* [n]  GFR_BUS_* */
   const double* vm_set;             /* [n]  slack / pv voltage magnitude */
   const double* g;                  /* [n]  series conductance of branch (parent[k], k), k >= 1 */

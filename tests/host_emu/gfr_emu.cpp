@@ -16,22 +16,22 @@ struct emu_env {
   FeederImage fi;
   EnvCfg cfg{};
   int solver = SOLVER_NEWTON;
-  int nf = NF_NEWTON;
   long long B = 0;
-  std::vector<double> state, obs, work, bat_soc0;
+  std::vector<double> state, obs, bat_soc0;
 };
 
-template <int NF>
-static Grp<1, NF> make_grp(const Layout& lay, double* work) {
-  Grp<1, NF> g;
-  g.lane = 0; g.mask = 1u; g.rec = work; g.n = lay.n;
-  return g;
-}
-
-static int fields(const Layout& lay, int solver) {
-  (void)lay;
-  return solver == SOLVER_NEWTON ? NF_NEWTON : NF_SWEEP;
-}
+struct EmuSlot {
+  std::vector<double> work;    // shared-memory slot
+  std::vector<D2> mg;          // the global scratch of the slot
+  explicit EmuSlot(const Layout& lay) : work(8 + (newton_slot_bytes(lay.n, lay.n_pool, 0) + sweep_slot_bytes(lay.n, 0)) / 8, 0.0),
+                                        mg(2 * (size_t)lay.n) {}
+  template <class G> G group(const Layout& lay) {
+    G g;
+    g.lane = 0; g.mask = 1u;
+    bind_slot(g, reinterpret_cast<unsigned char*>(work.data()), lay.n, lay.n_pool, mg.data());
+    return g;
+  }
+};
 
 extern "C" {
 
@@ -44,7 +44,6 @@ emu_env* emu_create(const gfr_feeder_desc* d, long long B, const gfr_env_cfg* c)
   const Layout& lay = e->fi.lay;
   e->B = B;
   e->solver = c->solver.solver == GFR_SOLVER_NEWTON ? SOLVER_NEWTON : SOLVER_SWEEP;
-  e->nf = fields(lay, e->solver);
   EnvCfg& k = e->cfg;
   k.dt = c->timestep; k.v_min = c->v_min; k.v_max = c->v_max; k.f_min = c->f_min; k.f_max = c->f_max;
   k.penalty = c->safety_penalty; k.load_noise = c->load_noise; k.tol = c->solver.tolerance;
@@ -53,9 +52,8 @@ emu_env* emu_create(const gfr_feeder_desc* d, long long B, const gfr_env_cfg* c)
   k.weather_variation = c->weather_variation != 0; k.max_it = c->solver.max_iterations;
   e->state.assign((size_t)B * lay.R, 0.0);
   e->obs.assign((size_t)B * lay.D, 0.0);
-  e->work.assign((size_t)e->nf * lay.n + 2, 0.0);
   e->bat_soc0.assign(d->bat_soc0, d->bat_soc0 + lay.Bt);
-  Grp<1, 1> g = make_grp<1>(lay, e->work.data());
+  Lanes<1> g; g.lane = 0; g.mask = 1u;
   for (long long i = 0; i < B; ++i)
     reset_instance<1>(g, lay, (const int*)e->fi.img.data(), (const double*)e->fi.img.data(), k, i,
                       e->state.data(), e->obs.data(), e->fi.load_pq.data(), e->bat_soc0.data(),
@@ -70,7 +68,7 @@ int emu_obs_dim(emu_env* e) { return e->fi.lay.D; }
 void emu_reset(emu_env* e, const uint64_t* seeds, const uint8_t* mask, const double* noise,
                double start_time) {
   const Layout& lay = e->fi.lay;
-  Grp<1, 1> g = make_grp<1>(lay, e->work.data());
+  Lanes<1> g; g.lane = 0; g.mask = 1u;
   for (long long i = 0; i < e->B; ++i) {
     if (mask && !mask[i]) continue;
     reset_instance<1>(g, lay, (const int*)e->fi.img.data(), (const double*)e->fi.img.data(), e->cfg, i,
@@ -90,12 +88,13 @@ void emu_step(emu_env* e, const double* actions, const double* noise, const gfr_
   o.episode_reward = out->episode_reward; o.noise_used = out->noise_used;
   const int* simg = (const int*)e->fi.img.data();
   const double* dimg = (const double*)e->fi.img.data();
+  EmuSlot slot(lay);
   for (long long i = 0; i < e->B; ++i) {
     if (e->solver == SOLVER_NEWTON)
-      step_instance<1, SOLVER_NEWTON>(make_grp<NF_NEWTON>(lay, e->work.data()), lay, simg, dimg, e->cfg, i,
+      step_instance<1, SOLVER_NEWTON>(slot.group<NGrp<1>>(lay), lay, simg, dimg, e->cfg, i,
                                       e->state.data(), e->obs.data(), actions, noise, o);
     else
-      step_instance<1, SOLVER_SWEEP>(make_grp<NF_SWEEP>(lay, e->work.data()), lay, simg, dimg, e->cfg, i,
+      step_instance<1, SOLVER_SWEEP>(slot.group<SGrp<1>>(lay), lay, simg, dimg, e->cfg, i,
                                      e->state.data(), e->obs.data(), actions, noise, o);
   }
 }
@@ -107,8 +106,7 @@ int emu_solve(const gfr_feeder_desc* d, long long B, const double* p_inj, const 
   if (!err.empty()) return -1;
   const Layout& lay = fi.lay;
   const int solver = c->solver == GFR_SOLVER_NEWTON ? SOLVER_NEWTON : SOLVER_SWEEP;
-  const int nf = fields(lay, solver);
-  std::vector<double> work((size_t)nf * lay.n + 2, 0.0);
+  EmuSlot slot(lay);
   EnvCfg k{};
   k.tol = c->tolerance; k.max_it = c->max_iterations; k.accel = c->acceleration != 0.0 ? c->acceleration : 1.0;
   SolOut o{};
@@ -119,9 +117,9 @@ int emu_solve(const gfr_feeder_desc* d, long long B, const double* p_inj, const 
   const double* dimg = (const double*)fi.img.data();
   for (long long i = 0; i < B; ++i) {
     if (solver == SOLVER_NEWTON)
-      solve_instance<1, SOLVER_NEWTON>(make_grp<NF_NEWTON>(lay, work.data()), lay, simg, dimg, k, i, p_inj, o);
+      solve_instance<1, SOLVER_NEWTON>(slot.group<NGrp<1>>(lay), lay, simg, dimg, k, i, p_inj, o);
     else
-      solve_instance<1, SOLVER_SWEEP>(make_grp<NF_SWEEP>(lay, work.data()), lay, simg, dimg, k, i, p_inj, o);
+      solve_instance<1, SOLVER_SWEEP>(slot.group<SGrp<1>>(lay), lay, simg, dimg, k, i, p_inj, o);
   }
   return 0;
 }
