@@ -46,7 +46,8 @@ enum { F_E = 0, F_F = 1, F_SCRATCH = 2 };
 enum { NF_SWEEP = 6, S_JR = 2, S_JI = 3, S_P = 4 };
 enum { SCRATCH_FIELDS_SWEEP = 2 };
 // bus flag bits
-enum { FL_PQ = 1, FL_FROM_IS_PARENT = 2, FL_FIXED_VM = 4, FL_THETA = 8 };   // PQ: |V| unknown; THETA: angle unknown
+enum { FL_PQ = 1, FL_FROM_IS_PARENT = 2, FL_FIXED_VM = 4, FL_THETA = 8,     // PQ: |V| unknown; THETA: angle unknown
+       FL_POOL_SHIFT = 8 };                                               // flags >> 8 = 3 * the bus's pool slot
 // record (persistent per-instance state) slots, in doubles
 enum { R_TIME = 0, R_FREQ, R_WIND, R_TEMP, R_CLOUD, R_TOTAL_LOSSES, R_EPISODE_REWARD, R_SEED,
        R_DRAWS, R_COUNTS, R_BAT };   // soc[Bt] then bpow[Bt] from R_BAT on
@@ -58,11 +59,11 @@ struct alignas(16) I4 { int x, y, z, w; };   // per-bus topology: parent, child 
 // plus the sizes; passed as a kernel parameter (constant bank).
 struct Layout {
   int n, nl, L, G, Bt, A, D, m, n_src, R, img_bytes, n_noise, n_pool;
-  int o_topo, o_child_idx, o_pool_slot, o_level_ptr, o_order, o_rank, o_line_of, o_branch_of_line, o_inj_ptr, o_inj_idx,
+  int o_topo, o_child_idx, o_child_pool, o_level_ptr, o_order, o_rank, o_line_of, o_branch_of_line, o_inj_ptr, o_inj_idx,
       o_gen_type;
   int o_gb, o_gbd, o_rx, o_rating, o_vm_set, o_load_base, o_gen_cap, o_gen_p0, o_gen_p1, o_gen_p2,
       o_bat_cap, o_bat_rating, o_bat_eff, o_profile;
-  double s_base, load_p_sum;
+  double s_base, inv_s_base, load_p_sum;
 };
 
 struct EnvCfg {
@@ -332,7 +333,7 @@ GFR_HD void newton_solve(const NGrp<LANES>& g, const Layout& lay, const int* sim
   const I4* topo = reinterpret_cast<const I4*>(simg + lay.o_topo);
   const int* level_ptr = simg + lay.o_level_ptr;
   const int* child_idx = simg + lay.o_child_idx;
-  const int* pool_slot = simg + lay.o_pool_slot;
+  const int* child_pool = simg + lay.o_child_pool;   // 3 * pool slot of every child, same indexing as child_idx
   const D2* gb = reinterpret_cast<const D2*>(dimg + lay.o_gb);      // branch series g, b (0 for the root)
   const D2* gbd = reinterpret_cast<const D2*>(dimg + lay.o_gbd);    // Re, Im of Y_kk
 
@@ -356,6 +357,7 @@ GFR_HD void newton_solve(const NGrp<LANES>& g, const Layout& lay, const int* sim
         P = fma(-y.x, a, fma(-y.y, s, P));
         Q = fma(-y.x, s, fma(y.y, a, Q));
       }
+#pragma unroll 1
       for (int q = t.y; q < t.z; ++q) {
         const int c = child_idx[q];
         const D2 vc = g.ef(c);
@@ -364,9 +366,11 @@ GFR_HD void newton_solve(const NGrp<LANES>& g, const Layout& lay, const int* sim
         P = fma(-y.x, a, fma(-y.y, s, P));
         Q = fma(-y.x, s, fma(y.y, a, Q));
       }
-      const int pq = t.w & FL_PQ, th = t.w & FL_THETA;
-      const double aP = th ? fabs(g.pspec(k) - P) : 0.0;      // the slack bus has no equations
-      const double aQ = pq ? fabs(Q) : 0.0;
+      double aP = fabs(g.pspec(k) - P), aQ = fabs(Q);
+      if ((t.w & (FL_PQ | FL_THETA)) != (FL_PQ | FL_THETA)) {   // slack: no equations; PV: no Q equation
+        if (!(t.w & FL_THETA)) aP = 0.0;
+        if (!(t.w & FL_PQ)) aQ = 0.0;
+      }
       const double loc = (aQ > aP || aQ != aQ) ? aQ : aP;
       mm = (loc > mm || loc != loc) ? loc : mm;
       D2 pc; pc.x = P; pc.y = Q;
@@ -388,25 +392,31 @@ GFR_HD void newton_solve(const NGrp<LANES>& g, const Layout& lay, const int* sim
         const D2 vk = g.ef(k), vp = g.ef(t.x);
         const D2 y = gb[k], yd = gbd[k];
         const D2 pc = g.vx(k);
-        const int pq = t.w & FL_PQ, th = t.w & FL_THETA;
         const double v2 = fma(vk.x, vk.x, vk.y * vk.y);
-        D2 d0, d1, r;
-        d0.x = th ? fma(-yd.y, v2, -pc.y) : 1.0;          // -Q - B v2
-        d0.y = th ? fma(yd.x, v2, pc.x) : 0.0;            //  P + G v2
-        d1.x = pq ? fma(-yd.x, v2, pc.x) : 0.0;           //  P - G v2
-        d1.y = pq ? fma(-yd.y, v2, pc.y) : 1.0;           //  Q - B v2
-        r.x = th ? (g.pspec(k) - pc.x) : 0.0;
-        r.y = pq ? (0.0 - pc.y) : 0.0;
+        D2 s0, s1, sc;                                   // children's contributions: plain sums
+        s0.x = s0.y = s1.x = s1.y = sc.x = sc.y = 0.0;
+#pragma unroll 1
         for (int q = t.y; q < t.z; ++q) {
-          const D2* e = g.poolp + 3 * pool_slot[child_idx[q]];
+          const D2* e = g.poolp + child_pool[q];
           const D2 c0 = e[0], c1 = e[1], cc = e[2];
-          if (th) { d0.x -= c0.x; d0.y -= c0.y; r.x -= cc.x; }
-          if (pq) { d1.x -= c1.x; d1.y -= c1.y; r.y -= cc.y; }
+          s0.x += c0.x; s0.y += c0.y; s1.x += c1.x; s1.y += c1.y; sc.x += cc.x; sc.y += cc.y;
         }
+        D2 d0, d1, r;
+        d0.x = fma(-yd.y, v2, -pc.y) - s0.x;          // -Q - B v2
+        d0.y = fma(yd.x, v2, pc.x) - s0.y;            //  P + G v2
+        d1.x = fma(-yd.x, v2, pc.x) - s1.x;           //  P - G v2
+        d1.y = fma(-yd.y, v2, pc.y) - s1.y;           //  Q - B v2
+        r.x = g.pspec(k) - pc.x - sc.x;
+        r.y = 0.0 - pc.y - sc.y;
         const double a = fma(vk.x, vp.x, vk.y * vp.y), s = fma(vk.y, vp.x, -vk.x * vp.y);
         const double ga = fma(-y.x, a, -y.y * s), al = fma(-y.x, s, y.y * a);     // J[k,p]
         const double gl = fma(-y.x, a, y.y * s), ll = fma(y.x, s, y.y * a);      // J[p,k] (th_pk = -th_kp)
-        const double u00 = th ? al : 0.0, u01 = th ? ga : 0.0, u10 = pq ? -ga : 0.0, u11 = pq ? al : 0.0;
+        double u00 = al, u01 = ga, u10 = -ga, u11 = al;
+        if ((t.w & (FL_PQ | FL_THETA)) != (FL_PQ | FL_THETA)) {
+          // a bus without the angle (slack) or magnitude (slack, PV) unknown: identity row, no coupling
+          if (!(t.w & FL_THETA)) { d0.x = 1.0; d0.y = 0.0; r.x = 0.0; u00 = 0.0; u01 = 0.0; }
+          if (!(t.w & FL_PQ)) { d1.x = 0.0; d1.y = 1.0; r.y = 0.0; u10 = 0.0; u11 = 0.0; }
+        }
         const double det = fma(d0.x, d1.y, -d0.y * d1.x);
         if (det == 0.0) singular = 1;                 // dgesv's exact-zero pivot (:188-190)
         const double inv = rcp_fast(det);
@@ -428,7 +438,7 @@ GFR_HD void newton_solve(const NGrp<LANES>& g, const Layout& lay, const int* sim
         c1.y = fma(-gl, m0.y, ll * m1.y);
         cc.x = fma(ll, v.x, gl * v.y);
         cc.y = fma(-gl, v.x, ll * v.y);
-        D2* e = g.poolp + 3 * pool_slot[k];
+        D2* e = g.poolp + (t.w >> FL_POOL_SHIFT);
         e[0] = c0; e[1] = c1; e[2] = cc;
       }
       g.sync();
@@ -833,7 +843,7 @@ GFR_HD void step_instance(const typename GroupOf<LANES, SOLVER>::type& g, const 
         else if (v < 0.0) ld += fabs(v);
       }
       // write after every lane has read its sources: F_P is not part of the scratch region
-      g.pspec(k) = (0.0 - ld / lay.s_base) + gn / lay.s_base;
+      g.pspec(k) = fma(gn, lay.inv_s_base, -ld * lay.inv_s_base);
     }
   }
   g.sync();

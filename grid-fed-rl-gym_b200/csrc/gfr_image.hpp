@@ -93,6 +93,7 @@ inline std::string build_feeder_image(const gfr_feeder_desc* d, FeederImage* out
   lay.D = 2 * n + 2 * (n - 1) + 1 + 2 * L + G + 2 * Bt;
   lay.n_src = L + G + Bt; lay.R = R_BAT + 2 * Bt; lay.n_noise = 4 + L;
   lay.s_base = d->s_base;
+  lay.inv_s_base = 1.0 / d->s_base;
   double lp = 0.0;
   for (int l = 0; l < L; ++l) lp = lp + d->load_p[l];   // sequential, as grid_env.py:744
   lay.load_p_sum = lp;
@@ -124,16 +125,6 @@ inline std::string build_feeder_image(const gfr_feeder_desc* d, FeederImage* out
     for (int g = 0; g < G; ++g) inj_idx[fill[d->gen_bus[g]]++] = L + g;
     for (int b = 0; b < Bt; ++b) inj_idx[fill[d->bat_bus[b]]++] = L + G + b;
   }
-  // per-bus topology records first (16-byte aligned at the image base)
-  std::vector<int32_t> topo(4 * (size_t)n);
-  for (int k = 0; k < n; ++k) {
-    topo[4 * k + 0] = k > 0 ? d->parent[k] : 0;
-    topo[4 * k + 1] = d->child_ptr[k];
-    topo[4 * k + 2] = d->child_ptr[k + 1];
-    topo[4 * k + 3] = flags[k];
-  }
-  lay.o_topo = ib.add_i(topo.data(), 4 * n);
-  lay.o_child_idx = ib.add_i(d->child_idx, n - 1);
   // pool plan: given by the caller (checked by replaying the schedule) or one slot per bus
   std::vector<int32_t> pool_slot(n);
   if (d->pool_slot) {
@@ -155,7 +146,20 @@ inline std::string build_feeder_image(const gfr_feeder_desc* d, FeederImage* out
     for (int k = 0; k < n; ++k) pool_slot[k] = k;
     lay.n_pool = n;
   }
-  lay.o_pool_slot = ib.add_i(pool_slot.data(), n);
+  // per-bus topology records first (16-byte aligned at the image base)
+  std::vector<int32_t> topo(4 * (size_t)n);
+  for (int k = 0; k < n; ++k) {
+    topo[4 * k + 0] = k > 0 ? d->parent[k] : 0;
+    topo[4 * k + 1] = d->child_ptr[k];
+    topo[4 * k + 2] = d->child_ptr[k + 1];
+    topo[4 * k + 3] = flags[k];      // | 3 * pool slot << FL_POOL_SHIFT, added below
+  }
+  for (int k = 0; k < n; ++k) topo[4 * k + 3] |= (3 * pool_slot[k]) << FL_POOL_SHIFT;
+  lay.o_topo = ib.add_i(topo.data(), 4 * n);
+  lay.o_child_idx = ib.add_i(d->child_idx, n - 1);
+  std::vector<int32_t> child_pool(n > 1 ? n - 1 : 0);
+  for (int q = 0; q < n - 1; ++q) child_pool[q] = 3 * pool_slot[d->child_idx[q]];
+  lay.o_child_pool = ib.add_i(child_pool.data(), n - 1);
   lay.o_level_ptr = ib.add_i(d->level_ptr, nl + 1);
   lay.o_order = ib.add_i(d->order, n);
   lay.o_rank = ib.add_i(rank.data(), n);
