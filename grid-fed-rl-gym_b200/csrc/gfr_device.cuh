@@ -447,18 +447,39 @@ GFR_HD void newton_solve(const NGrp<LANES>& g, const Layout& lay, const int* sim
       out->iterations = it + 1;
       break;
     }
-    // ---- back-substitute root -> leaf: x_k = v_k - M_k x_parent  (the root's M is 0: it has no branch)
-    for (int l = 0; l < nl; ++l) {
-      const int k1 = level_ptr[l + 1];
-      for (int k = g.first(level_ptr[l]); k < k1; k += LANES) {
-        const D2 m0 = g.mg[2 * k], m1 = g.mg[2 * k + 1];
-        const D2 x = g.vx(topo[k].x);
-        D2 v = g.vx(k);
-        v.x = fma(-m0.x, x.x, fma(-m0.y, x.y, v.x));
-        v.y = fma(-m1.x, x.x, fma(-m1.y, x.y, v.y));
-        g.vx(k) = v;
+    // ---- back-substitute root -> leaf: x_k = v_k - M_k x_parent  (the root's M is 0: it has no branch).
+    //      M comes back from the global scratch; the next level's is requested before this level's
+    //      barrier so that the L2 round trip overlaps it.
+    {
+      int nk = g.first(level_ptr[0]);
+      bool nv = nk < level_ptr[1];
+      D2 nm0, nm1;
+      nm0.x = nm0.y = nm1.x = nm1.y = 0.0;
+      if (nv) { nm0 = g.mg[2 * nk]; nm1 = g.mg[2 * nk + 1]; }
+      for (int l = 0; l < nl; ++l) {
+        const int k1 = level_ptr[l + 1];
+        int k = nk;
+        const bool valid = nv;
+        D2 m0 = nm0, m1 = nm1;
+        if (l + 1 < nl) {
+          nk = g.first(k1);
+          nv = nk < level_ptr[l + 2];
+          if (nv) { nm0 = g.mg[2 * nk]; nm1 = g.mg[2 * nk + 1]; }
+        }
+        if (valid) {
+          for (;;) {
+            const D2 x = g.vx(topo[k].x);
+            D2 v = g.vx(k);
+            v.x = fma(-m0.x, x.x, fma(-m0.y, x.y, v.x));
+            v.y = fma(-m1.x, x.x, fma(-m1.y, x.y, v.y));
+            g.vx(k) = v;
+            k += LANES;
+            if (k >= k1) break;
+            m0 = g.mg[2 * k]; m1 = g.mg[2 * k + 1];      // levels wider than the group: no prefetch
+          }
+        }
+        g.sync();
       }
-      g.sync();
     }
     // ---- polar update, every bus independently (:297-327):
     //      theta += a dtheta, |V| += a d|V|  <=>  V *= (1 + a x1) e^{j a x0}

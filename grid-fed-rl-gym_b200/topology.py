@@ -232,7 +232,7 @@ def _series_admittance(r: float, x: float) -> complex:
     return 1.0 / z if abs(z) > OPEN_Z else 0.0
 
 
-def _schedule(n: int, root: int, adj, width: Optional[int]):
+def _schedule(n: int, root: int, adj, width: Optional[int], alap: bool = True):
     """Order the buses for leaf -> root elimination on ``width`` lanes.
 
     Returns (order, parent_ref, level_of): ``order`` lists ref bus indices level by level,
@@ -271,6 +271,33 @@ def _schedule(n: int, root: int, adj, width: Optional[int]):
         ready = rest
     steps.reverse()                      # level 0 = last eliminated = root
     assert steps[0] == [root]
+    # As-late-as-possible pass: a bus that is not on a critical path is moved next to its parent's
+    # level when there is room, so that its contribution to the parent stays parked only briefly
+    # (fewer pool slots alive at once).  Parents are settled before their children.
+    level = {}
+    for l, members in enumerate(steps):
+        for v in members:
+            level[v] = l
+    if not alap:
+        bfs_moves = []
+    else:
+        bfs_moves = bfs[1:]
+    room = [None if width is None else width - len(members) for members in steps]
+    for v in bfs_moves:                  # breadth-first from the root: parents first
+        target = level[parent_ref[v][0]] + 1
+        cur = level[v]
+        while target < cur:
+            if room[target] is None or room[target] > 0:
+                if room[target] is not None:
+                    room[target] -= 1
+                    room[cur] += 1
+                level[v] = target
+                break
+            target += 1
+    steps = [[] for _ in steps]
+    for v in bfs:
+        steps[level[v]].append(v)
+    assert all(steps) and steps[0] == [root]
     order, level_of = [], {}
     for l, members in enumerate(steps):
         for v in sorted(members, key=lambda v: (parent_ref[v][0], v)):
@@ -380,37 +407,47 @@ def compile_feeder(feeder, renewable_sources: Optional[Sequence[str]] = None,
     if width is not None and int(width) < 1:
         raise TopologyError("width must be >= 1")
     root_ref = slack if root == "slack" else tree_center(n, adj, slack)
-    order, parent_ref, level_of = _schedule(n, root_ref, adj, None if width is None else int(width))
-    rank = np.empty(n, dtype=np.int32)
-    rank[np.array(order)] = np.arange(n, dtype=np.int32)
+    def layout(alap: bool):
+        order, parent_ref, level_of = _schedule(n, root_ref, adj, None if width is None else int(width), alap)
+        rank = np.empty(n, dtype=np.int32)
+        rank[np.array(order)] = np.arange(n, dtype=np.int32)
 
-    parent = np.full(n, -1, dtype=np.int32)
-    line_of = np.full(n, -1, dtype=np.int32)
-    from_is_parent = np.zeros(n, dtype=np.int32)
-    g = np.zeros(n); b = np.zeros(n); r = np.zeros(n); x = np.zeros(n); rating = np.zeros(n)
-    for k in range(1, n):
-        u, li = parent_ref[order[k]]
-        parent[k] = rank[u]
-        line_of[k] = li
-        ln = lines[li]
-        from_is_parent[k] = 1 if index[ln.from_bus] == u else 0
-        g[k], b[k] = ys[li].real, ys[li].imag
-        r[k], x[k] = ln.resistance, ln.reactance
-        rating[k] = ln.rating
-    levels = np.array([level_of[v] for v in order])
-    n_levels = int(levels.max()) + 1
-    level_ptr = np.searchsorted(levels, np.arange(n_levels + 1)).astype(np.int32)
-    child_cnt = np.bincount(parent[1:], minlength=n) if n > 1 else np.zeros(n, dtype=np.int64)
-    child_ptr = np.zeros(n + 1, dtype=np.int32)
-    child_ptr[1:] = np.cumsum(child_cnt)
-    child_idx = np.zeros(max(n - 1, 0), dtype=np.int32)
-    fill = child_ptr[:-1].copy()
-    for k in range(1, n):
-        child_idx[fill[parent[k]]] = k
-        fill[parent[k]] += 1
-    for k in range(1, n):
-        assert parent[k] < k and levels[parent[k]] < levels[k]
-    pool_slot, n_pool = plan_pool(parent, level_ptr)
+        parent = np.full(n, -1, dtype=np.int32)
+        line_of = np.full(n, -1, dtype=np.int32)
+        from_is_parent = np.zeros(n, dtype=np.int32)
+        g = np.zeros(n); b = np.zeros(n); r = np.zeros(n); x = np.zeros(n); rating = np.zeros(n)
+        for k in range(1, n):
+            u, li = parent_ref[order[k]]
+            parent[k] = rank[u]
+            line_of[k] = li
+            ln = lines[li]
+            from_is_parent[k] = 1 if index[ln.from_bus] == u else 0
+            g[k], b[k] = ys[li].real, ys[li].imag
+            r[k], x[k] = ln.resistance, ln.reactance
+            rating[k] = ln.rating
+        levels = np.array([level_of[v] for v in order])
+        n_levels = int(levels.max()) + 1
+        level_ptr = np.searchsorted(levels, np.arange(n_levels + 1)).astype(np.int32)
+        child_cnt = np.bincount(parent[1:], minlength=n) if n > 1 else np.zeros(n, dtype=np.int64)
+        child_ptr = np.zeros(n + 1, dtype=np.int32)
+        child_ptr[1:] = np.cumsum(child_cnt)
+        child_idx = np.zeros(max(n - 1, 0), dtype=np.int32)
+        fill = child_ptr[:-1].copy()
+        for k in range(1, n):
+            child_idx[fill[parent[k]]] = k
+            fill[parent[k]] += 1
+        for k in range(1, n):
+            assert parent[k] < k and levels[parent[k]] < levels[k]
+        pool_slot, n_pool = plan_pool(parent, level_ptr)
+        return dict(order=order, rank=rank, parent=parent, line_of=line_of, from_is_parent=from_is_parent,
+                    g=g, b=b, r=r, x=x, rating=rating, levels=levels, n_levels=n_levels, level_ptr=level_ptr,
+                    child_ptr=child_ptr, child_idx=child_idx, pool_slot=pool_slot, n_pool=n_pool)
+
+    # two valid schedules of the same length: keep the one that parks fewer contributions at once
+    lay = min((layout(True), layout(False)), key=lambda d: d["n_pool"])
+    order, rank, parent, line_of, from_is_parent = (lay[k] for k in ("order", "rank", "parent", "line_of", "from_is_parent"))
+    g, b, r, x, rating = (lay[k] for k in ("g", "b", "r", "x", "rating"))
+    level_ptr, child_ptr, child_idx, pool_slot, n_pool = (lay[k] for k in ("level_ptr", "child_ptr", "child_idx", "pool_slot", "n_pool"))
 
     tmap = {"slack": BUS_SLACK, "pv": BUS_PV}
     bus_type = np.array([tmap.get(buses[i].bus_type, BUS_PQ) for i in order], dtype=np.int32)
