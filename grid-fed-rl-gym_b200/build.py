@@ -31,10 +31,10 @@ def up_to_date() -> bool:
     return all(os.path.getmtime(os.path.join(CSRC, d)) <= t for d in DEPENDS)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and up_to_date():
+def build(force: bool = False, verbose: bool = False, defines=()) -> str:
+    if not force and not defines and up_to_date():
         return OUT
-    cmd = [find_nvcc(), *NVCC_FLAGS, "-o", OUT, *SOURCES]
+    cmd = [find_nvcc(), *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-o", OUT, *SOURCES]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     res = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
@@ -46,4 +46,5 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv,
+                defines=[a[2:] for a in sys.argv[1:] if a.startswith("-D")]))

@@ -68,7 +68,7 @@ make_group(const Layout& lay, unsigned char* smem, int slot_bytes, D2* mscratch)
                          : (((1u << (LANES & 31)) - 1u) << (((threadIdx.x & 31) / LANES) * LANES));
   const int slot = threadIdx.x / LANES;
   const int E = blockDim.x / LANES;
-  D2* mg = mscratch ? mscratch + ((size_t)blockIdx.x * E + slot) * 2 * (size_t)lay.n : nullptr;
+  D2* mg = mscratch ? mscratch + ((size_t)blockIdx.x * E + slot) * (newton_scratch_doubles(lay.n) / 2) : nullptr;
   bind_slot(g, smem + kSmemHeader + lay.img_bytes + (size_t)slot * slot_bytes, lay.n, lay.n_pool, mg);
   return g;
 }
@@ -283,8 +283,12 @@ int plan_launch(const gfr_feeder* f, bool step, int solver, int lanes, long long
       if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, threads, smem) != cudaSuccess) { cudaGetLastError(); continue; }
       if (nb > c) nb = c;
       const long long resident = (long long)nb * E;
-      // more resident instances win; on a tie more, smaller CTAs (they even out the last wave)
-      if (resident > best_resident || (resident == best_resident && resident > 0 && nb > best.ctas_per_sm)) {
+      // more resident instances win.  On a tie: a short launch (few waves) takes more, smaller CTAs,
+      // which even out its last wave; a long one takes fewer, so that fewer copies of the image are staged
+      const bool short_launch = B < 8 * (long long)f->sm_count * (resident > 0 ? resident : 1);
+      const bool tie = resident == best_resident && resident > 0 &&
+                       (short_launch ? nb > best.ctas_per_sm : nb < best.ctas_per_sm);
+      if (resident > best_resident || tie) {
         best_resident = resident;
         best.lanes = lanes; best.threads = threads; best.smem = smem; best.ctas_per_sm = nb;
       }
@@ -300,7 +304,7 @@ int plan_launch(const gfr_feeder* f, bool step, int solver, int lanes, long long
   best.grid = (int)grid;
   best.slot_bytes = (int)per_env;
   // Newton spills D^-1 U (32 B per bus) of every resident instance slot to global memory
-  best.mscratch_bytes = solver == GFR_SOLVER_NEWTON ? (size_t)grid * E * lay.n * 32 : 0;
+  best.mscratch_bytes = solver == GFR_SOLVER_NEWTON ? (size_t)grid * E * newton_scratch_doubles(lay.n) * 8 : 0;
   *out = best;
   *fn_out = fn;
   return GFR_OK;

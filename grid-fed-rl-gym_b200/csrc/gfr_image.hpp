@@ -131,15 +131,23 @@ inline std::string build_feeder_image(const gfr_feeder_desc* d, FeederImage* out
     if (d->n_pool < 1 || d->n_pool > n) return "n_pool must be in [1, n]";
     std::vector<int> owner(d->n_pool, -1);        // which bus's contribution a slot holds
     for (int l = nl - 1; l >= 0; --l) {
+      // a bus may take over a slot of one of its own children (it reads them before it writes);
+      // any other slot it writes must have been free before this level started
+      std::vector<int> before(owner);
       for (int k = d->level_ptr[l]; k < d->level_ptr[l + 1]; ++k) {
         const int sl = d->pool_slot[k];
         if (sl < 0 || sl >= d->n_pool) return "pool_slot out of range";
-        if (owner[sl] >= 0) return "pool_slot reuses a slot that is still live";
+        const int prev = before[sl];
+        if (prev >= 0 && d->parent[prev] != k) return "pool_slot reuses a slot that is still live";
+        if (owner[sl] >= 0 && owner[sl] != prev) return "two buses of one level share a pool slot";
         owner[sl] = k;
         pool_slot[k] = sl;
       }
       for (int k = d->level_ptr[l]; k < d->level_ptr[l + 1]; ++k)
-        for (int q = d->child_ptr[k]; q < d->child_ptr[k + 1]; ++q) owner[d->pool_slot[d->child_idx[q]]] = -1;
+        for (int q = d->child_ptr[k]; q < d->child_ptr[k + 1]; ++q) {
+          const int cs = d->pool_slot[d->child_idx[q]];
+          if (owner[cs] == d->child_idx[q]) owner[cs] = -1;
+        }
     }
     lay.n_pool = d->n_pool;
   } else {

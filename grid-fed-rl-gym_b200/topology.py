@@ -308,9 +308,9 @@ def _schedule(n: int, root: int, adj, width: Optional[int], alap: bool = True):
 
 def plan_pool(parent: np.ndarray, level_ptr: np.ndarray):
     """Slot of every bus's contribution to its parent.  A contribution is written when its bus is
-    eliminated (levels run last -> first) and read when the parent is; the slot is free again once
-    the parent's level is done.  Slots released by a level are only handed out to later levels, so
-    a level never writes a slot another lane of the same level still reads."""
+    eliminated (levels run last -> first) and read when the parent is.  The parent inherits its first
+    child's slot; slots released by a level are only handed out to later levels, so a level never
+    writes a slot another lane of the same level still reads."""
     n = parent.size
     slot = np.zeros(n, dtype=np.int32)
     free: List[int] = []
@@ -320,14 +320,19 @@ def plan_pool(parent: np.ndarray, level_ptr: np.ndarray):
         kids[parent[k]].append(k)
     for l in range(level_ptr.size - 2, -1, -1):
         members = range(int(level_ptr[l]), int(level_ptr[l + 1]))
+        released: List[int] = []
         for k in members:
-            if free:
+            if kids[k]:
+                # a parent reads its children's entries before it writes its own (same lane, program
+                # order), so it can take over its first child's slot; the others are released
+                slot[k] = slot[kids[k][0]]
+                released.extend(int(slot[c]) for c in kids[k][1:])
+            elif free:
                 slot[k] = free.pop()
             else:
                 slot[k] = n_pool
                 n_pool += 1
-        for k in members:                      # their children's contributions have been consumed
-            free.extend(int(slot[c]) for c in kids[k])
+        free.extend(released)                  # only later levels may reuse what this level read
     return slot, max(n_pool, 1)
 
 

@@ -24,7 +24,7 @@ struct EmuSlot {
   std::vector<double> work;    // shared-memory slot
   std::vector<D2> mg;          // the global scratch of the slot
   explicit EmuSlot(const Layout& lay) : work(8 + (newton_slot_bytes(lay.n, lay.n_pool, 0) + sweep_slot_bytes(lay.n, 0)) / 8, 0.0),
-                                        mg(2 * (size_t)lay.n) {}
+                                        mg(newton_scratch_doubles(lay.n) / 2 + 1) {}
   template <class G> G group(const Layout& lay) {
     G g;
     g.lane = 0; g.mask = 1u;
