@@ -353,3 +353,63 @@ def test_sharding_is_seed_stable():
         part.reset(seed=42)
         op = part.step(act[lo:hi])[0]
         assert torch.equal(op, ow[lo:hi])
+
+
+def _synthetic(n, seed, scale):
+    import grid_fed_rl_b200 as m
+    cfg = m.NetworkConfig(num_buses=n, connectivity=0.0, load_probability=0.9, dg_probability=0.4,
+                          min_load_kw=20, max_load_kw=300, line_length_range=(0.05, 1.5))
+    f = m.repair_topology(m.SyntheticFeeder(cfg, seed=seed))
+    for ld in f.loads:                       # as generated the feeder is far beyond its loadability
+        ld.base_power *= scale; ld.active_power *= scale; ld.reactive_power *= scale
+    return f
+
+
+@pytest.mark.parametrize("lanes", (8, 32))
+def test_synthetic_300_bus_feeder_vs_oracle(lanes):
+    """A larger radial feeder with hundreds of loads / generators / batteries (BASELINE config 5's
+    generator at a size the dense oracle still solves quickly)."""
+    import grid_fed_rl_b200 as m
+    f = _synthetic(300, 300, 0.1)
+    kw = dict(timestep=60.0, renewable_sources=["solar", "wind"], tolerance=1e-8)
+    B = 6
+    env = m.BatchedGridEnvironment(f, B, lanes=lanes, repair=False, **kw)
+    ref = port.PortEnv(f, B, **kw)
+    rs = np.random.RandomState(lanes)
+    nz0 = np.concatenate([rs.random_sample((B, 1)), rs.standard_normal((B, 3))], axis=1)
+    env.reset(noise=nz0, options={"start_time": 13 * 3600.0}); ref.reset(nz0, start_time=13 * 3600.0)
+    lay = obs_layout(ref.n, ref.m, ref.L, ref.G, ref.Bt)
+    for t in range(3):
+        act = rs.uniform(-1, 1, size=(B, ref.A))
+        nz = np.concatenate([rs.random_sample((B, 1)), rs.standard_normal((B, 3 + ref.L))], axis=1)
+        obs, reward, term, trunc, info = env.step(act, nz)
+        r = ref.step(act, nz)
+        o = obs.cpu().numpy()
+        assert r["converged"].all() and bool(info["power_flow_converged"].all())
+        assert np.max(np.abs(o[:, lay["vm"]] - r["obs"][:, lay["vm"]])) <= TOL_PU
+        assert np.max(np.abs(o[:, lay["va"]] - r["obs"][:, lay["va"]])) <= TOL_PU
+        assert np.max(np.abs(o[:, lay["p"]] - r["obs"][:, lay["p"]])) / ref.s_base <= TOL_PU
+        assert np.allclose(o[:, lay["gen"]], r["obs"][:, lay["gen"]], rtol=1e-12, atol=1e-6)
+        assert np.allclose(o[:, lay["soc"]], r["obs"][:, lay["soc"]], atol=1e-12)
+        assert np.allclose(reward.cpu().numpy(), r["reward"], rtol=1e-9, atol=1e-6)
+        assert np.all(np.abs(info["iterations"].cpu().numpy().astype(int) - r["iterations"]) <= 1)
+
+
+def test_synthetic_1000_bus_feeder_runs():
+    """BASELINE config 5's feeder: n = 1000, D = 6320, 403 actions.  Functional check: both solvers
+    converge to the same state (the dense oracle is too slow at this size)."""
+    import grid_fed_rl_b200 as m
+    f = _synthetic(1000, 1000, 0.03)
+    kw = dict(timestep=60.0, renewable_sources=["solar", "wind"], repair=False, start_time=12 * 3600.0)
+    a = m.BatchedGridEnvironment(f, 64, solver="newton", tolerance=1e-9, lanes=32, **kw)
+    b = m.BatchedGridEnvironment(f, 64, solver="sweep", tolerance=1e-11, lanes=32, **kw)
+    assert a.obs_dim == 6320 and a.act_dim == 403
+    a.reset(seed=1); b.reset(seed=1)
+    g = torch.Generator(device="cuda"); g.manual_seed(0)
+    for _ in range(2):
+        act = a.sample_actions(g)
+        oa, ra, _, _, ia = a.step(act)
+        ob, rb, _, _, ib = b.step(act)
+        assert bool(ia["power_flow_converged"].all()) and bool(ib["power_flow_converged"].all())
+        assert torch.max(torch.abs(oa[:, :2000] - ob[:, :2000])) <= TOL_PU
+        assert torch.allclose(ra, rb, rtol=1e-9, atol=1e-5)
