@@ -372,6 +372,13 @@ int gfr_feeder_create(const gfr_feeder_desc* d, int device, gfr_feeder** out) {
   if (!guard.ok) return fail(GFR_E_CUDA, "no usable CUDA device (this library has no CPU fallback)");
   cudaDeviceProp prop;
   GFR_CUDA(cudaGetDeviceProperties(&prop, device));
+  // a large feeder keeps its shared memory for the working set: drop the flat-start factor table
+  if (kSmemHeader + (size_t)fi.lay.img_bytes + newton_slot_bytes(fi.lay.n, fi.lay.n_pool, 0) >
+      (size_t)prop.sharedMemPerBlockOptin / 2) {
+    fi = FeederImage();
+    std::string complaint = build_feeder_image(d, &fi, false);
+    if (!complaint.empty()) return fail(GFR_E_ARG, complaint);
+  }
 
   auto* f = new gfr_feeder();
   f->device = device;

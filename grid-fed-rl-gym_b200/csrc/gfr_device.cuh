@@ -61,7 +61,7 @@ struct Layout {
   int n, nl, L, G, Bt, A, D, m, n_src, R, img_bytes, n_noise, n_pool;
   int o_topo, o_child_idx, o_child_pool, o_level_ptr, o_order, o_rank, o_line_of, o_branch_of_line, o_inj_ptr, o_inj_idx,
       o_gen_type;
-  int o_gb, o_gbd, o_rx, o_rating, o_vm_set, o_load_base, o_gen_cap, o_gen_p0, o_gen_p1, o_gen_p2,
+  int o_gb, o_gbd, o_rx, o_f0, o_rating, o_vm_set, o_load_base, o_gen_cap, o_gen_p0, o_gen_p1, o_gen_p2,
       o_bat_cap, o_bat_rating, o_bat_eff, o_profile;
   double s_base, inv_s_base, load_p_sum;
 };
@@ -347,6 +347,7 @@ GFR_HD void newton_solve(const NGrp<LANES>& g, const Layout& lay, const int* sim
   const int* child_pool = simg + lay.o_child_pool;   // 3 * pool slot of every child, same indexing as child_idx
   const D2* gb = reinterpret_cast<const D2*>(dimg + lay.o_gb);      // branch series g, b (0 for the root)
   const D2* gbd = reinterpret_cast<const D2*>(dimg + lay.o_gbd);    // Re, Im of Y_kk
+  const D2* f0 = lay.o_f0 >= 0 ? reinterpret_cast<const D2*>(dimg + lay.o_f0) : nullptr;   // flat-start factors
 
   out->converged = 0;
   out->iterations = max_it;
@@ -394,6 +395,48 @@ GFR_HD void newton_solve(const NGrp<LANES>& g, const Layout& lay, const int* sim
       out->iterations = it + 1;
       break;
     }
+    // ---- first iteration: every instance starts from the same flat profile, so its Jacobian - and
+    //      the whole elimination of it - is a property of the feeder.  The host factorised it once
+    //      (image: D^-1, D^-1 U and J[p,k] per bus); only the right-hand side is instance data.
+    if (it == 0 && f0 != nullptr) {
+      for (int l = nl - 1; l >= 0; --l) {
+        const int k1 = level_ptr[l + 1];
+        for (int k = g.first(level_ptr[l]); k < k1; k += LANES) {
+          const I4 t = topo[k];
+          const D2 pc = g.vx(k);
+          D2 sc; sc.x = sc.y = 0.0;
+#pragma unroll 1
+          for (int q = t.y; q < t.z; ++q) {
+            const D2 cc = g.poolp[child_pool[q] + 2];
+            sc.x += cc.x; sc.y += cc.y;
+          }
+          double r0 = g.pspec(k) - pc.x - sc.x, r1 = 0.0 - pc.y - sc.y;
+          if (!(t.w & FL_THETA)) r0 = 0.0;
+          if (!(t.w & FL_PQ)) r1 = 0.0;
+          const D2 i0 = f0[5 * k], i1 = f0[5 * k + 1], lp = f0[5 * k + 4];   // D^-1 rows, (ll, gl)
+          D2 v, cc;
+          v.x = fma(i0.x, r0, i0.y * r1);
+          v.y = fma(i1.x, r0, i1.y * r1);
+          cc.x = fma(lp.x, v.x, lp.y * v.y);
+          cc.y = fma(-lp.y, v.x, lp.x * v.y);
+          g.vx(k) = v;
+          g.poolp[(t.w >> FL_POOL_SHIFT) + 2] = cc;
+        }
+        g.sync();
+      }
+      for (int l = 0; l < nl; ++l) {
+        const int k1 = level_ptr[l + 1];
+        for (int k = g.first(level_ptr[l]); k < k1; k += LANES) {
+          const D2 m0 = f0[5 * k + 2], m1 = f0[5 * k + 3];
+          const D2 x = g.vx(topo[k].x);
+          D2 v = g.vx(k);
+          v.x = fma(-m0.x, x.x, fma(-m0.y, x.y, v.x));
+          v.y = fma(-m1.x, x.x, fma(-m1.y, x.y, v.y));
+          g.vx(k) = v;
+        }
+        g.sync();
+      }
+    } else {
     // ---- assemble + eliminate leaf -> root (power_flow.py:213-295 with D2, then the solve of :187)
     int singular = 0;
     for (int l = nl - 1; l >= 0; --l) {
@@ -492,6 +535,7 @@ GFR_HD void newton_solve(const NGrp<LANES>& g, const Layout& lay, const int* sim
         g.sync();
       }
     }
+    }   // first iteration / general iteration
     // ---- polar update, every bus independently (:297-327):
     //      theta += a dtheta, |V| += a d|V|  <=>  V *= (1 + a x1) e^{j a x0}
     for (int k = g.lane; k < n; k += LANES) {

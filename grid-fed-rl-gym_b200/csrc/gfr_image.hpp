@@ -34,7 +34,8 @@ struct FeederImage {
 };
 
 // returns an empty string on success, the complaint otherwise
-inline std::string build_feeder_image(const gfr_feeder_desc* d, FeederImage* out) {
+// flat_start_factors: include the factorisation of the flat-start Jacobian (80 B per bus)
+inline std::string build_feeder_image(const gfr_feeder_desc* d, FeederImage* out, bool flat_start_factors = true) {
   const int n = d->n_bus, nl = d->n_levels, L = d->n_load, G = d->n_gen, Bt = d->n_bat;
   if (n < 1 || nl < 1 || L < 0 || G < 0 || Bt < 0) return "bad feeder dimensions";
   if (!(d->s_base > 0.0)) return "s_base must be > 0";
@@ -188,6 +189,53 @@ inline std::string build_feeder_image(const gfr_feeder_desc* d, FeederImage* out
   lay.o_gb = dbase + ib.add_d(gb.data(), 2 * n);
   lay.o_gbd = dbase + ib.add_d(gbd.data(), 2 * n);
   lay.o_rx = dbase + ib.add_d(rx.data(), 2 * n);
+  // Factorisation of the flat-start Jacobian (the first Newton iteration of every instance):
+  // the same leaf -> root block elimination the kernel runs, done once here.
+  {
+    std::vector<double> f0(10 * (size_t)n, 0.0), C(4 * (size_t)n, 0.0);
+    bool ok = flat_start_factors;
+    for (int l = nl - 1; l >= 0 && ok; --l) {
+      for (int k = d->level_ptr[l]; k < d->level_ptr[l + 1]; ++k) {
+        const bool th = d->bus_type[k] != GFR_BUS_SLACK, pq = d->bus_type[k] == GFR_BUS_PQ;
+        const double vk = pq ? 1.0 : d->vm_set[k];
+        auto vm = [&](int j) { return d->bus_type[j] == GFR_BUS_PQ ? 1.0 : d->vm_set[j]; };
+        const double v2 = vk * vk;
+        double P = d->gdiag[k] * v2, Q = -d->bdiag[k] * v2;
+        if (k > 0) { const double a = vk * vm(d->parent[k]); P += -d->g[k] * a; Q += d->b[k] * a; }
+        for (int q = d->child_ptr[k]; q < d->child_ptr[k + 1]; ++q) {
+          const int c = d->child_idx[q];
+          const double a = vk * vm(c);
+          P += -d->g[c] * a; Q += d->b[c] * a;
+        }
+        double d00 = -Q - d->bdiag[k] * v2, d01 = P + d->gdiag[k] * v2, d10 = P - d->gdiag[k] * v2,
+               d11 = Q - d->bdiag[k] * v2;
+        for (int q = d->child_ptr[k]; q < d->child_ptr[k + 1]; ++q) {
+          const double* cc = &C[4 * (size_t)d->child_idx[q]];
+          d00 -= cc[0]; d01 -= cc[1]; d10 -= cc[2]; d11 -= cc[3];
+        }
+        const double a = k > 0 ? vk * vm(d->parent[k]) : 0.0;
+        const double gk = k > 0 ? d->g[k] : 0.0, bk = k > 0 ? d->b[k] : 0.0;
+        const double ga = -gk * a, al = bk * a, gl = -gk * a, ll = bk * a;      // sin = 0 at a flat start
+        double u00 = al, u01 = ga, u10 = -ga, u11 = al;
+        if (!th) { d00 = 1.0; d01 = 0.0; u00 = u01 = 0.0; }
+        if (!pq) { d10 = 0.0; d11 = 1.0; u10 = u11 = 0.0; }
+        const double det = d00 * d11 - d01 * d10;
+        if (det == 0.0 || !(det == det)) { ok = false; break; }
+        const double inv = 1.0 / det;
+        const double i00 = d11 * inv, i01 = -d01 * inv, i10 = -d10 * inv, i11 = d00 * inv;
+        const double m00 = i00 * u00 + i01 * u10, m01 = i00 * u01 + i01 * u11,
+                     m10 = i10 * u00 + i11 * u10, m11 = i10 * u01 + i11 * u11;
+        double* o = &f0[10 * (size_t)k];
+        o[0] = i00; o[1] = i01; o[2] = i10; o[3] = i11;
+        o[4] = m00; o[5] = m01; o[6] = m10; o[7] = m11;
+        o[8] = ll; o[9] = gl;
+        double* cc = &C[4 * (size_t)k];
+        cc[0] = ll * m00 + gl * m10; cc[1] = ll * m01 + gl * m11;
+        cc[2] = -gl * m00 + ll * m10; cc[3] = -gl * m01 + ll * m11;
+      }
+    }
+    lay.o_f0 = ok ? dbase + ib.add_d(f0.data(), 10 * n) : -1;     // singular at the flat start: no shortcut
+  }
   lay.o_rating = dbase + ib.add_d(d->rating, n);
   lay.o_vm_set = dbase + ib.add_d(d->vm_set, n);
   lay.o_load_base = dbase + ib.add_d(d->load_base, L);
