@@ -94,7 +94,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(k)
             except Exception:
                 pass
-            self._stop_evt.wait(0.05)
+            self._stop_evt.wait(0.004)
 
     def stop(self):
         self._stop_evt.set()
@@ -294,7 +294,6 @@ def run_gpu(args):
     l0 = lib.gfr_launch_count()
     ms = timed(dev_step, K)
     launches = lib.gfr_launch_count() - l0
-    clocks = sampler.stop()
     info = env._info()
     conv_frac = float(info["power_flow_converged"].double().mean().item())
     mean_it = float(info["iterations"].double().mean().item())
@@ -322,6 +321,7 @@ def run_gpu(args):
     for i in range(3):
         e2e_step(i)
     ms_e2e = timed(e2e_step, K)
+    clocks = sampler.stop()          # sampled across both timed regions
     e2e_value = B * world * K / (ms_e2e * 1e-3)
 
     if rank == 0:
@@ -346,7 +346,8 @@ def run_gpu(args):
                          "frac": achieved / peak, "traffic": TRAFFIC_BYTES.get((args.workload, B)),
                          "peak_source": how, "algorithmic_bytes_per_env_step": abytes,
                          "kernel": f"step_kernel<{li['lanes']},{solver}>", "kernel_ms": ms / K,
-                         "note": "fp64-latency bound, not HBM bound: see DESIGN.md / profiles/"},
+                         "note": "FP64-issue / latency bound, not HBM bound (ncu: FP64 pipe 32 %, DRAM 3 %): "
+                                 "see DESIGN.md section 5 and profiles/"},
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": B * A * 8,
                     "d2h_bytes_per_step": B * 10, "ms_per_step": ms_e2e / K,
                     "note": "pinned host actions in, reward + terminated + truncated out, every step; "
@@ -355,7 +356,7 @@ def run_gpu(args):
         }
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline(spec, tol if solver == "newton" else 1e-8,
-                                                *{"ieee123": (128, 8), "ieee34": (1024, 8), "ieee13": (8192, 8)}[spec])
+                                                *{"ieee123": (256, 12), "ieee34": (2048, 12), "ieee13": (16384, 12)}[spec])
         print(json.dumps(line), flush=True)
     env.close()
     if world > 1:
@@ -364,13 +365,18 @@ def run_gpu(args):
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the step kernel, from the ncu --set full
 # capture summarised under profiles/ (keyed by workload and instances per launch)
-TRAFFIC_BYTES = {}
+TRAFFIC_BYTES = {
+    # profiles/r01_ncu_ieee123_final.txt: 33.7 MB read + 531.2 MB written per launch of step_kernel<16, newton>
+    # (below the 772.7 MB of algorithmic bytes: part of the previous step's observation lines are still
+    # dirty in the 126 MB L2 when they are overwritten)
+    ("ieee123", 131072): 564.9e6,
+}
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="ieee123", choices=sorted(WORKLOADS))
