@@ -56,3 +56,33 @@ def max_over_ranks(value: float, device=None) -> float:
 def global_seeds(seed: int, start: int, count: int, device=None) -> torch.Tensor:
     """Philox keys of the instances [start, start + count): ``seed + global id``."""
     return torch.arange(count, dtype=torch.int64, device=device) + int(seed) + int(start)
+
+
+def fedavg_all_reduce(parameters: Dict[str, torch.Tensor], num_samples: float,
+                      group=None) -> Dict[str, torch.Tensor]:
+    """Sample-weighted average of per-rank client parameters - the reference's
+    ``FedAvgAggregator.aggregate`` (federated/core.py:233-258: ``sum_i (n_i / N) p_i``) with the
+    list of clients replaced by the ranks of a process group.  Every tensor is packed into one
+    flat bucket (plus the sample count), one all-reduce (NCCL over NVLink / NVSwitch on GPUs)
+    moves it, and the result is unpacked into new tensors of the original shapes and dtypes.
+    A rank with ``num_samples == 0`` contributes nothing; if no rank has samples the result is
+    empty, as upstream."""
+    names = list(parameters)
+    if not names:
+        return {}
+    ref = parameters[names[0]]
+    flat = torch.cat([parameters[k].reshape(-1).to(torch.float64) for k in names]
+                     + [torch.zeros(1, dtype=torch.float64, device=ref.device)])
+    flat[:-1] *= float(num_samples)
+    flat[-1] = float(num_samples)
+    if is_distributed():
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    total = float(flat[-1].item())
+    if total == 0.0:
+        return {}
+    out, o = {}, 0
+    for k in names:
+        n = parameters[k].numel()
+        out[k] = (flat[o:o + n] / total).reshape(parameters[k].shape).to(parameters[k].dtype)
+        o += n
+    return out

@@ -28,7 +28,11 @@ def _worker(rank, world, port, total, out):
         local[-1] = hi - lo
         red = gd.all_reduce_stats(local.clone())
         slowest = gd.max_over_ranks(10.0 + rank)
-        out.put((rank, lo, hi, seeds.tolist(), red.tolist(), slowest))
+        # FedAvg over ranks: rank r holds parameters filled with r + 1 and has (r + 1) * 10 samples
+        params = {"w": torch.full((3, 2), float(rank + 1)), "b": torch.full((4,), float(rank + 1), dtype=torch.float64)}
+        avg = gd.fedavg_all_reduce(params, (rank + 1) * 10)
+        out.put((rank, lo, hi, seeds.tolist(), red.tolist(), slowest,
+                 {k: (v.tolist(), str(v.dtype)) for k, v in avg.items()}))
     finally:
         dist.destroy_process_group()
 
@@ -51,6 +55,12 @@ def test_shards_cover_and_reduce(total):
     for r in res:
         assert r[4][-1] == total and r[4][0] == sum(7 + i for i in range(total))
         assert r[5] == 11.0
+        # sum_i (n_i / N) p_i = (10 * 1 + 20 * 2) / 30 (federated/core.py:233-258)
+        w, wt = r[6]["w"]
+        b, bt = r[6]["b"]
+        assert wt == "torch.float32" and bt == "torch.float64"
+        assert all(abs(x - 50.0 / 30.0) < 1e-6 for row in w for x in row) and len(w) == 3
+        assert all(abs(x - 50.0 / 30.0) < 1e-12 for x in b)
 
 
 def test_shard_range_properties():
@@ -66,3 +76,5 @@ def test_shard_range_properties():
     # single process: reductions are the identity
     v = torch.arange(len(gd.STAT_KEYS), dtype=torch.float64)
     assert torch.equal(gd.all_reduce_stats(v.clone()), v) and gd.max_over_ranks(3.5) == 3.5
+    p = {"w": torch.arange(6.0).reshape(2, 3)}
+    assert torch.equal(gd.fedavg_all_reduce(p, 5)["w"], p["w"]) and gd.fedavg_all_reduce(p, 0) == {}
