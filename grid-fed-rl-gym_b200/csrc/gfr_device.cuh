@@ -356,6 +356,19 @@ GFR_HD void newton_solve(const NGrp<LANES>& g, const Layout& lay, const int* sim
   for (int it = 0; it < max_it; ++it) {
     // ---- calculated injections + mismatch, every bus independently (power_flow.py:150-166)
     double mm = 0.0;
+    if (it == 0 && f0 != nullptr) {
+      // the calculated injections of the flat profile are feeder constants too (image, entry 5)
+      for (int k = g.lane; k < n; k += LANES) {
+        const int fl = topo[k].w;
+        const D2 pc = f0[6 * k + 5];
+        double aP = fabs(g.pspec(k) - pc.x), aQ = fabs(pc.y);
+        if (!(fl & FL_THETA)) aP = 0.0;
+        if (!(fl & FL_PQ)) aQ = 0.0;
+        const double loc = (aQ > aP || aQ != aQ) ? aQ : aP;
+        mm = (loc > mm || loc != loc) ? loc : mm;
+        g.vx(k) = pc;
+      }
+    } else
     for (int k = g.lane; k < n; k += LANES) {
       const I4 t = topo[k];
       const D2 vk = g.ef(k);
@@ -413,7 +426,7 @@ GFR_HD void newton_solve(const NGrp<LANES>& g, const Layout& lay, const int* sim
           double r0 = g.pspec(k) - pc.x - sc.x, r1 = 0.0 - pc.y - sc.y;
           if (!(t.w & FL_THETA)) r0 = 0.0;
           if (!(t.w & FL_PQ)) r1 = 0.0;
-          const D2 i0 = f0[5 * k], i1 = f0[5 * k + 1], lp = f0[5 * k + 4];   // D^-1 rows, (ll, gl)
+          const D2 i0 = f0[6 * k], i1 = f0[6 * k + 1], lp = f0[6 * k + 4];   // D^-1 rows, (ll, gl)
           D2 v, cc;
           v.x = fma(i0.x, r0, i0.y * r1);
           v.y = fma(i1.x, r0, i1.y * r1);
@@ -427,7 +440,7 @@ GFR_HD void newton_solve(const NGrp<LANES>& g, const Layout& lay, const int* sim
       for (int l = 0; l < nl; ++l) {
         const int k1 = level_ptr[l + 1];
         for (int k = g.first(level_ptr[l]); k < k1; k += LANES) {
-          const D2 m0 = f0[5 * k + 2], m1 = f0[5 * k + 3];
+          const D2 m0 = f0[6 * k + 2], m1 = f0[6 * k + 3];
           const D2 x = g.vx(topo[k].x);
           D2 v = g.vx(k);
           v.x = fma(-m0.x, x.x, fma(-m0.y, x.y, v.x));

@@ -34,7 +34,7 @@ struct FeederImage {
 };
 
 // returns an empty string on success, the complaint otherwise
-// flat_start_factors: include the factorisation of the flat-start Jacobian (80 B per bus)
+// flat_start_factors: include the factorisation of the flat-start Jacobian (96 B per bus)
 inline std::string build_feeder_image(const gfr_feeder_desc* d, FeederImage* out, bool flat_start_factors = true) {
   const int n = d->n_bus, nl = d->n_levels, L = d->n_load, G = d->n_gen, Bt = d->n_bat;
   if (n < 1 || nl < 1 || L < 0 || G < 0 || Bt < 0) return "bad feeder dimensions";
@@ -192,7 +192,7 @@ inline std::string build_feeder_image(const gfr_feeder_desc* d, FeederImage* out
   // Factorisation of the flat-start Jacobian (the first Newton iteration of every instance):
   // the same leaf -> root block elimination the kernel runs, done once here.
   {
-    std::vector<double> f0(10 * (size_t)n, 0.0), C(4 * (size_t)n, 0.0);
+    std::vector<double> f0(12 * (size_t)n, 0.0), C(4 * (size_t)n, 0.0);
     bool ok = flat_start_factors;
     for (int l = nl - 1; l >= 0 && ok; --l) {
       for (int k = d->level_ptr[l]; k < d->level_ptr[l + 1]; ++k) {
@@ -225,16 +225,17 @@ inline std::string build_feeder_image(const gfr_feeder_desc* d, FeederImage* out
         const double i00 = d11 * inv, i01 = -d01 * inv, i10 = -d10 * inv, i11 = d00 * inv;
         const double m00 = i00 * u00 + i01 * u10, m01 = i00 * u01 + i01 * u11,
                      m10 = i10 * u00 + i11 * u10, m11 = i10 * u01 + i11 * u11;
-        double* o = &f0[10 * (size_t)k];
+        double* o = &f0[12 * (size_t)k];
         o[0] = i00; o[1] = i01; o[2] = i10; o[3] = i11;
         o[4] = m00; o[5] = m01; o[6] = m10; o[7] = m11;
         o[8] = ll; o[9] = gl;
+        o[10] = P; o[11] = Q;                          // calculated injections of the flat profile
         double* cc = &C[4 * (size_t)k];
         cc[0] = ll * m00 + gl * m10; cc[1] = ll * m01 + gl * m11;
         cc[2] = -gl * m00 + ll * m10; cc[3] = -gl * m01 + ll * m11;
       }
     }
-    lay.o_f0 = ok ? dbase + ib.add_d(f0.data(), 10 * n) : -1;     // singular at the flat start: no shortcut
+    lay.o_f0 = ok ? dbase + ib.add_d(f0.data(), 12 * n) : -1;     // singular at the flat start: no shortcut
   }
   lay.o_rating = dbase + ib.add_d(d->rating, n);
   lay.o_vm_set = dbase + ib.add_d(d->vm_set, n);
