@@ -31,6 +31,8 @@ WORKLOADS = {
     "ieee13_newton": ("ieee13", 65536, "newton", 1e-6, 50),
     "ieee34_newton": ("ieee34", 262144, "newton", 1e-6, 50),
     "ieee123_sweep": ("ieee123", 131072, "sweep", 1e-8, 50),
+    # configs[4]: synthetic 1,000-bus radial feeder, 16,384 instances over 8 GPUs
+    "synthetic1000": ("synthetic1000", 2048, "newton", 1e-6, 50),
 }
 ENV_KW = dict(timestep=1.0, renewable_sources=["solar", "wind"], stochastic_loads=True,
               weather_variation=True)
@@ -39,6 +41,15 @@ START_TIME = 12 * 3600.0     # daylight, so the solar branch is exercised (SURVE
 
 def make_feeder(spec):
     import grid_fed_rl_b200 as m
+    if spec == "synthetic1000":
+        # ScalableFeeder(1000)'s parameters (synthetic.py:236-252) but radial; loads scaled by 0.03 so that
+        # the feeder is inside its loadability (sum P = 0.43 pu)
+        cfg = m.NetworkConfig(num_buses=1000, connectivity=0.0, load_probability=0.9, dg_probability=0.4,
+                              min_load_kw=20, max_load_kw=300, line_length_range=(0.05, 1.5))
+        f = m.repair_topology(m.SyntheticFeeder(cfg, seed=1000))
+        for ld in f.loads:
+            ld.base_power *= 0.03; ld.active_power *= 0.03; ld.reactive_power *= 0.03
+        return f
     f = {"ieee13": m.IEEE13Bus, "ieee34": lambda: m.IEEE34Bus(seed=0),
          "ieee123": lambda: m.IEEE123Bus(seed=0)}[spec]()
     return m.repair_topology(f)
@@ -185,7 +196,7 @@ def run_reference(args):
     if int(os.environ.get("RANK", "0")) != 0:
         return
     cores = os.cpu_count() or 1
-    per_proc = {"ieee123": 48, "ieee34": 384, "ieee13": 2048}[spec]
+    per_proc = {"ieee123": 48, "ieee34": 384, "ieee13": 2048, "synthetic1000": 1}[spec]
     ptol = tol if solver == "newton" else 1e-8
     steps, warm = max(1, args.steps), max(0, args.warmup)
     ctx = mp.get_context("spawn")
@@ -356,7 +367,7 @@ def run_gpu(args):
         }
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline(spec, tol if solver == "newton" else 1e-8,
-                                                *{"ieee123": (256, 12), "ieee34": (2048, 12), "ieee13": (16384, 12)}[spec])
+                                                *{"ieee123": (256, 12), "ieee34": (2048, 12), "ieee13": (16384, 12), "synthetic1000": (2, 2)}[spec])
         print(json.dumps(line), flush=True)
     env.close()
     if world > 1:

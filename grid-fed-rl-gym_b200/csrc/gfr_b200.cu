@@ -59,45 +59,54 @@ __device__ __forceinline__ void stage_image(unsigned char* smem, const void* img
   } while (!ok);
 }
 
+constexpr int kRedBytes = 128;    // cross-warp reduction scratch of a CTA-wide group (16 doubles)
+
+// Shared memory of a CTA: [mbarrier 16 B][feeder image, if staged][reduction scratch, if LANES > 32][slots]
 template <int LANES, int SOLVER>
 __device__ __forceinline__ typename GroupOf<LANES, SOLVER>::type
-make_group(const Layout& lay, unsigned char* smem, int slot_bytes, D2* mscratch) {
+make_group(const Layout& lay, unsigned char* work, int slot_bytes, D2* mscratch) {
   typename GroupOf<LANES, SOLVER>::type g;
   g.lane = threadIdx.x % LANES;
-  g.mask = (LANES == 32) ? 0xffffffffu
+  g.mask = (LANES >= 32) ? 0xffffffffu
                          : (((1u << (LANES & 31)) - 1u) << (((threadIdx.x & 31) / LANES) * LANES));
+  g.red = reinterpret_cast<double*>(work);
+  if (LANES > 32) work += kRedBytes;
   const int slot = threadIdx.x / LANES;
   const int E = blockDim.x / LANES;
   D2* mg = mscratch ? mscratch + ((size_t)blockIdx.x * E + slot) * (newton_scratch_doubles(lay.n) / 2) : nullptr;
-  bind_slot(g, smem + kSmemHeader + lay.img_bytes + (size_t)slot * slot_bytes, lay.n, lay.n_pool, mg);
+  bind_slot(g, work + (size_t)slot * slot_bytes, lay.n, lay.n_pool, mg);
   return g;
 }
 
-template <int LANES, int SOLVER>
+// IMG_SMEM: the feeder image is staged into shared memory (small / medium feeders); otherwise it is
+// read through L1 / L2 from global memory and all of shared memory goes to the working sets.
+template <int LANES, int SOLVER, bool IMG_SMEM>
 __global__ void __launch_bounds__(kMaxThreads)
 step_kernel(const Layout lay, const EnvCfg cfg, const void* __restrict__ img, const int slot_bytes,
             D2* __restrict__ mscratch, double* __restrict__ state, double* __restrict__ obs,
             const double* __restrict__ actions, const double* __restrict__ noise, const StepOut o,
             const long long B) {
   extern __shared__ __align__(16) unsigned char smem[];
-  stage_image(smem, img, lay.img_bytes);
-  const int* simg = (const int*)(smem + kSmemHeader);
-  const double* dimg = (const double*)(smem + kSmemHeader);
-  const auto g = make_group<LANES, SOLVER>(lay, smem, slot_bytes, mscratch);
+  if (IMG_SMEM) stage_image(smem, img, lay.img_bytes);
+  const int* simg = IMG_SMEM ? (const int*)(smem + kSmemHeader) : (const int*)img;
+  const double* dimg = IMG_SMEM ? (const double*)(smem + kSmemHeader) : (const double*)img;
+  const auto g = make_group<LANES, SOLVER>(lay, smem + kSmemHeader + (IMG_SMEM ? lay.img_bytes : 0),
+                                           slot_bytes, mscratch);
   const int E = blockDim.x / LANES;
   for (long long env = (long long)blockIdx.x * E + threadIdx.x / LANES; env < B; env += (long long)gridDim.x * E)
     step_instance<LANES, SOLVER>(g, lay, simg, dimg, cfg, env, state, obs, actions, noise, o);
 }
 
-template <int LANES, int SOLVER>
+template <int LANES, int SOLVER, bool IMG_SMEM>
 __global__ void __launch_bounds__(kMaxThreads)
 solve_kernel(const Layout lay, const EnvCfg cfg, const void* __restrict__ img, const int slot_bytes,
              D2* __restrict__ mscratch, const double* __restrict__ p_inj, const SolOut o, const long long B) {
   extern __shared__ __align__(16) unsigned char smem[];
-  stage_image(smem, img, lay.img_bytes);
-  const int* simg = (const int*)(smem + kSmemHeader);
-  const double* dimg = (const double*)(smem + kSmemHeader);
-  const auto g = make_group<LANES, SOLVER>(lay, smem, slot_bytes, mscratch);
+  if (IMG_SMEM) stage_image(smem, img, lay.img_bytes);
+  const int* simg = IMG_SMEM ? (const int*)(smem + kSmemHeader) : (const int*)img;
+  const double* dimg = IMG_SMEM ? (const double*)(smem + kSmemHeader) : (const double*)img;
+  const auto g = make_group<LANES, SOLVER>(lay, smem + kSmemHeader + (IMG_SMEM ? lay.img_bytes : 0),
+                                           slot_bytes, mscratch);
   const int E = blockDim.x / LANES;
   for (long long env = (long long)blockIdx.x * E + threadIdx.x / LANES; env < B; env += (long long)gridDim.x * E)
     solve_instance<LANES, SOLVER>(g, lay, simg, dimg, cfg, env, p_inj, o);
@@ -113,6 +122,7 @@ reset_kernel(const Layout lay, const EnvCfg cfg, const void* __restrict__ img,
              const long long B) {
   constexpr int LANES = 4;
   Lanes<LANES> g;
+  g.red = nullptr;
   g.lane = threadIdx.x % LANES;
   g.mask = ((1u << LANES) - 1u) << (((threadIdx.x & 31) / LANES) * LANES);
   const int* simg = (const int*)img;
@@ -204,7 +214,7 @@ struct gfr_env {
 
 namespace {
 
-struct LaunchPlan { int lanes, threads, grid; size_t smem; int ctas_per_sm; int slot_bytes; size_t mscratch_bytes; };
+struct LaunchPlan { int lanes, threads, grid; size_t smem; int ctas_per_sm; int slot_bytes; size_t mscratch_bytes; bool img_smem; };
 
 // shared memory of one instance slot; 0 if the scratch it doubles as cannot hold the sources
 size_t slot_bytes(const Layout& lay, int solver) {
@@ -215,64 +225,77 @@ size_t slot_bytes(const Layout& lay, int solver) {
 int auto_lanes(const Layout& lay, int solver) {
   if (lay.n <= 20) return solver == GFR_SOLVER_SWEEP ? 1 : 4;
   if (lay.n <= 64) return 4;
-  return 16;
+  if (lay.n <= 400) return 16;
+  return 128;                      // one CTA per instance
 }
 
 template <int SOLVER>
-const void* step_fn(int lanes) {
-  switch (lanes) {
-    case 1: return (const void*)step_kernel<1, SOLVER>;
-    case 2: return (const void*)step_kernel<2, SOLVER>;
-    case 4: return (const void*)step_kernel<4, SOLVER>;
-    case 8: return (const void*)step_kernel<8, SOLVER>;
-    case 16: return (const void*)step_kernel<16, SOLVER>;
-    case 32: return (const void*)step_kernel<32, SOLVER>;
+const void* step_fn(int lanes, bool img_smem) {
+  if (img_smem) {
+    switch (lanes) {
+      case 1: return (const void*)step_kernel<1, SOLVER, true>;
+      case 2: return (const void*)step_kernel<2, SOLVER, true>;
+      case 4: return (const void*)step_kernel<4, SOLVER, true>;
+      case 8: return (const void*)step_kernel<8, SOLVER, true>;
+      case 16: return (const void*)step_kernel<16, SOLVER, true>;
+      case 32: return (const void*)step_kernel<32, SOLVER, true>;
+    }
+  } else {
+    switch (lanes) {
+      case 32: return (const void*)step_kernel<32, SOLVER, false>;
+      case 64: return (const void*)step_kernel<64, SOLVER, false>;
+      case 128: return (const void*)step_kernel<128, SOLVER, false>;
+      case 256: return (const void*)step_kernel<256, SOLVER, false>;
+    }
   }
   return nullptr;
 }
 template <int SOLVER>
-const void* solve_fn(int lanes) {
-  switch (lanes) {
-    case 1: return (const void*)solve_kernel<1, SOLVER>;
-    case 2: return (const void*)solve_kernel<2, SOLVER>;
-    case 4: return (const void*)solve_kernel<4, SOLVER>;
-    case 8: return (const void*)solve_kernel<8, SOLVER>;
-    case 16: return (const void*)solve_kernel<16, SOLVER>;
-    case 32: return (const void*)solve_kernel<32, SOLVER>;
+const void* solve_fn(int lanes, bool img_smem) {
+  if (img_smem) {
+    switch (lanes) {
+      case 1: return (const void*)solve_kernel<1, SOLVER, true>;
+      case 2: return (const void*)solve_kernel<2, SOLVER, true>;
+      case 4: return (const void*)solve_kernel<4, SOLVER, true>;
+      case 8: return (const void*)solve_kernel<8, SOLVER, true>;
+      case 16: return (const void*)solve_kernel<16, SOLVER, true>;
+      case 32: return (const void*)solve_kernel<32, SOLVER, true>;
+    }
+  } else {
+    switch (lanes) {
+      case 32: return (const void*)solve_kernel<32, SOLVER, false>;
+      case 64: return (const void*)solve_kernel<64, SOLVER, false>;
+      case 128: return (const void*)solve_kernel<128, SOLVER, false>;
+      case 256: return (const void*)solve_kernel<256, SOLVER, false>;
+    }
   }
   return nullptr;
 }
-const void* kernel_fn(bool step, int solver, int lanes) {
-  if (step) return solver == GFR_SOLVER_NEWTON ? step_fn<SOLVER_NEWTON>(lanes) : step_fn<SOLVER_SWEEP>(lanes);
-  return solver == GFR_SOLVER_NEWTON ? solve_fn<SOLVER_NEWTON>(lanes) : solve_fn<SOLVER_SWEEP>(lanes);
+const void* kernel_fn(bool step, int solver, int lanes, bool img_smem) {
+  if (step) return solver == GFR_SOLVER_NEWTON ? step_fn<SOLVER_NEWTON>(lanes, img_smem) : step_fn<SOLVER_SWEEP>(lanes, img_smem);
+  return solver == GFR_SOLVER_NEWTON ? solve_fn<SOLVER_NEWTON>(lanes, img_smem) : solve_fn<SOLVER_SWEEP>(lanes, img_smem);
 }
 
-// Instance slots per CTA and CTAs per SM: the split of an SM's shared memory (each CTA carries one
-// copy of the feeder image) that keeps the most instances resident, checked against the kernel's
-// real register use through the occupancy API.
-int plan_launch(const gfr_feeder* f, bool step, int solver, int lanes, long long B, LaunchPlan* out,
-                const void** fn_out) {
-  const Layout& lay = f->lay;
-  if (lanes == 0) lanes = auto_lanes(lay, solver);
-  if (lanes != 1 && lanes != 2 && lanes != 4 && lanes != 8 && lanes != 16 && lanes != 32)
-    return fail(GFR_E_ARG, "lanes must be 0 (auto), 1, 2, 4, 8, 16 or 32");
-  const void* fn = kernel_fn(step, solver, lanes);
-  const size_t per_env = slot_bytes(lay, solver);
-  if (!per_env)
-    return fail(GFR_E_LIMIT, "more loads + generators + batteries than the solver's working set can stage "
-                             "(sweep: 2 per bus on average)");
-  GFR_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, f->smem_optin));
-  const size_t fixed = kSmemHeader + (size_t)lay.img_bytes;
+// One candidate split of an SM: `c` CTAs of E instance slots each.
+struct PlanTry { long long resident = 0; LaunchPlan plan{}; };
+
+PlanTry plan_mode(const gfr_feeder* f, const void* fn, int lanes, bool img_smem, size_t per_env, long long B) {
+  PlanTry best;
+  if (!fn) return best;
+  if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, f->smem_optin) != cudaSuccess) {
+    cudaGetLastError();
+    return best;
+  }
+  const size_t fixed = kSmemHeader + (img_smem ? (size_t)f->lay.img_bytes : 0) + (lanes > 32 ? kRedBytes : 0);
   const size_t sm_total = (size_t)f->smem_per_sm;
   const int gran = lanes >= 32 ? 1 : 32 / lanes;         // whole warps
-  long long best_resident = 0;
-  LaunchPlan best{};
   // pass 0: whole warps only; pass 1 (only if nothing fits): a partial warp
-  for (int pass = 0; pass < 2 && !best_resident; ++pass) {
+  for (int pass = 0; pass < 2 && !best.resident; ++pass) {
     for (int c = 1; c <= 16; ++c) {
       const size_t share = sm_total / c;
       if (share < fixed + per_env + 1024) break;
       long long E = (long long)((share - 1024 - fixed) / per_env);
+      if (lanes > 32) E = 1;                              // one CTA per instance
       if (E * lanes > kMaxThreads) E = kMaxThreads / lanes;
       if (pass == 0) E -= E % gran;
       if (E < 1) continue;
@@ -281,32 +304,59 @@ int plan_launch(const gfr_feeder* f, bool step, int solver, int lanes, long long
       if (smem > (size_t)f->smem_optin) continue;
       int nb = 0;
       if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, threads, smem) != cudaSuccess) { cudaGetLastError(); continue; }
-      if (nb > c) nb = c;
+      if (nb > c && lanes <= 32) nb = c;
       const long long resident = (long long)nb * E;
       // more resident instances win.  On a tie: a short launch (few waves) takes more, smaller CTAs,
       // which even out its last wave; a long one takes fewer, so that fewer copies of the image are staged
       const bool short_launch = B < 8 * (long long)f->sm_count * (resident > 0 ? resident : 1);
-      const bool tie = resident == best_resident && resident > 0 &&
-                       (short_launch ? nb > best.ctas_per_sm : nb < best.ctas_per_sm);
-      if (resident > best_resident || tie) {
-        best_resident = resident;
-        best.lanes = lanes; best.threads = threads; best.smem = smem; best.ctas_per_sm = nb;
+      const bool tie = resident == best.resident && resident > 0 &&
+                       (short_launch ? nb > best.plan.ctas_per_sm : nb < best.plan.ctas_per_sm);
+      if (resident > best.resident || tie) {
+        best.resident = resident;
+        best.plan.lanes = lanes; best.plan.threads = threads; best.plan.smem = smem; best.plan.ctas_per_sm = nb;
+        best.plan.img_smem = img_smem;
       }
+      if (lanes > 32) break;                               // E is fixed: the occupancy API said how many CTAs fit
     }
   }
-  if (!best_resident)
-    return fail(GFR_E_LIMIT, "feeder image + one instance's working set exceed the shared memory of an SM");
-  const long long E = best.threads / lanes;
+  return best;
+}
+
+// Instance slots per CTA and CTAs per SM: the split of an SM's shared memory that keeps the most
+// instances resident, checked against the kernel's real register use through the occupancy API.
+// Small and medium feeders stage one copy of the feeder image per CTA; when that leaves fewer than
+// four instances resident (or the group is CTA-wide) the image is read from global memory instead.
+int plan_launch(const gfr_feeder* f, bool step, int solver, int lanes, long long B, LaunchPlan* out,
+                const void** fn_out) {
+  const Layout& lay = f->lay;
+  if (lanes == 0) lanes = auto_lanes(lay, solver);
+  if (lanes != 1 && lanes != 2 && lanes != 4 && lanes != 8 && lanes != 16 && lanes != 32 && lanes != 64 &&
+      lanes != 128 && lanes != 256)
+    return fail(GFR_E_ARG, "lanes must be 0 (auto), 1, 2, 4, 8, 16, 32 (part of a warp) or 64, 128, 256 (one CTA per instance)");
+  const size_t per_env = slot_bytes(lay, solver);
+  if (!per_env)
+    return fail(GFR_E_LIMIT, "more loads + generators + batteries than the solver's working set can stage "
+                             "(sweep: 2 per bus on average)");
+  PlanTry best;
+  if (lanes <= 32) best = plan_mode(f, kernel_fn(step, solver, lanes, true), lanes, true, per_env, B);
+  if (lanes > 32 || (lanes == 32 && best.resident < 4)) {
+    PlanTry alt = plan_mode(f, kernel_fn(step, solver, lanes, false), lanes, false, per_env, B);
+    if (alt.resident > best.resident) best = alt;
+  }
+  if (!best.resident)
+    return fail(GFR_E_LIMIT, "one instance's working set (plus the feeder image) exceeds the shared memory of an SM");
+  LaunchPlan plan = best.plan;
+  const long long E = plan.threads / lanes;
   long long tiles = (B + E - 1) / E;
-  long long grid = (long long)f->sm_count * best.ctas_per_sm;
+  long long grid = (long long)f->sm_count * plan.ctas_per_sm;
   if (grid > tiles) grid = tiles;
   if (grid < 1) grid = 1;
-  best.grid = (int)grid;
-  best.slot_bytes = (int)per_env;
+  plan.grid = (int)grid;
+  plan.slot_bytes = (int)per_env;
   // Newton spills D^-1 U (32 B per bus) of every resident instance slot to global memory
-  best.mscratch_bytes = solver == GFR_SOLVER_NEWTON ? (size_t)grid * E * newton_scratch_doubles(lay.n) * 8 : 0;
-  *out = best;
-  *fn_out = fn;
+  plan.mscratch_bytes = solver == GFR_SOLVER_NEWTON ? (size_t)grid * E * newton_scratch_doubles(lay.n) * 8 : 0;
+  *out = plan;
+  *fn_out = kernel_fn(step, solver, lanes, plan.img_smem);
   return GFR_OK;
 }
 
@@ -372,14 +422,6 @@ int gfr_feeder_create(const gfr_feeder_desc* d, int device, gfr_feeder** out) {
   if (!guard.ok) return fail(GFR_E_CUDA, "no usable CUDA device (this library has no CPU fallback)");
   cudaDeviceProp prop;
   GFR_CUDA(cudaGetDeviceProperties(&prop, device));
-  // a large feeder keeps its shared memory for the working set: drop the flat-start factor table
-  if (kSmemHeader + (size_t)fi.lay.img_bytes + newton_slot_bytes(fi.lay.n, fi.lay.n_pool, 0) >
-      (size_t)prop.sharedMemPerBlockOptin / 2) {
-    fi = FeederImage();
-    std::string complaint = build_feeder_image(d, &fi, false);
-    if (!complaint.empty()) return fail(GFR_E_ARG, complaint);
-  }
-
   auto* f = new gfr_feeder();
   f->device = device;
   f->sm_count = prop.multiProcessorCount;

@@ -79,63 +79,56 @@ struct SolveStat {
 
 // ----------------------------------------------------------------------------- group ops
 
+struct OpMaxNan { GFR_HD double operator()(double v, double w) const { return (w > v || w != w) ? w : v; } };
+struct OpMinNan { GFR_HD double operator()(double v, double w) const { return (w < v || w != w) ? w : v; } };
+struct OpMax { GFR_HD double operator()(double v, double w) const { return fmax(v, w); } };
+struct OpMin { GFR_HD double operator()(double v, double w) const { return fmin(v, w); } };
+struct OpSum { GFR_HD double operator()(double v, double w) const { return v + w; } };
+
+// The threads that cooperate on one instance.  LANES <= 32: part of one warp, group barrier =
+// __syncwarp(mask), reductions by shuffles.  LANES > 32: the whole CTA owns the instance ("one
+// CTA per instance" for large feeders), barrier = __syncthreads(), reductions go warp-first and
+// then through `red` (shared memory, LANES / 32 doubles).
 template <int LANES>
 struct Lanes {
   int lane;        // lane inside the group
-  unsigned mask;   // the group's lanes inside its warp
+  unsigned mask;   // LANES <= 32: the group's lanes inside its warp
+  double* red;     // LANES > 32: cross-warp reduction scratch
   // first index >= k0 owned by this lane (lane k % LANES owns bus k in every phase)
   GFR_HD int first(int k0) const { return k0 + ((lane - k0) & (LANES - 1)); }
 
   GFR_HD void sync() const {
 #if defined(__CUDA_ARCH__)
-    if (LANES > 1) __syncwarp(mask);
+    if (LANES > 32) __syncthreads();
+    else if (LANES > 1) __syncwarp(mask);
 #endif
   }
-  GFR_HD double gmax_nan(double v) const {   // NaN-propagating max (numpy semantics)
+  template <class Op>
+  GFR_HD double reduce(double v, Op op) const {   // every lane gets the result
 #if defined(__CUDA_ARCH__)
+    if (LANES <= 32) {
 #pragma unroll
-    for (int o = LANES / 2; o > 0; o >>= 1) {
-      double w = __shfl_xor_sync(mask, v, o);
-      v = (w > v || w != w) ? w : v;
+      for (int o = LANES / 2; o > 0; o >>= 1) v = op(v, __shfl_xor_sync(mask, v, o));
+    } else {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v = op(v, __shfl_xor_sync(0xffffffffu, v, o));
+      __syncthreads();                              // the previous reduction has been read by everyone
+      if ((lane & 31) == 0) red[lane >> 5] = v;
+      __syncthreads();
+      v = red[0];
+#pragma unroll
+      for (int w = 1; w < LANES / 32; ++w) v = op(v, red[w]);
     }
 #endif
     return v;
   }
-  GFR_HD double gmax(double v) const {
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-    for (int o = LANES / 2; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(mask, v, o));
-#endif
-    return v;
-  }
-  GFR_HD double gmin(double v) const {
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-    for (int o = LANES / 2; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(mask, v, o));
-#endif
-    return v;
-  }
-  GFR_HD double gsum(double v) const {
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-    for (int o = LANES / 2; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o);
-#endif
-    return v;
-  }
-  GFR_HD int gsum(int v) const {
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-    for (int o = LANES / 2; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o);
-#endif
-    return v;
-  }
-  GFR_HD int gor(int v) const {
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-    for (int o = LANES / 2; o > 0; o >>= 1) v |= __shfl_xor_sync(mask, v, o);
-#endif
-    return v;
-  }
+  GFR_HD double gmax_nan(double v) const { return reduce(v, OpMaxNan()); }   // NaN-propagating (numpy semantics)
+  GFR_HD double gmin_nan(double v) const { return reduce(v, OpMinNan()); }
+  GFR_HD double gmax(double v) const { return reduce(v, OpMax()); }
+  GFR_HD double gmin(double v) const { return reduce(v, OpMin()); }
+  GFR_HD double gsum(double v) const { return reduce(v, OpSum()); }
+  GFR_HD int gsum(int v) const { return (int)reduce((double)v, OpSum()); }      // small counts: exact
+  GFR_HD int gor(int v) const { return reduce(v ? 1.0 : 0.0, OpMax()) != 0.0; }
 };
 
 // sweep working set: one record of NF_SWEEP doubles per bus
@@ -980,18 +973,7 @@ GFR_HD void step_instance(const typename GroupOf<LANES, SOLVER>::type& g, const 
   loss_pu = g.gsum(loss_pu);
   over80 = g.gsum(over80);
   vmax = g.gmax_nan(vmax);
-  {
-    // NaN-propagating min
-    double v = vmin;
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-    for (int off = LANES / 2; off > 0; off >>= 1) {
-      double w = __shfl_xor_sync(g.mask, v, off);
-      v = (w < v || w != w) ? w : v;
-    }
-#endif
-    vmin = v;
-  }
+  vmin = g.gmin_nan(vmin);
   v_hi = g.gor(v_hi); v_lo = g.gor(v_lo);
   tot_ren = g.gsum(tot_ren); tot_used = g.gsum(tot_used); soc_reward = g.gsum(soc_reward);
 

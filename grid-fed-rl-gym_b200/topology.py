@@ -524,7 +524,9 @@ def auto_lanes(n_bus: int, solver: str = "newton") -> int:
         return 1 if solver == "sweep" else 4
     if n_bus <= 64:
         return 4
-    return 16
+    if n_bus <= 400:
+        return 16
+    return 128                       # one CTA per instance, feeder image read from global memory
 
 
 def compile_for_solver(feeder, solver: str = "newton", lanes: int = 0,

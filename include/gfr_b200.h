@@ -95,7 +95,9 @@ typedef struct {
   int32_t max_iterations;
   double tolerance;                 /* newton: max |dP|,|dQ| (pu); sweep: max |dV| (pu) */
   double acceleration;              /* newton only; reference default 1.0 */
-  int32_t lanes;                    /* 0 = auto; threads cooperating on one instance (4,8,16,32 or CTA size) */
+  int32_t lanes;                    /* 0 = auto; threads cooperating on one instance: 1..32 (part of a warp,
+                                       feeder image staged in shared memory) or 64, 128, 256 (one CTA per
+                                       instance, feeder image read from global memory) */
   int32_t reserved;
 } gfr_solver_cfg;
 

@@ -62,6 +62,18 @@ def test_newton_step_matches_reference_trace(name, lanes):
     assert exact >= 0.9 * g["obs"].shape[0]
 
 
+@pytest.mark.parametrize("lanes", (64, 256))
+@pytest.mark.parametrize("name", ("trace_ieee13_s0", "trace_ieee34_s0", "trace_ieee123_s0", "trace_fixture3_s0"))
+def test_cta_per_instance_matches_reference_trace(name, lanes):
+    """LANES > 32: one CTA per instance, CTA barriers, feeder image read from global memory."""
+    g = load_golden(name)
+    exact = replay_trace(_factory("newton", lanes), g, ctx=f"{name}/cta{lanes}")
+    assert exact >= 0.9 * g["obs"].shape[0]
+    gs = port_trace(g, tolerance=1e-10)
+    exact = replay_trace(_factory("sweep", lanes, 1e-11), gs, ctx=f"{name}/sweep/cta{lanes}", check_iterations=False)
+    assert exact >= 0.9 * g["obs"].shape[0]
+
+
 @pytest.mark.parametrize("lanes", (1, 8, 32))
 @pytest.mark.parametrize("name", golden_names("trace_"))
 def test_sweep_step_matches_oracle_trace(name, lanes):
@@ -365,7 +377,7 @@ def _synthetic(n, seed, scale):
     return f
 
 
-@pytest.mark.parametrize("lanes", (8, 32))
+@pytest.mark.parametrize("lanes", (8, 32, 128))
 def test_synthetic_300_bus_feeder_vs_oracle(lanes):
     """A larger radial feeder with hundreds of loads / generators / batteries (BASELINE config 5's
     generator at a size the dense oracle still solves quickly)."""
@@ -401,7 +413,8 @@ def test_synthetic_1000_bus_feeder_runs():
     import grid_fed_rl_b200 as m
     f = _synthetic(1000, 1000, 0.03)
     kw = dict(timestep=60.0, renewable_sources=["solar", "wind"], repair=False, start_time=12 * 3600.0)
-    a = m.BatchedGridEnvironment(f, 64, solver="newton", tolerance=1e-9, lanes=32, **kw)
+    a = m.BatchedGridEnvironment(f, 64, solver="newton", tolerance=1e-9, **kw)          # auto: one CTA per instance
+    assert a.launch_info()["lanes"] == 128
     b = m.BatchedGridEnvironment(f, 64, solver="sweep", tolerance=1e-11, lanes=32, **kw)
     assert a.obs_dim == 6320 and a.act_dim == 403
     a.reset(seed=1); b.reset(seed=1)
