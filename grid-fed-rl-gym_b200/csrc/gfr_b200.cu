@@ -24,7 +24,13 @@ using namespace gfr;
 namespace {
 
 constexpr int kSmemHeader = 16;   // the mbarrier, keeps the image 16-byte aligned
-constexpr int kMaxThreads = 512;  // per CTA: leaves 128 registers per thread
+// threads per CTA the kernels are compiled for (sets their register budget: 65536 / threads).
+// 16-lane groups are the ones that want more than 512 threads (IEEE-123: 38 instances x 16 lanes).
+#ifndef GFR_MAX_THREADS_16
+#define GFR_MAX_THREADS_16 512
+#endif
+constexpr int kMaxThreads = 512;
+constexpr int max_threads_for(int lanes) { return lanes == 16 ? GFR_MAX_THREADS_16 : kMaxThreads; }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
@@ -81,7 +87,7 @@ make_group(const Layout& lay, unsigned char* work, int slot_bytes, D2* mscratch)
 // IMG_SMEM: the feeder image is staged into shared memory (small / medium feeders); otherwise it is
 // read through L1 / L2 from global memory and all of shared memory goes to the working sets.
 template <int LANES, int SOLVER, bool IMG_SMEM>
-__global__ void __launch_bounds__(kMaxThreads)
+__global__ void __launch_bounds__(max_threads_for(LANES))
 step_kernel(const Layout lay, const EnvCfg cfg, const void* __restrict__ img, const int slot_bytes,
             D2* __restrict__ mscratch, double* __restrict__ state, double* __restrict__ obs,
             const double* __restrict__ actions, const double* __restrict__ noise, const StepOut o,
@@ -98,7 +104,7 @@ step_kernel(const Layout lay, const EnvCfg cfg, const void* __restrict__ img, co
 }
 
 template <int LANES, int SOLVER, bool IMG_SMEM>
-__global__ void __launch_bounds__(kMaxThreads)
+__global__ void __launch_bounds__(max_threads_for(LANES))
 solve_kernel(const Layout lay, const EnvCfg cfg, const void* __restrict__ img, const int slot_bytes,
              D2* __restrict__ mscratch, const double* __restrict__ p_inj, const SolOut o, const long long B) {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -296,7 +302,7 @@ PlanTry plan_mode(const gfr_feeder* f, const void* fn, int lanes, bool img_smem,
       if (share < fixed + per_env + 1024) break;
       long long E = (long long)((share - 1024 - fixed) / per_env);
       if (lanes > 32) E = 1;                              // one CTA per instance
-      if (E * lanes > kMaxThreads) E = kMaxThreads / lanes;
+      if (E * lanes > max_threads_for(lanes)) E = max_threads_for(lanes) / lanes;
       if (pass == 0) E -= E % gran;
       if (E < 1) continue;
       const int threads = (int)(E * lanes);

@@ -59,7 +59,7 @@ struct alignas(16) I4 { int x, y, z, w; };   // per-bus topology: parent, child 
 // plus the sizes; passed as a kernel parameter (constant bank).
 struct Layout {
   int n, nl, L, G, Bt, A, D, m, n_src, R, img_bytes, n_noise, n_pool;
-  int o_topo, o_child_idx, o_child_pool, o_level_ptr, o_order, o_rank, o_line_of, o_branch_of_line, o_inj_ptr, o_inj_idx,
+  int o_topo, o_child_idx, o_child_pool, o_level_ptr, o_rank, o_branch_of_line, o_inj_ptr, o_inj_idx,
       o_gen_type;
   int o_gb, o_gbd, o_rx, o_f0, o_rating, o_vm_set, o_load_base, o_gen_cap, o_gen_p0, o_gen_p1, o_gen_p2,
       o_bat_cap, o_bat_rating, o_bat_eff, o_profile;

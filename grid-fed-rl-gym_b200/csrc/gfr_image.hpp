@@ -100,7 +100,7 @@ inline std::string build_feeder_image(const gfr_feeder_desc* d, FeederImage* out
   lay.load_p_sum = lp;
 
   ImageBuilder ib;
-  std::vector<int32_t> flags(n), rank(n), bol(n > 1 ? n - 1 : 0), line_of(n);
+  std::vector<int32_t> flags(n), rank(n), bol(n > 1 ? n - 1 : 0);
   for (int k = 0; k < n; ++k) {
     int fl = 0;
     if (d->bus_type[k] == GFR_BUS_PQ) fl |= FL_PQ;
@@ -110,7 +110,6 @@ inline std::string build_feeder_image(const gfr_feeder_desc* d, FeederImage* out
     if (d->from_is_parent[k]) fl |= FL_FROM_IS_PARENT;
     flags[k] = fl;
     rank[d->order[k]] = k;
-    line_of[k] = d->line_of[k];
     if (k > 0) bol[d->line_of[k]] = k;
   }
   // injection sources per bus: loads, then generators, then batteries (reference accumulation order)
@@ -170,9 +169,7 @@ inline std::string build_feeder_image(const gfr_feeder_desc* d, FeederImage* out
   for (int q = 0; q < n - 1; ++q) child_pool[q] = 3 * pool_slot[d->child_idx[q]];
   lay.o_child_pool = ib.add_i(child_pool.data(), n - 1);
   lay.o_level_ptr = ib.add_i(d->level_ptr, nl + 1);
-  lay.o_order = ib.add_i(d->order, n);
   lay.o_rank = ib.add_i(rank.data(), n);
-  lay.o_line_of = ib.add_i(line_of.data(), n);
   lay.o_branch_of_line = ib.add_i(bol.data(), n - 1);
   lay.o_inj_ptr = ib.add_i(inj_ptr.data(), n + 1);
   lay.o_inj_idx = ib.add_i(inj_idx.data(), lay.n_src);
