@@ -17,7 +17,7 @@ __all__ = [
     "GridEnvironmentError", "GridLimitError", "InvalidActionError", "InvalidConfigurationError",
     "NativeRuntimeError", "NetworkTopologyError", "PowerFlowError",
     "BatchedGridEnvironment", "B200PowerFlowSolver", "shard_range",
-    "GridEnvironment", "VectorizedEnvironment", "RolloutBuffer", "collect_random_data",
+    "GridEnvironment", "VectorizedEnvironment", "RolloutBuffer", "collect_random_data", "HostStepper",
 ]
 
 
@@ -35,4 +35,7 @@ def __getattr__(name):
     if name in ("GridEnvironment", "VectorizedEnvironment", "RolloutBuffer", "collect_random_data"):
         from . import compat
         return getattr(compat, name)
+    if name == "HostStepper":
+        from .pipeline import HostStepper
+        return HostStepper
     raise AttributeError(name)

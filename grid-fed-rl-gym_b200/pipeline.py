@@ -1,0 +1,78 @@
+"""Host-driven stepping with the PCIe copies off the critical path.
+
+``HostStepper`` is for callers whose actions live in host memory (a CPU policy, a recorded
+action log, the reference's own loops): every step still copies that step's actions host ->
+device and its reward / done flags device -> host, but the copy of step t+1's actions runs on a
+second stream while step t's kernel executes, and the results come back through pinned buffers
+one step behind the submissions (depth-2 software pipeline).  ``depth=1`` degenerates to the
+plain copy - step - copy - synchronise sequence.
+"""
+
+from __future__ import annotations
+
+from collections import deque
+from typing import Deque, Dict, Tuple
+
+import torch
+
+from .env import BatchedGridEnvironment
+
+
+class HostStepper:
+    def __init__(self, env: BatchedGridEnvironment, depth: int = 2) -> None:
+        if depth < 1:
+            raise ValueError("depth must be >= 1")
+        self.env, self.depth = env, depth
+        dev, B, A = env.device, env.num_envs, env.act_dim
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self._act = [torch.empty(B, A, dtype=torch.float64, device=dev) for _ in range(depth)]
+        self._host = [dict(reward=torch.empty(B, dtype=torch.float64).pin_memory(),
+                           terminated=torch.empty(B, dtype=torch.bool).pin_memory(),
+                           truncated=torch.empty(B, dtype=torch.bool).pin_memory())
+                      for _ in range(depth)]
+        self._copied = [torch.cuda.Event() for _ in range(depth)]
+        self._done = [torch.cuda.Event() for _ in range(depth)]
+        self._busy = [False] * depth
+        self._pending: Deque[int] = deque()
+        self._n = 0
+
+    @property
+    def h2d_bytes_per_step(self) -> int:
+        return self.env.num_envs * self.env.act_dim * 8
+
+    @property
+    def d2h_bytes_per_step(self) -> int:
+        return self.env.num_envs * (8 + 1 + 1)
+
+    def submit(self, host_actions: torch.Tensor) -> None:
+        """Queue one step.  ``host_actions``: pinned fp64 ``[B, A]`` (a pageable tensor works but
+        makes the copy synchronous)."""
+        j = self._n % self.depth
+        if len(self._pending) >= self.depth:
+            raise RuntimeError("pipeline full: call result() first")
+        compute = torch.cuda.current_stream(self.env.device)
+        with torch.cuda.stream(self.copy_stream):
+            if self._busy[j]:
+                self.copy_stream.wait_event(self._done[j])      # the step that last read this buffer
+            self._act[j].copy_(host_actions, non_blocking=True)
+            self._copied[j].record(self.copy_stream)
+        compute.wait_event(self._copied[j])
+        _, reward, term, trunc, _ = self.env.step(self._act[j])
+        h = self._host[j]
+        h["reward"].copy_(reward, non_blocking=True)
+        h["terminated"].copy_(term, non_blocking=True)
+        h["truncated"].copy_(trunc, non_blocking=True)
+        self._done[j].record(compute)
+        self._busy[j] = True
+        self._pending.append(j)
+        self._n += 1
+
+    def result(self) -> Dict[str, torch.Tensor]:
+        """Host tensors (pinned, reused ``depth`` steps later) of the oldest submitted step."""
+        j = self._pending.popleft()
+        self._done[j].synchronize()
+        return self._host[j]
+
+    def drain(self) -> None:
+        while self._pending:
+            self.result()

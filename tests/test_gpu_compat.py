@@ -107,3 +107,32 @@ def test_rollout_buffer_matches_a_step_by_step_loop():
     assert torch.allclose(buf.denormalize_observation(z), ref, atol=1e-9)
     out = buf.to_numpy()
     assert out["terminals"].dtype == bool and out["actions"].shape == (192, env.act_dim)
+
+
+def test_host_stepper_pipeline_matches_plain_stepping():
+    """Depth-2 pipelining of the host copies must not change a single result."""
+    import grid_fed_rl_b200 as m
+    f = m.repair_topology(m.IEEE13Bus())
+    kw = dict(renewable_sources=["solar", "wind"], timestep=60.0, repair=False, start_time=10 * 3600.0)
+    a = m.BatchedGridEnvironment(f, 512, **kw); a.reset(seed=3)
+    rs = np.random.RandomState(0)
+    acts = [torch.from_numpy(rs.uniform(-1, 1, size=(512, a.act_dim))).pin_memory() for _ in range(7)]
+    plain = []
+    for x in acts:
+        _, r, t, u, _ = a.step(x)
+        plain.append((r.cpu().clone(), t.cpu().clone(), u.cpu().clone()))
+    for depth in (1, 2, 3):
+        # a fresh environment each time: wind / temperature / cloud survive a reset, as upstream
+        b = m.BatchedGridEnvironment(f, 512, **kw); b.reset(seed=3)
+        st = m.HostStepper(b, depth=depth)
+        got = []
+        for i, x in enumerate(acts):
+            st.submit(x)
+            if i + 1 >= depth:
+                h = st.result(); got.append((h["reward"].clone(), h["terminated"].clone(), h["truncated"].clone()))
+        while st._pending:
+            h = st.result(); got.append((h["reward"].clone(), h["terminated"].clone(), h["truncated"].clone()))
+        assert len(got) == len(plain)
+        for (r0, t0, u0), (r1, t1, u1) in zip(plain, got):
+            assert torch.equal(r0, r1) and torch.equal(t0, t1) and torch.equal(u0, u1)
+        assert st.h2d_bytes_per_step == 512 * a.act_dim * 8 and st.d2h_bytes_per_step == 512 * 10
