@@ -426,3 +426,62 @@ def test_synthetic_1000_bus_feeder_runs():
         assert bool(ia["power_flow_converged"].all()) and bool(ib["power_flow_converged"].all())
         assert torch.max(torch.abs(oa[:, :2000] - ob[:, :2000])) <= TOL_PU
         assert torch.allclose(ra, rb, rtol=1e-9, atol=1e-5)
+
+
+def test_edge_case_feeders_vs_oracle():
+    """Smallest feeders, no loads, a single instance, out-of-range actions, loads driven to zero."""
+    import grid_fed_rl_b200 as m
+    cases = []
+    two = m.SimpleRadialFeeder(2)
+    cases.append(("two buses", two, {}))
+    bare = m.SimpleRadialFeeder(4)
+    bare.loads.clear()                                  # no loads at all: only the template battery
+    cases.append(("no loads", bare, {}))
+    cases.append(("radial 7, no renewables, deterministic", m.SimpleRadialFeeder(7),
+                  dict(stochastic_loads=False, weather_variation=False)))
+    for name, f, extra in cases:
+        for B in (1, 5):
+            for solver, tol, ptol in (("newton", 1e-9, 1e-9), ("sweep", 1e-12, 1e-10)):
+                kw = dict(timestep=900.0, renewable_sources=["solar", "wind"], **extra)
+                env = m.BatchedGridEnvironment(f, B, solver=solver, tolerance=tol, repair=False, **kw)
+                ref = port.PortEnv(f, B, tolerance=ptol, **kw)
+                rs = np.random.RandomState(B)
+                nz0 = np.concatenate([rs.random_sample((B, 1)), rs.standard_normal((B, 3))], axis=1)
+                o0, _ = env.reset(noise=nz0, options={"start_time": 6 * 3600.0})
+                r0 = ref.reset(nz0, start_time=6 * 3600.0)
+                assert np.max(np.abs(o0.cpu().numpy() - r0)) < 1e-9, name
+                for t in range(6):
+                    act = rs.uniform(-3, 3, size=(B, ref.A))          # out of range: never clipped upstream
+                    nz = np.concatenate([rs.random_sample((B, 1)), rs.standard_normal((B, 3 + ref.L))], axis=1)
+                    if ref.L:
+                        nz[:, 4] = -15.0                                  # 1 + 0.1 z < 0: the load clamps at zero
+                    obs, reward, term, trunc, info = env.step(act, nz)
+                    r = ref.step(act, nz)
+                    assert np.array_equal(info["power_flow_converged"].cpu().numpy(), r["converged"]), name
+                    assert r["converged"].all(), name
+                    assert np.max(np.abs(obs.cpu().numpy()[:, :2 * ref.n] - r["obs"][:, :2 * ref.n])) <= TOL_PU, name
+                    assert np.allclose(obs.cpu().numpy(), r["obs"], rtol=1e-9, atol=1e-6), name
+                    assert np.allclose(reward.cpu().numpy(), r["reward"], rtol=1e-9, atol=1e-6), name
+                    assert np.array_equal(info["constraint_violation_count"].cpu().numpy(), r["viol_count"]), name
+                    assert np.array_equal(trunc.cpu().numpy(), r["truncated"]), name
+                env.close()
+
+
+def test_bad_arguments_raise():
+    import grid_fed_rl_b200 as m
+    f = m.repair_topology(m.IEEE13Bus())
+    with pytest.raises(m.InvalidConfigurationError):
+        m.BatchedGridEnvironment(f, 4, solver="gauss")
+    with pytest.raises(m.InvalidConfigurationError):
+        m.BatchedGridEnvironment(f, 0)
+    with pytest.raises(m.InvalidConfigurationError):
+        m.BatchedGridEnvironment(f, 4, lanes=3)
+    with pytest.raises(m.InvalidConfigurationError):
+        m.BatchedGridEnvironment(f, 4, device="cpu")
+    with pytest.raises(m.NetworkTopologyError):
+        m.BatchedGridEnvironment(m.IEEE34Bus(seed=0), 4, repair=False)      # meshed / disconnected as shipped
+    env = m.BatchedGridEnvironment(f, 4, renewable_sources=["solar"])
+    with pytest.raises(m.InvalidActionError):
+        env.step(np.zeros((4, env.act_dim + 1)))
+    with pytest.raises(m.InvalidActionError):
+        env.step(np.zeros((3, env.act_dim)))
