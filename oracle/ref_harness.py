@@ -336,6 +336,20 @@ TRACE_CASES = {
                                                timestep=20.0, tolerance=1e-4, max_iterations=20)),
     "trace_ieee123_s0": ("ieee123", 24, 0, dict(start_time=10 * 3600.0)),
     "trace_ieee123_s1": ("ieee123", 16, 1, dict(start_time=14 * 3600.0, timestep=300.0, tolerance=1e-8)),
+    # long runs (>= 3 seeds x >= 1000 steps on the feeders the reference can step quickly;
+    # IEEE-123 costs ~1 s per reference solve, so its long traces are 150 steps)
+    "trace_ieee13_long_s10": ("ieee13", 1000, 10, dict(start_time=6.5 * 3600.0, timestep=45.0)),
+    "trace_ieee13_long_s11": ("ieee13", 1000, 11, dict(start_time=15 * 3600.0, timestep=20.0, episode_length=300,
+                                                       nan_steps=(333, 334, 700))),
+    "trace_ieee13_long_s12": ("ieee13", 1000, 12, dict(start_time=0.0, timestep=90.0, tolerance=1e-8,
+                                                       renewable_sources=("wind",))),
+    "trace_ieee34_long_s10": ("ieee34", 1000, 10, dict(start_time=7 * 3600.0, timestep=40.0)),
+    "trace_ieee34_long_s11": ("ieee34", 1000, 11, dict(start_time=16.5 * 3600.0, timestep=10.0, episode_length=400)),
+    "trace_ieee34_long_s12": ("ieee34", 1000, 12, dict(start_time=11 * 3600.0, timestep=60.0, tolerance=1e-8,
+                                                       renewable_sources=("solar", "wind"))),
+    "trace_ieee123_long_s10": ("ieee123", 150, 10, dict(start_time=8 * 3600.0, timestep=120.0)),
+    "trace_ieee123_long_s11": ("ieee123", 150, 11, dict(start_time=13 * 3600.0, timestep=30.0, episode_length=60)),
+    "trace_ieee123_long_s12": ("ieee123", 150, 12, dict(start_time=18.5 * 3600.0, timestep=60.0, tolerance=1e-8)),
 }
 SOLVE_CASES = {
     "solve_fixture3": ("fixture3", 0, 4, 1e-10, 0.025),
