@@ -57,6 +57,8 @@ def _factory(solver, lanes, tol_override=None):
 @pytest.mark.parametrize("lanes", LANES)
 @pytest.mark.parametrize("name", golden_names("trace_"))
 def test_newton_step_matches_reference_trace(name, lanes):
+    if "_long_" in name and lanes not in (4, 16):
+        pytest.skip("long traces run at two lane counts")
     g = load_golden(name)
     exact = replay_trace(_factory("newton", lanes), g, ctx=f"{name}/lanes{lanes}")
     assert exact >= 0.9 * g["obs"].shape[0]
@@ -75,7 +77,7 @@ def test_cta_per_instance_matches_reference_trace(name, lanes):
 
 
 @pytest.mark.parametrize("lanes", (1, 8, 32))
-@pytest.mark.parametrize("name", golden_names("trace_"))
+@pytest.mark.parametrize("name", [n for n in golden_names("trace_") if "_long_" not in n])
 def test_sweep_step_matches_oracle_trace(name, lanes):
     g = port_trace(load_golden(name), tolerance=1e-10)
     exact = replay_trace(_factory("sweep", lanes, 1e-11), g, ctx=f"{name}/sweep/lanes{lanes}",
