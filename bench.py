@@ -11,6 +11,7 @@ reward, observation - one kernel launch.  Inputs (actions) are resident in HBM f
 device->host read of reward + done flags every step.
 """
 import argparse
+import ctypes
 import json
 import os
 import sys
@@ -348,6 +349,9 @@ def run_gpu(args):
     e2e_value = B * world * K / (ms_e2e * 1e-3)
     e2e_serial = B * world * K / (ms_serial * 1e-3)
 
+    fp64_peak = ctypes.c_double(0.0)
+    if rank == 0:
+        _native.check(lib, lib.gfr_fp64_peak(local, ctypes.byref(fp64_peak)))
     if rank == 0:
         soa = env.soa
         abytes = algorithmic_bytes(soa)
@@ -370,8 +374,18 @@ def run_gpu(args):
                          "frac": achieved / peak, "traffic": TRAFFIC_BYTES.get((args.workload, B)),
                          "peak_source": how, "algorithmic_bytes_per_env_step": abytes,
                          "kernel": f"step_kernel<{li['lanes']},{solver}>", "kernel_ms": ms / K,
-                         "note": "FP64-issue / latency bound, not HBM bound (ncu: FP64 pipe 32 %, DRAM 3 %): "
-                                 "see DESIGN.md section 5 and profiles/"},
+                         "note": "not HBM bound: ncu shows the L1 / shared-memory data pipe at 72 %, issue slots 54 %, "
+                                 "FP64 pipe 32 %, DRAM 3 % (DESIGN.md section 5, profiles/); see also `fp64`"},
+            # FP64 side (the contract's roofline bounds are hbm | tensor; this kernel is neither): FP64 pipe
+            # operations per env-step (ncu, profiles/: executed DFMA / DMUL / DADD / DSETP thread
+            # instructions / instances) x env-steps/s, against the DFMA issue rate measured on this
+            # device just now (gfr_fp64_peak: TFLOP/s at 2 flop per DFMA, so ops/s = TFLOP/s / 2)
+            "fp64": {"lane_ops_per_env_step": FP64_LANE_OPS.get(args.workload),
+                     "achieved_gops": (FP64_LANE_OPS[args.workload] * value / world / 1e9)
+                                      if args.workload in FP64_LANE_OPS else None,
+                     "peak_gops": fp64_peak.value * 1e3 / 2.0, "peak_dfma_tflops": fp64_peak.value,
+                     "frac": (FP64_LANE_OPS[args.workload] * value / world / 1e9 / (fp64_peak.value * 1e3 / 2.0))
+                             if fp64_peak.value and args.workload in FP64_LANE_OPS else None},
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": stepper.h2d_bytes_per_step,
                     "d2h_bytes_per_step": stepper.d2h_bytes_per_step, "ms_per_step": ms_e2e / K,
                     "serial_value": e2e_serial, "serial_ms_per_step": ms_serial / K,
@@ -389,6 +403,9 @@ def run_gpu(args):
     if world > 1:
         dist.destroy_process_group()
 
+
+# FP64 lane operations per env-step (ncu: executed warp instructions x FP64 share x active lanes / instances)
+FP64_LANE_OPS = {"ieee123": 60000}      # profiles/r01_ncu_ieee123_final.txt: 8.05e9 / 131072 = 61.4 k before the last trim
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the step kernel, from the ncu --set full
 # capture summarised under profiles/ (keyed by workload and instances per launch)

@@ -141,6 +141,20 @@ reset_kernel(const Layout lay, const EnvCfg cfg, const void* __restrict__ img,
   }
 }
 
+// FP64 pipe microbenchmark: 8 independent DFMA chains per thread (the roofline denominator that
+// MEASURED_PEAKS.json does not carry)
+__global__ void __launch_bounds__(256) dfma_peak_kernel(double* __restrict__ out, const int iters, const double seed) {
+  double a0 = seed + threadIdx.x, a1 = a0 + 1.0, a2 = a0 + 2.0, a3 = a0 + 3.0, a4 = a0 + 4.0, a5 = a0 + 5.0,
+         a6 = a0 + 6.0, a7 = a0 + 7.0;
+  const double m = 1.0000001, c = 1e-9;
+#pragma unroll 4
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+    a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+  }
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+
 __global__ void noise_fill_kernel(const long long B, const int n_slots,
                                   const uint64_t* __restrict__ seeds,
                                   const uint64_t* __restrict__ draws, double* __restrict__ out) {
@@ -631,6 +645,35 @@ int gfr_noise_fill(int device, int64_t B, int32_t n_slots, const uint64_t* seeds
   noise_fill_kernel<<<(int)grid, 256, 0, (cudaStream_t)stream>>>(B, n_slots, seeds, draws, out);
   g_launches.fetch_add(1);
   GFR_CUDA(cudaGetLastError());
+  return GFR_OK;
+}
+
+int gfr_fp64_peak(int device, double* tflops) {
+  if (!tflops) return fail(GFR_E_ARG, "null argument");
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail(GFR_E_CUDA, "no usable CUDA device (this library has no CPU fallback)");
+  cudaDeviceProp prop;
+  GFR_CUDA(cudaGetDeviceProperties(&prop, device));
+  const int threads = 256, blocks = prop.multiProcessorCount * 8, iters = 1 << 15;
+  double* d_out = nullptr;
+  GFR_CUDA(cudaMalloc((void**)&d_out, (size_t)blocks * threads * 8));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  double best_ms = 1e30;
+  for (int rep = 0; rep < 5; ++rep) {             // the first repetitions warm the clocks up
+    cudaEventRecord(e0, 0);
+    dfma_peak_kernel<<<blocks, threads>>>(d_out, iters, 1.0 + rep);
+    cudaEventRecord(e1, 0);
+    cudaError_t es = cudaEventSynchronize(e1);
+    g_launches.fetch_add(1);
+    if (es != cudaSuccess) { cudaFree(d_out); return cuda_fail(es, "dfma_peak_kernel"); }
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (rep >= 2 && ms < best_ms) best_ms = ms;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(d_out);
+  *tflops = 2.0 * 8.0 * (double)iters * (double)blocks * threads / (best_ms * 1e-3) / 1e12;
   return GFR_OK;
 }
 

@@ -203,6 +203,10 @@ int gfr_solve(const gfr_feeder* f, int64_t B, const double* p_inj, const gfr_sol
 int gfr_noise_fill(int device, int64_t B, int32_t n_slots, const uint64_t* seeds,
                    const uint64_t* draws, double* out, void* stream);
 
+/* Measured FP64 FMA throughput of the device (TFLOP/s, 2 flop per DFMA): the denominator for the
+ * FP64 side of the roofline, which the driver-written MEASURED_PEAKS.json does not carry. */
+int gfr_fp64_peak(int device, double* tflops);
+
 /* Launch bookkeeping for benchmarks: kernels launched by this library since load. */
 int64_t gfr_launch_count(void);
 
