@@ -298,10 +298,14 @@ def _schedule(n: int, root: int, adj, width: Optional[int], alap: bool = True):
     for v in bfs:
         steps[level[v]].append(v)
     assert all(steps) and steps[0] == [root]
-    order, level_of = [], {}
+    # Inside a level the buses follow their parents' positions: consecutive lanes then gather from
+    # (nearly) consecutive parent entries - distinct shared-memory banks - and the children of one
+    # bus sit next to each other.
+    order, level_of, pos = [], {}, {-1: -1}
     for l, members in enumerate(steps):
-        for v in sorted(members, key=lambda v: (parent_ref[v][0], v)):
+        for v in sorted(members, key=lambda v: (pos[parent_ref[v][0]], v)):
             level_of[v] = l
+            pos[v] = len(order)
             order.append(v)
     return order, parent_ref, level_of
 
