@@ -17,7 +17,7 @@ __all__ = [
     "GridEnvironmentError", "GridLimitError", "InvalidActionError", "InvalidConfigurationError",
     "NativeRuntimeError", "NetworkTopologyError", "PowerFlowError",
     "BatchedGridEnvironment", "B200PowerFlowSolver", "shard_range",
-    "GridEnvironment", "VectorizedEnvironment", "RolloutBuffer", "collect_random_data", "HostStepper",
+    "GridEnvironment", "VectorizedEnvironment", "RolloutBuffer", "collect_random_data", "GraphedCollector", "HostStepper",
 ]
 
 
@@ -32,7 +32,7 @@ def __getattr__(name):
     if name == "B200PowerFlowSolver":
         from .solver import B200PowerFlowSolver
         return B200PowerFlowSolver
-    if name in ("GridEnvironment", "VectorizedEnvironment", "RolloutBuffer", "collect_random_data"):
+    if name in ("GridEnvironment", "VectorizedEnvironment", "RolloutBuffer", "collect_random_data", "GraphedCollector"):
         from . import compat
         return getattr(compat, name)
     if name == "HostStepper":

@@ -211,14 +211,86 @@ class RolloutBuffer:
         return out
 
 
+class GraphedCollector:
+    """``chunk`` consecutive steps of the U(-1, 1) policy - action sampling, the fused step, the
+    copies into a staging block and the masked reset of finished instances - captured once in a
+    CUDA graph and replayed: one graph launch per ``chunk`` steps instead of a dozen Python-issued
+    launches per step.  That matters for small feeders, whose step kernel (0.14 ms for 65 536
+    IEEE-13 instances) is shorter than the host-side launch work around it."""
+
+    def __init__(self, env: BatchedGridEnvironment, chunk: int = 8, dtype=torch.float32) -> None:
+        if env.auto_reset or env.copy_outputs:
+            raise ValueError("GraphedCollector needs an environment with auto_reset=False, copy_outputs=False")
+        self.env, self.chunk = env, int(chunk)
+        B, D, A, dev = env.num_envs, env.obs_dim, env.act_dim, env.device
+        z = dict(device=dev, dtype=dtype)
+        self.stage = dict(observations=torch.empty(chunk, B, D, **z), actions=torch.empty(chunk, B, A, **z),
+                          rewards=torch.empty(chunk, B, **z), next_observations=torch.empty(chunk, B, D, **z),
+                          terminals=torch.empty(chunk, B, **z))
+        self._obs = env.get_observation().clone()
+        self._graph = None
+
+    def _body(self) -> None:
+        env, st = self.env, self.stage
+        for k in range(self.chunk):
+            act = torch.rand(env.num_envs, env.act_dim, dtype=torch.float64, device=env.device) * 2.0 - 1.0
+            nxt, reward, term, trunc, _ = env.step(act)
+            done = term | trunc
+            st["observations"][k].copy_(self._obs)
+            st["actions"][k].copy_(act)
+            st["rewards"][k].copy_(reward)
+            st["next_observations"][k].copy_(nxt)
+            st["terminals"][k].copy_(done)
+            env.reset(mask=done)                     # rewrites the observation rows of finished instances only
+            self._obs.copy_(env.get_observation())
+
+    def run_chunk(self) -> Dict[str, torch.Tensor]:
+        """Advance ``chunk`` steps; returns the staging block (overwritten by the next call)."""
+        if self._graph is None:
+            # first chunk eagerly (it also warms every allocation up), then capture for all later ones
+            self._body()
+            torch.cuda.synchronize(self.env.device)
+            graph = torch.cuda.CUDAGraph()
+            snapshot = self.env.state_dict()
+            obs_snapshot = self._obs.clone()
+            first = {k: v.clone() for k, v in self.stage.items()}
+            with torch.cuda.graph(graph):
+                self._body()
+            # capturing records launches without running them, but be explicit that nothing moved
+            self.env.load_state_dict(snapshot)
+            self._obs.copy_(obs_snapshot)
+            for k, v in first.items():
+                self.stage[k].copy_(v)
+            self._graph = graph
+            return self.stage
+        self._graph.replay()
+        return self.stage
+
+
 def collect_random_data(env: BatchedGridEnvironment, num_steps: int, normalize: bool = False,
-                        generator: Optional[torch.Generator] = None,
-                        dtype=torch.float32) -> RolloutBuffer:
+                        generator: Optional[torch.Generator] = None, dtype=torch.float32,
+                        graph_chunk: int = 0) -> RolloutBuffer:
     """``collect_random_data(env, n)`` (base.py:268-298) for a batched environment: ``num_steps``
     batched steps of a U(-1, 1) policy -> ``num_steps * num_envs`` transitions, instances that
-    terminate or truncate are reset (masked) before their next step.  Nothing leaves the GPU."""
+    terminate or truncate are reset (masked) before their next step.  Nothing leaves the GPU.
+    ``graph_chunk > 0`` replays that many steps per CUDA-graph launch (``GraphedCollector``; actions
+    then come from torch's default CUDA generator)."""
     B = env.num_envs
     buf = RolloutBuffer(num_steps * B, env.obs_dim, env.act_dim, env.device, dtype)
+    if graph_chunk > 0:
+        env.reset()
+        col = GraphedCollector(env, graph_chunk, dtype)
+        left = num_steps
+        while left > 0:
+            st = col.run_chunk()
+            take = min(left, graph_chunk)
+            buf.add(st["observations"][:take].reshape(take * B, -1), st["actions"][:take].reshape(take * B, -1),
+                    st["rewards"][:take].reshape(-1), st["next_observations"][:take].reshape(take * B, -1),
+                    st["terminals"][:take].reshape(-1))
+            left -= take
+        if normalize:
+            buf.normalize()
+        return buf
     obs, _ = env.reset()
     obs = obs.clone()
     for _ in range(num_steps):

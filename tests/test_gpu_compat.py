@@ -136,3 +136,44 @@ def test_host_stepper_pipeline_matches_plain_stepping():
         for (r0, t0, u0), (r1, t1, u1) in zip(plain, got):
             assert torch.equal(r0, r1) and torch.equal(t0, t1) and torch.equal(u0, u1)
         assert st.h2d_bytes_per_step == 512 * a.act_dim * 8 and st.d2h_bytes_per_step == 512 * 10
+
+
+def test_graphed_collection_is_consistent_and_faster_to_launch():
+    """collect_random_data through a CUDA graph: same transition structure as the eager loop."""
+    import time
+    import grid_fed_rl_b200 as m
+    f = m.repair_topology(m.IEEE13Bus())
+    kw = dict(renewable_sources=["solar", "wind"], episode_length=6, timestep=60.0, repair=False,
+              solver="newton")
+    B, T, chunk = 4096, 24, 8
+    env = m.BatchedGridEnvironment(f, B, **kw); env.reset(seed=1)
+    torch.manual_seed(0)
+    buf = m.collect_random_data(env, T, dtype=torch.float64, graph_chunk=chunk)
+    assert buf.size == T * B
+    d = buf.get_all_data()
+    o = d["observations"].view(T, B, -1); n = d["next_observations"].view(T, B, -1)
+    done = d["terminals"].view(T, B).bool()
+    assert bool(done[5].all()) and bool(done[11].all()) and not bool(done[:5].any())     # episode_length = 6
+    for t in range(T - 1):
+        keep = ~done[t]
+        assert torch.equal(o[t + 1][keep], n[t][keep])
+        assert torch.all(o[t + 1][done[t]][:, 0] == 1.0)                                # reset rows
+    a = d["actions"]
+    assert float(a.min()) >= -1.0 and float(a.max()) <= 1.0 and abs(float(a.mean())) < 0.01
+    assert not torch.equal(d["actions"].view(T, B, -1)[0], d["actions"].view(T, B, -1)[chunk])   # replays draw anew
+    assert torch.isfinite(d["rewards"]).all()
+    # launch cost: graph replay vs the eager loop on the same environment size
+    e1 = m.BatchedGridEnvironment(f, B, **kw); e1.reset(seed=1)
+    m.collect_random_data(e1, chunk)
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    m.collect_random_data(e1, 64)
+    torch.cuda.synchronize(); t_eager = time.perf_counter() - t0
+    e2 = m.BatchedGridEnvironment(f, B, **kw); e2.reset(seed=1)
+    col = m.GraphedCollector(e2, chunk)
+    col.run_chunk(); col.run_chunk()                     # eager chunk + capture, then one replay
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    for _ in range(64 // chunk):
+        col.run_chunk()
+    torch.cuda.synchronize(); t_graph = time.perf_counter() - t0
+    print(f"64 steps x {B} instances: eager loop {t_eager * 1e3:.1f} ms, graph replay {t_graph * 1e3:.1f} ms")
+    assert t_graph < t_eager
