@@ -1,10 +1,12 @@
 // gfr_b200.cu - kernels (sm_100a) and the C ABI declared in include/gfr_b200.h.
 //
 // Launch shape: persistent CTAs; a group of LANES threads takes instance after instance
-// (stride gridDim * groups-per-CTA) and never meets a CTA-wide barrier after the prologue,
-// so an instance whose solve converges early frees its group early.  The prologue stages
-// the compiled feeder ("image") into shared memory with ONE bulk async copy (TMA,
-// cp.async.bulk -> SASS UBLKCP) completed on an mbarrier.
+// (stride gridDim * groups-per-CTA).  Warp-sized groups never meet a CTA-wide barrier after the
+// prologue, so an instance whose solve converges early frees its group early; CTA-wide groups
+// (LANES > 32, one instance per CTA) synchronise with __syncthreads.  The prologue stages the
+// compiled feeder ("image") into shared memory with ONE bulk async copy (TMA, cp.async.bulk ->
+// SASS UBLKCP) completed on an mbarrier, unless the plan reads it from global memory.
+// plan_launch() picks instance slots per CTA and CTAs per SM with the occupancy API.
 #include <cuda_runtime.h>
 
 #include <atomic>

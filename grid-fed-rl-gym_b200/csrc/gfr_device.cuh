@@ -1,11 +1,13 @@
 // gfr_device.cuh - per-instance math of the batched GridEnvironment.step path.
 //
-// One "group" of LANES threads (1, 2, 4, 8, 16 or 32, always inside one warp) owns one
-// feeder instance at a time.  The instance's working set lives in shared memory, the
-// compiled feeder (the "image") sits next to it, staged once per CTA with one bulk
-// (TMA) copy.  Buses are numbered in LEVEL order (breadth-first from the slack bus, k = 0);
-// lane `k % LANES` owns bus k in every phase, so a lane only ever needs a group barrier
-// when it reads another bus's slots.
+// One "group" of LANES threads owns one feeder instance at a time: 1..32 lanes inside one warp
+// (group barrier = __syncwarp) or, for large feeders, the whole CTA (64, 128, 256 lanes, barrier =
+// __syncthreads).  The instance's working set lives in shared memory; the compiled feeder (the
+// "image") is staged next to it once per CTA with one bulk (TMA) copy, or read from global memory
+// when the group is CTA-wide.  Buses are numbered in LEVEL order: the host's leaf -> root
+// elimination schedule (topology.compile_feeder), k = 0 being the root of the elimination tree.
+// Lane `k % LANES` owns bus k in every phase, so a lane only needs a group barrier when it reads
+// another bus's data.
 //
 // The functions are __host__ __device__ so that tests/host_emu can run the LANES = 1
 // instantiation on a CPU to debug control flow without a GPU.  That harness is test
