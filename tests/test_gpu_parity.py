@@ -487,3 +487,35 @@ def test_bad_arguments_raise():
         env.step(np.zeros((4, env.act_dim + 1)))
     with pytest.raises(m.InvalidActionError):
         env.step(np.zeros((3, env.act_dim)))
+
+
+def test_diverging_instances_are_data_not_errors():
+    """An overloaded feeder: the reference runs Newton to max_iterations and reports
+    converged=False; the env keeps stepping (grid_env.py:724-731).  Flags and iteration counts must
+    agree with the oracle; the (chaotic) voltages are not compared."""
+    import grid_fed_rl_b200 as m
+    f = m.repair_topology(m.IEEE13Bus())
+    for ld in f.loads:
+        ld.base_power *= 9.0; ld.active_power *= 9.0; ld.reactive_power *= 9.0
+    kw = dict(timestep=60.0, renewable_sources=["solar", "wind"], tolerance=1e-6, max_iterations=12)
+    B = 48
+    for lanes in (4, 16):
+        env = m.BatchedGridEnvironment(f, B, lanes=lanes, repair=False, **kw)
+        ref = port.PortEnv(f, B, **kw)
+        rs = np.random.RandomState(3)
+        nz0 = np.concatenate([rs.random_sample((B, 1)), rs.standard_normal((B, 3))], axis=1)
+        env.reset(noise=nz0, options={"start_time": 18 * 3600.0}); ref.reset(nz0, start_time=18 * 3600.0)
+        act = rs.uniform(-1, 1, size=(B, ref.A))
+        nz = np.concatenate([rs.random_sample((B, 1)), rs.standard_normal((B, 3 + ref.L))], axis=1)
+        with np.errstate(all="ignore"):
+            r = ref.step(act, nz)
+        obs, reward, term, trunc, info = env.step(act, nz)
+        conv = info["power_flow_converged"].cpu().numpy()
+        assert not r["converged"].all(), "the case is meant to diverge"
+        assert np.array_equal(conv, r["converged"])
+        its = info["iterations"].cpu().numpy().astype(int)
+        assert np.all(np.abs(its - r["iterations"])[r["converged"]] <= 1)
+        assert np.all(its[~r["converged"]] == 12)
+        env.step(act, nz)                                   # and the environment keeps going
+        assert int(info["current_step"].min()) == 2
+        env.close()
