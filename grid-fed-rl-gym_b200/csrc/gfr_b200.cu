@@ -244,10 +244,13 @@ size_t slot_bytes(const Layout& lay, int solver) {
                                      : sweep_slot_bytes(lay.n, lay.n_src);
 }
 
-int auto_lanes(const Layout& lay, int solver) {
+int auto_lanes(const Layout& lay, int solver) {      // same thresholds as topology.auto_lanes (measured, profiles/)
   if (lay.n <= 20) return solver == GFR_SOLVER_SWEEP ? 1 : 4;
-  if (lay.n <= 64) return 4;
-  if (lay.n <= 400) return 16;
+  if (lay.n <= 45) return 4;
+  if (lay.n <= 90) return 8;
+  if (lay.n <= 160) return 16;
+  if (lay.n <= 400) return 32;
+  if (lay.n <= 650) return 64;
   return 128;                      // one CTA per instance
 }
 

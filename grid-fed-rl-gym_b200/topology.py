@@ -549,15 +549,23 @@ def compile_feeder(feeder, renewable_sources: Optional[Sequence[str]] = None,
 
 
 def auto_lanes(n_bus: int, solver: str = "newton") -> int:
-    """Threads cooperating on one instance when the caller does not say (tuned on B200, see
-    profiles/): one thread per instance for the smallest feeders, part of a warp otherwise."""
+    """Threads cooperating on one instance when the caller does not say.  Thresholds from
+    measurements on B200 (profiles/r01_tune_lanes_newton.txt, profiles/r01_bench_all_configs.txt):
+    a few lanes for the smallest feeders, part of a warp up to a few hundred buses, one CTA per
+    instance (feeder image read from global memory) beyond."""
     if n_bus <= 20:
         return 1 if solver == "sweep" else 4
-    if n_bus <= 64:
+    if n_bus <= 45:
         return 4
-    if n_bus <= 400:
+    if n_bus <= 90:
+        return 8
+    if n_bus <= 160:
         return 16
-    return 128                       # one CTA per instance, feeder image read from global memory
+    if n_bus <= 400:
+        return 32
+    if n_bus <= 650:
+        return 64
+    return 128
 
 
 def compile_for_solver(feeder, solver: str = "newton", lanes: int = 0,
