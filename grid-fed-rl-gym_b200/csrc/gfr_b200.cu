@@ -420,8 +420,6 @@ int check_solver_cfg(const gfr_feeder* f, const gfr_solver_cfg* c) {
     return fail(GFR_E_ARG, "solver must be GFR_SOLVER_SWEEP or GFR_SOLVER_NEWTON");
   if (c->max_iterations < 1) return fail(GFR_E_ARG, "max_iterations must be >= 1");
   if (!(c->tolerance > 0.0)) return fail(GFR_E_ARG, "tolerance must be > 0");
-  if (c->solver == GFR_SOLVER_SWEEP && !f->root_is_slack)
-    return fail(GFR_E_ARG, "the sweep solver needs the slack bus at the root (k = 0) of the level order");
   if (c->solver == GFR_SOLVER_SWEEP && f->has_pv)
     return fail(GFR_E_ARG, "the sweep solver handles slack + PQ buses only; use GFR_SOLVER_NEWTON for PV buses");
   return GFR_OK;

@@ -49,6 +49,7 @@ enum { NF_SWEEP = 6, S_JR = 2, S_JI = 3, S_P = 4 };
 enum { SCRATCH_FIELDS_SWEEP = 2 };
 // bus flag bits
 enum { FL_PQ = 1, FL_FROM_IS_PARENT = 2, FL_FIXED_VM = 4, FL_THETA = 8,     // PQ: |V| unknown; THETA: angle unknown
+       FL_SLACK_PATH = 16,                                                // on the path slack -> root (slack included, root not)
        FL_POOL_SHIFT = 8 };                                               // flags >> 8 = 3 * the bus's pool slot
 // record (persistent per-instance state) slots, in doubles
 enum { R_TIME = 0, R_FREQ, R_WIND, R_TEMP, R_CLOUD, R_TOTAL_LOSSES, R_EPISODE_REWARD, R_SEED,
@@ -60,7 +61,7 @@ struct alignas(16) I4 { int x, y, z, w; };   // per-bus topology: parent, child 
 // Where everything is inside the feeder image (ints / doubles counted from the image base)
 // plus the sizes; passed as a kernel parameter (constant bank).
 struct Layout {
-  int n, nl, L, G, Bt, A, D, m, n_src, R, img_bytes, n_noise, n_pool;
+  int n, nl, L, G, Bt, A, D, m, n_src, R, img_bytes, n_noise, n_pool, k_slack;
   int o_topo, o_child_idx, o_child_pool, o_level_ptr, o_rank, o_branch_of_line, o_inj_ptr, o_inj_idx,
       o_gen_type;
   int o_gb, o_gbd, o_rx, o_f0, o_rating, o_vm_set, o_load_base, o_gen_cap, o_gen_p0, o_gen_p1, o_gen_p2,
@@ -561,58 +562,92 @@ GFR_HD void newton_solve(const NGrp<LANES>& g, const Layout& lay, const int* sim
   }
 }
 
-// Backward / forward sweep on the same tree (no counterpart in the reference, SURVEY F6;
-// compared with the reference's Newton-Raphson at tight tolerance).  Constant-power
-// injections P + j0; convergence on max(|de|, |df|) over buses.
+// Backward / forward sweep (no counterpart in the reference; compared with the
+// reference's Newton-Raphson at tight tolerance).  Constant-power injections P + j0, convergence on
+// max(|de|, |df|) over buses.  The iteration is the classic one - branch currents from the present
+// voltages, then voltages from the slack outwards - but it runs on the SAME center-rooted levels as
+// the Newton elimination, which halves the sequential depth of a feeder whose slack sits at one end:
+//   up   (leaf -> root)  A(k) = injected current of k (0 for the slack) + sum of A(children)
+//   down (root -> leaf)  W(k) = W(parent) + z_k T(k),  T(k) = A(k) - [k on the slack -> root path] A(root)
+//                        (what leaves subtree(k) through its branch; the slack's own injection is
+//                        -A(root) by Kirchhoff), W = voltage relative to the root
+//   fix  (every bus)     V(k) = V_slack - W(slack) + W(k)
 template <int LANES>
 GFR_HD void sweep_solve(const SGrp<LANES>& g, const Layout& lay, const int* simg,
                         const double* dimg, double tol, int max_it, SolveStat* out) {
-  const int nl = lay.nl;
+  const int n = lay.n, nl = lay.nl, ks = lay.k_slack;
   const I4* topo = reinterpret_cast<const I4*>(simg + lay.o_topo);
   const int* level_ptr = simg + lay.o_level_ptr;
   const int* child_idx = simg + lay.o_child_idx;
   const D2* rx = reinterpret_cast<const D2*>(dimg + lay.o_rx);
+  const double vslack = dimg[lay.o_vm_set + ks];
   out->converged = 0;
   out->iterations = max_it;
   out->max_mismatch = INFINITY;
   for (int it = 0; it < max_it; ++it) {
-    // backward: branch current into bus k = its own draw plus its children's
-    for (int l = nl - 1; l >= 1; --l) {
+    for (int l = nl - 1; l >= 0; --l) {
       const int k1 = level_ptr[l + 1];
       for (int k = g.first(level_ptr[l]); k < k1; k += LANES) {
         const I4 t = topo[k];
         const D2 v = g.at2(F_E, k);
-        const double w = g.at(S_P, k) / (v.x * v.x + v.y * v.y);   // injected current = conj(S / V) = P V / |V|^2
-        D2 j;
-        j.x = -w * v.x; j.y = -w * v.y;
+        const double w = (t.w & FL_THETA) ? g.at(S_P, k) / fma(v.x, v.x, v.y * v.y) : 0.0;   // conj(S / V) = P V / |V|^2
+        D2 a;
+        a.x = w * v.x; a.y = w * v.y;
+#pragma unroll 1
         for (int q = t.y; q < t.z; ++q) {
-          const D2 jc = g.at2(S_JR, child_idx[q]);
-          j.x += jc.x; j.y += jc.y;
+          const D2 ac = g.at2(S_JR, child_idx[q]);
+          a.x += ac.x; a.y += ac.y;
         }
-        g.at2(S_JR, k) = j;
+        g.at2(S_JR, k) = a;
       }
       g.sync();
     }
-    // forward: V_k = V_parent - z_k J_k
+    const D2 atot = g.at2(S_JR, 0);
+    g.sync();                                          // everyone has A(root) before the root's slot is reused
     double mm = 0.0;
-    for (int l = 1; l < nl; ++l) {
+    for (int l = 0; l < nl; ++l) {
       const int k1 = level_ptr[l + 1];
       for (int k = g.first(level_ptr[l]); k < k1; k += LANES) {
-        const D2 vp = g.at2(F_E, topo[k].x);
-        const D2 j = g.at2(S_JR, k);
-        const D2 z = rx[k];
-        const D2 vo = g.at2(F_E, k);
-        D2 vn;
-        vn.x = vp.x - (z.x * j.x - z.y * j.y);
-        vn.y = vp.y - (z.x * j.y + z.y * j.x);
-        const double de = fabs(vn.x - vo.x), df = fabs(vn.y - vo.y);
-        const double loc = (df > de || df != df) ? df : de;
-        mm = (loc > mm || loc != loc) ? loc : mm;
-        g.at2(F_E, k) = vn;
+        const I4 t = topo[k];
+        D2 w;
+        w.x = 0.0; w.y = 0.0;
+        if (k > 0) {
+          D2 a = g.at2(S_JR, k);
+          if (t.w & FL_SLACK_PATH) { a.x -= atot.x; a.y -= atot.y; }
+          const D2 wp = g.at2(S_JR, t.x);
+          const D2 z = rx[k];
+          w.x = wp.x + fma(z.x, a.x, -z.y * a.y);
+          w.y = wp.y + fma(z.x, a.y, z.y * a.x);
+        }
+        g.at2(S_JR, k) = w;
+        if (ks == 0) {                                 // slack at the root: W is already V - V_slack
+          const D2 vo = g.at2(F_E, k);
+          D2 vn;
+          vn.x = vslack + w.x; vn.y = w.y;
+          const double de = fabs(vn.x - vo.x), df = fabs(vn.y - vo.y);
+          const double loc = (df > de || df != df) ? df : de;
+          mm = (loc > mm || loc != loc) ? loc : mm;
+          g.at2(F_E, k) = vn;
+        }
       }
       g.sync();
     }
+    const D2 ws = g.at2(S_JR, ks);
+    if (ks != 0)
+    for (int k = g.lane; k < n; k += LANES) {
+      const D2 w = g.at2(S_JR, k);
+      const D2 vo = g.at2(F_E, k);
+      D2 vn;
+      vn.x = (vslack - ws.x) + w.x;
+      vn.y = (0.0 - ws.y) + w.y;
+      if (k == ks) { vn.x = vslack; vn.y = 0.0; }
+      const double de = fabs(vn.x - vo.x), df = fabs(vn.y - vo.y);
+      const double loc = (df > de || df != df) ? df : de;
+      mm = (loc > mm || loc != loc) ? loc : mm;
+      g.at2(F_E, k) = vn;
+    }
     mm = g.gmax_nan(mm);
+    g.sync();
     out->max_mismatch = mm;
     if (mm < tol) {
       out->converged = 1;

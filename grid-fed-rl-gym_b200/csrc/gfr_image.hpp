@@ -125,6 +125,13 @@ inline std::string build_feeder_image(const gfr_feeder_desc* d, FeederImage* out
     for (int g = 0; g < G; ++g) inj_idx[fill[d->gen_bus[g]]++] = L + g;
     for (int b = 0; b < Bt; ++b) inj_idx[fill[d->bat_bus[b]]++] = L + G + b;
   }
+  // the slack bus and the path from it to the root of the elimination tree (sweep)
+  {
+    int ks = 0;
+    for (int k = 0; k < n; ++k) if (d->bus_type[k] == GFR_BUS_SLACK) ks = k;
+    lay.k_slack = ks;
+    for (int k = ks; k > 0; k = d->parent[k]) flags[k] |= FL_SLACK_PATH;
+  }
   // pool plan: given by the caller (checked by replaying the schedule) or one slot per bus
   std::vector<int32_t> pool_slot(n);
   if (d->pool_slot) {

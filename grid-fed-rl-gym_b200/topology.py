@@ -571,11 +571,17 @@ def auto_lanes(n_bus: int, solver: str = "newton") -> int:
 def compile_for_solver(feeder, solver: str = "newton", lanes: int = 0,
                        renewable_sources: Optional[Sequence[str]] = None,
                        with_components: bool = True):
-    """``compile_feeder`` with the traversal the given solver / lane count wants: Newton
-    eliminates towards the tree's center, the sweep towards the slack bus; levels are capped at
-    the lane count (Hu's schedule).  Returns (FeederSoA, lanes)."""
+    """``compile_feeder`` with the traversal the kernels want: both solvers walk the tree rooted
+    at its center when that shortens it (the sweep handles the slack bus wherever it sits, Newton
+    always gains); levels are capped at the lane count (Hu's schedule).  Returns (FeederSoA, lanes)."""
     lanes = int(lanes) or auto_lanes(len(feeder.buses), solver)
-    soa = compile_feeder(feeder, renewable_sources=renewable_sources, with_components=with_components,
-                         root="center" if solver in ("newton", "newton_raphson") else "slack",
-                         width=lanes if lanes > 1 else None)
+    kw = dict(renewable_sources=renewable_sources, with_components=with_components,
+              width=lanes if lanes > 1 else None)
+    soa = compile_feeder(feeder, root="center", **kw)
+    if solver == "sweep":
+        # the sweep pays one extra bus-parallel pass per iteration when the slack is not the root:
+        # only worth it if the center-rooted tree is clearly shallower
+        alt = compile_feeder(feeder, root="slack", **kw)
+        if soa.n_levels > 0.75 * alt.n_levels:
+            soa = alt
     return soa, lanes

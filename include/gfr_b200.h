@@ -43,8 +43,8 @@ typedef struct gfr_feeder gfr_feeder;   /* compiled topology, device resident */
 typedef struct gfr_env gfr_env;         /* B environment instances on one device */
 
 /* Host-side description of a radial feeder, arrays in LEVEL order: k = 0 is the ROOT of the
- * elimination tree (the slack bus for the sweep solver; any bus, e.g. the tree's center, for
- * Newton), every bus sits in a later level than its parent, levels may be capped to the number
+ * traversal tree (any bus; the tree's center halves the sequential depth of a feeder whose slack
+ * bus sits at one end), every bus sits in a later level than its parent, levels may be capped to the number
  * of cooperating lanes.  The order only shapes the device-side traversal: results are always
  * reported in ref order.
  * Produced by grid_fed_rl_b200.topology.compile_feeder from feeder.buses / .lines / .loads /
