@@ -35,14 +35,16 @@ enum { SOLVER_SWEEP = 0, SOLVER_NEWTON = 1 };
 enum { BUS_SLACK = 0, BUS_PV = 1, BUS_PQ = 2 };
 enum { GEN_SOLAR = 0, GEN_WIND = 1 };
 // An instance's working set in shared memory (buses in level order):
-//   Newton:  ef[n] (e + jf, 16 B) | vx[n] (16 B) | pool[n_pool] (48 B)   (+ P[n] unless GFR_P_GLOBAL)
-//            vx holds (P_calc, Q_calc) after the mismatch pass, D^-1 r after elimination and the
-//            correction after back-substitution; a pool entry holds one bus's Schur contribution
-//            to its parent (L D^-1 U, L D^-1 r) from the moment it is eliminated until the parent
-//            is - the host plans the slots (pool_slot[k]); D^-1 U itself, only needed again in the
-//            back-substitution, is spilled to an L2-resident scratch (global memory).
+//   Newton:  ef[n] (e + jf, 16 B) | pool[n_pool] (64 B)
+//            A pool entry carries what one bus hands to its parent during the leaf -> root
+//            elimination - its Schur contribution (L D^-1 U, L D^-1 r) and its branch's share of the
+//            parent's calculated injection - from the moment the bus is eliminated until the parent
+//            is; the host plans the slots (pool_slot[k]).  On the way back (root -> leaf) the same
+//            slot carries the parent's correction down to the bus.  D^-1 U and D^-1 r, only needed
+//            again in the back-substitution, and the specified injections live in a per-slot
+//            scratch in global memory that stays L2 resident.
 //   sweep:   one record per bus, 6 doubles: e f | Jr Ji | P pad  (Jr + jJi = branch current)
-// Before the solve the same space (Newton: vx + pool; sweep: the J fields) carries the load /
+// Before the solve the same space (Newton: ef + pool; sweep: the J fields) carries the load /
 // generator / battery powers into the per-bus injection sums.
 enum { F_E = 0, F_F = 1, F_SCRATCH = 2 };
 enum { NF_SWEEP = 6, S_JR = 2, S_JI = 3, S_P = 4 };
@@ -50,7 +52,8 @@ enum { SCRATCH_FIELDS_SWEEP = 2 };
 // bus flag bits
 enum { FL_PQ = 1, FL_FROM_IS_PARENT = 2, FL_FIXED_VM = 4, FL_THETA = 8,     // PQ: |V| unknown; THETA: angle unknown
        FL_SLACK_PATH = 16,                                                // on the path slack -> root (slack included, root not)
-       FL_POOL_SHIFT = 8 };                                               // flags >> 8 = 3 * the bus's pool slot
+       FL_INHERIT = 32,                                                   // the bus's pool slot is also its first child's
+       FL_POOL_SHIFT = 8 };                                               // flags >> 8 = the bus's pool slot
 // record (persistent per-instance state) slots, in doubles
 enum { R_TIME = 0, R_FREQ, R_WIND, R_TEMP, R_CLOUD, R_TOTAL_LOSSES, R_EPISODE_REWARD, R_SEED,
        R_DRAWS, R_COUNTS, R_BAT };   // soc[Bt] then bpow[Bt] from R_BAT on
@@ -125,6 +128,19 @@ struct Lanes {
 #endif
     return v;
   }
+  GFR_HD double bcast(double v, int src) const {    // lane `src`'s value, to every lane
+#if defined(__CUDA_ARCH__)
+    if (LANES > 32) {
+      __syncthreads();
+      if (lane == src) red[0] = v;
+      __syncthreads();
+      v = red[0];
+    } else if (LANES > 1) {
+      v = __shfl_sync(mask, v, src, LANES);
+    }
+#endif
+    return v;
+  }
   GFR_HD double gmax_nan(double v) const { return reduce(v, OpMaxNan()); }   // NaN-propagating (numpy semantics)
   GFR_HD double gmin_nan(double v) const { return reduce(v, OpMinNan()); }
   GFR_HD double gmax(double v) const { return reduce(v, OpMax()); }
@@ -151,44 +167,42 @@ struct SGrp : Lanes<LANES> {
 };
 
 // Newton working set (see the layout note above)
+// a pool entry is four 16-byte fields: c0, c1 (L D^-1 U rows), cc (L D^-1 r), fl (branch share of P, Q),
+// stored field-major (field f of slot s at poolp[f * n_pool + s]): the lanes of a level then touch
+// consecutive 16-byte units wherever their slots are consecutive instead of every fourth one
+enum { POOL_D2 = 4 };
 template <int LANES>
 struct NGrp : Lanes<LANES> {
-  D2* efp;        // [n]      shared
-  D2* vxp;        // [n]      shared, followed directly by the pool
-  D2* poolp;      // [3 * n_pool] shared
-  double* pp;     // [n]      shared
-  D2* mg;         // [2 * n]  GLOBAL scratch of this instance slot: D^-1 U per bus
+  D2* efp;        // [n]      shared, followed directly by the pool
+  D2* poolp;      // [POOL_D2][n_pool] shared
+  int np;         // n_pool
+  double* pp;     // [n]      specified injections (global scratch, right after mg)
+  D2* mg;         // [3 * n]  GLOBAL scratch of this instance slot: D^-1 U (2) and D^-1 r (1) per bus
   GFR_HD D2& ef(int k) const { return efp[k]; }
-  GFR_HD D2& vx(int k) const { return vxp[k]; }
-  GFR_HD double& pspec(int k) const { return pp[k]; }   // shared, or global right after mg (GFR_P_GLOBAL)
-  GFR_HD double& scr(int j) const { return reinterpret_cast<double*>(vxp)[j]; }   // vx + pool, flat
+  GFR_HD double& pspec(int k) const { return pp[k]; }
+  GFR_HD double& scr(int j) const { return reinterpret_cast<double*>(efp)[j]; }   // ef + pool, flat
 };
 
 template <int LANES, int SOLVER> struct GroupOf { typedef NGrp<LANES> type; };
 template <int LANES> struct GroupOf<LANES, SOLVER_SWEEP> { typedef SGrp<LANES> type; };
 
 // bytes of shared memory one instance slot needs (0 if the sources do not fit the scratch)
-#ifndef GFR_P_GLOBAL
-#define GFR_P_GLOBAL 1      // 1: the specified injections live in the global scratch instead of shared memory
-                            //    (measured on B200: +11 % at 8 lanes on IEEE-123, +13 % on IEEE-34)
-#endif
 GFR_HD size_t newton_slot_bytes(int n, int n_pool, int n_src) {
-  if (n_src > 2 * n + 6 * n_pool) return 0;
-  return (size_t)n * 32 + (size_t)n_pool * 48 + (GFR_P_GLOBAL ? 0 : (((size_t)n * 8 + 15) / 16) * 16);
+  if (n_src > 2 * n + 2 * POOL_D2 * n_pool) return 0;
+  return (size_t)n * 16 + (size_t)n_pool * (16 * POOL_D2);
 }
-// doubles of global scratch per instance slot (Newton)
-GFR_HD size_t newton_scratch_doubles(int n) { return (size_t)n * 4 + (GFR_P_GLOBAL ? (((size_t)n + 1) / 2) * 2 : 0); }
+// doubles of global scratch per instance slot (Newton): D^-1 U, D^-1 r (48 B per bus) + specified injections
+GFR_HD size_t newton_scratch_doubles(int n) { return (size_t)n * 6 + (((size_t)n + 1) / 2) * 2; }
 GFR_HD size_t sweep_slot_bytes(int n, int n_src) {
   if (n_src > SCRATCH_FIELDS_SWEEP * n) return 0;
   return (size_t)n * NF_SWEEP * 8;
 }
 template <int LANES>
 GFR_HD void bind_slot(NGrp<LANES>& g, unsigned char* slot, int n, int n_pool, D2* mg) {
+  g.np = n_pool;
   g.efp = reinterpret_cast<D2*>(slot);
-  g.vxp = g.efp + n;
-  g.poolp = g.vxp + n;
-  g.pp = GFR_P_GLOBAL ? reinterpret_cast<double*>(mg + 2 * (size_t)n)
-                      : reinterpret_cast<double*>(g.poolp + 3 * (size_t)n_pool);
+  g.poolp = g.efp + n;
+  g.pp = reinterpret_cast<double*>(mg + 3 * (size_t)n);
   g.mg = mg;
 }
 template <int LANES>
@@ -197,6 +211,16 @@ GFR_HD void bind_slot(SGrp<LANES>& g, unsigned char* slot, int n, int, D2*) {
   g.n = n;
 }
 
+
+// Store of a value nobody on the chip reads again this launch (observation, outputs): evict-first,
+// so that the stream does not push the solver's L2-resident scratch out.
+GFR_HD void st_stream(double* p, double v) {
+#if defined(__CUDA_ARCH__)
+  __stcs(p, v);
+#else
+  *p = v;
+#endif
+}
 
 // 1 / x for a normal, finite x: hardware seed + two Newton steps (~1 ulp), no slow-path call.
 GFR_HD double rcp_fast(double x) {
@@ -243,6 +267,30 @@ GFR_HD void sincos_small(double x, double* s, double* c) {
     sn = s2; cs = c2;
   }
   *s = sn; *c = cs;
+}
+
+// atan2(f, e) of a bus voltage.  In any state a feeder can be operated in e > 0 and |f / e| is a few
+// degrees: the odd series in t = f / e to t^21 is exact to < 1 ulp for |t| <= 0.16 (next term
+// t^23 / 23 < 3e-20); anything else takes the library call.
+GFR_HD double atan2_bus(double f, double e) {
+  if (e > 0.25 && e < 4.0) {
+    const double t = f * rcp_fast(e);
+    if (fabs(t) <= 0.16) {
+      const double z = t * t;
+      double p = 1.0 / 21.0;
+      p = fma(p, z, -1.0 / 19.0);
+      p = fma(p, z, 1.0 / 17.0);
+      p = fma(p, z, -1.0 / 15.0);
+      p = fma(p, z, 1.0 / 13.0);
+      p = fma(p, z, -1.0 / 11.0);
+      p = fma(p, z, 1.0 / 9.0);
+      p = fma(p, z, -1.0 / 7.0);
+      p = fma(p, z, 1.0 / 5.0);
+      p = fma(p, z, -1.0 / 3.0);
+      return fma(t * z, p, t);
+    }
+  }
+  return atan2(f, e);
 }
 
 // ----------------------------------------------------------------------------- Philox4x32-10
@@ -329,18 +377,131 @@ GFR_HD void flat_start(const G& g, const Layout& lay, const int* simg, const dou
 //   diagonal block  J[i,i]   = [[ -Q_i - B_ii |Vi|^2, P_i + G_ii |Vi|^2 ], [ P_i - G_ii |Vi|^2, Q_i - B_ii |Vi|^2 ]]
 // with G_ij + jB_ij = -(g + jb) of the branch and everything written on e + jf = |V| e^{j theta}:
 //   |Vi||Vj| cos th_ij = ei ej + fi fj,  |Vi||Vj| sin th_ij = fi ej - ei fj   (no trigonometry).
+// The entries of a branch's two off-diagonal blocks are also that branch's terms of the calculated
+// injections: P_k = G_kk |Vk|^2 + ga_k + sum_c gl_c,  Q_k = -B_kk |Vk|^2 + al_k + sum_c ll_c
+// (ga, al: block J[k,p] of the bus's own branch; gl, ll: block J[k,c] of a child's branch), so the
+// elimination pass gets the mismatch for free once each child hands (gl, ll) up with its Schur terms.
 // Elimination of bus k (all its children done): D_k = J[k,k] - sum_c C_c, r_k = mismatch_k - sum_c cc_c,
 //   M_k = D_k^-1 J[k,p], v_k = D_k^-1 r_k, and its contribution to the parent p:
 //   C_k = J[p,k] M_k, cc_k = J[p,k] v_k.   Back-substitution: x_k = v_k - M_k x_p.
+struct BranchT { double ga, al, gl, ll; };
+// vk: the bus below the branch, vp: its parent, y: series g + jb
+GFR_HD BranchT branch_terms(const D2 vk, const D2 vp, const D2 y) {
+  const double a = fma(vk.x, vp.x, vk.y * vp.y), s = fma(vk.y, vp.x, -vk.x * vp.y);
+  BranchT t;
+  t.ga = fma(-y.x, a, -y.y * s); t.al = fma(-y.x, s, y.y * a);     // J[k,p]
+  t.gl = fma(-y.x, a, y.y * s);  t.ll = fma(y.x, s, y.y * a);      // J[p,k] (th_pk = -th_kp)
+  return t;
+}
+
+// max |mismatch| of the present voltages, every bus independently (power_flow.py:150-166); same
+// arithmetic, term by term, as the elimination pass below
+template <int LANES>
+GFR_HD double newton_mismatch(const NGrp<LANES>& g, const Layout& lay, const int* simg, const double* dimg) {
+  const I4* topo = reinterpret_cast<const I4*>(simg + lay.o_topo);
+  const int* child_idx = simg + lay.o_child_idx;
+  const D2* gb = reinterpret_cast<const D2*>(dimg + lay.o_gb);
+  const D2* gbd = reinterpret_cast<const D2*>(dimg + lay.o_gbd);
+  double mm = 0.0;
+  for (int k = g.lane; k < lay.n; k += LANES) {
+    const I4 t = topo[k];
+    const D2 vk = g.ef(k);
+    const D2 yd = gbd[k];
+    const double v2 = fma(vk.x, vk.x, vk.y * vk.y);
+    const BranchT bt = branch_terms(vk, g.ef(t.x), gb[k]);
+    D2 sf; sf.x = sf.y = 0.0;
+#pragma unroll 1
+    for (int q = t.y; q < t.z; ++q) {
+      const int c = child_idx[q];
+      const BranchT ct = branch_terms(g.ef(c), vk, gb[c]);
+      sf.x += ct.gl; sf.y += ct.ll;
+    }
+    const double P = fma(yd.x, v2, bt.ga) + sf.x, Q = fma(-yd.y, v2, bt.al) + sf.y;
+    double aP = fabs(g.pspec(k) - P), aQ = fabs(Q);
+    if ((t.w & (FL_PQ | FL_THETA)) != (FL_PQ | FL_THETA)) {   // slack: no equations; PV: no Q equation
+      if (!(t.w & FL_THETA)) aP = 0.0;
+      if (!(t.w & FL_PQ)) aQ = 0.0;
+    }
+    const double loc = (aQ > aP || aQ != aQ) ? aQ : aP;
+    mm = (loc > mm || loc != loc) ? loc : mm;
+  }
+  return g.gmax_nan(mm);
+}
+
+// Back-substitution root -> leaf fused with the polar update (power_flow.py:297-327):
+//   x_k = v_k - M_k x_parent (the root's M is 0: it has no branch), then
+//   theta += a dtheta, |V| += a d|V|  <=>  V *= (1 + a x1) e^{j a x0}.
+// x_parent comes down through the bus's own pool slot (the parent put it there), x_k goes into the
+// slots of the children.  M and v come back from the global scratch (first iteration: M from the
+// image); the next level's are requested before this level's barrier so that the L2 round trip
+// overlaps it.
+template <int LANES>
+GFR_HD void newton_back_update(const NGrp<LANES>& g, const Layout& lay, const int* simg, const D2* f0,
+                               double accel) {
+  const int nl = lay.nl;
+  const I4* topo = reinterpret_cast<const I4*>(simg + lay.o_topo);
+  const int* level_ptr = simg + lay.o_level_ptr;
+  const int* child_pool = simg + lay.o_child_pool;
+  int nk = g.first(level_ptr[0]);
+  bool nv = nk < level_ptr[1];
+  D2 nm0, nm1, nvv;
+  nm0.x = nm0.y = nm1.x = nm1.y = nvv.x = nvv.y = 0.0;
+#define GFR_LOAD_MV(kk, a0, a1, av)                                        \
+  do {                                                                     \
+    if (f0) { a0 = f0[6 * (kk) + 2]; a1 = f0[6 * (kk) + 3]; }              \
+    else { a0 = g.mg[3 * (kk)]; a1 = g.mg[3 * (kk) + 1]; }                 \
+    av = g.mg[3 * (kk) + 2];                                               \
+  } while (0)
+  if (nv) GFR_LOAD_MV(nk, nm0, nm1, nvv);
+  for (int l = 0; l < nl; ++l) {
+    const int k1 = level_ptr[l + 1];
+    int k = nk;
+    const bool valid = nv;
+    D2 m0 = nm0, m1 = nm1, v = nvv;
+    if (l + 1 < nl) {
+      nk = g.first(k1);
+      nv = nk < level_ptr[l + 2];
+      if (nv) GFR_LOAD_MV(nk, nm0, nm1, nvv);
+    }
+    if (valid) {
+      for (;;) {
+        const I4 t = topo[k];
+        D2 x; x.x = x.y = 0.0;
+        if (k > 0) x = g.poolp[t.w >> FL_POOL_SHIFT];      // field 0 of its own slot
+        v.x = fma(-m0.x, x.x, fma(-m0.y, x.y, v.x));
+        v.y = fma(-m1.x, x.x, fma(-m1.y, x.y, v.y));
+        {
+          int q = t.y;
+          if (t.w & FL_INHERIT) { g.poolp[t.w >> FL_POOL_SHIFT] = v; ++q; }     // first child: same slot, no index load
+#pragma unroll 1
+          for (; q < t.z; ++q) g.poolp[child_pool[q]] = v;
+        }
+        double sn, cs;
+        sincos_small(accel * v.x, &sn, &cs);
+        const double sc = fma(accel, v.y, 1.0);
+        const D2 e = g.ef(k);
+        D2 w;
+        w.x = sc * fma(e.x, cs, -e.y * sn);
+        w.y = sc * fma(e.x, sn, e.y * cs);
+        g.ef(k) = w;
+        k += LANES;
+        if (k >= k1) break;
+        GFR_LOAD_MV(k, m0, m1, v);                     // levels wider than the group: no prefetch
+      }
+    }
+    g.sync();
+  }
+#undef GFR_LOAD_MV
+}
+
 template <int LANES>
 GFR_HD void newton_solve(const NGrp<LANES>& g, const Layout& lay, const int* simg,
                          const double* dimg, double tol, int max_it, double accel,
                          SolveStat* out) {
-  const int n = lay.n, nl = lay.nl;
+  const int n = lay.n, nl = lay.nl, np = lay.n_pool;
   const I4* topo = reinterpret_cast<const I4*>(simg + lay.o_topo);
   const int* level_ptr = simg + lay.o_level_ptr;
-  const int* child_idx = simg + lay.o_child_idx;
-  const int* child_pool = simg + lay.o_child_pool;   // 3 * pool slot of every child, same indexing as child_idx
+  const int* child_pool = simg + lay.o_child_pool;   // pool slot of every child, indexed like child_idx
   const D2* gb = reinterpret_cast<const D2*>(dimg + lay.o_gb);      // branch series g, b (0 for the root)
   const D2* gbd = reinterpret_cast<const D2*>(dimg + lay.o_gbd);    // Re, Im of Y_kk
   const D2* f0 = lay.o_f0 >= 0 ? reinterpret_cast<const D2*>(dimg + lay.o_f0) : nullptr;   // flat-start factors
@@ -348,12 +509,16 @@ GFR_HD void newton_solve(const NGrp<LANES>& g, const Layout& lay, const int* sim
   out->converged = 0;
   out->iterations = max_it;
   out->max_mismatch = INFINITY;
+  double mm_prev = INFINITY, rate = 1.0;     // mismatch of the previous iterate, observed mm / mm_prev^2
 
   for (int it = 0; it < max_it; ++it) {
-    // ---- calculated injections + mismatch, every bus independently (power_flow.py:150-166)
-    double mm = 0.0;
+    double mm;
     if (it == 0 && f0 != nullptr) {
-      // the calculated injections of the flat profile are feeder constants too (image, entry 5)
+      // ---- first iteration: every instance starts from the same flat profile, so its calculated
+      //      injections, its Jacobian and the whole elimination of it are properties of the feeder.
+      //      The host factorised it once (image: D^-1, D^-1 U, J[p,k] and (P, Q) per bus); only the
+      //      right-hand side is instance data.
+      mm = 0.0;
       for (int k = g.lane; k < n; k += LANES) {
         const int fl = topo[k].w;
         const D2 pc = f0[6 * k + 5];
@@ -362,62 +527,28 @@ GFR_HD void newton_solve(const NGrp<LANES>& g, const Layout& lay, const int* sim
         if (!(fl & FL_PQ)) aQ = 0.0;
         const double loc = (aQ > aP || aQ != aQ) ? aQ : aP;
         mm = (loc > mm || loc != loc) ? loc : mm;
-        g.vx(k) = pc;
       }
-    } else
-    for (int k = g.lane; k < n; k += LANES) {
-      const I4 t = topo[k];
-      const D2 vk = g.ef(k);
-      const D2 yd = gbd[k];
-      const double v2 = fma(vk.x, vk.x, vk.y * vk.y);
-      double P = yd.x * v2, Q = -yd.y * v2;
-      {
-        const D2 vp = g.ef(t.x);
-        const D2 y = gb[k];
-        const double a = fma(vk.x, vp.x, vk.y * vp.y), s = fma(vk.y, vp.x, -vk.x * vp.y);
-        P = fma(-y.x, a, fma(-y.y, s, P));
-        Q = fma(-y.x, s, fma(y.y, a, Q));
+      mm = g.gmax_nan(mm);
+      out->max_mismatch = mm;
+      if (mm < tol) {                                   // checked before the update (:168-171)
+        out->converged = 1;
+        out->iterations = it + 1;
+        break;
       }
-#pragma unroll 1
-      for (int q = t.y; q < t.z; ++q) {
-        const int c = child_idx[q];
-        const D2 vc = g.ef(c);
-        const D2 y = gb[c];
-        const double a = fma(vk.x, vc.x, vk.y * vc.y), s = fma(vk.y, vc.x, -vk.x * vc.y);
-        P = fma(-y.x, a, fma(-y.y, s, P));
-        Q = fma(-y.x, s, fma(y.y, a, Q));
-      }
-      double aP = fabs(g.pspec(k) - P), aQ = fabs(Q);
-      if ((t.w & (FL_PQ | FL_THETA)) != (FL_PQ | FL_THETA)) {   // slack: no equations; PV: no Q equation
-        if (!(t.w & FL_THETA)) aP = 0.0;
-        if (!(t.w & FL_PQ)) aQ = 0.0;
-      }
-      const double loc = (aQ > aP || aQ != aQ) ? aQ : aP;
-      mm = (loc > mm || loc != loc) ? loc : mm;
-      D2 pc; pc.x = P; pc.y = Q;
-      g.vx(k) = pc;
-    }
-    mm = g.gmax_nan(mm);
-    out->max_mismatch = mm;
-    if (mm < tol) {                                   // checked before the update (:168-171)
-      out->converged = 1;
-      out->iterations = it + 1;
-      break;
-    }
-    // ---- first iteration: every instance starts from the same flat profile, so its Jacobian - and
-    //      the whole elimination of it - is a property of the feeder.  The host factorised it once
-    //      (image: D^-1, D^-1 U and J[p,k] per bus); only the right-hand side is instance data.
-    if (it == 0 && f0 != nullptr) {
       for (int l = nl - 1; l >= 0; --l) {
         const int k1 = level_ptr[l + 1];
         for (int k = g.first(level_ptr[l]); k < k1; k += LANES) {
           const I4 t = topo[k];
-          const D2 pc = g.vx(k);
+          const D2 pc = f0[6 * k + 5];
           D2 sc; sc.x = sc.y = 0.0;
+          {
+            int q = t.y;
+            if (t.w & FL_INHERIT) { sc = g.poolp[2 * np + (t.w >> FL_POOL_SHIFT)]; ++q; }
 #pragma unroll 1
-          for (int q = t.y; q < t.z; ++q) {
-            const D2 cc = g.poolp[child_pool[q] + 2];
-            sc.x += cc.x; sc.y += cc.y;
+            for (; q < t.z; ++q) {
+              const D2 cc = g.poolp[2 * np + child_pool[q]];
+              sc.x += cc.x; sc.y += cc.y;
+            }
           }
           double r0 = g.pspec(k) - pc.x - sc.x, r1 = 0.0 - pc.y - sc.y;
           if (!(t.w & FL_THETA)) r0 = 0.0;
@@ -428,137 +559,116 @@ GFR_HD void newton_solve(const NGrp<LANES>& g, const Layout& lay, const int* sim
           v.y = fma(i1.x, r0, i1.y * r1);
           cc.x = fma(lp.x, v.x, lp.y * v.y);
           cc.y = fma(-lp.y, v.x, lp.x * v.y);
-          g.vx(k) = v;
-          g.poolp[(t.w >> FL_POOL_SHIFT) + 2] = cc;
+          g.mg[3 * k + 2] = v;
+          g.poolp[2 * np + (t.w >> FL_POOL_SHIFT)] = cc;
         }
         g.sync();
       }
-      for (int l = 0; l < nl; ++l) {
+      newton_back_update(g, lay, simg, f0, accel);
+    } else {
+      // ---- the iterate is expected to have converged (quadratic rate seen so far): a mismatch-only
+      //      pass settles it without the elimination
+      if (rate * mm_prev * mm_prev < 0.25 * tol) {
+        mm = newton_mismatch(g, lay, simg, dimg);
+        if (mm < tol) {
+          out->max_mismatch = mm;
+          out->converged = 1;
+          out->iterations = it + 1;
+          break;
+        }
+      }
+      // ---- mismatch + assemble + eliminate, leaf -> root (power_flow.py:150-166, :213-295 with D2,
+      //      then the solve of :187)
+      mm = 0.0;
+      int singular = 0;
+      for (int l = nl - 1; l >= 0; --l) {
         const int k1 = level_ptr[l + 1];
         for (int k = g.first(level_ptr[l]); k < k1; k += LANES) {
-          const D2 m0 = f0[6 * k + 2], m1 = f0[6 * k + 3];
-          const D2 x = g.vx(topo[k].x);
-          D2 v = g.vx(k);
-          v.x = fma(-m0.x, x.x, fma(-m0.y, x.y, v.x));
-          v.y = fma(-m1.x, x.x, fma(-m1.y, x.y, v.y));
-          g.vx(k) = v;
-        }
-        g.sync();
-      }
-    } else {
-    // ---- assemble + eliminate leaf -> root (power_flow.py:213-295 with D2, then the solve of :187)
-    int singular = 0;
-    for (int l = nl - 1; l >= 0; --l) {
-      const int k1 = level_ptr[l + 1];
-      for (int k = g.first(level_ptr[l]); k < k1; k += LANES) {
-        const I4 t = topo[k];
-        const D2 vk = g.ef(k), vp = g.ef(t.x);
-        const D2 y = gb[k], yd = gbd[k];
-        const D2 pc = g.vx(k);
-        const double v2 = fma(vk.x, vk.x, vk.y * vk.y);
-        D2 s0, s1, sc;                                   // children's contributions: plain sums
-        s0.x = s0.y = s1.x = s1.y = sc.x = sc.y = 0.0;
+          const I4 t = topo[k];
+          const D2 vk = g.ef(k);
+          const D2 yd = gbd[k];
+          const double v2 = fma(vk.x, vk.x, vk.y * vk.y);
+          const BranchT bt = branch_terms(vk, g.ef(t.x), gb[k]);
+          D2 s0, s1, sc, sf;                               // children's contributions: plain sums
+          s0.x = s0.y = s1.x = s1.y = sc.x = sc.y = sf.x = sf.y = 0.0;
+          D2* const own = g.poolp + (t.w >> FL_POOL_SHIFT);
+          {
+            int q = t.y;
+            if (t.w & FL_INHERIT) {                        // first child: same slot, no index load
+              s0 = own[0]; s1 = own[np]; sc = own[2 * np]; sf = own[3 * np];
+              ++q;
+            }
 #pragma unroll 1
-        for (int q = t.y; q < t.z; ++q) {
-          const D2* e = g.poolp + child_pool[q];
-          const D2 c0 = e[0], c1 = e[1], cc = e[2];
-          s0.x += c0.x; s0.y += c0.y; s1.x += c1.x; s1.y += c1.y; sc.x += cc.x; sc.y += cc.y;
-        }
-        D2 d0, d1, r;
-        d0.x = fma(-yd.y, v2, -pc.y) - s0.x;          // -Q - B v2
-        d0.y = fma(yd.x, v2, pc.x) - s0.y;            //  P + G v2
-        d1.x = fma(-yd.x, v2, pc.x) - s1.x;           //  P - G v2
-        d1.y = fma(-yd.y, v2, pc.y) - s1.y;           //  Q - B v2
-        r.x = g.pspec(k) - pc.x - sc.x;
-        r.y = 0.0 - pc.y - sc.y;
-        const double a = fma(vk.x, vp.x, vk.y * vp.y), s = fma(vk.y, vp.x, -vk.x * vp.y);
-        const double ga = fma(-y.x, a, -y.y * s), al = fma(-y.x, s, y.y * a);     // J[k,p]
-        const double gl = fma(-y.x, a, y.y * s), ll = fma(y.x, s, y.y * a);      // J[p,k] (th_pk = -th_kp)
-        double u00 = al, u01 = ga, u10 = -ga, u11 = al;
-        if ((t.w & (FL_PQ | FL_THETA)) != (FL_PQ | FL_THETA)) {
-          // a bus without the angle (slack) or magnitude (slack, PV) unknown: identity row, no coupling
-          if (!(t.w & FL_THETA)) { d0.x = 1.0; d0.y = 0.0; r.x = 0.0; u00 = 0.0; u01 = 0.0; }
-          if (!(t.w & FL_PQ)) { d1.x = 0.0; d1.y = 1.0; r.y = 0.0; u10 = 0.0; u11 = 0.0; }
-        }
-        const double det = fma(d0.x, d1.y, -d0.y * d1.x);
-        if (det == 0.0) singular = 1;                 // dgesv's exact-zero pivot (:188-190)
-        const double inv = rcp_fast(det);
-        const double i00 = d1.y * inv, i01 = -d0.y * inv, i10 = -d1.x * inv, i11 = d0.x * inv;
-        D2 m0, m1, v;
-        m0.x = fma(i00, u00, i01 * u10);
-        m0.y = fma(i00, u01, i01 * u11);
-        m1.x = fma(i10, u00, i11 * u10);
-        m1.y = fma(i10, u01, i11 * u11);
-        v.x = fma(i00, r.x, i01 * r.y);
-        v.y = fma(i10, r.x, i11 * r.y);
-        g.mg[2 * k] = m0;                              // D^-1 U: needed again in the back-substitution only
-        g.mg[2 * k + 1] = m1;
-        g.vx(k) = v;
-        D2 c0, c1, cc;                                 // contribution to the parent: L M, L v
-        c0.x = fma(ll, m0.x, gl * m1.x);
-        c0.y = fma(ll, m0.y, gl * m1.y);
-        c1.x = fma(-gl, m0.x, ll * m1.x);
-        c1.y = fma(-gl, m0.y, ll * m1.y);
-        cc.x = fma(ll, v.x, gl * v.y);
-        cc.y = fma(-gl, v.x, ll * v.y);
-        D2* e = g.poolp + (t.w >> FL_POOL_SHIFT);
-        e[0] = c0; e[1] = c1; e[2] = cc;
-      }
-      g.sync();
-    }
-    if (g.gor(singular)) {
-      out->iterations = it + 1;
-      break;
-    }
-    // ---- back-substitute root -> leaf: x_k = v_k - M_k x_parent  (the root's M is 0: it has no branch).
-    //      M comes back from the global scratch; the next level's is requested before this level's
-    //      barrier so that the L2 round trip overlaps it.
-    {
-      int nk = g.first(level_ptr[0]);
-      bool nv = nk < level_ptr[1];
-      D2 nm0, nm1;
-      nm0.x = nm0.y = nm1.x = nm1.y = 0.0;
-      if (nv) { nm0 = g.mg[2 * nk]; nm1 = g.mg[2 * nk + 1]; }
-      for (int l = 0; l < nl; ++l) {
-        const int k1 = level_ptr[l + 1];
-        int k = nk;
-        const bool valid = nv;
-        D2 m0 = nm0, m1 = nm1;
-        if (l + 1 < nl) {
-          nk = g.first(k1);
-          nv = nk < level_ptr[l + 2];
-          if (nv) { nm0 = g.mg[2 * nk]; nm1 = g.mg[2 * nk + 1]; }
-        }
-        if (valid) {
-          for (;;) {
-            const D2 x = g.vx(topo[k].x);
-            D2 v = g.vx(k);
-            v.x = fma(-m0.x, x.x, fma(-m0.y, x.y, v.x));
-            v.y = fma(-m1.x, x.x, fma(-m1.y, x.y, v.y));
-            g.vx(k) = v;
-            k += LANES;
-            if (k >= k1) break;
-            m0 = g.mg[2 * k]; m1 = g.mg[2 * k + 1];      // levels wider than the group: no prefetch
+            for (; q < t.z; ++q) {
+              const D2* e = g.poolp + child_pool[q];
+              const D2 c0 = e[0], c1 = e[np], cc = e[2 * np], fl = e[3 * np];
+              s0.x += c0.x; s0.y += c0.y; s1.x += c1.x; s1.y += c1.y; sc.x += cc.x; sc.y += cc.y;
+              sf.x += fl.x; sf.y += fl.y;
+            }
           }
+          const double P = fma(yd.x, v2, bt.ga) + sf.x, Q = fma(-yd.y, v2, bt.al) + sf.y;
+          D2 d0, d1, r;
+          r.x = g.pspec(k) - P;
+          r.y = 0.0 - Q;
+          double aP = fabs(r.x), aQ = fabs(Q);
+          r.x -= sc.x; r.y -= sc.y;
+          d0.x = fma(-yd.y, v2, -Q) - s0.x;             // -Q - B v2
+          d0.y = fma(yd.x, v2, P) - s0.y;               //  P + G v2
+          d1.x = fma(-yd.x, v2, P) - s1.x;              //  P - G v2
+          d1.y = fma(-yd.y, v2, Q) - s1.y;              //  Q - B v2
+          double u00 = bt.al, u01 = bt.ga, u10 = -bt.ga, u11 = bt.al;
+          if ((t.w & (FL_PQ | FL_THETA)) != (FL_PQ | FL_THETA)) {
+            // a bus without the angle (slack) or magnitude (slack, PV) unknown: no equation, identity
+            // row, no coupling
+            if (!(t.w & FL_THETA)) { aP = 0.0; d0.x = 1.0; d0.y = 0.0; r.x = 0.0; u00 = 0.0; u01 = 0.0; }
+            if (!(t.w & FL_PQ)) { aQ = 0.0; d1.x = 0.0; d1.y = 1.0; r.y = 0.0; u10 = 0.0; u11 = 0.0; }
+          }
+          const double loc = (aQ > aP || aQ != aQ) ? aQ : aP;
+          mm = (loc > mm || loc != loc) ? loc : mm;
+          const double det = fma(d0.x, d1.y, -d0.y * d1.x);
+          if (det == 0.0) singular = 1;                 // dgesv's exact-zero pivot (:188-190)
+          const double inv = rcp_fast(det);
+          const double i00 = d1.y * inv, i01 = -d0.y * inv, i10 = -d1.x * inv, i11 = d0.x * inv;
+          D2 m0, m1, v;
+          m0.x = fma(i00, u00, i01 * u10);
+          m0.y = fma(i00, u01, i01 * u11);
+          m1.x = fma(i10, u00, i11 * u10);
+          m1.y = fma(i10, u01, i11 * u11);
+          v.x = fma(i00, r.x, i01 * r.y);
+          v.y = fma(i10, r.x, i11 * r.y);
+          g.mg[3 * k] = m0;                              // needed again in the back-substitution only
+          g.mg[3 * k + 1] = m1;
+          g.mg[3 * k + 2] = v;
+          D2 c0, c1, cc, fl;                             // handed to the parent: L M, L v, (gl, ll)
+          c0.x = fma(bt.ll, m0.x, bt.gl * m1.x);
+          c0.y = fma(bt.ll, m0.y, bt.gl * m1.y);
+          c1.x = fma(-bt.gl, m0.x, bt.ll * m1.x);
+          c1.y = fma(-bt.gl, m0.y, bt.ll * m1.y);
+          cc.x = fma(bt.ll, v.x, bt.gl * v.y);
+          cc.y = fma(-bt.gl, v.x, bt.ll * v.y);
+          fl.x = bt.gl; fl.y = bt.ll;
+          own[0] = c0; own[np] = c1; own[2 * np] = cc; own[3 * np] = fl;
         }
         g.sync();
       }
+      mm = g.gmax_nan(mm);
+      out->max_mismatch = mm;
+      if (mm < tol) {                                   // checked before the update (:168-171)
+        out->converged = 1;
+        out->iterations = it + 1;
+        break;
+      }
+      if (g.gor(singular)) {
+        out->iterations = it + 1;
+        break;
+      }
+      newton_back_update(g, lay, simg, (const D2*)nullptr, accel);
     }
-    }   // first iteration / general iteration
-    // ---- polar update, every bus independently (:297-327):
-    //      theta += a dtheta, |V| += a d|V|  <=>  V *= (1 + a x1) e^{j a x0}
-    for (int k = g.lane; k < n; k += LANES) {
-      const D2 x = g.vx(k);
-      double sn, cs;
-      sincos_small(accel * x.x, &sn, &cs);
-      const double sc = fma(accel, x.y, 1.0);
-      const D2 v = g.ef(k);
-      D2 w;
-      w.x = sc * fma(v.x, cs, -v.y * sn);
-      w.y = sc * fma(v.x, sn, v.y * cs);
-      g.ef(k) = w;
+    {
+      const double q = mm / (mm_prev * mm_prev);
+      rate = (q > 1e-3 && q < 1e3) ? q : ((q >= 1e3) ? 1e3 : 1.0);
+      mm_prev = mm;
     }
-    g.sync();
   }
 }
 
@@ -711,7 +821,7 @@ GFR_HD void solve_instance(const typename GroupOf<LANES, SOLVER>::type& g, const
     const D2 vv = g.ef(k);
     double e = vv.x, f = vv.y;
     if (o.bus_voltages) o.bus_voltages[env * n + i] = sqrt(e * e + f * f);
-    if (o.bus_angles) o.bus_angles[env * n + i] = atan2(f, e);
+    if (o.bus_angles) o.bus_angles[env * n + i] = atan2_bus(f, e);
   }
   double loss = 0.0;
   const int* bol = simg + lay.o_branch_of_line;
@@ -870,7 +980,7 @@ GFR_HD void step_instance(const typename GroupOf<LANES, SOLVER>::type& g, const 
       soc = soc + en * eff / cap;
     }
     rec[R_BAT + b] = soc; rec[R_BAT + Bt + b] = cur;
-    ob[o_bat + 2 * b] = soc; ob[o_bat + 2 * b + 1] = cur;
+    st_stream(ob + o_bat + 2 * b, soc); st_stream(ob + o_bat + 2 * b + 1, cur);
     g.scr(L + G + b) = cur;
     soc_reward += (soc >= 0.2 && soc <= 0.8) ? 1.0 : -5.0;
   }
@@ -882,7 +992,13 @@ GFR_HD void step_instance(const typename GroupOf<LANES, SOLVER>::type& g, const 
   if (cfg.weather_variation || (cfg.stochastic_loads && !nz)) {
     double u, z1, z2, z3, dummy;
     if (nz) { u = nz[0]; z1 = nz[1]; z2 = nz[2]; z3 = nz[3]; }
-    else {
+    else if (LANES >= 4) {
+      // blocks 0..2 on lanes 0..2, shared by broadcast (one Philox + Box-Muller deep instead of three)
+      double a = 0.0, b = 0.0;
+      if (g.lane < 3) noise_block(seed, draw, (uint32_t)g.lane, &a, &b);
+      u = g.bcast(a, 0); z1 = g.bcast(a, 1); z2 = g.bcast(b, 1); z3 = g.bcast(a, 2); z_load0 = g.bcast(b, 2);
+      dummy = 0.0;
+    } else {
       noise_block(seed, draw, 0u, &u, &dummy);
       noise_block(seed, draw, 1u, &z1, &z2);
       noise_block(seed, draw, 2u, &z3, &z_load0);
@@ -901,7 +1017,7 @@ GFR_HD void step_instance(const typename GroupOf<LANES, SOLVER>::type& g, const 
   for (int gi = g.lane; gi < G; gi += LANES) {
     double p = renewable_power(lay, simg, dimg, gi, hour, wind, temp, cloud);
     double curtail = ((zero_action ? 0.0 : act[Bt + gi]) + 1.0) / 2.0;
-    ob[o_gen + gi] = p;
+    st_stream(ob + o_gen + gi, p);
     g.scr(L + gi) = p * curtail;
     tot_ren += p;
     tot_used += p - p * (1.0 - curtail);
@@ -980,8 +1096,8 @@ GFR_HD void step_instance(const typename GroupOf<LANES, SOLVER>::type& g, const 
       const D2 vv = g.ef(k);
       double e = vv.x, f = vv.y;
       double vm = sqrt(e * e + f * f);
-      ob[2 * i] = vm;
-      ob[2 * i + 1] = atan2(f, e);
+      st_stream(ob + 2 * i, vm);
+      st_stream(ob + 2 * i + 1, atan2_bus(f, e));
       dev += fabs(vm - 1.0);
       vmax = (vm > vmax || vm != vm) ? vm : vmax;
       vmin = (vm < vmin || vm != vm) ? vm : vmin;
@@ -1001,8 +1117,8 @@ GFR_HD void step_instance(const typename GroupOf<LANES, SOLVER>::type& g, const 
       double pw = P * lay.s_base;
       double rating = dimg[lay.o_rating + k];
       double loading = rating > 0.0 ? fabs(pw) / rating : 0.0;     // Line.update_state, base.py:261-264
-      ob[o_line + 2 * li] = pw;
-      ob[o_line + 2 * li + 1] = loading;
+      st_stream(ob + o_line + 2 * li, pw);
+      st_stream(ob + o_line + 2 * li + 1, loading);
       over80 += loading > 0.8;
     }
   }
@@ -1040,7 +1156,7 @@ GFR_HD void step_instance(const typename GroupOf<LANES, SOLVER>::type& g, const 
   episode_reward += reward;
 
   if (g.lane == 0) {
-    ob[o_freq] = freq;
+    st_stream(ob + o_freq, freq);
     rec[R_TIME] = t; rec[R_FREQ] = freq; rec[R_WIND] = wind; rec[R_TEMP] = temp; rec[R_CLOUD] = cloud;
     rec[R_TOTAL_LOSSES] = total_losses; rec[R_EPISODE_REWARD] = episode_reward;
     ((uint64_t*)rec)[R_DRAWS] = draw + 1ull;

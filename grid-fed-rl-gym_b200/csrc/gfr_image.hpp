@@ -167,13 +167,17 @@ inline std::string build_feeder_image(const gfr_feeder_desc* d, FeederImage* out
     topo[4 * k + 0] = k > 0 ? d->parent[k] : 0;
     topo[4 * k + 1] = d->child_ptr[k];
     topo[4 * k + 2] = d->child_ptr[k + 1];
-    topo[4 * k + 3] = flags[k];      // | 3 * pool slot << FL_POOL_SHIFT, added below
+    topo[4 * k + 3] = flags[k];      // | pool slot << FL_POOL_SHIFT, added below
   }
-  for (int k = 0; k < n; ++k) topo[4 * k + 3] |= (3 * pool_slot[k]) << FL_POOL_SHIFT;
+  for (int k = 0; k < n; ++k) {
+    topo[4 * k + 3] |= pool_slot[k] << FL_POOL_SHIFT;
+    if (d->child_ptr[k + 1] > d->child_ptr[k] && pool_slot[d->child_idx[d->child_ptr[k]]] == pool_slot[k])
+      topo[4 * k + 3] |= FL_INHERIT;
+  }
   lay.o_topo = ib.add_i(topo.data(), 4 * n);
   lay.o_child_idx = ib.add_i(d->child_idx, n - 1);
   std::vector<int32_t> child_pool(n > 1 ? n - 1 : 0);
-  for (int q = 0; q < n - 1; ++q) child_pool[q] = 3 * pool_slot[d->child_idx[q]];
+  for (int q = 0; q < n - 1; ++q) child_pool[q] = pool_slot[d->child_idx[q]];
   lay.o_child_pool = ib.add_i(child_pool.data(), n - 1);
   lay.o_level_ptr = ib.add_i(d->level_ptr, nl + 1);
   lay.o_rank = ib.add_i(rank.data(), n);

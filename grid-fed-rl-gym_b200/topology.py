@@ -24,6 +24,7 @@ from __future__ import annotations
 from dataclasses import dataclass, field
 from typing import Any, Dict, List, Optional, Sequence, Tuple
 
+import os
 import numpy as np
 
 # zero-length IEEE-13 entries keep their configured impedance, un-scaled, as pu
@@ -310,18 +311,24 @@ def _schedule(n: int, root: int, adj, width: Optional[int], alap: bool = True):
     return order, parent_ref, level_of
 
 
-def plan_pool(parent: np.ndarray, level_ptr: np.ndarray, contiguous: bool = False):
+def plan_pool(parent: np.ndarray, level_ptr: np.ndarray, contiguous: bool = False,
+              width: Optional[int] = None):
     """Slot of every bus's contribution to its parent.  A contribution is written when its bus is
-    eliminated (levels run last -> first) and read when the parent is.
+    eliminated (levels run last -> first) and read when the parent is; on the way back the same slot
+    carries the parent's correction to the bus.
 
     ``contiguous`` (measured on B200: +1 % at 16 lanes on IEEE-123, -6 % at 8 lanes because fewer
-    instances stay resident, so it is off by default): the buses of one level get consecutive slots, so that the consecutive
-    lanes that write them hit distinct shared-memory banks (a 48-byte entry spans 3 of the 8
-    16-byte bank groups; consecutive slots never collide inside a quarter-warp).  A level's block is
-    free again once the last parent of its buses has been eliminated; blocks are placed first-fit.
+    instances stay resident, so it is off by default): the buses of one level get consecutive slots.
+    A level's block is free again once the last parent of its buses has been eliminated; blocks are
+    placed first-fit.
 
-    Otherwise (default) slots are handed out one by one: a parent inherits its first child's slot, slots
-    released by a level are only reused by later levels.  Fewer slots, scattered accesses."""
+    Otherwise (default) slots are handed out one by one: a parent inherits its first child's slot
+    (the kernels use that: no index load for the first child), slots released by a level are only
+    reused by later levels.  A bus without children starts a chain of buses that will carry its
+    slot (itself, then every ancestor reached through first-child links); it takes the free slot
+    whose 16-byte bank group (slot mod 8) clashes least, over the levels of that chain, with the
+    slots other buses of the same level and quarter-warp (``width`` lanes per instance, lane = bus
+    index mod width) already hold, or a new slot when that avoids clashes."""
     n = parent.size
     slot = np.zeros(n, dtype=np.int32)
     nl = level_ptr.size - 1
@@ -349,6 +356,26 @@ def plan_pool(parent: np.ndarray, level_ptr: np.ndarray, contiguous: bool = Fals
     kids: List[List[int]] = [[] for _ in range(n)]
     for k in range(1, n):
         kids[parent[k]].append(k)
+    w = int(width) if width else 0
+    level = np.zeros(n, dtype=np.int64)
+    for l in range(nl):
+        level[int(level_ptr[l]):int(level_ptr[l + 1])] = l
+
+    def where(k: int) -> Tuple[int, int]:      # (level, quarter-warp) a bus's pool accesses happen in
+        return int(level[k]), ((k % w) // 8 if w > 8 else 0)
+
+    taken: dict = {}                            # (level, quarter) -> bank groups in use there
+    # candidates for a NEW slot: only the next index.  Looking further (up to 8: any bank group) removes
+    # more clashes but costs slots - measured on B200, IEEE-123 at 8 lanes: 24 slots / 56 resident
+    # instances per SM 69.1 M env-steps/s against 22 slots / 60 instances 72.9 M
+    grow = int(os.environ.get('GFR_POOL_GROW', '1'))
+
+    def chain(k: int) -> List[int]:             # the buses that will carry k's slot: k, then every
+        out = [k]                               # ancestor reached through first-child links
+        while parent[out[-1]] >= 0 and kids[parent[out[-1]]][0] == out[-1]:
+            out.append(int(parent[out[-1]]))
+        return out
+
     for l in range(nl - 1, -1, -1):
         members = range(int(level_ptr[l]), int(level_ptr[l + 1]))
         released: List[int] = []
@@ -358,11 +385,25 @@ def plan_pool(parent: np.ndarray, level_ptr: np.ndarray, contiguous: bool = Fals
                 # order), so it can take over its first child's slot; the others are released
                 slot[k] = slot[kids[k][0]]
                 released.extend(int(slot[c]) for c in kids[k][1:])
-            elif free:
-                slot[k] = free.pop()
+        for k in members:
+            if kids[k]:
+                continue
+            path = [where(b) for b in chain(k)]
+
+            def clashes(s: int) -> int:
+                return sum(1 for at in path if s % 8 in taken.get(at, ()))
+            # the candidate with the fewest clashes: a free slot, or a new one (indices skipped on the
+            # way to a new one's bank group join the free list); ties go to the smaller pool
+            cands = [(clashes(s), 0, s) for s in free] + [(clashes(n_pool + j), j + 1, n_pool + j) for j in range(grow)]
+            _, _, best = min(cands)
+            if best >= n_pool:
+                free.extend(range(n_pool, best))
+                n_pool = best + 1
             else:
-                slot[k] = n_pool
-                n_pool += 1
+                free.remove(best)
+            slot[k] = best
+            for at in path:
+                taken.setdefault(at, set()).add(best % 8)
         free.extend(released)                  # only later levels may reuse what this level read
     return slot, max(n_pool, 1)
 
@@ -474,7 +515,7 @@ def compile_feeder(feeder, renewable_sources: Optional[Sequence[str]] = None,
             fill[parent[k]] += 1
         for k in range(1, n):
             assert parent[k] < k and levels[parent[k]] < levels[k]
-        pool_slot, n_pool = plan_pool(parent, level_ptr, contiguous=pool_contiguous)
+        pool_slot, n_pool = plan_pool(parent, level_ptr, contiguous=pool_contiguous, width=width)
         return dict(order=order, rank=rank, parent=parent, line_of=line_of, from_is_parent=from_is_parent,
                     g=g, b=b, r=r, x=x, rating=rating, levels=levels, n_levels=n_levels, level_ptr=level_ptr,
                     child_ptr=child_ptr, child_idx=child_idx, pool_slot=pool_slot, n_pool=n_pool)

@@ -18,25 +18,28 @@ def ranges():
             if re.search(pat, lines[i]):
                 return i + 1
         raise KeyError(pat)
-    ns = find(r"GFR_HD void newton_solve")
-    m = find(r"calculated injections \+ mismatch", ns)
-    f0 = find(r"first iteration: every instance starts", m)
-    e = find(r"assemble \+ eliminate leaf -> root", f0)
-    b = find(r"back-substitute root -> leaf: x_k = v_k - M_k x_parent  \(the root", e)
-    u = find(r"polar update, every bus independently", b)
-    sw = find(r"GFR_HD void sweep_solve", u)
+    bt = find(r"struct BranchT")
+    mo = find(r"GFR_HD double newton_mismatch")
+    bu = find(r"Back-substitution root -> leaf fused with the polar update")
+    ns = find(r"GFR_HD void newton_solve", bu)
+    f0 = find(r"first iteration: every instance starts", ns)
+    pr = find(r"the iterate is expected to have converged", f0)
+    e = find(r"mismatch \+ assemble \+ eliminate, leaf -> root", pr)
+    sw = find(r"GFR_HD void sweep_solve", e)
     bf = find(r"GFR_HD void branch_flow", sw)
     st = find(r"GFR_HD void step_instance", bf)
     post = find(r"bus state -> observation", st)
     rs = find(r"GFR_HD void reset_instance", post)
     ph = find(r"Philox4x32-10")
     sol = find(r"// -+ solvers")
-    return [("group ops / helpers (inlined accessors, sync, reductions, rcp, sincos)", 1, ph - 1),
+    return [("group ops / helpers (inlined accessors, sync, reductions, rcp, sincos, atan)", 1, ph - 1),
             ("Philox + Box-Muller", ph, sol - 1),
-            ("newton: setup + flat start", sol, m - 1), ("newton M: injections + mismatch", m, f0 - 1),
-            ("newton first iteration (flat-start factors)", f0, e - 1),
-            ("newton E: assemble + eliminate", e, b - 1), ("newton B: back-substitution", b, u - 1),
-            ("newton U: polar update", u, sw - 1), ("sweep", sw, bf - 1),
+            ("newton: flat start, branch terms", sol, mo - 1), ("newton M: mismatch-only pass", mo, bu - 1),
+            ("newton B+U: back-substitution + polar update", bu, ns - 1),
+            ("newton: setup", ns, f0 - 1),
+            ("newton first iteration (flat-start factors)", f0, pr - 1),
+            ("newton: convergence prediction", pr, e - 1),
+            ("newton E: mismatch + assemble + eliminate", e, sw - 1), ("sweep", sw, bf - 1),
             ("line flows", bf, st - 1), ("step: actions, batteries, weather, loads, injections", st, post - 1),
             ("step: observation, reward, flags, state", post, rs - 1), ("reset", rs, 10 ** 9)]
 
