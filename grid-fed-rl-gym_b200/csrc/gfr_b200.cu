@@ -11,6 +11,7 @@
 
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -32,7 +33,10 @@ constexpr int kSmemHeader = 16;   // the mbarrier, keeps the image 16-byte align
 #define GFR_MAX_THREADS_16 512
 #endif
 constexpr int kMaxThreads = 512;
-constexpr int max_threads_for(int lanes) { return lanes == 16 ? GFR_MAX_THREADS_16 : kMaxThreads; }
+#ifndef GFR_WIDE_LANES
+#define GFR_WIDE_LANES 0      // groups up to this many lanes are compiled for 768 threads per CTA (80 registers): measured, no gain (IEEE-34 237M -> 230M)
+#endif
+constexpr int max_threads_for(int lanes) { return lanes == 16 ? GFR_MAX_THREADS_16 : (lanes <= GFR_WIDE_LANES ? 768 : kMaxThreads); }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
@@ -229,7 +233,7 @@ struct gfr_env {
   const void* fn = nullptr;
   double* d_state = nullptr;
   double* d_obs = nullptr;
-  D2* d_mscratch = nullptr;    // Newton: D^-1 U of every resident instance slot (L2 resident)
+  D2* d_mscratch = nullptr;    // Newton: D^-1 U, D^-1 r, specified injections of every resident instance slot (L2 resident)
   int slot_bytes = 0;
   bool obs_external = false;   // bound by gfr_env_bind_obs: caller-owned
 };
@@ -247,10 +251,15 @@ size_t slot_bytes(const Layout& lay, int solver) {
 int auto_lanes(const Layout& lay, int solver) {      // same thresholds as topology.auto_lanes (measured, profiles/)
   if (lay.n <= 20) return solver == GFR_SOLVER_SWEEP ? 1 : 4;
   if (lay.n <= 45) return 4;
-  if (lay.n <= 90) return 8;
-  if (lay.n <= 160) return 16;
+  if (solver == GFR_SOLVER_SWEEP) {
+    if (lay.n <= 90) return 8;
+    if (lay.n <= 160) return 16;
+  } else {
+    if (lay.n <= 160) return 8;
+    if (lay.n <= 250) return 16;
+  }
   if (lay.n <= 400) return 32;
-  if (lay.n <= 650) return 64;
+  if (lay.n <= 900) return 64;
   return 128;                      // one CTA per instance
 }
 

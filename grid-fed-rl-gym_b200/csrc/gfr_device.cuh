@@ -384,6 +384,9 @@ GFR_HD void flat_start(const G& g, const Layout& lay, const int* simg, const dou
 // Elimination of bus k (all its children done): D_k = J[k,k] - sum_c C_c, r_k = mismatch_k - sum_c cc_c,
 //   M_k = D_k^-1 J[k,p], v_k = D_k^-1 r_k, and its contribution to the parent p:
 //   C_k = J[p,k] M_k, cc_k = J[p,k] v_k.   Back-substitution: x_k = v_k - M_k x_p.
+#ifdef GFR_EMU_STATS
+static long long gfr_emu_stats[4];   // host debugging: mismatch-only passes, elimination passes, of those converged
+#endif
 struct BranchT { double ga, al, gl, ll; };
 // vk: the bus below the branch, vp: its parent, y: series g + jb
 GFR_HD BranchT branch_terms(const D2 vk, const D2 vp, const D2 y) {
@@ -428,20 +431,47 @@ GFR_HD double newton_mismatch(const NGrp<LANES>& g, const Layout& lay, const int
   return g.gmax_nan(mm);
 }
 
+// 16-byte asynchronous copy global -> shared (L2 only: the source was written by this very thread
+// moments ago), and the group bookkeeping around it.  The host build copies synchronously.
+GFR_HD void cp_async16(D2* dst_shared, const D2* src_global) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_shared)),
+               "l"(src_global)
+               : "memory");
+#else
+  *dst_shared = *src_global;
+#endif
+}
+GFR_HD void cp_async_commit() {
+#if defined(__CUDA_ARCH__)
+  asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+template <int N>
+GFR_HD void cp_async_wait() {
+#if defined(__CUDA_ARCH__)
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+#endif
+}
+
 // Back-substitution root -> leaf fused with the polar update (power_flow.py:297-327):
 //   x_k = v_k - M_k x_parent (the root's M is 0: it has no branch), then
 //   theta += a dtheta, |V| += a d|V|  <=>  V *= (1 + a x1) e^{j a x0}.
 // x_parent comes down through the bus's own pool slot (the parent put it there), x_k goes into the
 // slots of the children.  M and v come back from the global scratch (first iteration: M from the
-// image); the next level's are requested before this level's barrier so that the L2 round trip
-// overlaps it.
+// image).  Their L2 round trip is taken off the critical path by staging them TWO levels ahead with
+// cp.async into the pool's fields 1..3, which are dead on the way down (a ring of two level
+// buffers, 48 B per lane each); when the pool is too small for that ring (n_pool < 2 LANES) they
+// are loaded into registers one level ahead instead.
 template <int LANES>
 GFR_HD void newton_back_update(const NGrp<LANES>& g, const Layout& lay, const int* simg, const D2* f0,
                                double accel) {
-  const int nl = lay.nl;
+  const int nl = lay.nl, np = lay.n_pool;
   const I4* topo = reinterpret_cast<const I4*>(simg + lay.o_topo);
   const int* level_ptr = simg + lay.o_level_ptr;
   const int* child_pool = simg + lay.o_child_pool;
+  const bool staged = 2 * LANES <= np;
+  D2* const ring = g.poolp + np + 3 * g.lane;          // this lane's entry of level buffer 0; buffer 1 is 3 * LANES further
   int nk = g.first(level_ptr[0]);
   bool nv = nk < level_ptr[1];
   D2 nm0, nm1, nvv;
@@ -452,16 +482,51 @@ GFR_HD void newton_back_update(const NGrp<LANES>& g, const Layout& lay, const in
     else { a0 = g.mg[3 * (kk)]; a1 = g.mg[3 * (kk) + 1]; }                 \
     av = g.mg[3 * (kk) + 2];                                               \
   } while (0)
-  if (nv) GFR_LOAD_MV(nk, nm0, nm1, nvv);
+#define GFR_STAGE_MV(kk, dst)                                              \
+  do {                                                                     \
+    if (!f0) { cp_async16((dst), g.mg + 3 * (kk)); cp_async16((dst) + 1, g.mg + 3 * (kk) + 1); } \
+    cp_async16((dst) + 2, g.mg + 3 * (kk) + 2);                            \
+  } while (0)
+  if (staged) {
+    if (nv) GFR_STAGE_MV(nk, ring);
+    cp_async_commit();
+    if (nl > 1) {
+      const int k2 = g.first(level_ptr[1]);
+      if (k2 < level_ptr[2]) GFR_STAGE_MV(k2, ring + 3 * LANES);
+    }
+    cp_async_commit();
+  } else if (nv) {
+    GFR_LOAD_MV(nk, nm0, nm1, nvv);
+  }
   for (int l = 0; l < nl; ++l) {
     const int k1 = level_ptr[l + 1];
-    int k = nk;
-    const bool valid = nv;
-    D2 m0 = nm0, m1 = nm1, v = nvv;
-    if (l + 1 < nl) {
-      nk = g.first(k1);
-      nv = nk < level_ptr[l + 2];
-      if (nv) GFR_LOAD_MV(nk, nm0, nm1, nvv);
+    int k;
+    bool valid;
+    D2 m0, m1, v;
+    if (staged) {
+      k = g.first(level_ptr[l]);
+      valid = k < k1;
+      cp_async_wait<1>();                               // the older of the two groups in flight: this level's
+      D2* const my = ring + (l & 1) * (3 * LANES);
+      m0 = nm0; m1 = nm1;
+      if (valid) {
+        if (f0) { m0 = f0[6 * k + 2]; m1 = f0[6 * k + 3]; }
+        else { m0 = my[0]; m1 = my[1]; }
+      }
+      v = my[2];
+      if (l + 2 < nl) {                                 // the buffer is free again: level l + 2 goes there
+        const int k2 = g.first(level_ptr[l + 2]);
+        if (k2 < level_ptr[l + 3]) GFR_STAGE_MV(k2, my);
+      }
+      cp_async_commit();
+    } else {
+      k = nk; valid = nv;
+      m0 = nm0; m1 = nm1; v = nvv;
+      if (l + 1 < nl) {
+        nk = g.first(k1);
+        nv = nk < level_ptr[l + 2];
+        if (nv) GFR_LOAD_MV(nk, nm0, nm1, nvv);
+      }
     }
     if (valid) {
       for (;;) {
@@ -491,7 +556,9 @@ GFR_HD void newton_back_update(const NGrp<LANES>& g, const Layout& lay, const in
     }
     g.sync();
   }
+  if (staged) cp_async_wait<0>();
 #undef GFR_LOAD_MV
+#undef GFR_STAGE_MV
 }
 
 template <int LANES>
@@ -569,6 +636,9 @@ GFR_HD void newton_solve(const NGrp<LANES>& g, const Layout& lay, const int* sim
       // ---- the iterate is expected to have converged (quadratic rate seen so far): a mismatch-only
       //      pass settles it without the elimination
       if (rate * mm_prev * mm_prev < 0.25 * tol) {
+#ifdef GFR_EMU_STATS
+        ++gfr_emu_stats[0];
+#endif
         mm = newton_mismatch(g, lay, simg, dimg);
         if (mm < tol) {
           out->max_mismatch = mm;
@@ -652,6 +722,10 @@ GFR_HD void newton_solve(const NGrp<LANES>& g, const Layout& lay, const int* sim
         g.sync();
       }
       mm = g.gmax_nan(mm);
+#ifdef GFR_EMU_STATS
+      ++gfr_emu_stats[1];
+      if (mm < tol) ++gfr_emu_stats[2];
+#endif
       out->max_mismatch = mm;
       if (mm < tol) {                                   // checked before the update (:168-171)
         out->converged = 1;

@@ -591,20 +591,26 @@ def compile_feeder(feeder, renewable_sources: Optional[Sequence[str]] = None,
 
 def auto_lanes(n_bus: int, solver: str = "newton") -> int:
     """Threads cooperating on one instance when the caller does not say.  Thresholds from
-    measurements on B200 (profiles/r01_tune_lanes_newton.txt, profiles/r01_bench_all_configs.txt):
+    measurements on B200 (profiles/r01_tune_lanes_newton_v7.txt, profiles/r01_bench_all_configs_v7.txt):
     a few lanes for the smallest feeders, part of a warp up to a few hundred buses, one CTA per
     instance (feeder image read from global memory) beyond."""
     if n_bus <= 20:
         return 1 if solver == "sweep" else 4
     if n_bus <= 45:
         return 4
-    if n_bus <= 90:
-        return 8
-    if n_bus <= 160:
-        return 16
+    if solver == "sweep":
+        if n_bus <= 90:
+            return 8
+        if n_bus <= 160:
+            return 16
+    else:
+        if n_bus <= 160:
+            return 8
+        if n_bus <= 250:
+            return 16
     if n_bus <= 400:
         return 32
-    if n_bus <= 650:
+    if n_bus <= 900:
         return 64
     return 128
 

@@ -19,7 +19,9 @@ for n, B in ((30, 262144), (60, 131072), (100, 131072), (200, 65536), (300, 3276
         s = 0.4 / tot
         ld.base_power *= s; ld.active_power *= s; ld.reactive_power *= s
     row = []
-    for lanes in (4, 8, 16, 32, 64, 128, 256):
+    for lanes in (2, 4, 8, 16, 32, 64, 128, 256):
+        if lanes * 128 < n or lanes > 4 * n:
+            continue
         try:
             env = m.BatchedGridEnvironment(f, B, solver=solver, lanes=lanes, repair=False,
                                            renewable_sources=["solar", "wind"], start_time=43200.0,
