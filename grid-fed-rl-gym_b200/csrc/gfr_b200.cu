@@ -259,7 +259,7 @@ int auto_lanes(const Layout& lay, int solver) {      // same thresholds as topol
     if (lay.n <= 250) return 16;
   }
   if (lay.n <= 400) return 32;
-  if (lay.n <= 900) return 64;
+  if (lay.n <= 1500) return 64;
   return 128;                      // one CTA per instance
 }
 

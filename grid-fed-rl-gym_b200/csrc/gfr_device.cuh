@@ -177,7 +177,7 @@ struct NGrp : Lanes<LANES> {
   D2* poolp;      // [POOL_D2][n_pool] shared
   int np;         // n_pool
   double* pp;     // [n]      specified injections (global scratch, right after mg)
-  D2* mg;         // [3 * n]  GLOBAL scratch of this instance slot: D^-1 U (2) and D^-1 r (1) per bus
+  D2* mg;         // [3][n]   GLOBAL scratch of this instance slot: rows of D^-1 U (2) and D^-1 r (1), field-major
   GFR_HD D2& ef(int k) const { return efp[k]; }
   GFR_HD double& pspec(int k) const { return pp[k]; }
   GFR_HD double& scr(int j) const { return reinterpret_cast<double*>(efp)[j]; }   // ef + pool, flat
@@ -466,12 +466,12 @@ GFR_HD void cp_async_wait() {
 template <int LANES>
 GFR_HD void newton_back_update(const NGrp<LANES>& g, const Layout& lay, const int* simg, const D2* f0,
                                double accel) {
-  const int nl = lay.nl, np = lay.n_pool;
+  const int nl = lay.nl, np = lay.n_pool, nb = lay.n;
   const I4* topo = reinterpret_cast<const I4*>(simg + lay.o_topo);
   const int* level_ptr = simg + lay.o_level_ptr;
   const int* child_pool = simg + lay.o_child_pool;
   const bool staged = 2 * LANES <= np;
-  D2* const ring = g.poolp + np + 3 * g.lane;          // this lane's entry of level buffer 0; buffer 1 is 3 * LANES further
+  D2* const ring = g.poolp + np + g.lane;              // this lane's entries of level buffer 0 (field f at + f * LANES); buffer 1 is 3 * LANES further
   int nk = g.first(level_ptr[0]);
   bool nv = nk < level_ptr[1];
   D2 nm0, nm1, nvv;
@@ -479,13 +479,13 @@ GFR_HD void newton_back_update(const NGrp<LANES>& g, const Layout& lay, const in
 #define GFR_LOAD_MV(kk, a0, a1, av)                                        \
   do {                                                                     \
     if (f0) { a0 = f0[6 * (kk) + 2]; a1 = f0[6 * (kk) + 3]; }              \
-    else { a0 = g.mg[3 * (kk)]; a1 = g.mg[3 * (kk) + 1]; }                 \
-    av = g.mg[3 * (kk) + 2];                                               \
+    else { a0 = g.mg[(kk)]; a1 = g.mg[nb + (kk)]; }                        \
+    av = g.mg[2 * nb + (kk)];                                              \
   } while (0)
 #define GFR_STAGE_MV(kk, dst)                                              \
   do {                                                                     \
-    if (!f0) { cp_async16((dst), g.mg + 3 * (kk)); cp_async16((dst) + 1, g.mg + 3 * (kk) + 1); } \
-    cp_async16((dst) + 2, g.mg + 3 * (kk) + 2);                            \
+    if (!f0) { cp_async16((dst), g.mg + (kk)); cp_async16((dst) + LANES, g.mg + nb + (kk)); } \
+    cp_async16((dst) + 2 * LANES, g.mg + 2 * nb + (kk));                   \
   } while (0)
   if (staged) {
     if (nv) GFR_STAGE_MV(nk, ring);
@@ -511,9 +511,9 @@ GFR_HD void newton_back_update(const NGrp<LANES>& g, const Layout& lay, const in
       m0 = nm0; m1 = nm1;
       if (valid) {
         if (f0) { m0 = f0[6 * k + 2]; m1 = f0[6 * k + 3]; }
-        else { m0 = my[0]; m1 = my[1]; }
+        else { m0 = my[0]; m1 = my[LANES]; }
       }
-      v = my[2];
+      v = my[2 * LANES];
       if (l + 2 < nl) {                                 // the buffer is free again: level l + 2 goes there
         const int k2 = g.first(level_ptr[l + 2]);
         if (k2 < level_ptr[l + 3]) GFR_STAGE_MV(k2, my);
@@ -626,7 +626,7 @@ GFR_HD void newton_solve(const NGrp<LANES>& g, const Layout& lay, const int* sim
           v.y = fma(i1.x, r0, i1.y * r1);
           cc.x = fma(lp.x, v.x, lp.y * v.y);
           cc.y = fma(-lp.y, v.x, lp.x * v.y);
-          g.mg[3 * k + 2] = v;
+          g.mg[2 * n + k] = v;
           g.poolp[2 * np + (t.w >> FL_POOL_SHIFT)] = cc;
         }
         g.sync();
@@ -706,9 +706,9 @@ GFR_HD void newton_solve(const NGrp<LANES>& g, const Layout& lay, const int* sim
           m1.y = fma(i10, u01, i11 * u11);
           v.x = fma(i00, r.x, i01 * r.y);
           v.y = fma(i10, r.x, i11 * r.y);
-          g.mg[3 * k] = m0;                              // needed again in the back-substitution only
-          g.mg[3 * k + 1] = m1;
-          g.mg[3 * k + 2] = v;
+          g.mg[k] = m0;                                  // needed again in the back-substitution only
+          g.mg[n + k] = m1;
+          g.mg[2 * n + k] = v;
           D2 c0, c1, cc, fl;                             // handed to the parent: L M, L v, (gl, ll)
           c0.x = fma(bt.ll, m0.x, bt.gl * m1.x);
           c0.y = fma(bt.ll, m0.y, bt.gl * m1.y);

@@ -525,6 +525,10 @@ def compile_feeder(feeder, renewable_sources: Optional[Sequence[str]] = None,
     order, rank, parent, line_of, from_is_parent = (lay[k] for k in ("order", "rank", "parent", "line_of", "from_is_parent"))
     g, b, r, x, rating = (lay[k] for k in ("g", "b", "r", "x", "rating"))
     level_ptr, child_ptr, child_idx, pool_slot, n_pool = (lay[k] for k in ("level_ptr", "child_ptr", "child_idx", "pool_slot", "n_pool"))
+    if width is not None and 1 < int(width) <= 32 and os.environ.get("GFR_POOL_PAD", "1") == "1":
+        # the Newton back-substitution stages its operands two levels ahead in the pool's idle fields,
+        # which takes a pool of at least 2 x lanes slots; small feeders have shared memory to spare
+        n_pool = min(max(n_pool, 2 * int(width)), max(n, n_pool))
 
     tmap = {"slack": BUS_SLACK, "pv": BUS_PV}
     bus_type = np.array([tmap.get(buses[i].bus_type, BUS_PQ) for i in order], dtype=np.int32)
@@ -610,7 +614,7 @@ def auto_lanes(n_bus: int, solver: str = "newton") -> int:
             return 16
     if n_bus <= 400:
         return 32
-    if n_bus <= 900:
+    if n_bus <= 1500:
         return 64
     return 128
 

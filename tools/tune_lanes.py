@@ -10,7 +10,10 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import grid_fed_rl_b200 as m  # noqa: E402
 
 solver = sys.argv[1] if len(sys.argv) > 1 else "newton"
-for n, B in ((30, 262144), (60, 131072), (100, 131072), (200, 65536), (300, 32768), (500, 16384), (800, 8192)):
+SIZES = ((30, 262144), (60, 131072), (100, 131072), (200, 65536), (300, 32768), (500, 16384), (800, 8192))
+if os.environ.get("GFR_TUNE_SIZES"):
+    SIZES = tuple(s for s in SIZES if str(s[0]) in os.environ["GFR_TUNE_SIZES"].split(","))
+for n, B in SIZES:
     cfg = m.NetworkConfig(num_buses=n, connectivity=0.0, load_probability=0.9, dg_probability=0.3,
                           min_load_kw=20, max_load_kw=300, line_length_range=(0.05, 1.5))
     f = m.repair_topology(m.SyntheticFeeder(cfg, seed=n))
