@@ -478,7 +478,7 @@ GFR_HD void newton_back_update(const NGrp<LANES>& g, const Layout& lay, const in
   nm0.x = nm0.y = nm1.x = nm1.y = nvv.x = nvv.y = 0.0;
 #define GFR_LOAD_MV(kk, a0, a1, av)                                        \
   do {                                                                     \
-    if (f0) { a0 = f0[6 * (kk) + 2]; a1 = f0[6 * (kk) + 3]; }              \
+    if (f0) { a0 = f0[2 * nb + (kk)]; a1 = f0[3 * nb + (kk)]; }            \
     else { a0 = g.mg[(kk)]; a1 = g.mg[nb + (kk)]; }                        \
     av = g.mg[2 * nb + (kk)];                                              \
   } while (0)
@@ -510,7 +510,7 @@ GFR_HD void newton_back_update(const NGrp<LANES>& g, const Layout& lay, const in
       D2* const my = ring + (l & 1) * (3 * LANES);
       m0 = nm0; m1 = nm1;
       if (valid) {
-        if (f0) { m0 = f0[6 * k + 2]; m1 = f0[6 * k + 3]; }
+        if (f0) { m0 = f0[2 * nb + k]; m1 = f0[3 * nb + k]; }
         else { m0 = my[0]; m1 = my[LANES]; }
       }
       v = my[2 * LANES];
@@ -588,7 +588,7 @@ GFR_HD void newton_solve(const NGrp<LANES>& g, const Layout& lay, const int* sim
       mm = 0.0;
       for (int k = g.lane; k < n; k += LANES) {
         const int fl = topo[k].w;
-        const D2 pc = f0[6 * k + 5];
+        const D2 pc = f0[5 * n + k];
         double aP = fabs(g.pspec(k) - pc.x), aQ = fabs(pc.y);
         if (!(fl & FL_THETA)) aP = 0.0;
         if (!(fl & FL_PQ)) aQ = 0.0;
@@ -606,7 +606,7 @@ GFR_HD void newton_solve(const NGrp<LANES>& g, const Layout& lay, const int* sim
         const int k1 = level_ptr[l + 1];
         for (int k = g.first(level_ptr[l]); k < k1; k += LANES) {
           const I4 t = topo[k];
-          const D2 pc = f0[6 * k + 5];
+          const D2 pc = f0[5 * n + k];
           D2 sc; sc.x = sc.y = 0.0;
           {
             int q = t.y;
@@ -620,7 +620,7 @@ GFR_HD void newton_solve(const NGrp<LANES>& g, const Layout& lay, const int* sim
           double r0 = g.pspec(k) - pc.x - sc.x, r1 = 0.0 - pc.y - sc.y;
           if (!(t.w & FL_THETA)) r0 = 0.0;
           if (!(t.w & FL_PQ)) r1 = 0.0;
-          const D2 i0 = f0[6 * k], i1 = f0[6 * k + 1], lp = f0[6 * k + 4];   // D^-1 rows, (ll, gl)
+          const D2 i0 = f0[k], i1 = f0[n + k], lp = f0[4 * n + k];          // D^-1 rows, (ll, gl)
           D2 v, cc;
           v.x = fma(i0.x, r0, i0.y * r1);
           v.y = fma(i1.x, r0, i1.y * r1);

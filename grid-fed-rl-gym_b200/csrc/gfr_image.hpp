@@ -233,11 +233,15 @@ inline std::string build_feeder_image(const gfr_feeder_desc* d, FeederImage* out
         const double i00 = d11 * inv, i01 = -d01 * inv, i10 = -d10 * inv, i11 = d00 * inv;
         const double m00 = i00 * u00 + i01 * u10, m01 = i00 * u01 + i01 * u11,
                      m10 = i10 * u00 + i11 * u10, m11 = i10 * u01 + i11 * u11;
-        double* o = &f0[12 * (size_t)k];
-        o[0] = i00; o[1] = i01; o[2] = i10; o[3] = i11;
-        o[4] = m00; o[5] = m01; o[6] = m10; o[7] = m11;
-        o[8] = ll; o[9] = gl;
-        o[10] = P; o[11] = Q;                          // calculated injections of the flat profile
+        // six 16-byte fields per bus, field-major (field f of bus k at f0[2 * (f * n + k)]): the lanes
+        // of a level read consecutive 16-byte units
+        auto put = [&](int fld, double a0, double a1) {
+          f0[2 * ((size_t)fld * n + k)] = a0; f0[2 * ((size_t)fld * n + k) + 1] = a1;
+        };
+        put(0, i00, i01); put(1, i10, i11);
+        put(2, m00, m01); put(3, m10, m11);
+        put(4, ll, gl);
+        put(5, P, Q);                                  // calculated injections of the flat profile
         double* cc = &C[4 * (size_t)k];
         cc[0] = ll * m00 + gl * m10; cc[1] = ll * m01 + gl * m11;
         cc[2] = -gl * m00 + ll * m10; cc[3] = -gl * m01 + ll * m11;
