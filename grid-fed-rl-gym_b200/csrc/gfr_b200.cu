@@ -331,7 +331,7 @@ PlanTry plan_mode(const gfr_feeder* f, const void* fn, int lanes, bool img_smem,
       long long E = (long long)((share - 1024 - fixed) / per_env);
       if (lanes > 32) E = 1;                              // one CTA per instance
       if (E * lanes > max_threads_for(lanes)) E = max_threads_for(lanes) / lanes;
-      if (pass == 0) E -= E % gran;
+      if (pass == 0) E -= E % gran;                        // (a partial last warp was measured: no gain)
       if (E < 1) continue;
       const int threads = (int)(E * lanes);
       const size_t smem = fixed + per_env * (size_t)E;

@@ -53,13 +53,17 @@ enum { SCRATCH_FIELDS_SWEEP = 2 };
 enum { FL_PQ = 1, FL_FROM_IS_PARENT = 2, FL_FIXED_VM = 4, FL_THETA = 8,     // PQ: |V| unknown; THETA: angle unknown
        FL_SLACK_PATH = 16,                                                // on the path slack -> root (slack included, root not)
        FL_INHERIT = 32,                                                   // the bus's pool slot is also its first child's
-       FL_POOL_SHIFT = 8 };                                               // flags >> 8 = the bus's pool slot
+       FL_NO_SCATTER = 64,                                                // every child but the first reads the correction from this bus's slot
+       FL_POOL_SHIFT = 8, FL_POOL_MASK = 0xFFF,                           // bits 8..19: the bus's pool slot
+       FL_XSLOT_SHIFT = 20 };                                             // bits 20..31: the slot its parent's correction arrives in
 // record (persistent per-instance state) slots, in doubles
 enum { R_TIME = 0, R_FREQ, R_WIND, R_TEMP, R_CLOUD, R_TOTAL_LOSSES, R_EPISODE_REWARD, R_SEED,
        R_DRAWS, R_COUNTS, R_BAT };   // soc[Bt] then bpow[Bt] from R_BAT on
 
 struct alignas(16) D2 { double x, y; };
 struct alignas(16) I4 { int x, y, z, w; };   // per-bus topology: parent, child list begin, end, flags
+GFR_HD int pool_slot_of(int w) { return (w >> FL_POOL_SHIFT) & FL_POOL_MASK; }
+GFR_HD int x_slot_of(int w) { return (int)((unsigned)w >> FL_XSLOT_SHIFT); }
 
 // Where everything is inside the feeder image (ints / doubles counted from the image base)
 // plus the sizes; passed as a kernel parameter (constant bank).
@@ -532,14 +536,16 @@ GFR_HD void newton_back_update(const NGrp<LANES>& g, const Layout& lay, const in
       for (;;) {
         const I4 t = topo[k];
         D2 x; x.x = x.y = 0.0;
-        if (k > 0) x = g.poolp[t.w >> FL_POOL_SHIFT];      // field 0 of its own slot
+        if (k > 0) x = g.poolp[x_slot_of(t.w)];            // field 0 of its own slot, or of the parent's (see gfr_image.hpp)
         v.x = fma(-m0.x, x.x, fma(-m0.y, x.y, v.x));
         v.y = fma(-m1.x, x.x, fma(-m1.y, x.y, v.y));
         {
           int q = t.y;
-          if (t.w & FL_INHERIT) { g.poolp[t.w >> FL_POOL_SHIFT] = v; ++q; }     // first child: same slot, no index load
+          if (t.w & FL_INHERIT) { g.poolp[pool_slot_of(t.w)] = v; ++q; }        // first child: same slot, no index load
+          if (!(t.w & FL_NO_SCATTER)) {
 #pragma unroll 1
-          for (; q < t.z; ++q) g.poolp[child_pool[q]] = v;
+            for (; q < t.z; ++q) g.poolp[child_pool[q]] = v;
+          }
         }
         double sn, cs;
         sincos_small(accel * v.x, &sn, &cs);
@@ -610,7 +616,7 @@ GFR_HD void newton_solve(const NGrp<LANES>& g, const Layout& lay, const int* sim
           D2 sc; sc.x = sc.y = 0.0;
           {
             int q = t.y;
-            if (t.w & FL_INHERIT) { sc = g.poolp[2 * np + (t.w >> FL_POOL_SHIFT)]; ++q; }
+            if (t.w & FL_INHERIT) { sc = g.poolp[2 * np + pool_slot_of(t.w)]; ++q; }
 #pragma unroll 1
             for (; q < t.z; ++q) {
               const D2 cc = g.poolp[2 * np + child_pool[q]];
@@ -627,7 +633,7 @@ GFR_HD void newton_solve(const NGrp<LANES>& g, const Layout& lay, const int* sim
           cc.x = fma(lp.x, v.x, lp.y * v.y);
           cc.y = fma(-lp.y, v.x, lp.x * v.y);
           g.mg[2 * n + k] = v;
-          g.poolp[2 * np + (t.w >> FL_POOL_SHIFT)] = cc;
+          g.poolp[2 * np + pool_slot_of(t.w)] = cc;
         }
         g.sync();
       }
@@ -661,7 +667,7 @@ GFR_HD void newton_solve(const NGrp<LANES>& g, const Layout& lay, const int* sim
           const BranchT bt = branch_terms(vk, g.ef(t.x), gb[k]);
           D2 s0, s1, sc, sf;                               // children's contributions: plain sums
           s0.x = s0.y = s1.x = s1.y = sc.x = sc.y = sf.x = sf.y = 0.0;
-          D2* const own = g.poolp + (t.w >> FL_POOL_SHIFT);
+          D2* const own = g.poolp + pool_slot_of(t.w);
           {
             int q = t.y;
             if (t.w & FL_INHERIT) {                        // first child: same slot, no index load

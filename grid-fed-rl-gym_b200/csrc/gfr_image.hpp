@@ -169,10 +169,30 @@ inline std::string build_feeder_image(const gfr_feeder_desc* d, FeederImage* out
     topo[4 * k + 2] = d->child_ptr[k + 1];
     topo[4 * k + 3] = flags[k];      // | pool slot << FL_POOL_SHIFT, added below
   }
+  if (lay.n_pool > FL_POOL_MASK) return "more than 4095 pool slots";
+  // The correction a bus needs on the way down (root -> leaf) arrives in field 0 of a pool slot.
+  // Normally its parent scatters it into the slot of every child.  When the parent's first child c1
+  // shares the parent's slot (inheritance) and is a leaf, nothing overwrites that slot between the
+  // parent's turn and c1's, so every child that is handled no later than c1 simply reads the
+  // parent's slot, and a parent all of whose other children do so skips the scatter loop.
   for (int k = 0; k < n; ++k) {
-    topo[4 * k + 3] |= pool_slot[k] << FL_POOL_SHIFT;
-    if (d->child_ptr[k + 1] > d->child_ptr[k] && pool_slot[d->child_idx[d->child_ptr[k]]] == pool_slot[k])
-      topo[4 * k + 3] |= FL_INHERIT;
+    int xs = pool_slot[k];
+    if (k > 0) {
+      const int p = d->parent[k];
+      const int c1 = d->child_idx[d->child_ptr[p]];
+      const bool c1_leaf = d->child_ptr[c1 + 1] == d->child_ptr[c1];
+      if (c1_leaf && pool_slot[c1] == pool_slot[p] && level[k] <= level[c1]) xs = pool_slot[p];
+    }
+    topo[4 * k + 3] |= (pool_slot[k] << FL_POOL_SHIFT) | (int32_t)((uint32_t)xs << FL_XSLOT_SHIFT);
+  }
+  for (int k = 0; k < n; ++k) {
+    const int q0 = d->child_ptr[k], q1 = d->child_ptr[k + 1];
+    if (q1 == q0) continue;
+    if (pool_slot[d->child_idx[q0]] == pool_slot[k]) topo[4 * k + 3] |= FL_INHERIT;
+    bool all_read_mine = (topo[4 * k + 3] & FL_INHERIT) != 0;
+    for (int q = q0 + 1; q < q1 && all_read_mine; ++q)
+      all_read_mine = x_slot_of(topo[4 * d->child_idx[q] + 3]) == pool_slot[k] && pool_slot[d->child_idx[q]] != pool_slot[k];
+    if (all_read_mine && q1 - q0 > 1) topo[4 * k + 3] |= FL_NO_SCATTER;
   }
   lay.o_topo = ib.add_i(topo.data(), 4 * n);
   lay.o_child_idx = ib.add_i(d->child_idx, n - 1);

@@ -312,7 +312,8 @@ def _schedule(n: int, root: int, adj, width: Optional[int], alap: bool = True):
 
 
 def plan_pool(parent: np.ndarray, level_ptr: np.ndarray, contiguous: bool = False,
-              width: Optional[int] = None):
+              width: Optional[int] = None, child_ptr: Optional[np.ndarray] = None,
+              child_idx: Optional[np.ndarray] = None):
     """Slot of every bus's contribution to its parent.  A contribution is written when its bus is
     eliminated (levels run last -> first) and read when the parent is; on the way back the same slot
     carries the parent's correction to the bus.
@@ -354,8 +355,12 @@ def plan_pool(parent: np.ndarray, level_ptr: np.ndarray, contiguous: bool = Fals
     free: List[int] = []
     n_pool = 0
     kids: List[List[int]] = [[] for _ in range(n)]
-    for k in range(1, n):
-        kids[parent[k]].append(k)
+    if child_ptr is not None and child_idx is not None:      # the caller's child order: the first one is inherited from
+        for k in range(n):
+            kids[k] = [int(c) for c in child_idx[int(child_ptr[k]):int(child_ptr[k + 1])]]
+    else:
+        for k in range(1, n):
+            kids[parent[k]].append(k)
     w = int(width) if width else 0
     level = np.zeros(n, dtype=np.int64)
     for l in range(nl):
@@ -515,7 +520,20 @@ def compile_feeder(feeder, renewable_sources: Optional[Sequence[str]] = None,
             fill[parent[k]] += 1
         for k in range(1, n):
             assert parent[k] < k and levels[parent[k]] < levels[k]
-        pool_slot, n_pool = plan_pool(parent, level_ptr, contiguous=pool_contiguous, width=width)
+        # The first child of a bus shares its pool slot.  When that child is a leaf handled no earlier
+        # (on the way down) than its siblings, all of them read the parent's correction from that
+        # one slot and the parent does not scatter it (gfr_image.hpp): put such a child first.
+        for k in range(n):
+            q0, q1 = int(child_ptr[k]), int(child_ptr[k + 1])
+            if q1 - q0 < 2:
+                continue
+            kids_k = [int(c) for c in child_idx[q0:q1]]
+            deepest = max(int(levels[c]) for c in kids_k)
+            lead = next((c for c in kids_k if int(levels[c]) == deepest and child_ptr[c + 1] == child_ptr[c]), None)
+            if lead is not None:
+                child_idx[q0:q1] = [lead] + [c for c in kids_k if c != lead]
+        pool_slot, n_pool = plan_pool(parent, level_ptr, contiguous=pool_contiguous, width=width,
+                                      child_ptr=child_ptr, child_idx=child_idx)
         return dict(order=order, rank=rank, parent=parent, line_of=line_of, from_is_parent=from_is_parent,
                     g=g, b=b, r=r, x=x, rating=rating, levels=levels, n_levels=n_levels, level_ptr=level_ptr,
                     child_ptr=child_ptr, child_idx=child_idx, pool_slot=pool_slot, n_pool=n_pool)

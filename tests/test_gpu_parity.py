@@ -519,3 +519,49 @@ def test_diverging_instances_are_data_not_errors():
         env.step(act, nz)                                   # and the environment keeps going
         assert int(info["current_step"].min()) == 2
         env.close()
+
+
+@pytest.mark.parametrize("spec,lanes", (("ieee34", 4), ("ieee34", 8), ("ieee123", 8), ("ieee123", 16)))
+def test_pool_plans_are_bit_identical(spec, lanes):
+    """The host's pool plan only decides WHERE a bus parks what it hands to its parent: one slot per
+    bus (no inheritance, every child through the index list), level-contiguous slots, the tight plan
+    without padding (too small for the cp.async ring -> register prefetch) and the default plan
+    (first child through the inherited slot, staged operands) must give the same bits."""
+    import dataclasses
+    import grid_fed_rl_b200 as m
+    from grid_fed_rl_b200.topology import compile_feeder
+    f = m.repair_topology({"ieee34": lambda: m.IEEE34Bus(seed=0), "ieee123": lambda: m.IEEE123Bus(seed=0)}[spec]())
+    kw = dict(renewable_sources=["solar", "wind"], root="center", width=lanes)
+    default = compile_feeder(f, **kw)
+    n = default.n_bus
+    tight_slots = int(default.pool_slot.max()) + 1
+    plans = {
+        "default": default,
+        "per_bus": dataclasses.replace(default, pool_slot=np.arange(n, dtype=np.int32), n_pool=n),
+        "tight": dataclasses.replace(default, n_pool=tight_slots),
+        "contiguous": compile_feeder(f, pool_contiguous=True, **kw),
+    }
+    assert tight_slots <= default.n_pool
+    B = 96
+    g = torch.Generator(device="cuda"); g.manual_seed(5)
+    ref = None
+    for name, soa in plans.items():
+        env = m.BatchedGridEnvironment(soa, B, solver="newton", tolerance=1e-6, lanes=lanes, repair=False,
+                                       start_time=12 * 3600.0)
+        env.reset(seed=3)
+        if ref is None:
+            acts = [env.sample_actions(g) for _ in range(3)]
+        outs = []
+        for a in acts:
+            obs, reward, term, trunc, info = env.step(a)
+            outs.append((obs.clone(), reward.clone(), info["iterations"].clone(), info["max_mismatch"].clone()))
+        assert bool(info["power_flow_converged"].all()), name
+        if ref is None:
+            ref = outs
+        else:
+            for (o, r, it, mm), (o0, r0, it0, mm0) in zip(outs, ref):
+                if name == "contiguous":      # another schedule may order a level differently: same values to rounding
+                    assert torch.max(torch.abs(o - o0)) < 1e-9 and torch.equal(it, it0), name
+                else:
+                    assert torch.equal(o, o0) and torch.equal(r, r0) and torch.equal(it, it0) and torch.equal(mm, mm0), name
+        env.close()
