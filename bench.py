@@ -374,8 +374,8 @@ def run_gpu(args):
                          "frac": achieved / peak, "traffic": TRAFFIC_BYTES.get((args.workload, B)),
                          "peak_source": how, "algorithmic_bytes_per_env_step": abytes,
                          "kernel": f"step_kernel<{li['lanes']},{solver}>", "kernel_ms": ms / K,
-                         "note": "not HBM bound: ncu shows the L1 / shared-memory data pipe at 72 %, issue slots 54 %, "
-                                 "FP64 pipe 32 %, DRAM 3 % (DESIGN.md section 5, profiles/); see also `fp64`"},
+                         "note": "not HBM bound: ncu shows the L1 / shared-memory data pipe at 70 %, issue slots 56 %, "
+                                 "FP64 pipe 28 %, DRAM 7.5 % (DESIGN.md section 5, profiles/); see also `fp64`"},
             # FP64 side (the contract's roofline bounds are hbm | tensor; this kernel is neither): FP64 pipe
             # operations per env-step (ncu, profiles/: executed DFMA / DMUL / DADD / DSETP thread
             # instructions / instances) x env-steps/s, against the DFMA issue rate measured on this
@@ -404,16 +404,18 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
-# FP64 lane operations per env-step (ncu: executed warp instructions x FP64 share x active lanes / instances)
-FP64_LANE_OPS = {"ieee123": 60000}      # profiles/r01_ncu_ieee123_final.txt: 8.05e9 / 131072 = 61.4 k before the last trim
+# FP64 lane operations per env-step: ncu smsp__sass_thread_inst_executed_op_{dfma,dmul,dadd}_pred_on summed over
+# the launch / instances (profiles/r01_ncu_ieee123_v8.txt: (990 + 526 + 302) per cycle x 3.196 M cycles / 131072)
+FP64_LANE_OPS = {"ieee123": 44300}
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the step kernel, from the ncu --set full
 # capture summarised under profiles/ (keyed by workload and instances per launch)
 TRAFFIC_BYTES = {
-    # profiles/r01_ncu_ieee123_final.txt: 33.7 MB read + 531.2 MB written per launch of step_kernel<16, newton>
-    # (below the 772.7 MB of algorithmic bytes: part of the previous step's observation lines are still
-    # dirty in the 126 MB L2 when they are overwritten)
-    ("ieee123", 131072): 564.9e6,
+    # profiles/r01_ncu_ieee123_v8.txt: 37.3 MB read + 985.1 MB written per launch of step_kernel<8, newton>.
+    # The algorithmic bytes are 772.7 MB (of which the 2L static load columns of the observation, 199 MB, are
+    # never rewritten); the rest of the writes are the solver's scratch (D^-1 U, D^-1 r: 61 MB live, 2.1 GB
+    # written per launch) leaving the L2 under the observation stream
+    ("ieee123", 131072): 1022.3e6,
 }
 
 

