@@ -322,9 +322,10 @@ def run_gpu(args):
     from grid_fed_rl_b200.pipeline import HostStepper
     host_act = [a.cpu().pin_memory() for a in actions]
 
-    def e2e_run(depth):
-        stepper = HostStepper(env, depth=depth)
+    def e2e_run(depth, observations=False, k_steps=None):
+        stepper = HostStepper(env, depth=depth, observations=observations)
         checksum = [0.0]
+        K = k_steps or args.steps
 
         def run(k):
             for i in range(k):
@@ -343,6 +344,12 @@ def run_gpu(args):
         barrier()
         return max_over_ranks(ev0.elapsed_time(ev1), dev), stepper
 
+    # the same with every step's observation [B, D] copied to the host too (PCIe bound; fewer steps)
+    K_obs = max(2, min(K, 10))
+    ms_obs, stepper_obs = e2e_run(2, observations=True, k_steps=K_obs)
+    obs_value = B * world * K_obs / (ms_obs * 1e-3)
+    obs_d2h = stepper_obs.d2h_bytes_per_step
+    del stepper_obs
     ms_serial, stepper = e2e_run(1)
     ms_e2e, stepper = e2e_run(2)
     clocks = sampler.stop()          # sampled across the timed regions
@@ -389,10 +396,13 @@ def run_gpu(args):
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": stepper.h2d_bytes_per_step,
                     "d2h_bytes_per_step": stepper.d2h_bytes_per_step, "ms_per_step": ms_e2e / K,
                     "serial_value": e2e_serial, "serial_ms_per_step": ms_serial / K,
+                    "with_observations": {"value": obs_value, "d2h_bytes_per_step": obs_d2h, "steps": K_obs,
+                                          "gb_per_s_d2h": obs_d2h / (ms_obs / K_obs * 1e-3) / 1e9},
                     "note": "HostStepper (public API): pinned host actions in, reward + terminated + truncated "
                             "out, every step, each result read by the host; `value` = depth-2 pipeline (next "
                             "step's H2D overlaps the kernel), `serial_value` = copy-step-copy-sync; "
-                            "observations stay in HBM for a device policy"},
+                            "observations stay in HBM for a device policy (`with_observations`: every "
+                            "observation row copied to pinned host memory too - PCIe bound)"},
             "gpu_launches": int(launches), "clocks": clocks,
         }
         if world == 1 and not args.no_cpu:

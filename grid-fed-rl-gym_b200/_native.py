@@ -21,6 +21,7 @@ LIB_PATH = os.path.join(HERE, "libgfr_b200.so")
 GFR_OK, GFR_E_ARG, GFR_E_CUDA, GFR_E_LIMIT = 0, -1, -2, -3
 SOLVER_SWEEP, SOLVER_NEWTON = 0, 1
 SOLVERS = {"sweep": SOLVER_SWEEP, "newton": SOLVER_NEWTON, "newton_raphson": SOLVER_NEWTON}
+BUS_SLACK, BUS_PV, BUS_PQ = 0, 1, 2
 
 _i32p, _f64p, _u8p, _u64p = C.POINTER(C.c_int32), C.POINTER(C.c_double), C.POINTER(C.c_uint8), C.POINTER(C.c_uint64)
 
@@ -39,6 +40,12 @@ class FeederDesc(C.Structure):
         ("bat_cap", _f64p), ("bat_rating", _f64p), ("bat_eff", _f64p), ("bat_soc0", _f64p),
         ("load_profile", _f64p),
     ]
+
+
+class NetworkDesc(C.Structure):
+    _fields_ = [("n_bus", C.c_int32), ("n_line", C.c_int32), ("s_base", C.c_double),
+                ("bus_type", _i32p), ("vm_set", _f64p), ("line_from", _i32p), ("line_to", _i32p),
+                ("line_r", _f64p), ("line_x", _f64p), ("line_rating", _f64p)]
 
 
 class SolverCfg(C.Structure):
@@ -90,6 +97,10 @@ SIGNATURES: Dict[str, Tuple[object, List[object]]] = {
     "gfr_env_reset": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]),
     "gfr_env_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(StepOut), C.c_void_p]),
     "gfr_solve": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(SolverCfg), C.POINTER(SolOut), C.c_void_p]),
+    "gfr_network_create": (C.c_int, [C.POINTER(NetworkDesc), C.c_int, C.POINTER(C.c_void_p)]),
+    "gfr_network_destroy": (None, [C.c_void_p]),
+    "gfr_network_unknowns": (C.c_int, [C.c_void_p]),
+    "gfr_network_solve": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(SolverCfg), C.POINTER(SolOut), C.c_void_p]),
     "gfr_noise_fill": (C.c_int, [C.c_int, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gfr_fp64_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double)]),
     "gfr_launch_count": (C.c_int64, []),
@@ -133,6 +144,26 @@ def check(lib: C.CDLL, rc: int) -> None:
 
 def _ptr(arr: np.ndarray, ctype):
     return arr.ctypes.data_as(C.POINTER(ctype))
+
+
+def make_network_desc(buses, lines, s_base: float):
+    """``gfr_network_desc`` from the reference's ``List[Bus]`` / ``List[Line]`` (their order is kept)
+    + the numpy arrays that must outlive it.  No radiality requirement."""
+    index = {b.id: i for i, b in enumerate(buses)}
+    tmap = {"slack": BUS_SLACK, "pv": BUS_PV}
+    keep = dict(
+        bus_type=np.array([tmap.get(b.bus_type, BUS_PQ) for b in buses], dtype=np.int32),
+        vm_set=np.array([float(b.voltage_magnitude) for b in buses], dtype=np.float64),
+        line_from=np.array([index[l.from_bus] for l in lines], dtype=np.int32),
+        line_to=np.array([index[l.to_bus] for l in lines], dtype=np.int32),
+        line_r=np.array([float(l.resistance) for l in lines], dtype=np.float64),
+        line_x=np.array([float(l.reactance) for l in lines], dtype=np.float64),
+        line_rating=np.array([float(l.rating) for l in lines], dtype=np.float64))
+    d = NetworkDesc()
+    d.n_bus, d.n_line, d.s_base = len(buses), len(lines), float(s_base)
+    for k, a in keep.items():
+        setattr(d, k, _ptr(a, C.c_int32 if a.dtype == np.int32 else C.c_double))
+    return d, keep
 
 
 def make_feeder_desc(soa: FeederSoA):

@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libgfr_b200.so")
 SOURCES = ["gfr_b200.cu"]
-DEPENDS = ["gfr_b200.cu", "gfr_device.cuh", "gfr_image.hpp", os.path.join("..", "..", "include", "gfr_b200.h")]
+DEPENDS = ["gfr_b200.cu", "gfr_device.cuh", "gfr_dense.cuh", "gfr_image.hpp", os.path.join("..", "..", "include", "gfr_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC", "-cudart", "shared",
               "-Xlinker", "-rpath,/usr/local/cuda/lib64"]

@@ -9,15 +9,19 @@
 // plan_launch() picks instance slots per CTA and CTAs per SM with the occupancy API.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <atomic>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <string>
 #include <vector>
 
 #include "../../include/gfr_b200.h"
 #include "gfr_device.cuh"
+#include "gfr_dense.cuh"
 #include "gfr_image.hpp"
 
 using namespace gfr;
@@ -236,6 +240,15 @@ struct gfr_env {
   D2* d_mscratch = nullptr;    // Newton: D^-1 U, D^-1 r, specified injections of every resident instance slot (L2 resident)
   int slot_bytes = 0;
   bool obs_external = false;   // bound by gfr_env_bind_obs: caller-owned
+};
+
+struct gfr_network {
+  int device = 0;
+  int sm_count = 0;
+  int smem_optin = 0;
+  NetDev nd{};
+  void* d_ints = nullptr;       // one allocation each: the int arrays, the double arrays
+  void* d_dbls = nullptr;
 };
 
 namespace {
@@ -644,6 +657,123 @@ int gfr_solve(const gfr_feeder* f, int64_t B, const double* p_inj, const gfr_sol
   o.bus_angles = out->bus_angles; o.line_flows = out->line_flows; o.line_loadings = out->line_loadings;
   o.losses = out->losses; o.max_mismatch = out->max_mismatch;
   return launch_solve(f, plan, fn, ec, p_inj, o, B, (cudaStream_t)stream);
+}
+
+int gfr_network_create(const gfr_network_desc* d, int device, gfr_network** out) {
+  if (!d || !out) return fail(GFR_E_ARG, "null argument");
+  *out = nullptr;
+  const int n = d->n_bus, m = d->n_line;
+  if (n < 2 || m < 1) return fail(GFR_E_ARG, "a network needs at least two buses and one line");
+  if (!(d->s_base > 0.0)) return fail(GFR_E_ARG, "s_base must be > 0");
+  if (!d->bus_type || !d->vm_set || !d->line_from || !d->line_to || !d->line_r || !d->line_x || !d->line_rating)
+    return fail(GFR_E_ARG, "missing network array");
+  // unknowns in the reference's order (power_flow.py:213-295): angles of the non-slack buses, then |V| of the PQ buses
+  std::vector<int32_t> col_theta(n, -1), col_vm(n, -1);
+  int n_slack = 0, nt = 0;
+  for (int i = 0; i < n; ++i) {
+    if (d->bus_type[i] != GFR_BUS_SLACK && d->bus_type[i] != GFR_BUS_PV && d->bus_type[i] != GFR_BUS_PQ)
+      return fail(GFR_E_ARG, "unknown bus_type");
+    if (d->bus_type[i] == GFR_BUS_SLACK) { ++n_slack; continue; }
+    col_theta[i] = nt++;
+  }
+  if (n_slack != 1) return fail(GFR_E_ARG, "exactly one slack bus is required");
+  int N = nt;
+  for (int i = 0; i < n; ++i) if (d->bus_type[i] == GFR_BUS_PQ) col_vm[i] = N++;
+  // Ybus (power_flow.py:48-73): y = 1 / (r + jx), an impedance of magnitude <= 1e-12 is an open line;
+  // parallel lines merge into one neighbour entry
+  std::vector<double> line_y(2 * (size_t)m), ydiag(2 * (size_t)n, 0.0);
+  std::vector<std::map<int, std::pair<double, double>>> nb(n);
+  for (int k = 0; k < m; ++k) {
+    const int i = d->line_from[k], j = d->line_to[k];
+    if (i < 0 || i >= n || j < 0 || j >= n || i == j) return fail(GFR_E_ARG, "line end out of range");
+    const double r = d->line_r[k], x = d->line_x[k], z2 = r * r + x * x;
+    double g = 0.0, b = 0.0;
+    if (std::sqrt(z2) > 1e-12) { g = r / z2; b = -x / z2; }
+    if (!(g == g) || !(b == b)) return fail(GFR_E_ARG, "line with NaN impedance");
+    line_y[2 * k] = g; line_y[2 * k + 1] = b;
+    ydiag[2 * i] += g; ydiag[2 * i + 1] += b; ydiag[2 * j] += g; ydiag[2 * j + 1] += b;
+    auto& a = nb[i][j]; a.first -= g; a.second -= b;
+    auto& c = nb[j][i]; c.first -= g; c.second -= b;
+  }
+  std::vector<int32_t> adj_ptr(n + 1, 0), adj_idx;
+  std::vector<double> adj_y;
+  for (int i = 0; i < n; ++i) {
+    for (const auto& kv : nb[i]) { adj_idx.push_back(kv.first); adj_y.push_back(kv.second.first); adj_y.push_back(kv.second.second); }
+    adj_ptr[i + 1] = (int32_t)adj_idx.size();
+  }
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail(GFR_E_CUDA, "no usable CUDA device (this library has no CPU fallback)");
+  cudaDeviceProp prop;
+  GFR_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (dense_smem_bytes(n, N) > (size_t)prop.sharedMemPerBlockOptin)
+    return fail(GFR_E_LIMIT, "the dense Jacobian of this network exceeds the shared memory of an SM "
+                             "(non-slack + PQ buses <= ~165); radial feeders take the tree-ordered solver");
+  // pack: ints = bus_type | col_theta | col_vm | adj_ptr | adj_idx | line_from | line_to ; doubles (16-byte aligned
+  // pairs first) = adj_y | ydiag | line_y | vm_set | line_rating
+  std::vector<int32_t> ints;
+  auto addi = [&](const int32_t* p, size_t c) { size_t o = ints.size(); ints.insert(ints.end(), p, p + c); return o; };
+  const size_t o_bt = addi(d->bus_type, n), o_ct = addi(col_theta.data(), n), o_cv = addi(col_vm.data(), n),
+               o_ap = addi(adj_ptr.data(), n + 1), o_ai = addi(adj_idx.data(), adj_idx.size()),
+               o_lf = addi(d->line_from, m), o_lt = addi(d->line_to, m);
+  std::vector<double> dbls;
+  auto addd = [&](const double* p, size_t c) { size_t o = dbls.size(); dbls.insert(dbls.end(), p, p + c); return o; };
+  const size_t o_ay = addd(adj_y.data(), adj_y.size()), o_yd = addd(ydiag.data(), ydiag.size()),
+               o_ly = addd(line_y.data(), line_y.size()), o_vm = addd(d->vm_set, n), o_lr = addd(d->line_rating, m);
+  auto* net = new gfr_network();
+  net->device = device; net->sm_count = prop.multiProcessorCount; net->smem_optin = (int)prop.sharedMemPerBlockOptin;
+  cudaError_t e1 = cudaMalloc(&net->d_ints, ints.size() * 4), e2 = cudaMalloc(&net->d_dbls, dbls.size() * 8);
+  if (e1 == cudaSuccess) e1 = cudaMemcpy(net->d_ints, ints.data(), ints.size() * 4, cudaMemcpyHostToDevice);
+  if (e2 == cudaSuccess) e2 = cudaMemcpy(net->d_dbls, dbls.data(), dbls.size() * 8, cudaMemcpyHostToDevice);
+  if (e1 != cudaSuccess || e2 != cudaSuccess) { gfr_network_destroy(net); return cuda_fail(e1 != cudaSuccess ? e1 : e2, "cudaMalloc(network)"); }
+  const int* di = (const int*)net->d_ints;
+  const double* dd = (const double*)net->d_dbls;
+  NetDev& nd = net->nd;
+  nd.n = n; nd.m = m; nd.N = N; nd.n_theta = nt; nd.s_base = d->s_base;
+  nd.bus_type = di + o_bt; nd.col_theta = di + o_ct; nd.col_vm = di + o_cv; nd.adj_ptr = di + o_ap;
+  nd.adj_idx = di + o_ai; nd.line_from = di + o_lf; nd.line_to = di + o_lt;
+  nd.adj_y = (const D2*)(dd + o_ay); nd.ydiag = (const D2*)(dd + o_yd); nd.line_y = (const D2*)(dd + o_ly);
+  nd.vm_set = dd + o_vm; nd.line_rating = dd + o_lr;
+  *out = net;
+  return GFR_OK;
+}
+
+void gfr_network_destroy(gfr_network* net) {
+  if (!net) return;
+  DeviceGuard guard(net->device);
+  cudaFree(net->d_ints);
+  cudaFree(net->d_dbls);
+  delete net;
+}
+
+int gfr_network_unknowns(const gfr_network* net) { return net ? net->nd.N : 0; }
+
+int gfr_network_solve(const gfr_network* net, int64_t B, const double* p_inj, const gfr_solver_cfg* cfg,
+                      const gfr_sol_out* out, void* stream) {
+  if (!net || !p_inj || !cfg || !out) return fail(GFR_E_ARG, "null argument");
+  if (B < 1) return fail(GFR_E_ARG, "B must be >= 1");
+  if (cfg->max_iterations < 1) return fail(GFR_E_ARG, "max_iterations must be >= 1");
+  if (!(cfg->tolerance > 0.0)) return fail(GFR_E_ARG, "tolerance must be > 0");
+  DeviceGuard guard(net->device);
+  if (!guard.ok) return fail(GFR_E_CUDA, "no usable CUDA device (this library has no CPU fallback)");
+  const size_t smem = dense_smem_bytes(net->nd.n, net->nd.N);
+  GFR_CUDA(cudaFuncSetAttribute((const void*)dense_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                net->smem_optin));
+  const int threads = net->nd.N <= 48 ? 128 : 256;
+  int per_sm = 0;
+  GFR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)dense_solve_kernel, threads, smem));
+  if (per_sm < 1) return fail(GFR_E_LIMIT, "the dense Jacobian of this network exceeds the shared memory of an SM");
+  long long grid = (long long)net->sm_count * per_sm;
+  if (grid > B) grid = B;
+  SolOut o{};
+  o.converged = out->converged; o.iterations = out->iterations; o.bus_voltages = out->bus_voltages;
+  o.bus_angles = out->bus_angles; o.line_flows = out->line_flows; o.line_loadings = out->line_loadings;
+  o.losses = out->losses; o.max_mismatch = out->max_mismatch;
+  const double accel = cfg->acceleration != 0.0 ? cfg->acceleration : 1.0;
+  dense_solve_kernel<<<(int)grid, threads, smem, (cudaStream_t)stream>>>(net->nd, cfg->tolerance, cfg->max_iterations,
+                                                                         accel, p_inj, o, (long long)B);
+  g_launches.fetch_add(1);
+  GFR_CUDA(cudaGetLastError());
+  return GFR_OK;
 }
 
 int gfr_noise_fill(int device, int64_t B, int32_t n_slots, const uint64_t* seeds, const uint64_t* draws,

@@ -19,10 +19,13 @@ from .env import BatchedGridEnvironment
 
 
 class HostStepper:
-    def __init__(self, env: BatchedGridEnvironment, depth: int = 2) -> None:
+    def __init__(self, env: BatchedGridEnvironment, depth: int = 2, observations: bool = False) -> None:
+        """``observations=True`` also brings every step's observation ``[B, D]`` back to pinned host
+        memory (what the reference's list-returning ``step`` implies for a host policy): 8 D bytes per
+        instance per step over PCIe, which then bounds the rate."""
         if depth < 1:
             raise ValueError("depth must be >= 1")
-        self.env, self.depth = env, depth
+        self.env, self.depth, self.observations = env, depth, bool(observations)
         dev, B, A = env.device, env.num_envs, env.act_dim
         self.copy_stream = torch.cuda.Stream(device=dev)
         self._act = [torch.empty(B, A, dtype=torch.float64, device=dev) for _ in range(depth)]
@@ -30,6 +33,9 @@ class HostStepper:
                            terminated=torch.empty(B, dtype=torch.bool).pin_memory(),
                            truncated=torch.empty(B, dtype=torch.bool).pin_memory())
                       for _ in range(depth)]
+        if self.observations:
+            for h in self._host:
+                h["observations"] = torch.empty(B, env.obs_dim, dtype=torch.float64).pin_memory()
         self._copied = [torch.cuda.Event() for _ in range(depth)]
         self._done = [torch.cuda.Event() for _ in range(depth)]
         self._busy = [False] * depth
@@ -42,7 +48,7 @@ class HostStepper:
 
     @property
     def d2h_bytes_per_step(self) -> int:
-        return self.env.num_envs * (8 + 1 + 1)
+        return self.env.num_envs * (8 + 1 + 1 + (8 * self.env.obs_dim if self.observations else 0))
 
     def submit(self, host_actions: torch.Tensor) -> None:
         """Queue one step.  ``host_actions``: pinned fp64 ``[B, A]`` (a pageable tensor works but
@@ -57,8 +63,10 @@ class HostStepper:
             self._act[j].copy_(host_actions, non_blocking=True)
             self._copied[j].record(self.copy_stream)
         compute.wait_event(self._copied[j])
-        _, reward, term, trunc, _ = self.env.step(self._act[j])
+        obs, reward, term, trunc, _ = self.env.step(self._act[j])
         h = self._host[j]
+        if self.observations:
+            h["observations"].copy_(obs, non_blocking=True)
         h["reward"].copy_(reward, non_blocking=True)
         h["terminated"].copy_(term, non_blocking=True)
         h["truncated"].copy_(trunc, non_blocking=True)

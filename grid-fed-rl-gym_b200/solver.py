@@ -43,15 +43,65 @@ def _signature(buses, lines):
                   for l in lines))
 
 
+class NativeNetwork:
+    """A (possibly meshed) network resident on one device (``gfr_network``): buses and lines in the
+    caller's order, solved by the dense Newton-Raphson kernel."""
+
+    def __init__(self, buses, lines, s_base: float, device: torch.device) -> None:
+        self.lib = nat.load_library()
+        self.device = device
+        self.n_bus, self.n_line = len(buses), len(lines)
+        desc, self._keep = nat.make_network_desc(buses, lines, s_base)
+        h = C.c_void_p()
+        nat.check(self.lib, self.lib.gfr_network_create(C.byref(desc), device.index, C.byref(h)))
+        self.handle = h
+        self.unknowns = int(self.lib.gfr_network_unknowns(h))
+
+    def close(self) -> None:
+        if getattr(self, "handle", None):
+            self.lib.gfr_network_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self) -> None:
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def is_radial(buses, lines) -> bool:
+    """True when the lines form a spanning tree of the buses (what the tree-ordered kernels need)."""
+    if len(lines) != len(buses) - 1:
+        return False
+    index = {b.id: i for i, b in enumerate(buses)}
+    root = list(range(len(buses)))
+
+    def find(a):
+        while root[a] != a:
+            root[a] = root[root[a]]
+            a = root[a]
+        return a
+    for ln in lines:
+        a, b = find(index[ln.from_bus]), find(index[ln.to_bus])
+        if a == b:
+            return False
+        root[a] = b
+    return True
+
+
 class B200PowerFlowSolver:
-    """Batched radial load flow on one GPU.  ``method`` is "newton" (the reference's polar
-    Newton-Raphson iterates, solved by tree-ordered block elimination) or "sweep"
-    (backward / forward sweep)."""
+    """Batched load flow on one GPU.  ``method`` is "newton" (the reference's polar Newton-Raphson
+    iterates, solved by tree-ordered block elimination; radial feeders of any size), "sweep"
+    (backward / forward sweep; radial), "dense" (the same Newton-Raphson on the dense Jacobian with
+    a pivoted LU in shared memory, one CTA per instance: any connected network, cycles included, up
+    to ~80 buses) or "auto" ("newton" on a radial network, "dense" on a meshed one)."""
+
+    METHODS = tuple(sorted(set(nat.SOLVERS) | {"dense", "auto"}))
 
     def __init__(self, tolerance: float = 1e-6, max_iterations: int = 50, method: str = "newton",
                  acceleration_factor: float = 1.0, device="cuda", lanes: int = 0, **kwargs) -> None:
-        if method not in nat.SOLVERS:
-            raise InvalidConfigurationError(f"method must be one of {sorted(nat.SOLVERS)}")
+        if method not in self.METHODS:
+            raise InvalidConfigurationError(f"method must be one of {list(self.METHODS)}")
         self.tolerance, self.max_iterations = float(tolerance), int(max_iterations)
         self.method, self.acceleration_factor = method, float(acceleration_factor)
         self.lanes = int(lanes)
@@ -61,7 +111,8 @@ class B200PowerFlowSolver:
 
     # -- compiled topologies ------------------------------------------------------
     def _compile(self, feeder) -> FeederSoA:
-        soa, self._lanes_used = compile_for_solver(feeder, self.method, self.lanes, with_components=False)
+        method = "newton" if self.method in ("auto", "dense") else self.method
+        soa, self._lanes_used = compile_for_solver(feeder, method, self.lanes, with_components=False)
         return soa
 
     def _native(self, key, make_soa) -> NativeFeeder:
@@ -77,9 +128,50 @@ class B200PowerFlowSolver:
             self._cache[key] = nf
         return nf
 
+    def _use_dense(self, buses, lines) -> bool:
+        return self.method == "dense" or (self.method == "auto" and not is_radial(buses, lines))
+
+    def _network(self, buses, lines, s_base: float) -> NativeNetwork:
+        key = ("net", _signature(buses, lines), float(s_base))
+        net = self._cache.get(key)
+        if net is None:
+            net = NativeNetwork(buses, lines, s_base, _cuda_device(self._device_arg))
+            if len(self._cache) >= 8:
+                self._cache.pop(next(iter(self._cache))).close()
+            self._cache[key] = net
+        return net
+
+    def solve_network_batch(self, net: NativeNetwork, p_inj) -> PowerFlowSolution:
+        """The dense path: ``p_inj`` [B, n] per-unit injections in the network's bus order."""
+        dev, lib = net.device, net.lib
+        p = torch.as_tensor(p_inj)
+        if p.dim() == 1:
+            p = p[None, :]
+        if p.shape[1] != net.n_bus:
+            raise InvalidConfigurationError(f"p_inj must be [B, {net.n_bus}], got {tuple(p.shape)}")
+        p = p.to(device=dev, dtype=torch.float64).contiguous()
+        B, n, m = p.shape[0], net.n_bus, net.n_line
+        f64 = dict(dtype=torch.float64, device=dev)
+        out = dict(converged=torch.zeros(B, dtype=torch.uint8, device=dev),
+                   iterations=torch.zeros(B, dtype=torch.int32, device=dev),
+                   bus_voltages=torch.empty(B, n, **f64), bus_angles=torch.empty(B, n, **f64),
+                   line_flows=torch.empty(B, m, **f64), line_loadings=torch.empty(B, m, **f64),
+                   losses=torch.empty(B, **f64), max_mismatch=torch.empty(B, **f64))
+        so = nat.SolOut(*[out[k].data_ptr() for k, _ in nat.SolOut._fields_])
+        cfg = nat.make_solver_cfg("newton", self.tolerance, self.max_iterations, self.acceleration_factor, 0)
+        nat.check(lib, lib.gfr_network_solve(net.handle, B, p.data_ptr(), C.byref(cfg), C.byref(so),
+                                             torch.cuda.current_stream(dev).cuda_stream))
+        out["converged"] = out["converged"].view(torch.bool)
+        return PowerFlowSolution(**out)
+
     def solve_batch(self, feeder, p_inj) -> PowerFlowSolution:
         """``p_inj`` [B, n] per-unit injections (generation minus load) in ``feeder.buses`` order;
         returns a ``PowerFlowSolution`` of tensors with a leading B axis."""
+        if isinstance(feeder, NativeNetwork):
+            return self.solve_network_batch(feeder, p_inj)
+        if not isinstance(feeder, (NativeFeeder, FeederSoA)) and self._use_dense(feeder.buses, feeder.lines):
+            s_base = float(feeder.parameters.base_power) * 1e6
+            return self.solve_network_batch(self._network(feeder.buses, feeder.lines, s_base), p_inj)
         if isinstance(feeder, NativeFeeder):
             nf = feeder
         elif isinstance(feeder, FeederSoA):
@@ -102,9 +194,10 @@ class B200PowerFlowSolver:
                    line_flows=torch.empty(B, m, **f64), line_loadings=torch.empty(B, m, **f64),
                    losses=torch.empty(B, **f64), max_mismatch=torch.empty(B, **f64))
         so = nat.SolOut(*[out[k].data_ptr() for k, _ in nat.SolOut._fields_])
-        cfg = nat.make_solver_cfg(self.method, self.tolerance, self.max_iterations,
+        method = "newton" if self.method in ("auto", "dense") else self.method
+        cfg = nat.make_solver_cfg(method, self.tolerance, self.max_iterations,
                                   self.acceleration_factor,
-                                  self.lanes or auto_lanes(soa.n_bus, self.method))
+                                  self.lanes or auto_lanes(soa.n_bus, method))
         nat.check(lib, lib.gfr_solve(nf.handle, B, p.data_ptr(), C.byref(cfg), C.byref(so),
                                      torch.cuda.current_stream(dev).cuda_stream))
         out["converged"] = out["converged"].view(torch.bool)
@@ -121,8 +214,11 @@ class B200PowerFlowSolver:
     def _solve_reference_form(self, buses, lines, loads: Dict[Any, float],
                               generation: Dict[Any, float]) -> PowerFlowSolution:
         # power_flow.py:105-121: P_spec = generation - load at each bus id; Q_spec = 0
-        nf = self._native(("lists", _signature(buses, lines)),
-                          lambda: self._compile(_Topology(buses, lines, 1e-6)))
+        if self._use_dense(buses, lines):
+            nf = self._network(buses, lines, 1.0)
+        else:
+            nf = self._native(("lists", _signature(buses, lines)),
+                              lambda: self._compile(_Topology(buses, lines, 1e-6)))
         index = {b.id: i for i, b in enumerate(buses)}
         p = np.zeros((1, len(buses)))
         for bus, v in loads.items():

@@ -69,8 +69,12 @@ def _new_line(proto, **kw):
     return type(proto)(**kw)
 
 
-def repair_topology(feeder, zero_length_pu: Optional[Dict[str, Tuple[float, float]]] = None):
-    """Deviation D4 (ii)+(iii): see module docstring.  Returns a ``RepairedFeeder``."""
+def repair_topology(feeder, zero_length_pu: Optional[Dict[str, Tuple[float, float]]] = None,
+                    keep_cycles: bool = False):
+    """Deviation D4 (ii)+(iii): see module docstring.  Returns a ``RepairedFeeder``.
+    ``keep_cycles=True`` keeps the lines that close a cycle (only open lines are dropped, islands
+    are still chained to their list predecessor): a meshed network for the dense solver
+    (``B200PowerFlowSolver(method="dense")``); the tree-ordered kernels need the default."""
     overrides = IEEE13_ZERO_LENGTH_PU if zero_length_pu is None else zero_length_pu
     buses = list(feeder.buses)
     n = len(buses)
@@ -114,7 +118,7 @@ def repair_topology(feeder, zero_length_pu: Optional[Dict[str, Tuple[float, floa
             continue
         a, b = find(index[ln.from_bus]), find(index[ln.to_bus])
         if a == b:
-            dropped.append(ln)
+            (kept if keep_cycles else dropped).append(ln)
         else:
             root[a] = b
             kept.append(ln)
@@ -134,7 +138,7 @@ def repair_topology(feeder, zero_length_pu: Optional[Dict[str, Tuple[float, floa
     # order makes that impossible for i>slack, but check anyway
     if any(find(i) != find(slack) for i in range(n)):
         raise TopologyError("repair failed to connect every bus to the slack bus")
-    if len(kept) != n - 1:
+    if len(kept) != n - 1 and not keep_cycles:
         raise TopologyError("repair did not produce a spanning tree")
     return RepairedFeeder(feeder, kept, dropped, added)
 

@@ -198,6 +198,33 @@ int gfr_env_step(gfr_env* e, const double* actions, const double* noise, const g
 int gfr_solve(const gfr_feeder* f, int64_t B, const double* p_inj, const gfr_solver_cfg* cfg,
               const gfr_sol_out* out, void* stream);
 
+/* ---- meshed networks: the reference's dense Newton-Raphson as written ------------------------
+ * NewtonRaphsonSolver.solve on ANY connected network (cycles allowed): dense Ybus
+ * (power_flow.py:48-73, an impedance of magnitude <= 1e-12 is an open line), dense polar Jacobian
+ * (power_flow.py:213-295, deviation D2), LU with partial pivoting = np.linalg.solve / LAPACK dgesv
+ * (power_flow.py:187), one CTA per instance with the Jacobian in shared memory.  Bus and line order
+ * are the caller's (no renumbering).  Limit: (#non-slack + #PQ buses) <= ~165, else GFR_E_LIMIT -
+ * radial feeders of any size take gfr_solve. */
+typedef struct gfr_network gfr_network;
+typedef struct {
+  int32_t n_bus, n_line;
+  double s_base;                    /* VA: line_loadings = |S| s_base / rating (deviation D1) */
+  const int32_t* bus_type;          /* [n_bus] GFR_BUS_* (exactly one slack) */
+  const double* vm_set;             /* [n_bus] bus.voltage_magnitude (used for slack / PV buses) */
+  const int32_t* line_from;         /* [n_line] index into the buses */
+  const int32_t* line_to;           /* [n_line] */
+  const double* line_r;             /* [n_line] pu */
+  const double* line_x;             /* [n_line] pu */
+  const double* line_rating;        /* [n_line] VA */
+} gfr_network_desc;
+int gfr_network_create(const gfr_network_desc* desc, int device, gfr_network** out);
+void gfr_network_destroy(gfr_network* net);
+int gfr_network_unknowns(const gfr_network* net);          /* order of the dense Jacobian */
+/* p_inj [B, n_bus] pu (generation minus load, Q_spec = 0 as the reference); out arrays in the
+ * caller's bus / line order; cfg->solver and cfg->lanes are ignored. */
+int gfr_network_solve(const gfr_network* net, int64_t B, const double* p_inj, const gfr_solver_cfg* cfg,
+                      const gfr_sol_out* out, void* stream);
+
 /* The noise rows the in-kernel generator yields: out [B, n_slots] for keys seeds[B] and draw
  * counters draws[B] (slot 0 uniform, slots 1.. standard normal). */
 int gfr_noise_fill(int device, int64_t B, int32_t n_slots, const uint64_t* seeds,

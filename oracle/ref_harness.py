@@ -201,6 +201,23 @@ def make_feeder(ns, spec: str, use_reference_classes: bool = True):
             f = ns.synthetic.SyntheticFeeder(ns.synthetic.NetworkConfig(**cfg), seed=int(seed))
         else:
             f = mine.SyntheticFeeder(mine.NetworkConfig(**cfg), seed=int(seed))
+    elif spec.startswith("mesh"):
+        # meshed: 'mesh<N>:<seed>:<connectivity>' (SyntheticFeeder with extra ties), 'meshieee34' (the
+        # shipped IEEE-34 with its loop-closing line kept); repaired with keep_cycles=True
+        if spec == "meshieee34":
+            if use_reference_classes:
+                st = np.random.get_state(); np.random.seed(0); f = ns.feeders.IEEE34Bus(); np.random.set_state(st)
+            else:
+                f = mine.IEEE34Bus(seed=0)
+        else:
+            n, seed, conn = spec[4:].split(":")
+            cfg = dict(num_buses=int(n), connectivity=float(conn), load_probability=0.9, dg_probability=0.4,
+                       min_load_kw=20, max_load_kw=300, line_length_range=(0.05, 1.5))
+            if use_reference_classes:
+                f = ns.synthetic.SyntheticFeeder(ns.synthetic.NetworkConfig(**cfg), seed=int(seed))
+            else:
+                f = mine.SyntheticFeeder(mine.NetworkConfig(**cfg), seed=int(seed))
+        return mine.repair_topology(f, keep_cycles=True)
     else:
         raise ValueError(spec)
     return mine.repair_topology(f)
@@ -360,6 +377,11 @@ SOLVE_CASES = {
     "solve_synthetic60": ("synthetic60:7", 5, 4, 1e-8, 0.05),
     # deliberately infeasible loading: the reference runs to max_iterations, converged=False
     "solve_ieee13_overload": ("ieee13", 6, 2, 1e-6, 9.0),
+    # meshed networks (cycle lines kept): the reference's dense Newton-Raphson as it is
+    "meshsolve_ieee34": ("meshieee34", 7, 5, 1e-6, 1.0),
+    "meshsolve_synthetic40": ("mesh40:3:0.05", 8, 5, 1e-8, 0.05),
+    "meshsolve_synthetic72": ("mesh72:5:0.02", 9, 3, 1e-8, 0.03),
+    "meshsolve_synthetic24_overload": ("mesh24:2:0.1", 10, 2, 1e-6, 200.0),
 }
 
 

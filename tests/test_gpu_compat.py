@@ -136,6 +136,23 @@ def test_host_stepper_pipeline_matches_plain_stepping():
         for (r0, t0, u0), (r1, t1, u1) in zip(plain, got):
             assert torch.equal(r0, r1) and torch.equal(t0, t1) and torch.equal(u0, u1)
         assert st.h2d_bytes_per_step == 512 * a.act_dim * 8 and st.d2h_bytes_per_step == 512 * 10
+    # observations=True: every step's observation rows reach the host as well
+    a2 = m.BatchedGridEnvironment(f, 512, **kw); a2.reset(seed=3)
+    b = m.BatchedGridEnvironment(f, 512, **kw); b.reset(seed=3)
+    st = m.HostStepper(b, depth=2, observations=True)
+    assert st.d2h_bytes_per_step == 512 * (10 + 8 * b.obs_dim)
+    want = []
+    for x in acts[:4]:
+        o, _, _, _, _ = a2.step(x)
+        want.append(o.cpu().clone())
+    got = []
+    for i, x in enumerate(acts[:4]):
+        st.submit(x)
+        if i >= 1:
+            got.append(st.result()["observations"].clone())
+    while st._pending:
+        got.append(st.result()["observations"].clone())
+    assert len(got) == 4 and all(torch.equal(w, g) for w, g in zip(want, got))
 
 
 def test_graphed_collection_is_consistent_and_faster_to_launch():

@@ -565,3 +565,75 @@ def test_pool_plans_are_bit_identical(spec, lanes):
                 else:
                     assert torch.equal(o, o0) and torch.equal(r, r0) and torch.equal(it, it0) and torch.equal(mm, mm0), name
         env.close()
+
+
+# ----------------------------------------------------------------------------- meshed networks (dense path)
+
+@pytest.mark.parametrize("name", golden_names("meshsolve_"))
+def test_dense_solver_matches_reference_on_meshed_networks(name):
+    """Networks with cycles (loop-closing lines kept): the dense Newton-Raphson kernel against the
+    frozen outputs of the reference's own solver, through solve(buses, lines, loads, generation)
+    and through the batched form."""
+    import grid_fed_rl_b200 as m
+    from grid_fed_rl_b200.solver import is_radial
+    g = load_golden(name)
+    f = feeder_for(g)
+    assert not is_radial(f.buses, f.lines)
+    tol, max_it = float(g["meta"][0]), int(g["meta"][1])
+    for method in ("dense", "auto"):
+        solver = m.B200PowerFlowSolver(tolerance=tol, max_iterations=max_it, method=method)
+        sol = solver.solve_batch(f, g["p_spec"])
+        conv = g["converged"]
+        assert np.array_equal(sol.converged.cpu().numpy(), conv)
+        assert np.all(np.abs(sol.iterations.cpu().numpy().astype(int) - g["iterations"]) <= 1)
+        if conv.any():
+            for k in ("bus_voltages", "bus_angles", "line_flows", "losses"):
+                got = getattr(sol, k).cpu().numpy()
+                assert np.max(np.abs(got[conv] - g[k][conv])) <= TOL_PU, k
+            s_base = f.parameters.base_power * 1e6
+            got = sol.line_loadings.cpu().numpy()     # D1: |S| s_base / rating; the frozen reference has |S| / rating
+            assert np.allclose(got[conv], g["line_loadings"][conv] * s_base, rtol=1e-7, atol=1e-12)
+        # the reference's 4-argument call shape, one case
+        p = g["p_spec"][0]
+        loads = {b.id: -p[i] for i, b in enumerate(f.buses) if p[i] < 0}
+        gen = {b.id: p[i] for i, b in enumerate(f.buses) if p[i] > 0}
+        one = solver.solve(f.buses, f.lines, loads, gen)
+        assert one.converged == bool(conv[0]) and abs(one.iterations - int(g["iterations"][0])) <= 1
+        if conv[0]:
+            assert np.max(np.abs(one.bus_voltages - g["bus_voltages"][0])) <= TOL_PU
+            assert np.max(np.abs(one.line_flows - g["line_flows"][0])) <= TOL_PU
+        solver.close()
+
+
+def test_dense_and_tree_solvers_agree_on_radial_feeders():
+    """On a radial feeder both paths run the same Newton iterates: same iteration counts, same state."""
+    import grid_fed_rl_b200 as m
+    f = m.repair_topology(m.IEEE34Bus(seed=0))
+    rs = np.random.RandomState(3)
+    n = len(f.buses)
+    base = np.zeros(n)
+    idx = {b.id: i for i, b in enumerate(f.buses)}
+    for ld in f.loads:
+        base[idx[ld.bus]] += ld.base_power / (f.parameters.base_power * 1e6)
+    p = -base[None, :] * rs.uniform(0.2, 1.5, size=(300, n))
+    tree = m.B200PowerFlowSolver(tolerance=1e-8, method="newton").solve_batch(f, p)
+    dense = m.B200PowerFlowSolver(tolerance=1e-8, method="dense").solve_batch(f, p)
+    assert bool(tree.converged.all()) and bool(dense.converged.all())
+    assert torch.equal(tree.iterations, dense.iterations)
+    for k in ("bus_voltages", "bus_angles", "line_flows", "losses"):
+        assert torch.max(torch.abs(getattr(tree, k) - getattr(dense, k))) < 1e-10, k
+    assert torch.allclose(tree.line_loadings, dense.line_loadings, rtol=1e-9, atol=1e-12)
+
+
+def test_dense_solver_limits_and_singular_network():
+    import grid_fed_rl_b200 as m
+    f = m.repair_topology(m.IEEE123Bus(seed=0))          # 244 unknowns: does not fit an SM's shared memory
+    with pytest.raises(m.GridLimitError):
+        m.B200PowerFlowSolver(method="dense").solve_batch(f, np.zeros((1, len(f.buses))))
+    # a bus hanging on an open line (|z| <= 1e-12 -> y = 0, power_flow.py:61-64): singular Jacobian,
+    # the reference warns and stops; converged = False after one iteration
+    g = m.SimpleRadialFeeder(4)
+    g.lines[-1].resistance = g.lines[-1].reactance = 0.0
+    p = np.array([[0.0, -0.01, -0.01, -0.01]])
+    sol = m.B200PowerFlowSolver(method="dense").solve_batch(g, p)
+    assert not bool(sol.converged[0]) and int(sol.iterations[0]) == 1

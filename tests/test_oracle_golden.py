@@ -26,7 +26,7 @@ def test_port_env_matches_reference_trace(name):
     assert exact >= 0.9 * g["obs"].shape[0]
 
 
-@pytest.mark.parametrize("name", golden_names("solve_"))
+@pytest.mark.parametrize("name", golden_names("solve_") + golden_names("meshsolve_"))
 def test_port_solver_matches_reference(name):
     g = load_golden(name)
     f = feeder_for(g)
