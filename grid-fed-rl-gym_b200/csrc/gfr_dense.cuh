@@ -146,34 +146,37 @@ dense_solve_kernel(const NetDev net, const double tol, const int max_it, const d
         }
       }
       __syncthreads();
-      // ---- Gaussian elimination with partial pivoting on [J | rhs] (dgesv, :187)
+      // ---- Gaussian elimination with partial pivoting on [J | rhs] (dgesv, :187).  Two CTA barriers per
+      //      pivot column: the multipliers are formed on the fly (nothing reuses L: the right-hand side is
+      //      eliminated in the same sweep), and the warp that updates column k + 1 finds that column's
+      //      pivot - largest |entry|, the first among equals (idamax) - before the barrier that ends step k.
       int singular = 0;
-      for (int k = 0; k < N; ++k) {
-        // pivot: largest |J[i, k]|, i >= k, the smallest i among equals (idamax)
-        double best = -1.0;
-        int bi = k;
-        for (int i = k + tid; i < N; i += nt) {
-          const double a = fabs(J[i + k * ld]);
-          if (a > best || a != a) { if (!(best != best)) { best = a; bi = i; } }
-        }
+      {
+        // pivot of column 0 by warp 0
+        if (tid < 32) {
+          double best = -1.0;
+          int bi = 0;
+          for (int i = tid; i < N; i += 32) {
+            const double a = fabs(J[i]);
+            if ((a > best || a != a) && !(best != best)) { best = a; bi = i; }
+          }
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-          const double ob = __shfl_xor_sync(0xffffffffu, best, off);
-          const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
-          const bool take = (ob != ob && !(best != best)) || (!(best != best) && (ob > best || (ob == best && oi < bi)));
-          if (take) { best = ob; bi = oi; }
+          for (int off = 16; off > 0; off >>= 1) {
+            const double ob = __shfl_xor_sync(0xffffffffu, best, off);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+            const bool take = (ob != ob && !(best != best)) || (!(best != best) && (ob > best || (ob == best && oi < bi)));
+            if (take) { best = ob; bi = oi; }
+          }
+          if (tid == 0) { red[0] = best; redi[0] = bi; }
         }
-        if ((tid & 31) == 0) { red[tid >> 5] = best; redi[tid >> 5] = bi; }
         __syncthreads();
-        best = red[0]; bi = redi[0];
-        for (int w = 1; w < (nt >> 5); ++w) {
-          const double ob = red[w];
-          const int oi = redi[w];
-          const bool take = (ob != ob && !(best != best)) || (!(best != best) && (ob > best || (ob == best && oi < bi)));
-          if (take) { best = ob; bi = oi; }
-        }
+      }
+      for (int k = 0; k < N; ++k) {
+        const double best = red[0];
+        const int bi = redi[0];
         if (!(best > 0.0) && !(best != best)) { singular = 1; break; }   // exact-zero pivot (:188-190); NaN runs on
-        if (bi != k) {                                                   // (every scan of column k ended before the barrier above)
+        __syncthreads();                                                 // red is rewritten at the end of this step
+        if (bi != k) {
           for (int c = k + tid; c <= N; c += nt) {
             double* pa = c < N ? &J[k + c * ld] : &rhs[k];
             double* pb = c < N ? &J[bi + c * ld] : &rhs[bi];
@@ -182,27 +185,47 @@ dense_solve_kernel(const NetDev net, const double tol, const int max_it, const d
           __syncthreads();
         }
         const double rp = 1.0 / J[k + k * ld];
-        for (int i = k + 1 + tid; i < N; i += nt) J[i + k * ld] *= rp;   // multipliers
-        __syncthreads();
         {
           const int tx = tid & 31, ty = tid >> 5, ny = nt >> 5;
           for (int c = k + 1 + ty; c <= N; c += ny) {
             double* col = c < N ? &J[c * ld] : rhs;
             const double u = col[k];
-            for (int i = k + 1 + tx; i < N; i += 32) col[i] = fma(-J[i + k * ld], u, col[i]);
+            double nbest = -1.0;
+            int nbi = k + 1;
+            for (int i = k + 1 + tx; i < N; i += 32) {
+              const double v = fma(-(J[i + k * ld] * rp), u, col[i]);    // multiplier = entry x (1 / pivot), as dgetf2
+              col[i] = v;
+              const double a = fabs(v);
+              if ((a > nbest || a != a) && !(nbest != nbest)) { nbest = a; nbi = i; }
+            }
+            if (c == k + 1 && c < N) {                                   // warp 0, first column of its sweep: the next pivot
+#pragma unroll
+              for (int off = 16; off > 0; off >>= 1) {
+                const double ob = __shfl_xor_sync(0xffffffffu, nbest, off);
+                const int oi = __shfl_xor_sync(0xffffffffu, nbi, off);
+                const bool take = (ob != ob && !(nbest != nbest)) ||
+                                  (!(nbest != nbest) && (ob > nbest || (ob == nbest && oi < nbi)));
+                if (take) { nbest = ob; nbi = oi; }
+              }
+              if (tx == 0) { red[0] = nbest; redi[0] = nbi; }
+            }
           }
         }
         __syncthreads();
       }
       if (singular) { iterations = it + 1; break; }
-      // ---- back substitution: x_k = rhs_k / U_kk, then rhs_i -= U_ik x_k above it
-      for (int k = N - 1; k >= 0; --k) {
-        if (tid == 0) rhs[k] = rhs[k] / J[k + k * ld];
-        __syncthreads();
-        const double xk = rhs[k];
-        for (int i = tid; i < k; i += nt) rhs[i] = fma(-J[i + k * ld], xk, rhs[i]);
-        __syncthreads();
+      // ---- back substitution by warp 0 alone (warp barriers instead of 2 N CTA barriers):
+      //      x_k = rhs_k / U_kk, then rhs_i -= U_ik x_k above it
+      if (tid < 32) {
+        for (int k = N - 1; k >= 0; --k) {
+          const double xk = rhs[k] / J[k + k * ld];
+          __syncwarp();
+          if (tid == 0) rhs[k] = xk;
+          for (int i = tid; i < k; i += 32) rhs[i] = fma(-J[i + k * ld], xk, rhs[i]);
+          __syncwarp();
+        }
       }
+      __syncthreads();
       // ---- polar update (:297-327): theta += a dtheta, |V| += a d|V|  <=>  V *= (1 + a x_v) e^{j a x_theta}
       for (int i = tid; i < n; i += nt) {
         const int ct = net.col_theta[i], cv = net.col_vm[i];
