@@ -705,7 +705,7 @@ int gfr_network_create(const gfr_network_desc* d, int device, gfr_network** out)
   if (!guard.ok) return fail(GFR_E_CUDA, "no usable CUDA device (this library has no CPU fallback)");
   cudaDeviceProp prop;
   GFR_CUDA(cudaGetDeviceProperties(&prop, device));
-  if (dense_smem_bytes(n, N) > (size_t)prop.sharedMemPerBlockOptin)
+  if ((N <= 127 ? dense_reg_smem_bytes(n, N) : dense_smem_bytes(n, N)) > (size_t)prop.sharedMemPerBlockOptin)
     return fail(GFR_E_LIMIT, "the dense Jacobian of this network exceeds the shared memory of an SM "
                              "(non-slack + PQ buses <= ~165); radial feeders take the tree-ordered solver");
   // pack: ints = bus_type | col_theta | col_vm | adj_ptr | adj_idx | line_from | line_to ; doubles (16-byte aligned
@@ -755,12 +755,43 @@ int gfr_network_solve(const gfr_network* net, int64_t B, const double* p_inj, co
   if (!(cfg->tolerance > 0.0)) return fail(GFR_E_ARG, "tolerance must be > 0");
   DeviceGuard guard(net->device);
   if (!guard.ok) return fail(GFR_E_CUDA, "no usable CUDA device (this library has no CPU fallback)");
-  const size_t smem = dense_smem_bytes(net->nd.n, net->nd.N);
-  GFR_CUDA(cudaFuncSetAttribute((const void*)dense_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                net->smem_optin));
-  const int threads = net->nd.N <= 48 ? 128 : 256;
+  // kernel choice: [J | mismatch] in registers up to 127 unknowns (cfg->lanes: 0 = this choice, 1 = always the
+  // shared-memory kernel, 2 = the register kernel or GFR_E_LIMIT)
+  typedef void (*dense_fn)(const NetDev, const double, const int, const double, const double*, const SolOut, const long long);
+  const int N = net->nd.N;
+  if (cfg->lanes < 0 || cfg->lanes > 2) return fail(GFR_E_ARG, "lanes must be 0 (auto), 1 (shared-memory LU) or 2 (register LU) for a network solve");
+  if (cfg->lanes == 2 && N > 127) return fail(GFR_E_LIMIT, "the register-resident elimination takes at most 127 unknowns");
+  const bool in_regs = cfg->lanes != 1 && N <= 127;
+  dense_fn fn = dense_solve_kernel;
+  int threads = N <= 48 ? 128 : 256;
+  size_t smem = dense_smem_bytes(net->nd.n, N);
+  if (in_regs) {
+    smem = dense_reg_smem_bytes(net->nd.n, N);
+    // 8 x TX threads, R = ceil(N / 8) register rows each: TX = 8 up to 48 unknowns, 16 up to 80, 32 above
+    // (GFR_DENSE_TX overrides the choice where the tile fits, for tuning)
+    static const dense_fn by_tx8[] = { nullptr, dense_solve_reg_kernel<8, 1>, dense_solve_reg_kernel<8, 2>, dense_solve_reg_kernel<8, 3>,
+        dense_solve_reg_kernel<8, 4>, dense_solve_reg_kernel<8, 5>, dense_solve_reg_kernel<8, 6>, dense_solve_reg_kernel<8, 7>,
+        dense_solve_reg_kernel<8, 8>, dense_solve_reg_kernel<8, 9> };
+    static const dense_fn by_tx16[] = { nullptr, nullptr, dense_solve_reg_kernel<16, 2>, dense_solve_reg_kernel<16, 3>,
+        dense_solve_reg_kernel<16, 4>, dense_solve_reg_kernel<16, 5>, dense_solve_reg_kernel<16, 6>, dense_solve_reg_kernel<16, 7>,
+        dense_solve_reg_kernel<16, 8>, dense_solve_reg_kernel<16, 9>, dense_solve_reg_kernel<16, 10>, dense_solve_reg_kernel<16, 11>,
+        dense_solve_reg_kernel<16, 12> };
+    static const dense_fn by_tx32[] = { nullptr, nullptr, nullptr, nullptr, dense_solve_reg_kernel<32, 4>, dense_solve_reg_kernel<32, 5>,
+        dense_solve_reg_kernel<32, 6>, dense_solve_reg_kernel<32, 7>, dense_solve_reg_kernel<32, 8>, dense_solve_reg_kernel<32, 9>,
+        dense_solve_reg_kernel<32, 10>, dense_solve_reg_kernel<32, 11>, dense_solve_reg_kernel<32, 12>, dense_solve_reg_kernel<32, 13>,
+        dense_solve_reg_kernel<32, 14>, dense_solve_reg_kernel<32, 15>, dense_solve_reg_kernel<32, 16> };
+    const int R = (N + 7) / 8;
+    int tx = N <= 48 ? 8 : N <= 80 ? 16 : 32;
+    if (const char* e = std::getenv("GFR_DENSE_TX")) {
+      const int want = std::atoi(e);
+      if ((want == 8 && R <= 9) || (want == 16 && R >= 2 && R <= 12) || (want == 32 && R >= 4)) tx = want;
+    }
+    fn = tx == 8 ? by_tx8[R] : tx == 16 ? by_tx16[R] : by_tx32[R];
+    threads = 8 * tx;
+  }
+  GFR_CUDA(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, net->smem_optin));
   int per_sm = 0;
-  GFR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)dense_solve_kernel, threads, smem));
+  GFR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)fn, threads, smem));
   if (per_sm < 1) return fail(GFR_E_LIMIT, "the dense Jacobian of this network exceeds the shared memory of an SM");
   long long grid = (long long)net->sm_count * per_sm;
   if (grid > B) grid = B;
@@ -769,8 +800,8 @@ int gfr_network_solve(const gfr_network* net, int64_t B, const double* p_inj, co
   o.bus_angles = out->bus_angles; o.line_flows = out->line_flows; o.line_loadings = out->line_loadings;
   o.losses = out->losses; o.max_mismatch = out->max_mismatch;
   const double accel = cfg->acceleration != 0.0 ? cfg->acceleration : 1.0;
-  dense_solve_kernel<<<(int)grid, threads, smem, (cudaStream_t)stream>>>(net->nd, cfg->tolerance, cfg->max_iterations,
-                                                                         accel, p_inj, o, (long long)B);
+  fn<<<(int)grid, threads, smem, (cudaStream_t)stream>>>(net->nd, cfg->tolerance, cfg->max_iterations,
+                                                         accel, p_inj, o, (long long)B);
   g_launches.fetch_add(1);
   GFR_CUDA(cudaGetLastError());
   return GFR_OK;

@@ -92,16 +92,23 @@ def is_radial(buses, lines) -> bool:
 class B200PowerFlowSolver:
     """Batched load flow on one GPU.  ``method`` is "newton" (the reference's polar Newton-Raphson
     iterates, solved by tree-ordered block elimination; radial feeders of any size), "sweep"
-    (backward / forward sweep; radial), "dense" (the same Newton-Raphson on the dense Jacobian with
-    a pivoted LU in shared memory, one CTA per instance: any connected network, cycles included, up
-    to ~80 buses) or "auto" ("newton" on a radial network, "dense" on a meshed one)."""
+    (backward / forward sweep; radial), "dense" (the same Newton-Raphson on the dense Jacobian,
+    eliminated with partial pivoting by one CTA per instance: any connected network, cycles
+    included, up to ~80 buses; ``dense_kernel`` = "auto" | "shared" | "registers" picks where the
+    system lives during the elimination) or "auto" ("newton" on a radial network, "dense" on a
+    meshed one)."""
 
     METHODS = tuple(sorted(set(nat.SOLVERS) | {"dense", "auto"}))
+    DENSE_KERNELS = {"auto": 0, "shared": 1, "registers": 2}
 
     def __init__(self, tolerance: float = 1e-6, max_iterations: int = 50, method: str = "newton",
-                 acceleration_factor: float = 1.0, device="cuda", lanes: int = 0, **kwargs) -> None:
+                 acceleration_factor: float = 1.0, device="cuda", lanes: int = 0,
+                 dense_kernel: str = "auto", **kwargs) -> None:
         if method not in self.METHODS:
             raise InvalidConfigurationError(f"method must be one of {list(self.METHODS)}")
+        if dense_kernel not in self.DENSE_KERNELS:
+            raise InvalidConfigurationError(f"dense_kernel must be one of {list(self.DENSE_KERNELS)}")
+        self.dense_kernel = self.DENSE_KERNELS[dense_kernel]
         self.tolerance, self.max_iterations = float(tolerance), int(max_iterations)
         self.method, self.acceleration_factor = method, float(acceleration_factor)
         self.lanes = int(lanes)
@@ -158,7 +165,8 @@ class B200PowerFlowSolver:
                    line_flows=torch.empty(B, m, **f64), line_loadings=torch.empty(B, m, **f64),
                    losses=torch.empty(B, **f64), max_mismatch=torch.empty(B, **f64))
         so = nat.SolOut(*[out[k].data_ptr() for k, _ in nat.SolOut._fields_])
-        cfg = nat.make_solver_cfg("newton", self.tolerance, self.max_iterations, self.acceleration_factor, 0)
+        cfg = nat.make_solver_cfg("newton", self.tolerance, self.max_iterations, self.acceleration_factor,
+                                  self.dense_kernel)
         nat.check(lib, lib.gfr_network_solve(net.handle, B, p.data_ptr(), C.byref(cfg), C.byref(so),
                                              torch.cuda.current_stream(dev).cuda_stream))
         out["converged"] = out["converged"].view(torch.bool)

@@ -221,7 +221,9 @@ int gfr_network_create(const gfr_network_desc* desc, int device, gfr_network** o
 void gfr_network_destroy(gfr_network* net);
 int gfr_network_unknowns(const gfr_network* net);          /* order of the dense Jacobian */
 /* p_inj [B, n_bus] pu (generation minus load, Q_spec = 0 as the reference); out arrays in the
- * caller's bus / line order; cfg->solver and cfg->lanes are ignored. */
+ * caller's bus / line order; cfg->solver is ignored; cfg->lanes picks the kernel: 0 = automatic ([J | mismatch]
+ * held in registers up to 127 unknowns, in shared memory above), 1 = always shared memory, 2 = registers or
+ * GFR_E_LIMIT. */
 int gfr_network_solve(const gfr_network* net, int64_t B, const double* p_inj, const gfr_solver_cfg* cfg,
                       const gfr_sol_out* out, void* stream);
 

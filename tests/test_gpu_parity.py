@@ -580,8 +580,11 @@ def test_dense_solver_matches_reference_on_meshed_networks(name):
     f = feeder_for(g)
     assert not is_radial(f.buses, f.lines)
     tol, max_it = float(g["meta"][0]), int(g["meta"][1])
-    for method in ("dense", "auto"):
-        solver = m.B200PowerFlowSolver(tolerance=tol, max_iterations=max_it, method=method)
+    unknowns = 2 * (len(f.buses) - 1)
+    for method, where in (("dense", "auto"), ("auto", "auto"), ("dense", "shared"), ("dense", "registers")):
+        if where == "registers" and unknowns > 127:
+            continue
+        solver = m.B200PowerFlowSolver(tolerance=tol, max_iterations=max_it, method=method, dense_kernel=where)
         sol = solver.solve_batch(f, g["p_spec"])
         conv = g["converged"]
         assert np.array_equal(sol.converged.cpu().numpy(), conv)
@@ -625,6 +628,44 @@ def test_dense_and_tree_solvers_agree_on_radial_feeders():
     assert torch.allclose(tree.line_loadings, dense.line_loadings, rtol=1e-9, atol=1e-12)
 
 
+@pytest.mark.parametrize("num_buses,conn,seed", [(9, 0.3, 1), (14, 0.2, 2), (28, 0.08, 3), (33, 0.06, 4),
+                                                 (47, 0.04, 5), (49, 0.04, 6), (60, 0.03, 7), (70, 0.03, 8)])
+def test_dense_register_and_shared_memory_kernels_agree(num_buses, conn, seed):
+    """The register-resident Gauss-Jordan elimination (every tile shape: <= 31, <= 63, <= 95, <= 127
+    unknowns, sizes on both sides of each boundary) against the shared-memory LU: same pivots, so
+    the same convergence flags and iteration counts and the same state to rounding; above 127
+    unknowns "auto" is the shared-memory kernel and "registers" is refused."""
+    import grid_fed_rl_b200 as m
+    f = m.repair_topology(m.SyntheticFeeder(m.NetworkConfig(num_buses=num_buses, connectivity=conn,
+                                                            load_probability=0.9, dg_probability=0.3), seed=seed),
+                          keep_cycles=True)
+    n = len(f.buses)
+    rs = np.random.RandomState(seed)
+    base = np.zeros(n)
+    idx = {b.id: i for i, b in enumerate(f.buses)}
+    for ld in f.loads:
+        base[idx[ld.bus]] += ld.base_power / (f.parameters.base_power * 1e6)
+    p = -base[None, :] * (0.3 / max(base.sum(), 1e-9)) * rs.uniform(0.0, 2.0, size=(517, n))
+    p[5] *= 3000.0                                            # one instance far beyond the nose: must not converge
+    shared = m.B200PowerFlowSolver(tolerance=1e-8, max_iterations=15, method="dense", dense_kernel="shared")
+    a = shared.solve_batch(f, p)
+    unknowns = 2 * (n - 1)
+    if unknowns > 127:
+        with pytest.raises(m.GridLimitError):
+            m.B200PowerFlowSolver(method="dense", dense_kernel="registers").solve_batch(f, p)
+        b = m.B200PowerFlowSolver(tolerance=1e-8, max_iterations=15, method="dense").solve_batch(f, p)
+        for k in ("bus_voltages", "bus_angles", "line_flows", "losses", "iterations", "converged"):
+            assert torch.equal(getattr(a, k), getattr(b, k)), k
+        return
+    b = m.B200PowerFlowSolver(tolerance=1e-8, max_iterations=15, method="dense", dense_kernel="registers").solve_batch(f, p)
+    assert torch.equal(a.converged, b.converged)
+    assert int(a.converged.sum()) >= 500 and not bool(a.converged[5])
+    c = a.converged
+    assert torch.equal(a.iterations[c], b.iterations[c])
+    for k in ("bus_voltages", "bus_angles", "line_flows", "losses"):
+        assert torch.max(torch.abs(getattr(a, k)[c] - getattr(b, k)[c])) < 1e-10, k
+
+
 def test_dense_solver_limits_and_singular_network():
     import grid_fed_rl_b200 as m
     f = m.repair_topology(m.IEEE123Bus(seed=0))          # 244 unknowns: does not fit an SM's shared memory
@@ -635,5 +676,6 @@ def test_dense_solver_limits_and_singular_network():
     g = m.SimpleRadialFeeder(4)
     g.lines[-1].resistance = g.lines[-1].reactance = 0.0
     p = np.array([[0.0, -0.01, -0.01, -0.01]])
-    sol = m.B200PowerFlowSolver(method="dense").solve_batch(g, p)
-    assert not bool(sol.converged[0]) and int(sol.iterations[0]) == 1
+    for where in ("shared", "registers"):
+        sol = m.B200PowerFlowSolver(method="dense", dense_kernel=where).solve_batch(g, p)
+        assert not bool(sol.converged[0]) and int(sol.iterations[0]) == 1
