@@ -767,7 +767,8 @@ int gfr_network_solve(const gfr_network* net, int64_t B, const double* p_inj, co
   size_t smem = dense_smem_bytes(net->nd.n, N);
   if (in_regs) {
     smem = dense_reg_smem_bytes(net->nd.n, N);
-    // 8 x TX threads, R = ceil(N / 8) register rows each: TX = 8 up to 48 unknowns, 16 up to 80, 32 above
+    // 8 x TX threads, R = ceil(N / 8) register rows each: TX = 8 up to 56 unknowns, 16 up to 96, 32 above (measured
+    // sweep, profiles/r01_tune_dense.txt)
     // (GFR_DENSE_TX overrides the choice where the tile fits, for tuning)
     static const dense_fn by_tx8[] = { nullptr, dense_solve_reg_kernel<8, 1>, dense_solve_reg_kernel<8, 2>, dense_solve_reg_kernel<8, 3>,
         dense_solve_reg_kernel<8, 4>, dense_solve_reg_kernel<8, 5>, dense_solve_reg_kernel<8, 6>, dense_solve_reg_kernel<8, 7>,
@@ -781,7 +782,7 @@ int gfr_network_solve(const gfr_network* net, int64_t B, const double* p_inj, co
         dense_solve_reg_kernel<32, 10>, dense_solve_reg_kernel<32, 11>, dense_solve_reg_kernel<32, 12>, dense_solve_reg_kernel<32, 13>,
         dense_solve_reg_kernel<32, 14>, dense_solve_reg_kernel<32, 15>, dense_solve_reg_kernel<32, 16> };
     const int R = (N + 7) / 8;
-    int tx = N <= 48 ? 8 : N <= 80 ? 16 : 32;
+    int tx = N <= 56 ? 8 : N <= 96 ? 16 : 32;
     if (const char* e = std::getenv("GFR_DENSE_TX")) {
       const int want = std::atoi(e);
       if ((want == 8 && R <= 9) || (want == 16 && R >= 2 && R <= 12) || (want == 32 && R >= 4)) tx = want;

@@ -139,6 +139,55 @@ __device__ __forceinline__ void dense_jacobian(const NetDev& net, const D2* ef, 
   __syncthreads();
 }
 
+// Mismatch and Jacobian in ONE pass over the adjacency lists (the register kernel): the same arithmetic, term
+// by term, as dense_mismatch + dense_jacobian; J must be zero on entry (the caller clears it while the
+// elimination result is scattered).  The Jacobian of the converged iterate is wasted, once per solve.
+__device__ __forceinline__ double dense_mismatch_jacobian(const NetDev& net, const D2* ef, double* J, int ld,
+                                                          double* rhs, const double* __restrict__ pspec,
+                                                          double* red, int tid, int nt) {
+  double mm = 0.0;
+  for (int i = tid; i < net.n; i += nt) {
+    const D2 vi = ef[i];
+    const D2 yd = net.ydiag[i];
+    const int rt = net.col_theta[i], rv = net.col_vm[i];
+    const double v2 = fma(vi.x, vi.x, vi.y * vi.y);
+    double P = yd.x * v2, Q = -yd.y * v2;
+    for (int q = net.adj_ptr[i]; q < net.adj_ptr[i + 1]; ++q) {
+      const int j = net.adj_idx[q];
+      const D2 vj = ef[j];
+      const D2 y = net.adj_y[q];
+      const double a = fma(vi.x, vj.x, vi.y * vj.y), s = fma(vi.y, vj.x, -vi.x * vj.y);
+      P = fma(y.x, a, fma(y.y, s, P));
+      Q = fma(y.x, s, fma(-y.y, a, Q));
+      const int ct = net.col_theta[j], cv = net.col_vm[j];
+      if (rt < 0 || ct < 0) continue;                                  // the slack has no equations / unknowns
+      const double al = fma(y.x, s, -y.y * a);                         // |Vi||Vj| (G sin - B cos)
+      const double ga = fma(y.x, a, y.y * s);                          // |Vi||Vj| (G cos + B sin)
+      J[rt + ct * ld] = al;
+      if (cv >= 0) J[rt + cv * ld] = ga;
+      if (rv >= 0) {
+        J[rv + ct * ld] = -ga;
+        if (cv >= 0) J[rv + cv * ld] = al;
+      }
+    }
+    double aP = 0.0, aQ = 0.0;
+    if (rt >= 0) {
+      const double d = pspec[i] - P;
+      rhs[rt] = d; aP = fabs(d);
+      J[rt + rt * ld] = fma(-yd.y, v2, -Q);                          // dP/dtheta:    -Q - B v2
+      if (rv >= 0) {
+        J[rt + rv * ld] = fma(yd.x, v2, P);                          // V dP/dV:       P + G v2
+        J[rv + rt * ld] = fma(-yd.x, v2, P);                         // dQ/dtheta:     P - G v2
+        J[rv + rv * ld] = fma(-yd.y, v2, Q);                         // V dQ/dV:       Q - B v2
+      }
+    }
+    if (rv >= 0) { const double d = 0.0 - Q; rhs[rv] = d; aQ = fabs(d); }
+    const double loc = (aQ > aP || aQ != aQ) ? aQ : aP;
+    mm = (loc > mm || loc != loc) ? loc : mm;
+  }
+  return block_max_nan(mm, red);
+}
+
 // polar update (:297-327): theta += a dtheta, |V| += a d|V|  <=>  V *= (1 + a x_v) e^{j a x_theta}.  Ends with a barrier.
 __device__ __forceinline__ void dense_polar_update(const NetDev& net, D2* ef, const double* x, double accel,
                                                    int tid, int nt) {
@@ -325,7 +374,7 @@ dense_solve_kernel(const NetDev net, const double tol, const int max_it, const d
 //     mantissa bits, the lowest row among equals, a NaN beats everything (as numpy's / idamax's NaN handling).
 //     That is threshold pivoting with threshold 1 - 2^-13: any such row is as good a pivot as dgetf2's.  The
 //     winning lane zeroes its own entry of the published column (so the pivot row is "cleared" by a multiplier
-//     of zero), and publishes the row and 1 / pivot; a column of zeros (all upper words < 128: zeros and the
+//     of zero), and publishes the row and the pivot; a column of zeros (all upper words < 128: zeros and the
 //     deepest subnormals) is the reference's singular-matrix break (:188-190);
 //   * barrier;
 //   * the pivot row reaches the threads of its column group by warp shuffle (same tx = same warp; the row's
@@ -343,9 +392,9 @@ GFR_HD size_t dense_reg_smem_bytes(int n, int N) {
 // Shared-memory mailboxes of the elimination
 struct GJBoxes {
   double* Lbuf;      // [2][128] published pivot columns
-  double* pvv;       // [2] 1 / pivot
+  double* pvv;       // [2] pivot
   int* pvi;          // [2] pivot row, -1 = singular
-  double* rpiv;      // [128] 1 / pivot of the step that used the row
+  double* piv;       // [128] pivot of the step that used the row
   int* kof;          // [128] the step that used the row
 };
 
@@ -374,18 +423,18 @@ __device__ __forceinline__ bool gj_block(double (&a)[R][C], unsigned& used, cons
         double* mine = bx.Lbuf + (k & 1) * 128 + p;
         const double piv = *mine;
         *mine = 0.0;
-        const double ap = fabs(piv);
-        const double rp = (ap > 1e-280 && ap < 1e280) ? rcp_fast(piv) : 1.0 / piv;
-        bx.pvv[k & 1] = rp;
+        bx.pvv[k & 1] = piv;
         bx.pvi[k & 1] = p;
         bx.kof[p] = k;
-        bx.rpiv[p] = rp;
+        bx.piv[p] = piv;
       }
     }
     __syncthreads();
     const int p = bx.pvi[k & 1];
-    const double rp = bx.pvv[k & 1];
+    const double piv = bx.pvv[k & 1];
     if (p < 0) return false;                             // CTA-uniform
+    const double ap = fabs(piv);                         // the reciprocal overlaps the row broadcast below
+    const double rp = (ap > 1e-280 && ap < 1e280) ? rcp_fast(piv) : 1.0 / piv;
     const int pr = p >> 3, pty = p & 7;
     if (ty == pty) used |= 1u << pr;
     // the pivot row, for this thread's columns: from lane pty of the column group
@@ -413,8 +462,15 @@ __device__ __forceinline__ bool gj_block(double (&a)[R][C], unsigned& used, cons
 
 #define GFR_LIVE_CASE(i) case i: if constexpr (C >= i) ok = gj_block<TX, R, C, (C >= i ? i : 1)>(a, used, bx, k0, steps, ty, tx, gmask, lane_base); break;
 
+// CTAs per SM the register kernel is compiled for.  Small tiles: the tile plus ~56 registers of everything
+// else (measured: +5 % at 16 - 26 unknowns); larger ones are left to ptxas (a cap made them spill: -12 % at 38)
+constexpr int dense_reg_min_blocks(int TX, int R) {
+  const int C = 8 * R / TX + 1, regs = (2 * R * C + 56 + 7) / 8 * 8, b = 65536 / (8 * TX * regs);
+  return regs > 96 ? 0 : b > 24 ? 24 : b;   // 0 = no request
+}
+
 template <int TX, int R>
-__global__ void __launch_bounds__(8 * TX)
+__global__ void __launch_bounds__(8 * TX, dense_reg_min_blocks(TX, R))
 dense_solve_reg_kernel(const NetDev net, const double tol, const int max_it, const double accel,
                        const double* __restrict__ p_inj, const SolOut o, const long long B) {
   constexpr int TY = 8, C = 8 * R / TX + 1, nt = TY * TX;
@@ -431,8 +487,8 @@ dense_solve_reg_kernel(const NetDev net, const double tol, const int max_it, con
   bx.pvv = red + 32;
   bx.pvi = reinterpret_cast<int*>(red + 34);
   bx.Lbuf = red + 64;
-  bx.rpiv = bx.Lbuf + 256;
-  bx.kof = reinterpret_cast<int*>(bx.rpiv + 128);
+  bx.piv = bx.Lbuf + 256;
+  bx.kof = reinterpret_cast<int*>(bx.piv + 128);
   const int tid = threadIdx.x;
   const int ty = tid % TY, tx = tid / TY;
   const unsigned gmask = 0xffu << ((tid & 31) & ~7);
@@ -441,14 +497,14 @@ dense_solve_reg_kernel(const NetDev net, const double tol, const int max_it, con
   for (long long env = blockIdx.x; env < B; env += gridDim.x) {
     const double* pspec = p_inj + env * n;
     dense_flat_start(net, ef, tid, nt);
+    for (int q = tid; q < ld * N; q += nt) J[q] = 0.0;
     __syncthreads();
     int converged = 0, iterations = max_it;
     double max_mismatch = INFINITY;
     for (int it = 0; it < max_it; ++it) {
-      const double mm = dense_mismatch(net, ef, pq, rhs, pspec, red, tid, nt);
+      const double mm = dense_mismatch_jacobian(net, ef, J, ld, rhs, pspec, red, tid, nt);   // ends with a barrier
       max_mismatch = mm;
       if (mm < tol) { converged = 1; iterations = it + 1; break; }
-      dense_jacobian(net, ef, pq, J, ld, tid, nt);
       double a[R][C];
 #pragma unroll
       for (int r = 0; r < R; ++r)
@@ -479,12 +535,13 @@ dense_solve_reg_kernel(const NetDev net, const double tol, const int max_it, con
         }
       }
       if (!ok) { iterations = it + 1; break; }
-      __syncthreads();                                       // kof / rpiv of the last step; rhs is free
+      __syncthreads();                                       // kof / piv of the last step; J and rhs are free
+      for (int q = tid; q < ld * N; q += nt) J[q] = 0.0;     // for the next assembly pass
       if (tx == N % TX) {                                    // the right-hand-side column is local column 0 by now
 #pragma unroll
         for (int r = 0; r < R; ++r) {
           const int row = r * TY + ty;
-          if (row < N) rhs[bx.kof[row]] = a[r][0] * bx.rpiv[row];
+          if (row < N) rhs[bx.kof[row]] = a[r][0] / bx.piv[row];
         }
       }
       __syncthreads();

@@ -24,7 +24,7 @@ def injections(f, B, seed):
     return -base[None, :] * (0.4 / tot) * rs.uniform(0.5, 1.5, size=(B, n))
 
 
-def timed(solver, f, p, reps=5):
+def timed(solver, f, p, reps=10):
     p = torch.as_tensor(p, device="cuda")
     sol = solver.solve_batch(f, p)
     torch.cuda.synchronize()
