@@ -770,22 +770,31 @@ int gfr_network_solve(const gfr_network* net, int64_t B, const double* p_inj, co
     // 8 x TX threads, R = ceil(N / 8) register rows each: TX = 8 up to 56 unknowns, 16 up to 96, 32 above (measured
     // sweep, profiles/r01_tune_dense.txt)
     // (GFR_DENSE_TX overrides the choice where the tile fits, for tuning)
-    static const dense_fn by_tx8[] = { nullptr, dense_solve_reg_kernel<8, 1>, dense_solve_reg_kernel<8, 2>, dense_solve_reg_kernel<8, 3>,
-        dense_solve_reg_kernel<8, 4>, dense_solve_reg_kernel<8, 5>, dense_solve_reg_kernel<8, 6>, dense_solve_reg_kernel<8, 7>,
-        dense_solve_reg_kernel<8, 8>, dense_solve_reg_kernel<8, 9> };
-    static const dense_fn by_tx16[] = { nullptr, nullptr, dense_solve_reg_kernel<16, 2>, dense_solve_reg_kernel<16, 3>,
-        dense_solve_reg_kernel<16, 4>, dense_solve_reg_kernel<16, 5>, dense_solve_reg_kernel<16, 6>, dense_solve_reg_kernel<16, 7>,
-        dense_solve_reg_kernel<16, 8>, dense_solve_reg_kernel<16, 9>, dense_solve_reg_kernel<16, 10>, dense_solve_reg_kernel<16, 11>,
-        dense_solve_reg_kernel<16, 12> };
-    static const dense_fn by_tx32[] = { nullptr, nullptr, nullptr, nullptr, dense_solve_reg_kernel<32, 4>, dense_solve_reg_kernel<32, 5>,
-        dense_solve_reg_kernel<32, 6>, dense_solve_reg_kernel<32, 7>, dense_solve_reg_kernel<32, 8>, dense_solve_reg_kernel<32, 9>,
-        dense_solve_reg_kernel<32, 10>, dense_solve_reg_kernel<32, 11>, dense_solve_reg_kernel<32, 12>, dense_solve_reg_kernel<32, 13>,
-        dense_solve_reg_kernel<32, 14>, dense_solve_reg_kernel<32, 15>, dense_solve_reg_kernel<32, 16> };
+    // (the tuning sweep, tools/tune_dense.py, needs a build with -DGFR_DENSE_ALL_SHAPES: every thread grid at every
+    // R it can hold, selected with GFR_DENSE_TX; the default build carries the 16 shapes the rule above uses)
+#ifdef GFR_DENSE_ALL_SHAPES
+#define GFR_ALT(...) __VA_ARGS__
+#else
+#define GFR_ALT(...) nullptr
+#endif
+#define K dense_solve_reg_kernel
+    static const dense_fn by_tx8[] = { nullptr, K<8, 1>, K<8, 2>, K<8, 3>, K<8, 4>, K<8, 5>, K<8, 6>, K<8, 7>,
+                                       GFR_ALT(K<8, 8>), GFR_ALT(K<8, 9>) };
+    static const dense_fn by_tx16[] = { nullptr, nullptr, GFR_ALT(K<16, 2>), GFR_ALT(K<16, 3>), GFR_ALT(K<16, 4>),
+                                        GFR_ALT(K<16, 5>), GFR_ALT(K<16, 6>), GFR_ALT(K<16, 7>), K<16, 8>, K<16, 9>,
+                                        K<16, 10>, K<16, 11>, K<16, 12> };
+    static const dense_fn by_tx32[] = { nullptr, nullptr, nullptr, nullptr, GFR_ALT(K<32, 4>), GFR_ALT(K<32, 5>),
+                                        GFR_ALT(K<32, 6>), GFR_ALT(K<32, 7>), GFR_ALT(K<32, 8>), GFR_ALT(K<32, 9>),
+                                        GFR_ALT(K<32, 10>), GFR_ALT(K<32, 11>), GFR_ALT(K<32, 12>), K<32, 13>, K<32, 14>,
+                                        K<32, 15>, K<32, 16> };
+#undef K
+#undef GFR_ALT
     const int R = (N + 7) / 8;
     int tx = N <= 56 ? 8 : N <= 96 ? 16 : 32;
     if (const char* e = std::getenv("GFR_DENSE_TX")) {
       const int want = std::atoi(e);
-      if ((want == 8 && R <= 9) || (want == 16 && R >= 2 && R <= 12) || (want == 32 && R >= 4)) tx = want;
+      const dense_fn alt = want == 8 && R <= 9 ? by_tx8[R] : want == 16 && R <= 12 ? by_tx16[R] : want == 32 ? by_tx32[R] : nullptr;
+      if (alt) tx = want;
     }
     fn = tx == 8 ? by_tx8[R] : tx == 16 ? by_tx16[R] : by_tx32[R];
     threads = 8 * tx;

@@ -1,5 +1,6 @@
 """Thread-grid sweep for the register-resident dense kernel (GFR_DENSE_TX = 8 | 16 | 32 columns of
-8 threads; a grid that cannot hold the network falls back to the default choice).
+8 threads; a grid that cannot hold the network falls back to the default choice).  Needs the library built
+with every shape: python -m grid_fed_rl_b200.build --force -DGFR_DENSE_ALL_SHAPES
 usage: python tools/tune_dense.py"""
 import os
 import sys
