@@ -393,7 +393,25 @@ int plan_launch(const gfr_feeder* f, bool step, int solver, int lanes, long long
   if (!best.resident)
     return fail(GFR_E_LIMIT, "one instance's working set (plus the feeder image) exceeds the shared memory of an SM");
   LaunchPlan plan = best.plan;
-  const long long E = plan.threads / lanes;
+  long long E = plan.threads / lanes;
+  if (lanes <= 32) {
+    // A short launch (a few waves of resident instances) is evened out: the same number of waves, every CTA of
+    // every wave with the same number of instances - fewer slots per CTA instead of a nearly empty last wave
+    // (IEEE-13, 65 536 instances: 352 slots per SM made waves of 352 + 91; now 2 x 224), and a batch smaller than
+    // one wave spreads over all SMs instead of filling the first CTAs.
+    const long long ctas = (long long)f->sm_count * plan.ctas_per_sm;
+    const long long waves = (B + ctas * E - 1) / (ctas * E);
+    if (waves <= 8) {
+      const int gran = lanes >= 32 ? 1 : 32 / lanes;
+      long long need = (B + waves * ctas - 1) / (waves * ctas);
+      need = (need + gran - 1) / gran * gran;
+      if (need >= 1 && need < E) {
+        plan.smem -= per_env * (size_t)(E - need);
+        E = need;
+        plan.threads = (int)(E * lanes);
+      }
+    }
+  }
   long long tiles = (B + E - 1) / E;
   long long grid = (long long)f->sm_count * plan.ctas_per_sm;
   if (grid > tiles) grid = tiles;
