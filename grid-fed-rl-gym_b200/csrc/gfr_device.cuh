@@ -775,12 +775,27 @@ GFR_HD void sweep_solve(const SGrp<LANES>& g, const Layout& lay, const int* simg
   out->iterations = max_it;
   out->max_mismatch = INFINITY;
   for (int it = 0; it < max_it; ++it) {
+    if (LANES == 1) {
+      // one thread per instance: buses are numbered parent before child, so a plain descending loop that
+      // hands each subtree current to the parent needs no child lists (and no barriers)
+      D2 z0; z0.x = z0.y = 0.0;
+      for (int k = 0; k < n; ++k) g.at2(S_JR, k) = z0;
+      for (int k = n - 1; k >= 0; --k) {
+        const I4 t = topo[k];
+        const D2 v = g.at2(F_E, k);
+        const double w = (t.w & FL_THETA) ? g.at(S_P, k) * rcp_fast(fma(v.x, v.x, v.y * v.y)) : 0.0;
+        D2 a = g.at2(S_JR, k);
+        a.x = fma(w, v.x, a.x); a.y = fma(w, v.y, a.y);
+        g.at2(S_JR, k) = a;
+        if (k > 0) { D2& ap = g.at2(S_JR, t.x); ap.x += a.x; ap.y += a.y; }
+      }
+    } else
     for (int l = nl - 1; l >= 0; --l) {
       const int k1 = level_ptr[l + 1];
       for (int k = g.first(level_ptr[l]); k < k1; k += LANES) {
         const I4 t = topo[k];
         const D2 v = g.at2(F_E, k);
-        const double w = (t.w & FL_THETA) ? g.at(S_P, k) / fma(v.x, v.x, v.y * v.y) : 0.0;   // conj(S / V) = P V / |V|^2
+        const double w = (t.w & FL_THETA) ? g.at(S_P, k) * rcp_fast(fma(v.x, v.x, v.y * v.y)) : 0.0;   // conj(S / V) = P V / |V|^2
         D2 a;
         a.x = w * v.x; a.y = w * v.y;
 #pragma unroll 1
