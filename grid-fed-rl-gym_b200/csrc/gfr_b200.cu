@@ -94,6 +94,13 @@ make_group(const Layout& lay, unsigned char* work, int slot_bytes, D2* mscratch)
   return g;
 }
 
+// One thread per instance, small feeder, sweep: the specified injections live in the thread's local array
+// (the host sized the shared-memory slot without them, sweep_p_local)
+template <int LANES> __device__ __forceinline__ void use_local_injections(NGrp<LANES>&, const Layout&, double*) {}
+template <int LANES> __device__ __forceinline__ void use_local_injections(SGrp<LANES>& g, const Layout& lay, double* p_local) {
+  if (sweep_p_local(LANES, lay.n)) g.pp = p_local;
+}
+
 // IMG_SMEM: the feeder image is staged into shared memory (small / medium feeders); otherwise it is
 // read through L1 / L2 from global memory and all of shared memory goes to the working sets.
 template <int LANES, int SOLVER, bool IMG_SMEM>
@@ -106,8 +113,10 @@ step_kernel(const Layout lay, const EnvCfg cfg, const void* __restrict__ img, co
   if (IMG_SMEM) stage_image(smem, img, lay.img_bytes);
   const int* simg = IMG_SMEM ? (const int*)(smem + kSmemHeader) : (const int*)img;
   const double* dimg = IMG_SMEM ? (const double*)(smem + kSmemHeader) : (const double*)img;
-  const auto g = make_group<LANES, SOLVER>(lay, smem + kSmemHeader + (IMG_SMEM ? lay.img_bytes : 0),
-                                           slot_bytes, mscratch);
+  auto g = make_group<LANES, SOLVER>(lay, smem + kSmemHeader + (IMG_SMEM ? lay.img_bytes : 0),
+                                     slot_bytes, mscratch);
+  double p_local[LANES == 1 && SOLVER == SOLVER_SWEEP ? SWEEP_P_LOCAL_MAX : 1];
+  use_local_injections(g, lay, p_local);
   const int E = blockDim.x / LANES;
   for (long long env = (long long)blockIdx.x * E + threadIdx.x / LANES; env < B; env += (long long)gridDim.x * E)
     step_instance<LANES, SOLVER>(g, lay, simg, dimg, cfg, env, state, obs, actions, noise, o);
@@ -121,8 +130,10 @@ solve_kernel(const Layout lay, const EnvCfg cfg, const void* __restrict__ img, c
   if (IMG_SMEM) stage_image(smem, img, lay.img_bytes);
   const int* simg = IMG_SMEM ? (const int*)(smem + kSmemHeader) : (const int*)img;
   const double* dimg = IMG_SMEM ? (const double*)(smem + kSmemHeader) : (const double*)img;
-  const auto g = make_group<LANES, SOLVER>(lay, smem + kSmemHeader + (IMG_SMEM ? lay.img_bytes : 0),
-                                           slot_bytes, mscratch);
+  auto g = make_group<LANES, SOLVER>(lay, smem + kSmemHeader + (IMG_SMEM ? lay.img_bytes : 0),
+                                     slot_bytes, mscratch);
+  double p_local[LANES == 1 && SOLVER == SOLVER_SWEEP ? SWEEP_P_LOCAL_MAX : 1];
+  use_local_injections(g, lay, p_local);
   const int E = blockDim.x / LANES;
   for (long long env = (long long)blockIdx.x * E + threadIdx.x / LANES; env < B; env += (long long)gridDim.x * E)
     solve_instance<LANES, SOLVER>(g, lay, simg, dimg, cfg, env, p_inj, o);
@@ -256,9 +267,9 @@ namespace {
 struct LaunchPlan { int lanes, threads, grid; size_t smem; int ctas_per_sm; int slot_bytes; size_t mscratch_bytes; bool img_smem; };
 
 // shared memory of one instance slot; 0 if the scratch it doubles as cannot hold the sources
-size_t slot_bytes(const Layout& lay, int solver) {
+size_t slot_bytes(const Layout& lay, int solver, int lanes) {
   return solver == GFR_SOLVER_NEWTON ? newton_slot_bytes(lay.n, lay.n_pool, lay.n_src)
-                                     : sweep_slot_bytes(lay.n, lay.n_src);
+                                     : sweep_slot_bytes(lay.n, lay.n_src, sweep_p_local(lanes, lay.n));
 }
 
 int auto_lanes(const Layout& lay, int solver) {      // same thresholds as topology.auto_lanes (measured, profiles/)
@@ -380,7 +391,7 @@ int plan_launch(const gfr_feeder* f, bool step, int solver, int lanes, long long
   if (lanes != 1 && lanes != 2 && lanes != 4 && lanes != 8 && lanes != 16 && lanes != 32 && lanes != 64 &&
       lanes != 128 && lanes != 256)
     return fail(GFR_E_ARG, "lanes must be 0 (auto), 1, 2, 4, 8, 16, 32 (part of a warp) or 64, 128, 256 (one CTA per instance)");
-  const size_t per_env = slot_bytes(lay, solver);
+  const size_t per_env = slot_bytes(lay, solver, lanes);
   if (!per_env)
     return fail(GFR_E_LIMIT, "more loads + generators + batteries than the solver's working set can stage "
                              "(sweep: 2 per bus on average)");

@@ -43,11 +43,11 @@ enum { GEN_SOLAR = 0, GEN_WIND = 1 };
 //            slot carries the parent's correction down to the bus.  D^-1 U and D^-1 r, only needed
 //            again in the back-substitution, and the specified injections live in a per-slot
 //            scratch in global memory that stays L2 resident.
-//   sweep:   one record per bus, 6 doubles: e f | Jr Ji | P pad  (Jr + jJi = branch current)
+//   sweep:   40 B per bus in three arrays: e + jf | Jr + jJi (branch current) | P
 // Before the solve the same space (Newton: ef + pool; sweep: the J fields) carries the load /
 // generator / battery powers into the per-bus injection sums.
 enum { F_E = 0, F_F = 1, F_SCRATCH = 2 };
-enum { NF_SWEEP = 6, S_JR = 2, S_JI = 3, S_P = 4 };
+enum { S_JR = 2, S_P = 4 };                      // field tags of the sweep accessors
 enum { SCRATCH_FIELDS_SWEEP = 2 };
 // bus flag bits
 enum { FL_PQ = 1, FL_FROM_IS_PARENT = 2, FL_FIXED_VM = 4, FL_THETA = 8,     // PQ: |V| unknown; THETA: angle unknown
@@ -154,20 +154,18 @@ struct Lanes {
   GFR_HD int gor(int v) const { return reduce(v ? 1.0 : 0.0, OpMax()) != 0.0; }
 };
 
-// sweep working set: one record of NF_SWEEP doubles per bus
+// sweep working set, 40 B per bus in three arrays: e + jf | Jr + jJi (branch current, then W) | P
 template <int LANES>
 struct SGrp : Lanes<LANES> {
-  double* rec;
+  D2* efp;        // [n]
+  D2* jrp;        // [n]
+  double* pp;     // [n] specified injections
   int n;
-  GFR_HD double& at(int field, int k) const { return rec[k * NF_SWEEP + field]; }
-  GFR_HD D2& at2(int field, int k) const { return *reinterpret_cast<D2*>(rec + k * NF_SWEEP + field); }
-  GFR_HD D2& ef(int k) const { return at2(F_E, k); }
-  GFR_HD double& pspec(int k) const { return at(S_P, k); }
-  GFR_HD double& scr(int j) const {     // source j -> field F_SCRATCH + j / n of bus j % n
-    int f = F_SCRATCH;
-    while (j >= n) { j -= n; ++f; }
-    return rec[j * NF_SWEEP + f];
-  }
+  GFR_HD double& at(int, int k) const { return pp[k]; }                                   // S_P
+  GFR_HD D2& at2(int field, int k) const { return field == F_E ? efp[k] : jrp[k]; }       // F_E | S_JR
+  GFR_HD D2& ef(int k) const { return efp[k]; }
+  GFR_HD double& pspec(int k) const { return pp[k]; }
+  GFR_HD double& scr(int j) const { return reinterpret_cast<double*>(jrp)[j]; }           // sources: the J array, flat (2 n doubles)
 };
 
 // Newton working set (see the layout note above)
@@ -197,9 +195,14 @@ GFR_HD size_t newton_slot_bytes(int n, int n_pool, int n_src) {
 }
 // doubles of global scratch per instance slot (Newton): D^-1 U, D^-1 r (48 B per bus) + specified injections
 GFR_HD size_t newton_scratch_doubles(int n) { return (size_t)n * 6 + (((size_t)n + 1) / 2) * 2; }
-GFR_HD size_t sweep_slot_bytes(int n, int n_src) {
+// One thread per instance on a small feeder: the specified injections move to a per-thread local array (L1,
+// interleaved by thread), 32 B per bus stay in shared memory - 40 % more resident instances per SM
+enum { SWEEP_P_LOCAL_MAX = 20 };
+GFR_HD bool sweep_p_local(int lanes, int n) { return lanes == 1 && n <= SWEEP_P_LOCAL_MAX; }
+GFR_HD size_t sweep_slot_bytes(int n, int n_src, bool p_local = false) {
   if (n_src > SCRATCH_FIELDS_SWEEP * n) return 0;
-  return (size_t)n * NF_SWEEP * 8;
+  const size_t units = ((size_t)n * (p_local ? 32 : 40) + 15) / 16;   // 16-byte units, made odd: neighbouring instances'
+  return (units | 1) * 16;                                // slots then start 4 banks apart (conflict-free 128-bit accesses)
 }
 template <int LANES>
 GFR_HD void bind_slot(NGrp<LANES>& g, unsigned char* slot, int n, int n_pool, D2* mg) {
@@ -211,7 +214,9 @@ GFR_HD void bind_slot(NGrp<LANES>& g, unsigned char* slot, int n, int n_pool, D2
 }
 template <int LANES>
 GFR_HD void bind_slot(SGrp<LANES>& g, unsigned char* slot, int n, int, D2*) {
-  g.rec = reinterpret_cast<double*>(slot);
+  g.efp = reinterpret_cast<D2*>(slot);
+  g.jrp = g.efp + n;
+  g.pp = reinterpret_cast<double*>(g.jrp + n);
   g.n = n;
 }
 
@@ -1211,7 +1216,7 @@ GFR_HD void step_instance(const typename GroupOf<LANES, SOLVER>::type& g, const 
       loss_pu += ls;
       double pw = P * lay.s_base;
       double rating = dimg[lay.o_rating + k];
-      double loading = rating > 0.0 ? fabs(pw) / rating : 0.0;     // Line.update_state, base.py:261-264
+      double loading = rating > 0.0 ? fabs(pw) * rcp_fast(rating) : 0.0;     // Line.update_state, base.py:261-264 (|P| / rating)
       st_stream(ob + o_line + 2 * li, pw);
       st_stream(ob + o_line + 2 * li + 1, loading);
       over80 += loading > 0.8;
