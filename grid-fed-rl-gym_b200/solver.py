@@ -205,7 +205,7 @@ class B200PowerFlowSolver:
         method = "newton" if self.method in ("auto", "dense") else self.method
         cfg = nat.make_solver_cfg(method, self.tolerance, self.max_iterations,
                                   self.acceleration_factor,
-                                  self.lanes or auto_lanes(soa.n_bus, method))
+                                  self.lanes or getattr(soa, "lanes_hint", 0) or auto_lanes(soa.n_bus, method))
         nat.check(lib, lib.gfr_solve(nf.handle, B, p.data_ptr(), C.byref(cfg), C.byref(so),
                                      torch.cuda.current_stream(dev).cuda_stream))
         out["converged"] = out["converged"].view(torch.bool)

@@ -615,11 +615,16 @@ def compile_feeder(feeder, renewable_sources: Optional[Sequence[str]] = None,
     return FeederSoA(**soa)
 
 
-def auto_lanes(n_bus: int, solver: str = "newton") -> int:
+def auto_lanes(n_bus: int, solver: str = "newton", depth: Optional[int] = None) -> int:
     """Threads cooperating on one instance when the caller does not say.  Thresholds from
-    measurements on B200 (profiles/r01_tune_lanes_newton_v7.txt, profiles/r01_bench_all_configs_v7.txt):
+    measurements on B200 (profiles/r01_tune_lanes_newton_v7.txt, profiles/r01_bench_all_configs_v10.txt):
     a few lanes for the smallest feeders, part of a warp up to a few hundred buses, one CTA per
-    instance (feeder image read from global memory) beyond."""
+    instance (feeder image read from global memory) beyond.  ``depth`` = levels of the center-rooted
+    tree: a small feeder with fewer than four buses per level (IEEE-13: 13 / 4, IEEE-34: 34 / 12) keeps
+    only two Newton lanes busy (IEEE-13 510 M -> 566 M, IEEE-34 250 M -> 271 M env-steps/s; a bushier
+    30-bus random tree, 30 / 7, is faster on four)."""
+    if n_bus <= 45 and solver != "sweep" and depth and n_bus < 4 * depth:
+        return 2
     if n_bus <= 20:
         return 1 if solver == "sweep" else 4
     if n_bus <= 45:
@@ -647,7 +652,13 @@ def compile_for_solver(feeder, solver: str = "newton", lanes: int = 0,
     """``compile_feeder`` with the traversal the kernels want: both solvers walk the tree rooted
     at its center when that shortens it (the sweep handles the slack bus wherever it sits, Newton
     always gains); levels are capped at the lane count (Hu's schedule).  Returns (FeederSoA, lanes)."""
-    lanes = int(lanes) or auto_lanes(len(feeder.buses), solver)
+    if not int(lanes):
+        depth = None
+        if len(feeder.buses) <= 45 and solver != "sweep":      # the shape decides between two and four lanes
+            depth = compile_feeder(feeder, root="center", renewable_sources=renewable_sources,
+                                   with_components=False).n_levels
+        lanes = auto_lanes(len(feeder.buses), solver, depth)
+    lanes = int(lanes)
     kw = dict(renewable_sources=renewable_sources, with_components=with_components,
               width=lanes if lanes > 1 else None)
     soa = compile_feeder(feeder, root="center", **kw)
@@ -657,4 +668,5 @@ def compile_for_solver(feeder, solver: str = "newton", lanes: int = 0,
         alt = compile_feeder(feeder, root="slack", **kw)
         if soa.n_levels > 0.75 * alt.n_levels:
             soa = alt
+    soa.lanes_hint = lanes             # the lane count the level schedule was capped for
     return soa, lanes
