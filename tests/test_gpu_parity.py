@@ -14,7 +14,7 @@ from tests.golden_util import (TOL_PU, feeder_for, golden_names, load_golden, ob
 
 pytestmark = pytest.mark.gpu
 
-LANES = (1, 4, 8, 16, 32)
+LANES = (1, 2, 4, 8, 16, 32)
 REPL = 3      # replicas of the golden instance per batch: all must agree bit for bit
 
 
