@@ -785,10 +785,13 @@ GFR_HD void sweep_solve(const SGrp<LANES>& g, const Layout& lay, const int* simg
       // hands each subtree current to the parent needs no child lists (and no barriers)
       D2 z0; z0.x = z0.y = 0.0;
       for (int k = 0; k < n; ++k) g.at2(S_JR, k) = z0;
+      double p_next = g.at(S_P, n - 1);                // the injections may live in local memory (L1 / L2): one bus ahead
       for (int k = n - 1; k >= 0; --k) {
         const I4 t = topo[k];
         const D2 v = g.at2(F_E, k);
-        const double w = (t.w & FL_THETA) ? g.at(S_P, k) * rcp_fast(fma(v.x, v.x, v.y * v.y)) : 0.0;
+        const double p_k = p_next;
+        if (k > 0) p_next = g.at(S_P, k - 1);
+        const double w = (t.w & FL_THETA) ? p_k * rcp_fast(fma(v.x, v.x, v.y * v.y)) : 0.0;
         D2 a = g.at2(S_JR, k);
         a.x = fma(w, v.x, a.x); a.y = fma(w, v.y, a.y);
         g.at2(S_JR, k) = a;
@@ -815,9 +818,9 @@ GFR_HD void sweep_solve(const SGrp<LANES>& g, const Layout& lay, const int* simg
     const D2 atot = g.at2(S_JR, 0);
     g.sync();                                          // everyone has A(root) before the root's slot is reused
     double mm = 0.0;
-    for (int l = 0; l < nl; ++l) {
-      const int k1 = level_ptr[l + 1];
-      for (int k = g.first(level_ptr[l]); k < k1; k += LANES) {
+    for (int l = 0; l < (LANES == 1 ? 1 : nl); ++l) {      // one thread per instance: a single ascending loop over the buses
+      const int k1 = LANES == 1 ? n : level_ptr[l + 1];
+      for (int k = LANES == 1 ? 0 : g.first(level_ptr[l]); k < k1; k += LANES) {
         const I4 t = topo[k];
         D2 w;
         w.x = 0.0; w.y = 0.0;
