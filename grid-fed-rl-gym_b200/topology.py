@@ -617,7 +617,7 @@ def compile_feeder(feeder, renewable_sources: Optional[Sequence[str]] = None,
 
 def auto_lanes(n_bus: int, solver: str = "newton", depth: Optional[int] = None) -> int:
     """Threads cooperating on one instance when the caller does not say.  Thresholds from
-    measurements on B200 (profiles/r01_tune_lanes_newton_v7.txt, profiles/r01_bench_all_configs_v10.txt):
+    measurements on B200 (profiles/r01_tune_lanes_newton_v7.txt, profiles/r01_bench_all_configs_v11.txt):
     a few lanes for the smallest feeders, part of a warp up to a few hundred buses, one CTA per
     instance (feeder image read from global memory) beyond.  ``depth`` = levels of the center-rooted
     tree: a small feeder with fewer than four buses per level (IEEE-13: 13 / 4, IEEE-34: 34 / 12) keeps
