@@ -350,6 +350,60 @@ def test_full_size_properties_ieee123():
     assert torch.equal(o3, first) and torch.equal(r3, r1)
 
 
+@pytest.mark.parametrize("spec,B", [("ieee13", 65536), ("ieee34", 262144)])
+def test_full_size_properties_sweep_configs(spec, B):
+    """BASELINE configs 2 and 3 at their full sizes (IEEE-13 x 65,536 and IEEE-34 x 262,144, backward /
+    forward sweep, in-kernel noise): every instance converges, the observation is consistent with the
+    reported extremes and flags, a re-run is bit-identical, a different thread mapping and a smaller
+    batch (another launch plan: the wave-balanced one) give the same state, and the Newton kernel fed the
+    same noise rows lands on the same voltages (two algorithms, one fixed point)."""
+    import grid_fed_rl_b200 as m
+    from oracle.ref_harness import make_feeder
+    f = make_feeder(None, spec, use_reference_classes=False)
+    srcs = ["solar", "wind"] if spec == "ieee13" else ["solar"]
+    kw = dict(renewable_sources=srcs, repair=False, start_time=12 * 3600.0)
+    env = m.BatchedGridEnvironment(f, B, solver="sweep", tolerance=1e-10, record_noise=True, **kw)
+    env.reset(seed=21)
+    g = torch.Generator(device="cuda"); g.manual_seed(4)
+    act = env.sample_actions(g)
+    obs, reward, term, trunc, info = env.step(act)
+    assert bool(info["power_flow_converged"].all())
+    assert torch.isfinite(obs).all() and torch.isfinite(reward).all()
+    n, mlines = env.soa.n_bus, env.soa.n_line
+    lay = obs_layout(n, mlines, env.soa.n_load, env.soa.n_gen, env.soa.n_bat)
+    vm = obs[:, lay["vm"]]
+    assert torch.equal(info["max_voltage"], vm.max(dim=1).values)
+    assert torch.equal(info["min_voltage"], vm.min(dim=1).values)
+    assert torch.equal(info["constraint_violations"][:, 1], (vm < 0.95).any(dim=1))
+    assert torch.all(info["total_losses"] > 0)
+    first, r1 = obs.clone(), reward.clone()
+    noise = env.noise_used.clone()
+    # bit-identical re-run
+    env2 = m.BatchedGridEnvironment(f, B, solver="sweep", tolerance=1e-10, **kw)
+    env2.reset(seed=21)
+    o2, r2, _, _, _ = env2.step(act)
+    assert torch.equal(o2, first) and torch.equal(r2, r1)
+    env2.close()
+    # another thread mapping, another launch plan (a batch below one wave is spread over all SMs)
+    sub = 3000
+    for lanes in (1, 4):
+        e3 = m.BatchedGridEnvironment(f, sub, solver="sweep", tolerance=1e-10, lanes=lanes, **kw)
+        e3.reset(seed=21)
+        o3, r3, _, _, _ = e3.step(act[:sub])
+        assert torch.max(torch.abs(o3[:, lay["vm"]] - first[:sub, lay["vm"]])) < 1e-10
+        assert torch.allclose(r3, r1[:sub], rtol=1e-9, atol=1e-7)
+        e3.close()
+    # Newton on the same noise rows: same fixed point
+    e4 = m.BatchedGridEnvironment(f, sub, solver="newton", tolerance=1e-10, **kw)
+    e4.reset(seed=21)
+    o4, r4, _, _, i4 = e4.step(act[:sub], noise=noise[:sub])
+    assert bool(i4["power_flow_converged"].all())
+    assert torch.max(torch.abs(o4[:, lay["vm"]] - first[:sub, lay["vm"]])) < 1e-8
+    assert torch.max(torch.abs(o4[:, lay["va"]] - first[:sub, lay["va"]])) < 1e-8
+    e4.close()
+    env.close()
+
+
 def test_sharding_is_seed_stable():
     """Results do not depend on how instances are split over ranks."""
     import grid_fed_rl_b200 as m
