@@ -29,7 +29,8 @@ _i32p, _f64p, _u8p, _u64p = C.POINTER(C.c_int32), C.POINTER(C.c_double), C.POINT
 class FeederDesc(C.Structure):
     _fields_ = [
         ("n_bus", C.c_int32), ("n_levels", C.c_int32), ("n_load", C.c_int32), ("n_gen", C.c_int32),
-        ("n_bat", C.c_int32), ("n_pool", C.c_int32), ("s_base", C.c_double),
+        ("n_bat", C.c_int32), ("n_pool", C.c_int32), ("lanes_hint", C.c_int32), ("reserved", C.c_int32),
+        ("s_base", C.c_double),
         ("order", _i32p), ("parent", _i32p), ("level_ptr", _i32p), ("child_ptr", _i32p),
         ("child_idx", _i32p), ("pool_slot", _i32p),
         ("bus_type", _i32p), ("vm_set", _f64p), ("g", _f64p), ("b", _f64p), ("gdiag", _f64p),
@@ -58,7 +59,7 @@ class EnvCfg(C.Structure):
                 ("stochastic_loads", C.c_int32), ("weather_variation", C.c_int32),
                 ("reserved", C.c_int32), ("v_min", C.c_double), ("v_max", C.c_double),
                 ("f_min", C.c_double), ("f_max", C.c_double), ("safety_penalty", C.c_double),
-                ("load_noise", C.c_double), ("solver", SolverCfg)]
+                ("load_noise", C.c_double), ("solver", SolverCfg), ("env_id_offset", C.c_int64)]
 
 
 class StepOut(C.Structure):
@@ -104,6 +105,7 @@ SIGNATURES: Dict[str, Tuple[object, List[object]]] = {
     "gfr_noise_fill": (C.c_int, [C.c_int, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gfr_fp64_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double)]),
     "gfr_launch_count": (C.c_int64, []),
+    "gfr_auto_lanes": (C.c_int, [C.c_int, C.c_int, C.c_int]),
 }
 
 _LIB = None
@@ -188,6 +190,7 @@ def make_feeder_desc(soa: FeederSoA):
     d.n_bus, d.n_levels, d.n_load, d.n_gen, d.n_bat = (soa.n_bus, soa.n_levels, soa.n_load,
                                                       soa.n_gen, soa.n_bat)
     d.n_pool = int(soa.n_pool)
+    d.lanes_hint = int(getattr(soa, "lanes_hint", 0) or 0)
     d.s_base = float(soa.s_base)
     for name in ("order", "parent", "level_ptr", "child_ptr", "child_idx", "pool_slot", "bus_type", "line_of", "from_is_parent",
                  "load_bus", "gen_type", "gen_bus", "bat_bus"):
@@ -210,8 +213,9 @@ def make_solver_cfg(solver: str = "newton", tolerance: float = 1e-6, max_iterati
 
 def make_env_cfg(*, timestep=1.0, episode_length=86400, stochastic_loads=True,
                  weather_variation=True, voltage_limits=(0.95, 1.05), frequency_limits=(59.5, 60.5),
-                 safety_penalty=100.0, load_noise=0.1, solver_cfg: SolverCfg) -> EnvCfg:
+                 safety_penalty=100.0, load_noise=0.1, solver_cfg: SolverCfg,
+                 env_id_offset: int = 0) -> EnvCfg:
     return EnvCfg(float(timestep), int(episode_length), int(bool(stochastic_loads)),
                   int(bool(weather_variation)), 0, float(voltage_limits[0]), float(voltage_limits[1]),
                   float(frequency_limits[0]), float(frequency_limits[1]), float(safety_penalty),
-                  float(load_noise), solver_cfg)
+                  float(load_noise), solver_cfg, int(env_id_offset))

@@ -146,7 +146,7 @@ reset_kernel(const Layout lay, const EnvCfg cfg, const void* __restrict__ img,
              const double* __restrict__ load_pq, const double* __restrict__ bat_soc0,
              const uint64_t* __restrict__ seeds, const uint8_t* __restrict__ mask,
              const double* __restrict__ noise, const double start_time, const int construct,
-             const long long B) {
+             const long long env_id_offset, const long long B) {
   constexpr int LANES = 4;
   Lanes<LANES> g;
   g.red = nullptr;
@@ -158,7 +158,7 @@ reset_kernel(const Layout lay, const EnvCfg cfg, const void* __restrict__ img,
   for (long long env = (long long)blockIdx.x * E + threadIdx.x / LANES; env < B; env += (long long)gridDim.x * E) {
     if (mask && !mask[env]) continue;
     reset_instance<LANES>(g, lay, simg, dimg, cfg, env, state, obs, load_pq, bat_soc0, seeds, noise,
-                          start_time, construct != 0);
+                          start_time, construct != 0, env_id_offset);
   }
 }
 
@@ -233,6 +233,8 @@ struct gfr_feeder {
   Layout lay{};
   bool has_pv = false;
   bool root_is_slack = true;
+  int lanes_hint = 0;            // lane count the level schedule was capped for (0: not said)
+  int center_depth = 0;          // levels of the tree rooted at its center, uncapped
   void* d_img = nullptr;         // image
   double* d_load_pq = nullptr;   // [2L] static active / reactive power (observation)
   double* d_bat_soc0 = nullptr;  // [Bt]
@@ -251,6 +253,7 @@ struct gfr_env {
   D2* d_mscratch = nullptr;    // Newton: D^-1 U, D^-1 r, specified injections of every resident instance slot (L2 resident)
   int slot_bytes = 0;
   bool obs_external = false;   // bound by gfr_env_bind_obs: caller-owned
+  long long env_id_offset = 0; // global id of instance 0 (keys the construction-time Philox streams)
 };
 
 struct gfr_network {
@@ -272,18 +275,26 @@ size_t slot_bytes(const Layout& lay, int solver, int lanes) {
                                      : sweep_slot_bytes(lay.n, lay.n_src, sweep_p_local(lanes, lay.n));
 }
 
-int auto_lanes(const Layout& lay, int solver) {      // same thresholds as topology.auto_lanes (measured, profiles/)
-  if (lay.n <= 20) return solver == GFR_SOLVER_SWEEP ? 1 : 4;
-  if (lay.n <= 45) return 4;
+// Threads cooperating on one instance when the caller does not say: THE rule (exported as gfr_auto_lanes; the
+// Python side calls it instead of keeping a copy).  Thresholds from measurements on B200
+// (profiles/r01_tune_lanes_newton_v7.txt, profiles/r01_bench_all_configs_v11.txt): a few lanes for the smallest
+// feeders, part of a warp up to a few hundred buses, one CTA per instance (feeder image read from global memory)
+// beyond.  `depth` = levels of the center-rooted tree (0 = unknown): a small feeder with fewer than four buses per
+// level (IEEE-13: 13 / 4, IEEE-34: 34 / 12) keeps only two Newton lanes busy (IEEE-13 510 M -> 566 M, IEEE-34
+// 250 M -> 271 M env-steps/s; a bushier 30-bus random tree, 30 / 7, is faster on four).
+int auto_lanes_rule(int n, int solver, int depth) {
+  if (n <= 45 && solver != GFR_SOLVER_SWEEP && depth > 0 && n < 4 * depth) return 2;
+  if (n <= 20) return solver == GFR_SOLVER_SWEEP ? 1 : 4;
+  if (n <= 45) return 4;
   if (solver == GFR_SOLVER_SWEEP) {
-    if (lay.n <= 90) return 8;
-    if (lay.n <= 160) return 16;
+    if (n <= 90) return 8;
+    if (n <= 160) return 16;
   } else {
-    if (lay.n <= 160) return 8;
-    if (lay.n <= 250) return 16;
+    if (n <= 160) return 8;
+    if (n <= 250) return 16;
   }
-  if (lay.n <= 400) return 32;
-  if (lay.n <= 1500) return 64;
+  if (n <= 400) return 32;
+  if (n <= 1500) return 64;
   return 128;                      // one CTA per instance
 }
 
@@ -387,7 +398,8 @@ PlanTry plan_mode(const gfr_feeder* f, const void* fn, int lanes, bool img_smem,
 int plan_launch(const gfr_feeder* f, bool step, int solver, int lanes, long long B, LaunchPlan* out,
                 const void** fn_out) {
   const Layout& lay = f->lay;
-  if (lanes == 0) lanes = auto_lanes(lay, solver);
+  // the lane count the description's level schedule was capped for, else the rule
+  if (lanes == 0) lanes = f->lanes_hint > 0 ? f->lanes_hint : auto_lanes_rule(lay.n, solver, f->center_depth);
   if (lanes != 1 && lanes != 2 && lanes != 4 && lanes != 8 && lanes != 16 && lanes != 32 && lanes != 64 &&
       lanes != 128 && lanes != 256)
     return fail(GFR_E_ARG, "lanes must be 0 (auto), 1, 2, 4, 8, 16, 32 (part of a warp) or 64, 128, 256 (one CTA per instance)");
@@ -483,6 +495,7 @@ extern "C" {
 int gfr_abi_version(void) { return GFR_ABI_VERSION; }
 const char* gfr_last_error(void) { return g_err.c_str(); }
 int64_t gfr_launch_count(void) { return g_launches.load(); }
+int gfr_auto_lanes(int n_bus, int solver, int depth) { return auto_lanes_rule(n_bus, solver, depth); }
 
 int gfr_feeder_create(const gfr_feeder_desc* d, int device, gfr_feeder** out) {
   if (!d || !out) return fail(GFR_E_ARG, "null argument");
@@ -504,6 +517,8 @@ int gfr_feeder_create(const gfr_feeder_desc* d, int device, gfr_feeder** out) {
   f->lay = fi.lay;
   f->has_pv = fi.has_pv;
   f->root_is_slack = fi.root_is_slack;
+  f->lanes_hint = d->lanes_hint;
+  f->center_depth = fi.center_depth;
   const Layout& lay = f->lay;
   const int L = lay.L, Bt = lay.Bt;
   const size_t img_bytes = fi.img.size();
@@ -557,7 +572,7 @@ static int launch_reset(gfr_env* e, const uint64_t* seeds, const uint8_t* mask, 
   if (grid > cap) grid = cap;
   reset_kernel<<<(int)grid, threads, 0, s>>>(e->f->lay, e->cfg, e->f->d_img, e->d_state, e->d_obs,
                                             e->f->d_load_pq, e->f->d_bat_soc0, seeds, mask, noise,
-                                            start_time, construct, e->B);
+                                            start_time, construct, e->env_id_offset, e->B);
   g_launches.fetch_add(1);
   GFR_CUDA(cudaGetLastError());
   return GFR_OK;
@@ -578,6 +593,7 @@ int gfr_env_create(const gfr_feeder* f, int64_t n_envs, const gfr_env_cfg* cfg, 
   e->f = f; e->B = n_envs; e->cfg = ec; e->solver = cfg->solver.solver;
   e->lanes = plan.lanes; e->threads = plan.threads; e->grid = plan.grid; e->smem = plan.smem; e->fn = fn;
   e->slot_bytes = plan.slot_bytes;
+  e->env_id_offset = cfg->env_id_offset;
   cudaError_t e1 = cudaMalloc((void**)&e->d_state, (size_t)n_envs * f->lay.R * 8);
   cudaError_t e2 = cudaMalloc((void**)&e->d_obs, (size_t)n_envs * f->lay.D * 8);
   if (e1 == cudaSuccess && e2 == cudaSuccess && plan.mscratch_bytes)
@@ -853,7 +869,9 @@ int gfr_noise_fill(int device, int64_t B, int32_t n_slots, const uint64_t* seeds
   if (!guard.ok) return fail(GFR_E_CUDA, "no usable CUDA device (this library has no CPU fallback)");
   long long total = B * (long long)n_slots;
   long long grid = (total + 255) / 256;
-  if (grid > 148 * 8) grid = 148 * 8;
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  if (grid > (long long)sms * 8) grid = (long long)sms * 8;
   noise_fill_kernel<<<(int)grid, 256, 0, (cudaStream_t)stream>>>(B, n_slots, seeds, draws, out);
   g_launches.fetch_add(1);
   GFR_CUDA(cudaGetLastError());

@@ -1293,7 +1293,7 @@ GFR_HD void reset_instance(const Lanes<LANES>& g, const Layout& lay, const int* 
                            const double* dimg, const EnvCfg& cfg, long long env, double* state,
                            double* obs, const double* load_pq, const double* bat_soc0,
                            const uint64_t* seeds, const double* noise, double start_time,
-                           bool construct) {
+                           bool construct, long long env_id_offset) {
   const int n = lay.n, m = lay.m, L = lay.L, G = lay.G, Bt = lay.Bt, D = lay.D;
   double* rec = state + env * lay.R;
   double* ob = obs + env * D;
@@ -1304,7 +1304,8 @@ GFR_HD void reset_instance(const Lanes<LANES>& g, const Layout& lay, const int* 
   // wind / temperature / cloud survive a reset (grid_env.py:673-681); construction sets 5 / 25 / 0.3
   double wind = construct ? 5.0 : rec[R_WIND], temp = construct ? 25.0 : rec[R_TEMP],
          cloud = construct ? 0.3 : rec[R_CLOUD];
-  if (construct && !seeds) seed = (uint64_t)env;
+  // construction keys instance i with its GLOBAL id, so unseeded shards of one job draw different streams
+  if (construct && !seeds) seed = (uint64_t)(env_id_offset + env);
   const bool draws = cfg.weather_variation && !construct;
   if (draws) {
     double u, z1, z2, z3, dummy;
@@ -1314,8 +1315,11 @@ GFR_HD void reset_instance(const Lanes<LANES>& g, const Layout& lay, const int* 
       noise_block(seed, draw, 1u, &z1, &z2);
       noise_block(seed, draw, 2u, &z3, &dummy);
     }
+    // the reference resets its clock to 0 before this update (grid_env.py:372, :402): the reset observation is
+    // taken at t = 0 whatever `start_time` (a harness extension: the time of day the FIRST STEP starts from) says
     update_weather(hour_of(0.0), u, z1, z2, z3, &wind, &temp, &cloud);
   }
+  g.sync();   // every lane has read the record (weather, seed, draw counter) before lane 0 rewrites it
   for (int i = g.lane; i < n; i += LANES) { ob[2 * i] = 1.0; ob[2 * i + 1] = 0.0; }
   for (int li = g.lane; li < m; li += LANES) { ob[o_line + 2 * li] = 0.0; ob[o_line + 2 * li + 1] = 0.0; }
   for (int l = g.lane; l < 2 * L; l += LANES) ob[o_load + l] = load_pq[l];

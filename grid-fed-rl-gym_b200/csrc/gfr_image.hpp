@@ -1,6 +1,7 @@
 // gfr_image.hpp - host-side check of a gfr_feeder_desc and its packing into the "image" the
 // kernels read (ints first, then doubles; offsets recorded in gfr::Layout).
 #pragma once
+#include <algorithm>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -29,6 +30,7 @@ struct FeederImage {
   Layout lay{};
   bool has_pv = false;
   bool root_is_slack = false;
+  int center_depth = 0;            // levels of the tree rooted at its center (ceil(diameter / 2) + 1), uncapped
   std::vector<unsigned char> img;
   std::vector<double> load_pq;     // [2L] static active / reactive power (observation)
 };
@@ -89,6 +91,18 @@ inline std::string build_feeder_image(const gfr_feeder_desc* d, FeederImage* out
   for (int b = 0; b < Bt; ++b) if (d->bat_bus[b] < 0 || d->bat_bus[b] >= n) return "bat_bus out of range";
 
   FeederImage* f = out;
+  {
+    // depth of the tree rooted at its center: the longest path (in edges) is found leaf -> root from the two
+    // deepest subtrees of every bus (children come after their parent in level order)
+    std::vector<int> h(n, 0);
+    int diam = 0;
+    for (int k = n - 1; k > 0; --k) {
+      const int p = d->parent[k];
+      diam = std::max(diam, h[p] + h[k] + 1);
+      h[p] = std::max(h[p], h[k] + 1);
+    }
+    f->center_depth = (diam + 1) / 2 + 1;
+  }
   Layout& lay = f->lay;
   lay.n = n; lay.nl = nl; lay.L = L; lay.G = G; lay.Bt = Bt; lay.A = Bt + G; lay.m = n - 1;
   lay.D = 2 * n + 2 * (n - 1) + 1 + 2 * L + G + 2 * Bt;

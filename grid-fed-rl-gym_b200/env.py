@@ -31,7 +31,8 @@ from .topology import FeederSoA, TopologyError, compile_for_solver, repair_topol
 
 def _compile(feeder, renewable_sources, repair, solver, lanes) -> Tuple[FeederSoA, Any, int]:
     if isinstance(feeder, FeederSoA):
-        return feeder, None, int(lanes)
+        # a precompiled feeder runs on the lane count its level schedule was capped for
+        return feeder, None, int(lanes) or int(getattr(feeder, "lanes_hint", 0) or 0)
     try:
         if repair is True:
             feeder = repair_topology(feeder)
@@ -131,7 +132,7 @@ class BatchedGridEnvironment:
                                      weather_variation=weather_variation,
                                      voltage_limits=voltage_limits, frequency_limits=frequency_limits,
                                      safety_penalty=safety_penalty, load_noise=load_noise,
-                                     solver_cfg=scfg)
+                                     solver_cfg=scfg, env_id_offset=self.env_id_offset)
         h = C.c_void_p()
         with torch.cuda.device(self.device):
             nat.check(self.lib, self.lib.gfr_env_create(self._native_feeder.handle, self.num_envs,
@@ -194,11 +195,16 @@ class BatchedGridEnvironment:
         if x is None:
             return None
         t = torch.as_tensor(x) if not isinstance(x, torch.Tensor) else x
-        if tuple(t.shape) != tuple(shape):
-            if t.numel() == int(np.prod(shape)):
+        shape = tuple(int(v) for v in shape)
+        if tuple(t.shape) != shape:
+            # only an unambiguous 1-D form is accepted besides the exact shape: [B] when the row has one
+            # entry, [A] when there is one instance.  Anything else (a transposed [A, B], a flat [B * A])
+            # would scramble the per-instance rows, and the reference raises on a length mismatch too
+            # (utils/parallel_environment.py:74-75)
+            if len(shape) == 2 and t.dim() == 1 and t.numel() == shape[0] * shape[1] and 1 in shape:
                 t = t.reshape(shape)
             else:
-                raise InvalidActionError(f"{what} must have shape {tuple(shape)}, got {tuple(t.shape)}")
+                raise InvalidActionError(f"{what} must have shape {shape}, got {tuple(t.shape)}")
         if t.dtype != dtype or t.device != self.device or not t.is_contiguous():
             t = t.to(device=self.device, dtype=dtype, non_blocking=True).contiguous()
         return t

@@ -616,34 +616,13 @@ def compile_feeder(feeder, renewable_sources: Optional[Sequence[str]] = None,
 
 
 def auto_lanes(n_bus: int, solver: str = "newton", depth: Optional[int] = None) -> int:
-    """Threads cooperating on one instance when the caller does not say.  Thresholds from
-    measurements on B200 (profiles/r01_tune_lanes_newton_v7.txt, profiles/r01_bench_all_configs_v11.txt):
-    a few lanes for the smallest feeders, part of a warp up to a few hundred buses, one CTA per
-    instance (feeder image read from global memory) beyond.  ``depth`` = levels of the center-rooted
-    tree: a small feeder with fewer than four buses per level (IEEE-13: 13 / 4, IEEE-34: 34 / 12) keeps
-    only two Newton lanes busy (IEEE-13 510 M -> 566 M, IEEE-34 250 M -> 271 M env-steps/s; a bushier
-    30-bus random tree, 30 / 7, is faster on four)."""
-    if n_bus <= 45 and solver != "sweep" and depth and n_bus < 4 * depth:
-        return 2
-    if n_bus <= 20:
-        return 1 if solver == "sweep" else 4
-    if n_bus <= 45:
-        return 4
-    if solver == "sweep":
-        if n_bus <= 90:
-            return 8
-        if n_bus <= 160:
-            return 16
-    else:
-        if n_bus <= 160:
-            return 8
-        if n_bus <= 250:
-            return 16
-    if n_bus <= 400:
-        return 32
-    if n_bus <= 1500:
-        return 64
-    return 128
+    """Threads cooperating on one instance when the caller does not say.  The rule itself lives in the
+    native library (``gfr_auto_lanes`` in csrc/gfr_b200.cu, with the measurements it comes from) so that a
+    C-ABI caller passing ``lanes = 0`` and this module can never disagree; ``depth`` = levels of the
+    center-rooted tree (decides between two and four Newton lanes on small feeders)."""
+    from . import _native as nat
+    code = nat.SOLVERS.get(solver, nat.SOLVER_NEWTON)
+    return int(nat.load_library().gfr_auto_lanes(int(n_bus), code, int(depth or 0)))
 
 
 def compile_for_solver(feeder, solver: str = "newton", lanes: int = 0,

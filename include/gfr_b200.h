@@ -51,6 +51,9 @@ typedef struct gfr_env gfr_env;         /* B environment instances on one device
  * .generators (reference feeders/base.py:30-52; Bus/Line/Load environments/base.py:197-295). */
 typedef struct {
   int32_t n_bus, n_levels, n_load, n_gen, n_bat, n_pool;
+  int32_t lanes_hint;               /* lanes the level schedule was capped for (levels hold at most this many buses);
+                                       what `lanes = 0` resolves to.  0 = not said: gfr_auto_lanes decides */
+  int32_t reserved;
   double s_base;                    /* VA; feeder.parameters.base_power * 1e6 */
   const int32_t* order;             /* [n]  level k -> ref bus index */
   const int32_t* parent;            /* [n]  level index of the parent, -1 for k = 0 */
@@ -113,6 +116,8 @@ typedef struct {
   double safety_penalty;
   double load_noise;                /* TimeVaryingLoadModel noise_factor, reference 0.1 */
   gfr_solver_cfg solver;
+  int64_t env_id_offset;            /* global id of this env's instance 0 (a shard of a larger job): until a reset
+                                       gives seeds, instance i draws from the Philox stream keyed env_id_offset + i */
 } gfr_env_cfg;
 
 /* Per-step results besides the observation (reference step() 5-tuple + info, grid_env.py:610-619). */
@@ -235,6 +240,11 @@ int gfr_noise_fill(int device, int64_t B, int32_t n_slots, const uint64_t* seeds
 /* Measured FP64 FMA throughput of the device (TFLOP/s, 2 flop per DFMA): the denominator for the
  * FP64 side of the roofline, which the driver-written MEASURED_PEAKS.json does not carry. */
 int gfr_fp64_peak(int device, double* tflops);
+
+/* Threads cooperating on one instance when `lanes = 0` and the description carries no lanes_hint: the measured
+ * rule (n_bus, GFR_SOLVER_*, depth = levels of the tree rooted at its center, 0 if unknown).  The one copy of it:
+ * grid_fed_rl_b200.topology.auto_lanes calls this. */
+int gfr_auto_lanes(int n_bus, int solver, int depth);
 
 /* Launch bookkeeping for benchmarks: kernels launched by this library since load. */
 int64_t gfr_launch_count(void);

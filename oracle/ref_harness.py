@@ -375,6 +375,9 @@ SOLVE_CASES = {
     "solve_ieee34": ("ieee34", 3, 6, 1e-6, 1.0),
     "solve_ieee123": ("ieee123", 4, 3, 1e-6, 1.0),
     "solve_synthetic60": ("synthetic60:7", 5, 4, 1e-8, 0.05),
+    # BASELINE config 5's feeder (ScalableFeeder(1000)'s parameters, radial, loads x 0.03 as bench.py runs it):
+    # the reference's dense Newton-Raphson costs minutes per solve at this size - two cases
+    "solve_synthetic1000": ("synthetic1000:1000", 11, 2, 1e-6, 0.03),
     # deliberately infeasible loading: the reference runs to max_iterations, converged=False
     "solve_ieee13_overload": ("ieee13", 6, 2, 1e-6, 9.0),
     # meshed networks (cycle lines kept): the reference's dense Newton-Raphson as it is
@@ -385,11 +388,117 @@ SOLVE_CASES = {
 }
 
 
+# --------------------------------------------------------------------------- feeder tables
+
+FEEDER_SPECS = ("radial3", "radial13", "radial34", "fixture3", "ieee13", "ieee34", "ieee123",
+                "synthetic60:7", "synthetic300:300", "synthetic1000:1000", "scalable100:5",
+                "mesh40:3:0.05", "mesh72:5:0.02", "meshieee34", "meshieee123")
+
+
+def raw_feeder(ns, spec: str, use_reference_classes: bool = True):
+    """The generator's output BEFORE any repair (D4-i only: the seed), for the table comparison."""
+    sys.path.insert(0, REPO_ROOT)
+    import grid_fed_rl_b200 as mine
+    if spec.startswith("scalable"):
+        n, seed = spec[8:].split(":")
+        return (ns.synthetic.ScalableFeeder(int(n), seed=int(seed)) if use_reference_classes
+                else mine.ScalableFeeder(int(n), seed=int(seed)))
+    if spec in ("ieee34", "meshieee34", "ieee123", "meshieee123"):
+        cls = "IEEE34Bus" if "34" in spec else "IEEE123Bus"
+        if use_reference_classes:
+            st = np.random.get_state(); np.random.seed(0); f = getattr(ns.feeders, cls)(); np.random.set_state(st)
+            return f
+        return getattr(mine, cls)(seed=0)
+    if spec == "ieee13":
+        return ns.feeders.IEEE13Bus() if use_reference_classes else mine.IEEE13Bus()
+    f = make_feeder(ns, spec, use_reference_classes)          # radial / fixture / synthetic / mesh: no repair needed
+    return getattr(f, "source", f)
+
+
+def feeder_table(f) -> Dict[str, np.ndarray]:
+    """Every field of a feeder the hot path reads, as plain arrays (ids as strings)."""
+    import json
+    gens = {str(k): {kk: (vv if isinstance(vv, str) else float(vv)) if not isinstance(vv, (int, np.integer)) or isinstance(vv, bool)
+                     else int(vv) for kk, vv in v.items()} for k, v in f.generators.items()}
+    return dict(
+        bus_id=np.array([str(b.id) for b in f.buses]), bus_type=np.array([str(b.bus_type) for b in f.buses]),
+        bus_vm=np.array([float(b.voltage_magnitude) for b in f.buses]),
+        bus_level=np.array([float(b.voltage_level) for b in f.buses]),
+        line_id=np.array([str(l.id) for l in f.lines]), line_from=np.array([str(l.from_bus) for l in f.lines]),
+        line_to=np.array([str(l.to_bus) for l in f.lines]),
+        line_r=np.array([float(l.resistance) for l in f.lines]), line_x=np.array([float(l.reactance) for l in f.lines]),
+        line_rating=np.array([float(l.rating) for l in f.lines]),
+        load_id=np.array([str(l.id) for l in f.loads]), load_bus=np.array([str(l.bus) for l in f.loads]),
+        load_base=np.array([float(l.base_power) for l in f.loads]),
+        load_p=np.array([float(l.active_power) for l in f.loads]),
+        load_q=np.array([float(l.reactive_power) for l in f.loads]),
+        generators=np.array(json.dumps(gens, sort_keys=True)),
+        gen_keys=np.array([str(k) for k in f.generators] or [""]),     # dict order = action order (grid_env.py:629-651)
+        base_power=np.array(float(f.parameters.base_power)), base_voltage=np.array(float(f.parameters.base_voltage)))
+
+
+def freeze_feeders(ns, out_dir: str) -> None:
+    """tests/golden/feeders.npz: the reference generators' raw output and the repaired (D4) network for
+    every feeder spec the tests and the bench use (tests/test_feeders.py compares this package's own
+    generators with it, field by field)."""
+    sys.path.insert(0, REPO_ROOT)
+    import grid_fed_rl_b200 as mine
+    data = {}
+    for spec in FEEDER_SPECS:
+        raw = raw_feeder(ns, spec)
+        for k, v in feeder_table(raw).items():
+            data[f"{spec}/raw/{k}"] = v
+        fixed = mine.repair_topology(raw, keep_cycles=spec.startswith("mesh"))
+        for k, v in feeder_table(fixed).items():
+            if k.startswith("line_"):
+                data[f"{spec}/repaired/{k}"] = v
+        print("feeder", spec, len(raw.buses), "buses", len(raw.lines), "->", len(fixed.lines), "lines",
+              len(raw.loads), "loads", len(raw.generators), "generators", flush=True)
+    np.savez_compressed(os.path.join(out_dir, "feeders.npz"), **data)
+
+
+def freeze_dataset(ns, out_dir: str) -> None:
+    """tests/golden/dataset_gridDataset.npz: the reference's GridDataset (algorithms/base.py:180-265) fed a seeded
+    transition dict - its normalisation statistics, normalised arrays, ``__len__`` and ``__getitem__`` - for
+    the RolloutBuffer parity test."""
+    import torch
+    from grid_fed_rl.algorithms.base import GridDataset
+    rs = np.random.RandomState(7)
+    N, D, A = 257, 19, 3
+    raw = dict(observations=rs.normal(2.0, 5.0, size=(N, D)), actions=rs.uniform(-1, 1, size=(N, A)),
+               rewards=rs.normal(-30.0, 12.0, size=N), next_observations=rs.normal(2.0, 5.0, size=(N, D)),
+               terminals=(rs.random_sample(N) < 0.1))
+    raw["observations"][:, 4] = 3.25          # a constant column: std 0 -> the reference's epsilon decides
+    raw["next_observations"][:, 4] = 3.25
+    out = {"raw_" + k: np.asarray(v) for k, v in raw.items()}
+    probe_a = rs.normal(size=(5, A)).astype(np.float32)
+    probe_o = rs.normal(size=(5, D)).astype(np.float32)
+    out["probe_action"], out["probe_observation"] = probe_a, probe_o
+    for norm in (True, False):
+        ds = GridDataset(**{k: np.array(v) for k, v in raw.items()}, normalize=norm, device="cpu")
+        tag = "norm" if norm else "plain"
+        out[f"{tag}_size"] = np.array(ds.size)
+        for k in ("observations", "actions", "rewards", "next_observations", "terminals"):
+            out[f"{tag}_{k}"] = np.asarray(getattr(ds, k))                       # float64 numpy, as the reference holds them
+            out[f"{tag}_all_{k}"] = ds.get_all_data()[k].detach().cpu().numpy()  # float32 tensors, as learners get them
+        out[f"{tag}_denorm_action"] = ds.denormalize_action(torch.from_numpy(probe_a)).numpy()
+        out[f"{tag}_denorm_observation"] = ds.denormalize_observation(torch.from_numpy(probe_o)).numpy()
+        if norm:
+            for k in ("obs_mean", "obs_std", "action_mean", "action_std", "reward_mean", "reward_std"):
+                out["stat_" + k] = np.asarray(getattr(ds, k), dtype=float)
+    np.savez_compressed(os.path.join(out_dir, "dataset_gridDataset.npz"), **out)
+    print("dataset", sorted(out), flush=True)
+
+
 def main() -> None:
     ns = build()
     out_dir = os.path.join(REPO_ROOT, "tests", "golden")
     os.makedirs(out_dir, exist_ok=True)
     only = set(sys.argv[1:])
+    if not only or "feeders" in only:
+        freeze_feeders(ns, out_dir)
+    if not only or "dataset" in only:
+        freeze_dataset(ns, out_dir)
     for name, (spec, seed, count, tol, scale) in SOLVE_CASES.items():
         if only and name not in only:
             continue

@@ -57,7 +57,7 @@ emu_env* emu_create(const gfr_feeder_desc* d, long long B, const gfr_env_cfg* c)
   for (long long i = 0; i < B; ++i)
     reset_instance<1>(g, lay, (const int*)e->fi.img.data(), (const double*)e->fi.img.data(), k, i,
                       e->state.data(), e->obs.data(), e->fi.load_pq.data(), e->bat_soc0.data(),
-                      nullptr, nullptr, 0.0, true);
+                      nullptr, nullptr, 0.0, true, (long long)c->env_id_offset);
   return e;
 }
 
@@ -73,7 +73,7 @@ void emu_reset(emu_env* e, const uint64_t* seeds, const uint8_t* mask, const dou
     if (mask && !mask[i]) continue;
     reset_instance<1>(g, lay, (const int*)e->fi.img.data(), (const double*)e->fi.img.data(), e->cfg, i,
                       e->state.data(), e->obs.data(), e->fi.load_pq.data(), e->bat_soc0.data(), seeds,
-                      noise, start_time, false);
+                      noise, start_time, false, 0);
   }
 }
 
