@@ -314,6 +314,16 @@ def run_gpu(args):
         dist.all_reduce(t)
         conv_frac, mean_it = (t / world).tolist()
     value = B * world * K / (ms * 1e-3)
+    if args.kernel_only:                 # tuning aid (tools/): the device-resident arm only
+        sampler.stop()
+        if rank == 0:
+            print(json.dumps({"value": value, "ms_per_step": ms / K, "mean_iterations": mean_it,
+                              "converged_frac": conv_frac,
+                              "config": {"launch": env.launch_info(), "instances_per_gpu": B}}), flush=True)
+        env.close()
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     # ---- end-to-end arm: every step copies ITS actions from pinned host memory (H2D) and its reward +
     #      done flags back (D2H), and the host reads each step's result.  Measured twice through the
@@ -441,6 +451,7 @@ def main():
     ap.add_argument("--envs", type=int, default=0, help="instances per GPU (default: the workload's)")
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--kernel-only", action="store_true", help="tuning aid: time the device-resident arm only")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

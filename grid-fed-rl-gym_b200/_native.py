@@ -32,7 +32,7 @@ class FeederDesc(C.Structure):
         ("n_bat", C.c_int32), ("n_pool", C.c_int32), ("lanes_hint", C.c_int32), ("reserved", C.c_int32),
         ("s_base", C.c_double),
         ("order", _i32p), ("parent", _i32p), ("level_ptr", _i32p), ("child_ptr", _i32p),
-        ("child_idx", _i32p), ("pool_slot", _i32p),
+        ("child_idx", _i32p), ("pool_slot", _i32p), ("lane_of", _i32p),
         ("bus_type", _i32p), ("vm_set", _f64p), ("g", _f64p), ("b", _f64p), ("gdiag", _f64p),
         ("bdiag", _f64p), ("r", _f64p), ("x", _f64p), ("line_of", _i32p), ("from_is_parent", _i32p),
         ("rating", _f64p), ("load_bus", _i32p), ("load_base", _f64p), ("load_p", _f64p),
@@ -192,9 +192,12 @@ def make_feeder_desc(soa: FeederSoA):
     d.n_pool = int(soa.n_pool)
     d.lanes_hint = int(getattr(soa, "lanes_hint", 0) or 0)
     d.s_base = float(soa.s_base)
-    for name in ("order", "parent", "level_ptr", "child_ptr", "child_idx", "pool_slot", "bus_type", "line_of", "from_is_parent",
+    for name in ("order", "parent", "level_ptr", "child_ptr", "child_idx", "bus_type", "line_of", "from_is_parent",
                  "load_bus", "gen_type", "gen_bus", "bat_bus"):
         setattr(d, name, i32(name))
+    for name in ("pool_slot", "lane_of"):                # optional: NULL = the library decides
+        if getattr(soa, name, None) is not None:
+            setattr(d, name, i32(name))
     for name in ("vm_set", "g", "b", "gdiag", "bdiag", "r", "x", "rating", "load_base", "load_p",
                  "load_q", "gen_cap", "gen_p0", "gen_p1", "gen_p2", "bat_cap", "bat_rating",
                  "bat_eff", "bat_soc0", "load_profile"):

@@ -89,8 +89,8 @@ make_group(const Layout& lay, unsigned char* work, int slot_bytes, D2* mscratch)
   if (LANES > 32) work += kRedBytes;
   const int slot = threadIdx.x / LANES;
   const int E = blockDim.x / LANES;
-  D2* mg = mscratch ? mscratch + ((size_t)blockIdx.x * E + slot) * (newton_scratch_doubles(lay.n) / 2) : nullptr;
-  bind_slot(g, work + (size_t)slot * slot_bytes, lay.n, lay.n_pool, mg);
+  D2* mg = mscratch ? mscratch + ((size_t)blockIdx.x * E + slot) * (newton_scratch_doubles(lay.P) / 2) : nullptr;
+  bind_slot(g, work + (size_t)slot * slot_bytes, lay, mg);
   return g;
 }
 
@@ -225,23 +225,32 @@ struct DeviceGuard {
 
 }  // namespace
 
+// one compiled image per (solver, lanes) a feeder has been asked to run on, built on first use
+struct ImageDev {
+  Layout lay{};
+  void* d_img = nullptr;
+  int n_reg_edges = 0;
+};
+
 struct gfr_feeder {
   int device = 0;
   int sm_count = 0;
   int smem_optin = 0;
   int smem_per_sm = 0;
-  Layout lay{};
+  Layout lay{};                  // sizes only (n, L, G, Bt, A, D, R, ...): offsets belong to an image
   bool has_pv = false;
   bool root_is_slack = true;
   int lanes_hint = 0;            // lane count the level schedule was capped for (0: not said)
   int center_depth = 0;          // levels of the tree rooted at its center, uncapped
-  void* d_img = nullptr;         // image
+  DescCopy desc;                 // the description, kept to build further images
+  mutable std::map<int, ImageDev> images;   // key = solver * 1024 + lanes
   double* d_load_pq = nullptr;   // [2L] static active / reactive power (observation)
   double* d_bat_soc0 = nullptr;  // [Bt]
 };
 
 struct gfr_env {
   const gfr_feeder* f = nullptr;
+  const ImageDev* img = nullptr;
   long long B = 0;
   EnvCfg cfg{};
   int solver = GFR_SOLVER_NEWTON;
@@ -268,6 +277,25 @@ struct gfr_network {
 namespace {
 
 struct LaunchPlan { int lanes, threads, grid; size_t smem; int ctas_per_sm; int slot_bytes; size_t mscratch_bytes; bool img_smem; };
+
+// the image of a feeder for one (solver, lanes): built and uploaded on first use
+int image_for(const gfr_feeder* f, int solver, int lanes, const ImageDev** out) {
+  const int key = solver * 1024 + lanes;
+  auto it = f->images.find(key);
+  if (it != f->images.end()) { *out = &it->second; return GFR_OK; }
+  FeederImage fi;
+  std::string complaint = build_feeder_image(&f->desc.d, lanes, solver, &fi);
+  if (!complaint.empty()) return fail(GFR_E_ARG, complaint);
+  ImageDev dev;
+  dev.lay = fi.lay;
+  dev.n_reg_edges = fi.n_reg_edges;
+  GFR_CUDA(cudaMalloc(&dev.d_img, fi.img.size()));
+  cudaError_t ce = cudaMemcpy(dev.d_img, fi.img.data(), fi.img.size(), cudaMemcpyHostToDevice);
+  if (ce != cudaSuccess) { cudaFree(dev.d_img); return cuda_fail(ce, "cudaMemcpy(image)"); }
+  auto ins = f->images.emplace(key, dev);
+  *out = &ins.first->second;
+  return GFR_OK;
+}
 
 // shared memory of one instance slot; 0 if the scratch it doubles as cannot hold the sources
 size_t slot_bytes(const Layout& lay, int solver, int lanes) {
@@ -348,14 +376,14 @@ const void* kernel_fn(bool step, int solver, int lanes, bool img_smem) {
 // One candidate split of an SM: `c` CTAs of E instance slots each.
 struct PlanTry { long long resident = 0; LaunchPlan plan{}; };
 
-PlanTry plan_mode(const gfr_feeder* f, const void* fn, int lanes, bool img_smem, size_t per_env, long long B) {
+PlanTry plan_mode(const gfr_feeder* f, const Layout& lay, const void* fn, int lanes, bool img_smem, size_t per_env, long long B) {
   PlanTry best;
   if (!fn) return best;
   if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, f->smem_optin) != cudaSuccess) {
     cudaGetLastError();
     return best;
   }
-  const size_t fixed = kSmemHeader + (img_smem ? (size_t)f->lay.img_bytes : 0) + (lanes > 32 ? kRedBytes : 0);
+  const size_t fixed = kSmemHeader + (img_smem ? (size_t)lay.img_bytes : 0) + (lanes > 32 ? kRedBytes : 0);
   const size_t sm_total = (size_t)f->smem_per_sm;
   const int gran = lanes >= 32 ? 1 : 32 / lanes;         // whole warps
   // pass 0: whole warps only; pass 1 (only if nothing fits): a partial warp
@@ -396,21 +424,24 @@ PlanTry plan_mode(const gfr_feeder* f, const void* fn, int lanes, bool img_smem,
 // Small and medium feeders stage one copy of the feeder image per CTA; when that leaves fewer than
 // four instances resident (or the group is CTA-wide) the image is read from global memory instead.
 int plan_launch(const gfr_feeder* f, bool step, int solver, int lanes, long long B, LaunchPlan* out,
-                const void** fn_out) {
-  const Layout& lay = f->lay;
+                const void** fn_out, const ImageDev** img_out) {
   // the lane count the description's level schedule was capped for, else the rule
-  if (lanes == 0) lanes = f->lanes_hint > 0 ? f->lanes_hint : auto_lanes_rule(lay.n, solver, f->center_depth);
+  if (lanes == 0) lanes = f->lanes_hint > 0 ? f->lanes_hint : auto_lanes_rule(f->lay.n, solver, f->center_depth);
   if (lanes != 1 && lanes != 2 && lanes != 4 && lanes != 8 && lanes != 16 && lanes != 32 && lanes != 64 &&
       lanes != 128 && lanes != 256)
     return fail(GFR_E_ARG, "lanes must be 0 (auto), 1, 2, 4, 8, 16, 32 (part of a warp) or 64, 128, 256 (one CTA per instance)");
+  const ImageDev* im = nullptr;
+  if (int rc = image_for(f, solver, lanes, &im)) return rc;
+  const Layout& lay = im->lay;
+  *img_out = im;
   const size_t per_env = slot_bytes(lay, solver, lanes);
   if (!per_env)
     return fail(GFR_E_LIMIT, "more loads + generators + batteries than the solver's working set can stage "
                              "(sweep: 2 per bus on average)");
   PlanTry best;
-  if (lanes <= 32) best = plan_mode(f, kernel_fn(step, solver, lanes, true), lanes, true, per_env, B);
+  if (lanes <= 32) best = plan_mode(f, lay, kernel_fn(step, solver, lanes, true), lanes, true, per_env, B);
   if (lanes > 32 || (lanes == 32 && best.resident < 4)) {
-    PlanTry alt = plan_mode(f, kernel_fn(step, solver, lanes, false), lanes, false, per_env, B);
+    PlanTry alt = plan_mode(f, lay, kernel_fn(step, solver, lanes, false), lanes, false, per_env, B);
     if (alt.resident > best.resident) best = alt;
   }
   if (!best.resident)
@@ -442,7 +473,7 @@ int plan_launch(const gfr_feeder* f, bool step, int solver, int lanes, long long
   plan.grid = (int)grid;
   plan.slot_bytes = (int)per_env;
   // Newton spills D^-1 U (32 B per bus) of every resident instance slot to global memory
-  plan.mscratch_bytes = solver == GFR_SOLVER_NEWTON ? (size_t)grid * E * newton_scratch_doubles(lay.n) * 8 : 0;
+  plan.mscratch_bytes = solver == GFR_SOLVER_NEWTON ? (size_t)grid * E * newton_scratch_doubles(lay.P) * 8 : 0;
   *out = plan;
   *fn_out = kernel_fn(step, solver, lanes, plan.img_smem);
   return GFR_OK;
@@ -450,26 +481,26 @@ int plan_launch(const gfr_feeder* f, bool step, int solver, int lanes, long long
 
 int launch_step(const gfr_env* e, const double* actions, const double* noise, const StepOut& o,
                 cudaStream_t s) {
-  const void* img = e->f->d_img;
+  const void* img = e->img->d_img;
   double* state = e->d_state;
   double* obs = e->d_obs;
   long long B = e->B;
   int slot = e->slot_bytes;
   D2* ms = e->d_mscratch;
-  void* args[] = {(void*)&e->f->lay, (void*)&e->cfg, (void*)&img, (void*)&slot, (void*)&ms, (void*)&state,
+  void* args[] = {(void*)&e->img->lay, (void*)&e->cfg, (void*)&img, (void*)&slot, (void*)&ms, (void*)&state,
                   (void*)&obs, (void*)&actions, (void*)&noise, (void*)&o, (void*)&B};
   GFR_CUDA(cudaLaunchKernel(e->fn, dim3(e->grid), dim3(e->threads), args, e->smem, s));
   g_launches.fetch_add(1);
   return GFR_OK;
 }
 
-int launch_solve(const gfr_feeder* f, const LaunchPlan& p, const void* fn, const EnvCfg& cfg,
+int launch_solve(const ImageDev* im, const LaunchPlan& p, const void* fn, const EnvCfg& cfg,
                  const double* p_inj, const SolOut& o, long long B, cudaStream_t s) {
-  const void* img = f->d_img;
+  const void* img = im->d_img;
   int slot = p.slot_bytes;
   D2* ms = nullptr;
   if (p.mscratch_bytes) GFR_CUDA(cudaMallocAsync((void**)&ms, p.mscratch_bytes, s));   // stream-ordered scratch
-  void* args[] = {(void*)&f->lay, (void*)&cfg, (void*)&img, (void*)&slot, (void*)&ms, (void*)&p_inj, (void*)&o,
+  void* args[] = {(void*)&im->lay, (void*)&cfg, (void*)&img, (void*)&slot, (void*)&ms, (void*)&p_inj, (void*)&o,
                   (void*)&B};
   cudaError_t le = cudaLaunchKernel(fn, dim3(p.grid), dim3(p.threads), args, p.smem, s);
   if (ms) cudaFreeAsync(ms, s);
@@ -500,9 +531,11 @@ int gfr_auto_lanes(int n_bus, int solver, int depth) { return auto_lanes_rule(n_
 int gfr_feeder_create(const gfr_feeder_desc* d, int device, gfr_feeder** out) {
   if (!d || !out) return fail(GFR_E_ARG, "null argument");
   *out = nullptr;
+  // the description is checked (and a first image built on the host) before a device is asked for
   FeederImage fi;
   {
-    std::string complaint = build_feeder_image(d, &fi);
+    const int lanes0 = d->lanes_hint > 0 && d->lanes_hint <= 256 ? d->lanes_hint : 1;
+    std::string complaint = build_feeder_image(d, lanes0, GFR_SOLVER_NEWTON, &fi);
     if (!complaint.empty()) return fail(GFR_E_ARG, complaint);
   }
   DeviceGuard guard(device);
@@ -519,24 +552,20 @@ int gfr_feeder_create(const gfr_feeder_desc* d, int device, gfr_feeder** out) {
   f->root_is_slack = fi.root_is_slack;
   f->lanes_hint = d->lanes_hint;
   f->center_depth = fi.center_depth;
-  const Layout& lay = f->lay;
-  const int L = lay.L, Bt = lay.Bt;
-  const size_t img_bytes = fi.img.size();
-  const std::vector<unsigned char>& img = fi.img;
+  f->desc.assign(d);
+  const int Bt = f->lay.Bt;
   const std::vector<double>& load_pq = fi.load_pq;
-  cudaError_t e1 = cudaMalloc(&f->d_img, img_bytes);
   cudaError_t e2 = cudaMalloc((void**)&f->d_load_pq, load_pq.size() * 8);
   cudaError_t e3 = cudaMalloc((void**)&f->d_bat_soc0, ((size_t)Bt + 1) * 8);
-  if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
+  if (e2 != cudaSuccess || e3 != cudaSuccess) {
     gfr_feeder_destroy(f);
-    return cuda_fail(e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3), "cudaMalloc(feeder)");
+    return cuda_fail(e2 != cudaSuccess ? e2 : e3, "cudaMalloc(feeder)");
   }
-  cudaError_t c1 = cudaMemcpy(f->d_img, img.data(), img_bytes, cudaMemcpyHostToDevice);
   cudaError_t c2 = cudaMemcpy(f->d_load_pq, load_pq.data(), load_pq.size() * 8, cudaMemcpyHostToDevice);
   cudaError_t c3 = Bt ? cudaMemcpy(f->d_bat_soc0, d->bat_soc0, (size_t)Bt * 8, cudaMemcpyHostToDevice) : cudaSuccess;
-  if (c1 != cudaSuccess || c2 != cudaSuccess || c3 != cudaSuccess) {
+  if (c2 != cudaSuccess || c3 != cudaSuccess) {
     gfr_feeder_destroy(f);
-    return cuda_fail(c1 != cudaSuccess ? c1 : (c2 != cudaSuccess ? c2 : c3), "cudaMemcpy(feeder)");
+    return cuda_fail(c2 != cudaSuccess ? c2 : c3, "cudaMemcpy(feeder)");
   }
   *out = f;
   return GFR_OK;
@@ -545,7 +574,7 @@ int gfr_feeder_create(const gfr_feeder_desc* d, int device, gfr_feeder** out) {
 void gfr_feeder_destroy(gfr_feeder* f) {
   if (!f) return;
   DeviceGuard guard(f->device);
-  cudaFree(f->d_img);
+  for (auto& kv : f->images) cudaFree(kv.second.d_img);
   cudaFree(f->d_load_pq);
   cudaFree(f->d_bat_soc0);
   delete f;
@@ -570,7 +599,7 @@ static int launch_reset(gfr_env* e, const uint64_t* seeds, const uint8_t* mask, 
   long long grid = (e->B + per_cta - 1) / per_cta;
   const long long cap = (long long)e->f->sm_count * 16;
   if (grid > cap) grid = cap;
-  reset_kernel<<<(int)grid, threads, 0, s>>>(e->f->lay, e->cfg, e->f->d_img, e->d_state, e->d_obs,
+  reset_kernel<<<(int)grid, threads, 0, s>>>(e->img->lay, e->cfg, e->img->d_img, e->d_state, e->d_obs,
                                             e->f->d_load_pq, e->f->d_bat_soc0, seeds, mask, noise,
                                             start_time, construct, e->env_id_offset, e->B);
   g_launches.fetch_add(1);
@@ -588,9 +617,10 @@ int gfr_env_create(const gfr_feeder* f, int64_t n_envs, const gfr_env_cfg* cfg, 
   if (!guard.ok) return fail(GFR_E_CUDA, "no usable CUDA device (this library has no CPU fallback)");
   LaunchPlan plan;
   const void* fn = nullptr;
-  if (int rc = plan_launch(f, true, cfg->solver.solver, cfg->solver.lanes, n_envs, &plan, &fn)) return rc;
+  const ImageDev* im = nullptr;
+  if (int rc = plan_launch(f, true, cfg->solver.solver, cfg->solver.lanes, n_envs, &plan, &fn, &im)) return rc;
   auto* e = new gfr_env();
-  e->f = f; e->B = n_envs; e->cfg = ec; e->solver = cfg->solver.solver;
+  e->f = f; e->img = im; e->B = n_envs; e->cfg = ec; e->solver = cfg->solver.solver;
   e->lanes = plan.lanes; e->threads = plan.threads; e->grid = plan.grid; e->smem = plan.smem; e->fn = fn;
   e->slot_bytes = plan.slot_bytes;
   e->env_id_offset = cfg->env_id_offset;
@@ -693,7 +723,8 @@ int gfr_solve(const gfr_feeder* f, int64_t B, const double* p_inj, const gfr_sol
   if (!guard.ok) return fail(GFR_E_CUDA, "no usable CUDA device (this library has no CPU fallback)");
   LaunchPlan plan;
   const void* fn = nullptr;
-  if (int rc = plan_launch(f, false, cfg->solver, cfg->lanes, B, &plan, &fn)) return rc;
+  const ImageDev* im = nullptr;
+  if (int rc = plan_launch(f, false, cfg->solver, cfg->lanes, B, &plan, &fn, &im)) return rc;
   EnvCfg ec{};
   ec.tol = cfg->tolerance; ec.max_it = cfg->max_iterations;
   ec.accel = cfg->acceleration != 0.0 ? cfg->acceleration : 1.0;
@@ -701,7 +732,7 @@ int gfr_solve(const gfr_feeder* f, int64_t B, const double* p_inj, const gfr_sol
   o.converged = out->converged; o.iterations = out->iterations; o.bus_voltages = out->bus_voltages;
   o.bus_angles = out->bus_angles; o.line_flows = out->line_flows; o.line_loadings = out->line_loadings;
   o.losses = out->losses; o.max_mismatch = out->max_mismatch;
-  return launch_solve(f, plan, fn, ec, p_inj, o, B, (cudaStream_t)stream);
+  return launch_solve(im, plan, fn, ec, p_inj, o, B, (cudaStream_t)stream);
 }
 
 int gfr_network_create(const gfr_network_desc* d, int device, gfr_network** out) {

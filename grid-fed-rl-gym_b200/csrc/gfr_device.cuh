@@ -34,28 +34,31 @@ namespace gfr {
 enum { SOLVER_SWEEP = 0, SOLVER_NEWTON = 1 };
 enum { BUS_SLACK = 0, BUS_PV = 1, BUS_PQ = 2 };
 enum { GEN_SOLAR = 0, GEN_WIND = 1 };
-// An instance's working set in shared memory (buses in level order):
-//   Newton:  ef[n] (e + jf, 16 B) | pool[n_pool] (64 B)
-//            A pool entry carries what one bus hands to its parent during the leaf -> root
-//            elimination - its Schur contribution (L D^-1 U, L D^-1 r) and its branch's share of the
-//            parent's calculated injection - from the moment the bus is eliminated until the parent
-//            is; the host plans the slots (pool_slot[k]).  On the way back (root -> leaf) the same
-//            slot carries the parent's correction down to the bus.  D^-1 U and D^-1 r, only needed
-//            again in the back-substitution, and the specified injections live in a per-slot
-//            scratch in global memory that stays L2 resident.
+// An instance's working set in shared memory:
+//   Newton:  ef[n] (e + jf, 16 B per bus) | pool[4][n_pool] (16-byte fields)
+//            The elimination runs on a SCHEDULE: row after row (leaf -> root), lane l of the group taking
+//            position row * LANES + l.  The host lets a lane follow a path of the tree, so most buses are
+//            eliminated right after one of their children on the same lane: that child's Schur terms
+//            (L D^-1 U, L D^-1 r) and its branch's share of the parent's calculated injection stay in
+//            REGISTERS, and the parent's correction comes back down the same way.  Only the other
+//            children go through a pool slot (planned by the host: held from the child's row up to the
+//            parent's; field 0 carries the correction on the way down).  D^-1 U and D^-1 r, only needed
+//            again in the back-substitution, and the specified injections live in a per-slot scratch
+//            in global memory, by position, that stays L2 resident; the back-substitution stages them
+//            two rows ahead with cp.async into the pool's fields 1..3 (dead on the way down).
 //   sweep:   40 B per bus in three arrays: e + jf | Jr + jJi (branch current) | P
 // Before the solve the same space (Newton: ef + pool; sweep: the J fields) carries the load /
-// generator / battery powers into the per-bus injection sums.
+// generator / battery powers into the per-position injection sums.
 enum { F_E = 0, F_F = 1, F_SCRATCH = 2 };
 enum { S_JR = 2, S_P = 4 };                      // field tags of the sweep accessors
 enum { SCRATCH_FIELDS_SWEEP = 2 };
-// bus flag bits
+// bus flag bits (word z of a schedule record / word w of the sweep's topology record)
 enum { FL_PQ = 1, FL_FROM_IS_PARENT = 2, FL_FIXED_VM = 4, FL_THETA = 8,     // PQ: |V| unknown; THETA: angle unknown
        FL_SLACK_PATH = 16,                                                // on the path slack -> root (slack included, root not)
-       FL_INHERIT = 32,                                                   // the bus's pool slot is also its first child's
-       FL_NO_SCATTER = 64,                                                // every child but the first reads the correction from this bus's slot
-       FL_POOL_SHIFT = 8, FL_POOL_MASK = 0xFFF,                           // bits 8..19: the bus's pool slot
-       FL_XSLOT_SHIFT = 20 };                                             // bits 20..31: the slot its parent's correction arrives in
+       FL_C_REG = 32,                                                     // Newton: the bus eliminated just before on this lane is a child (the "heir"): its Schur terms are in registers
+       FL_P_REG = 64,                                                     // Newton: this bus is its parent's heir: nothing goes through the pool, either way
+       FL_VALID = 128,                                                    // the schedule position holds a bus
+       FL_POOL_SHIFT = 8, FL_POOL_MASK = 0xFFF };                         // bits 8..19: the bus's pool slot
 // record (persistent per-instance state) slots, in doubles
 enum { R_TIME = 0, R_FREQ, R_WIND, R_TEMP, R_CLOUD, R_TOTAL_LOSSES, R_EPISODE_REWARD, R_SEED,
        R_DRAWS, R_COUNTS, R_BAT };   // soc[Bt] then bpow[Bt] from R_BAT on
@@ -63,16 +66,29 @@ enum { R_TIME = 0, R_FREQ, R_WIND, R_TEMP, R_CLOUD, R_TOTAL_LOSSES, R_EPISODE_RE
 struct alignas(16) D2 { double x, y; };
 struct alignas(16) I4 { int x, y, z, w; };   // per-bus topology: parent, child list begin, end, flags
 GFR_HD int pool_slot_of(int w) { return (w >> FL_POOL_SHIFT) & FL_POOL_MASK; }
-GFR_HD int x_slot_of(int w) { return (int)((unsigned)w >> FL_XSLOT_SHIFT); }
+// A schedule record (one per position p = row * lanes + lane, 16 bytes):
+//   x = bus k | parent's k << 16 (indices into ef)      y = first entry of the bus's child list
+//   z = flags | pool slot << 8                           w = children handed over through the pool | all children << 16
+// The child list (child_ent, child_slot) holds the heir first - if there is one - then the others.
+GFR_HD int rec_bus(const I4& t) { return (int)((unsigned)t.x & 0xFFFFu); }
+GFR_HD int rec_parent(const I4& t) { return (int)((unsigned)t.x >> 16); }
+GFR_HD int rec_pool_kids(const I4& t) { return (int)((unsigned)t.w & 0xFFFFu); }
+GFR_HD int rec_all_kids(const I4& t) { return (int)((unsigned)t.w >> 16); }
 
 // Where everything is inside the feeder image (ints / doubles counted from the image base)
 // plus the sizes; passed as a kernel parameter (constant bank).
 struct Layout {
   int n, nl, L, G, Bt, A, D, m, n_src, R, img_bytes, n_noise, n_pool, k_slack;
-  int o_topo, o_child_idx, o_child_pool, o_level_ptr, o_rank, o_branch_of_line, o_inj_ptr, o_inj_idx,
-      o_gen_type;
-  int o_gb, o_gbd, o_rx, o_f0, o_rating, o_vm_set, o_load_base, o_gen_cap, o_gen_p0, o_gen_p1, o_gen_p2,
-      o_bat_cap, o_bat_rating, o_bat_eff, o_profile;
+  int nrows, P;                  // schedule: rows and positions (Newton: rows x lanes; sweep: P = n, position = bus)
+  // by position, every image
+  int o_sched, o_rank, o_rankp, o_branch_of_line, o_inj_ptr, o_inj_idx, o_gen_type;
+  int o_gb, o_rating, o_vm_set;
+  // Newton
+  int o_child_ent, o_child_slot, o_gbd, o_f0;
+  // sweep (compact per-bus arrays)
+  int o_topo, o_child_idx, o_level_ptr, o_rx;
+  // components
+  int o_load_base, o_gen_cap, o_gen_p0, o_gen_p1, o_gen_p2, o_bat_cap, o_bat_rating, o_bat_eff, o_profile;
   double s_base, inv_s_base, load_p_sum;
 };
 
@@ -99,11 +115,19 @@ struct OpSum { GFR_HD double operator()(double v, double w) const { return v + w
 // __syncwarp(mask), reductions by shuffles.  LANES > 32: the whole CTA owns the instance ("one
 // CTA per instance" for large feeders), barrier = __syncthreads(), reductions go warp-first and
 // then through `red` (shared memory, LANES / 32 doubles).
+#if !defined(__CUDACC__)
+// host emulation (tests/host_emu): the lanes of a group are host threads that meet at a barrier
+struct EmuTeam { int lanes; void (*barrier)(void*); void* ctx; double* red; };
+#endif
+
 template <int LANES>
 struct Lanes {
   int lane;        // lane inside the group
   unsigned mask;   // LANES <= 32: the group's lanes inside its warp
   double* red;     // LANES > 32: cross-warp reduction scratch
+#if !defined(__CUDACC__)
+  EmuTeam* team = nullptr;
+#endif
   // first index >= k0 owned by this lane (lane k % LANES owns bus k in every phase)
   GFR_HD int first(int k0) const { return k0 + ((lane - k0) & (LANES - 1)); }
 
@@ -111,6 +135,8 @@ struct Lanes {
 #if defined(__CUDA_ARCH__)
     if (LANES > 32) __syncthreads();
     else if (LANES > 1) __syncwarp(mask);
+#elif !defined(__CUDACC__)
+    if (LANES > 1 && team) team->barrier(team->ctx);
 #endif
   }
   template <class Op>
@@ -129,6 +155,15 @@ struct Lanes {
 #pragma unroll
       for (int w = 1; w < LANES / 32; ++w) v = op(v, red[w]);
     }
+#elif !defined(__CUDACC__)
+    if (LANES > 1 && team) {
+      team->red[lane] = v;
+      team->barrier(team->ctx);
+      double r = team->red[0];
+      for (int w = 1; w < LANES; ++w) r = op(r, team->red[w]);
+      team->barrier(team->ctx);
+      v = r;
+    }
 #endif
     return v;
   }
@@ -141,6 +176,13 @@ struct Lanes {
       v = red[0];
     } else if (LANES > 1) {
       v = __shfl_sync(mask, v, src, LANES);
+    }
+#elif !defined(__CUDACC__)
+    if (LANES > 1 && team) {
+      if (lane == src) team->red[0] = v;
+      team->barrier(team->ctx);
+      v = team->red[0];
+      team->barrier(team->ctx);
     }
 #endif
     return v;
@@ -170,18 +212,17 @@ struct SGrp : Lanes<LANES> {
 
 // Newton working set (see the layout note above)
 // a pool entry is four 16-byte fields: c0, c1 (L D^-1 U rows), cc (L D^-1 r), fl (branch share of P, Q),
-// stored field-major (field f of slot s at poolp[f * n_pool + s]): the lanes of a level then touch
-// consecutive 16-byte units wherever their slots are consecutive instead of every fourth one
+// stored field-major (field f of slot s at poolp[f * n_pool + s])
 enum { POOL_D2 = 4 };
 template <int LANES>
 struct NGrp : Lanes<LANES> {
   D2* efp;        // [n]      shared, followed directly by the pool
   D2* poolp;      // [POOL_D2][n_pool] shared
   int np;         // n_pool
-  double* pp;     // [n]      specified injections (global scratch, right after mg)
-  D2* mg;         // [3][n]   GLOBAL scratch of this instance slot: rows of D^-1 U (2) and D^-1 r (1), field-major
+  double* pp;     // [P]      specified injections by position (global scratch, right after mg)
+  D2* mg;         // [3][P]   GLOBAL scratch of this instance slot: rows of D^-1 U (2) and D^-1 r (1), field-major, by position
   GFR_HD D2& ef(int k) const { return efp[k]; }
-  GFR_HD double& pspec(int k) const { return pp[k]; }
+  GFR_HD double& pspec(int p) const { return pp[p]; }
   GFR_HD double& scr(int j) const { return reinterpret_cast<double*>(efp)[j]; }   // ef + pool, flat
 };
 
@@ -193,8 +234,8 @@ GFR_HD size_t newton_slot_bytes(int n, int n_pool, int n_src) {
   if (n_src > 2 * n + 2 * POOL_D2 * n_pool) return 0;
   return (size_t)n * 16 + (size_t)n_pool * (16 * POOL_D2);
 }
-// doubles of global scratch per instance slot (Newton): D^-1 U, D^-1 r (48 B per bus) + specified injections
-GFR_HD size_t newton_scratch_doubles(int n) { return (size_t)n * 6 + (((size_t)n + 1) / 2) * 2; }
+// doubles of global scratch per instance slot (Newton): D^-1 U, D^-1 r (48 B per position) + specified injections
+GFR_HD size_t newton_scratch_doubles(int P) { return (size_t)P * 6 + (((size_t)P + 1) / 2) * 2; }
 // One thread per instance on a small feeder: the specified injections move to a per-thread local array (L1,
 // interleaved by thread), 32 B per bus stay in shared memory - 40 % more resident instances per SM
 enum { SWEEP_P_LOCAL_MAX = 20 };
@@ -205,15 +246,16 @@ GFR_HD size_t sweep_slot_bytes(int n, int n_src, bool p_local = false) {
   return (units | 1) * 16;                                // slots then start 4 banks apart (conflict-free 128-bit accesses)
 }
 template <int LANES>
-GFR_HD void bind_slot(NGrp<LANES>& g, unsigned char* slot, int n, int n_pool, D2* mg) {
-  g.np = n_pool;
+GFR_HD void bind_slot(NGrp<LANES>& g, unsigned char* slot, const Layout& lay, D2* mg) {
+  g.np = lay.n_pool;
   g.efp = reinterpret_cast<D2*>(slot);
-  g.poolp = g.efp + n;
-  g.pp = reinterpret_cast<double*>(mg + 3 * (size_t)n);
+  g.poolp = g.efp + lay.n;
+  g.pp = reinterpret_cast<double*>(mg + 3 * (size_t)lay.P);
   g.mg = mg;
 }
 template <int LANES>
-GFR_HD void bind_slot(SGrp<LANES>& g, unsigned char* slot, int n, int, D2*) {
+GFR_HD void bind_slot(SGrp<LANES>& g, unsigned char* slot, const Layout& lay, D2*) {
+  const int n = lay.n;
   g.efp = reinterpret_cast<D2*>(slot);
   g.jrp = g.efp + n;
   g.pp = reinterpret_cast<double*>(g.jrp + n);
@@ -363,12 +405,14 @@ GFR_HD double noise_slot(uint64_t seed, uint64_t draw, int s) {
 template <class G, int LANES>
 GFR_HD void flat_start_t(const G& g, const Lanes<LANES>&, const Layout& lay, const int* simg,
                          const double* dimg) {
-  const I4* topo = reinterpret_cast<const I4*>(simg + lay.o_topo);
-  for (int k = g.lane; k < lay.n; k += LANES) {
+  const I4* sched = reinterpret_cast<const I4*>(simg + lay.o_sched);
+  for (int p = g.lane; p < lay.P; p += LANES) {
+    const I4 t = sched[p];
+    if (!(t.z & FL_VALID)) continue;
     D2 v;
-    v.x = (topo[k].w & FL_FIXED_VM) ? dimg[lay.o_vm_set + k] : 1.0;
+    v.x = (t.z & FL_FIXED_VM) ? dimg[lay.o_vm_set + p] : 1.0;
     v.y = 0.0;
-    g.ef(k) = v;
+    g.ef(rec_bus(t)) = v;
   }
   g.sync();
 }
@@ -407,32 +451,35 @@ GFR_HD BranchT branch_terms(const D2 vk, const D2 vp, const D2 y) {
 }
 
 // max |mismatch| of the present voltages, every bus independently (power_flow.py:150-166); same
-// arithmetic, term by term, as the elimination pass below
+// arithmetic, term by term and in the same order, as the elimination pass below
 template <int LANES>
 GFR_HD double newton_mismatch(const NGrp<LANES>& g, const Layout& lay, const int* simg, const double* dimg) {
-  const I4* topo = reinterpret_cast<const I4*>(simg + lay.o_topo);
-  const int* child_idx = simg + lay.o_child_idx;
+  const I4* sched = reinterpret_cast<const I4*>(simg + lay.o_sched);
+  const int* child_ent = simg + lay.o_child_ent;
   const D2* gb = reinterpret_cast<const D2*>(dimg + lay.o_gb);
   const D2* gbd = reinterpret_cast<const D2*>(dimg + lay.o_gbd);
   double mm = 0.0;
-  for (int k = g.lane; k < lay.n; k += LANES) {
-    const I4 t = topo[k];
-    const D2 vk = g.ef(k);
-    const D2 yd = gbd[k];
+  for (int p = g.lane; p < lay.P; p += LANES) {
+    const I4 t = sched[p];
+    if (!(t.z & FL_VALID)) continue;
+    const D2 vk = g.ef(rec_bus(t));
+    const D2 yd = gbd[p];
+    const double ps = g.pspec(p);
     const double v2 = fma(vk.x, vk.x, vk.y * vk.y);
-    const BranchT bt = branch_terms(vk, g.ef(t.x), gb[k]);
+    const BranchT bt = branch_terms(vk, g.ef(rec_parent(t)), gb[p]);
     D2 sf; sf.x = sf.y = 0.0;
+    const int q1 = t.y + rec_all_kids(t);
 #pragma unroll 1
-    for (int q = t.y; q < t.z; ++q) {
-      const int c = child_idx[q];
-      const BranchT ct = branch_terms(g.ef(c), vk, gb[c]);
+    for (int q = t.y; q < q1; ++q) {
+      const unsigned e = (unsigned)child_ent[q];
+      const BranchT ct = branch_terms(g.ef((int)(e & 0xFFFFu)), vk, gb[e >> 16]);
       sf.x += ct.gl; sf.y += ct.ll;
     }
     const double P = fma(yd.x, v2, bt.ga) + sf.x, Q = fma(-yd.y, v2, bt.al) + sf.y;
-    double aP = fabs(g.pspec(k) - P), aQ = fabs(Q);
-    if ((t.w & (FL_PQ | FL_THETA)) != (FL_PQ | FL_THETA)) {   // slack: no equations; PV: no Q equation
-      if (!(t.w & FL_THETA)) aP = 0.0;
-      if (!(t.w & FL_PQ)) aQ = 0.0;
+    double aP = fabs(ps - P), aQ = fabs(Q);
+    if ((t.z & (FL_PQ | FL_THETA)) != (FL_PQ | FL_THETA)) {   // slack: no equations; PV: no Q equation
+      if (!(t.z & FL_THETA)) aP = 0.0;
+      if (!(t.z & FL_PQ)) aQ = 0.0;
     }
     const double loc = (aQ > aP || aQ != aQ) ? aQ : aP;
     mm = (loc > mm || loc != loc) ? loc : mm;
@@ -466,109 +513,66 @@ GFR_HD void cp_async_wait() {
 // Back-substitution root -> leaf fused with the polar update (power_flow.py:297-327):
 //   x_k = v_k - M_k x_parent (the root's M is 0: it has no branch), then
 //   theta += a dtheta, |V| += a d|V|  <=>  V *= (1 + a x1) e^{j a x0}.
-// x_parent comes down through the bus's own pool slot (the parent put it there), x_k goes into the
-// slots of the children.  M and v come back from the global scratch (first iteration: M from the
-// image).  Their L2 round trip is taken off the critical path by staging them TWO levels ahead with
-// cp.async into the pool's fields 1..3, which are dead on the way down (a ring of two level
-// buffers, 48 B per lane each); when the pool is too small for that ring (n_pool < 2 LANES) they
-// are loaded into registers one level ahead instead.
+// x_parent is in the lane's registers when the bus is its parent's heir (the lane handled the parent one
+// row earlier), else in field 0 of the bus's own pool slot (the parent put it there); x_k goes into the
+// slots of the children that are not the heir.  M and v come back from the global scratch (first
+// iteration: M from the image).  Their L2 round trip is taken off the critical path by staging them TWO
+// rows ahead with cp.async into the pool's fields 1..3, which are dead on the way down (a ring of two
+// row buffers, 48 B per lane each; the host sizes the pool for it: n_pool >= 2 LANES).
 template <int LANES>
 GFR_HD void newton_back_update(const NGrp<LANES>& g, const Layout& lay, const int* simg, const D2* f0,
                                double accel) {
-  const int nl = lay.nl, np = lay.n_pool, nb = lay.n;
-  const I4* topo = reinterpret_cast<const I4*>(simg + lay.o_topo);
-  const int* level_ptr = simg + lay.o_level_ptr;
-  const int* child_pool = simg + lay.o_child_pool;
-  const bool staged = 2 * LANES <= np;
-  D2* const ring = g.poolp + np + g.lane;              // this lane's entries of level buffer 0 (field f at + f * LANES); buffer 1 is 3 * LANES further
-  int nk = g.first(level_ptr[0]);
-  bool nv = nk < level_ptr[1];
-  D2 nm0, nm1, nvv;
-  nm0.x = nm0.y = nm1.x = nm1.y = nvv.x = nvv.y = 0.0;
-#define GFR_LOAD_MV(kk, a0, a1, av)                                        \
+  const int nrows = lay.nrows, np = lay.n_pool, P = lay.P;
+  const I4* sched = reinterpret_cast<const I4*>(simg + lay.o_sched);
+  const int* child_slot = simg + lay.o_child_slot;
+  D2* const ring = g.poolp + np + g.lane;              // this lane's entries of row buffer 0 (field f at + f * LANES); buffer 1 is 3 * LANES further
+  // idle positions are staged too (their scratch entries exist): no record is needed this early
+#define GFR_STAGE_MV(row_, dst)                                            \
   do {                                                                     \
-    if (f0) { a0 = f0[2 * nb + (kk)]; a1 = f0[3 * nb + (kk)]; }            \
-    else { a0 = g.mg[(kk)]; a1 = g.mg[nb + (kk)]; }                        \
-    av = g.mg[2 * nb + (kk)];                                              \
+    const int ps_ = (row_) * LANES + g.lane;                               \
+    if (!f0) { cp_async16((dst), g.mg + ps_); cp_async16((dst) + LANES, g.mg + P + ps_); } \
+    cp_async16((dst) + 2 * LANES, g.mg + 2 * P + ps_);                     \
   } while (0)
-#define GFR_STAGE_MV(kk, dst)                                              \
-  do {                                                                     \
-    if (!f0) { cp_async16((dst), g.mg + (kk)); cp_async16((dst) + LANES, g.mg + nb + (kk)); } \
-    cp_async16((dst) + 2 * LANES, g.mg + 2 * nb + (kk));                   \
-  } while (0)
-  if (staged) {
-    if (nv) GFR_STAGE_MV(nk, ring);
-    cp_async_commit();
-    if (nl > 1) {
-      const int k2 = g.first(level_ptr[1]);
-      if (k2 < level_ptr[2]) GFR_STAGE_MV(k2, ring + 3 * LANES);
-    }
-    cp_async_commit();
-  } else if (nv) {
-    GFR_LOAD_MV(nk, nm0, nm1, nvv);
-  }
-  for (int l = 0; l < nl; ++l) {
-    const int k1 = level_ptr[l + 1];
-    int k;
-    bool valid;
+  GFR_STAGE_MV(0, ring);
+  cp_async_commit();
+  if (nrows > 1) GFR_STAGE_MV(1, ring + 3 * LANES);
+  cp_async_commit();
+  D2 hx; hx.x = hx.y = 0.0;                            // the correction of the bus this lane handled in the previous row
+  for (int row = 0; row < nrows; ++row) {
+    const int p = row * LANES + g.lane;
+    const I4 t = sched[p];
+    cp_async_wait<1>();                               // the older of the two groups in flight: this row's
+    D2* const my = ring + (row & 1) * (3 * LANES);
     D2 m0, m1, v;
-    if (staged) {
-      k = g.first(level_ptr[l]);
-      valid = k < k1;
-      cp_async_wait<1>();                               // the older of the two groups in flight: this level's
-      D2* const my = ring + (l & 1) * (3 * LANES);
-      m0 = nm0; m1 = nm1;
-      if (valid) {
-        if (f0) { m0 = f0[2 * nb + k]; m1 = f0[3 * nb + k]; }
-        else { m0 = my[0]; m1 = my[LANES]; }
-      }
-      v = my[2 * LANES];
-      if (l + 2 < nl) {                                 // the buffer is free again: level l + 2 goes there
-        const int k2 = g.first(level_ptr[l + 2]);
-        if (k2 < level_ptr[l + 3]) GFR_STAGE_MV(k2, my);
-      }
-      cp_async_commit();
-    } else {
-      k = nk; valid = nv;
-      m0 = nm0; m1 = nm1; v = nvv;
-      if (l + 1 < nl) {
-        nk = g.first(k1);
-        nv = nk < level_ptr[l + 2];
-        if (nv) GFR_LOAD_MV(nk, nm0, nm1, nvv);
-      }
-    }
-    if (valid) {
-      for (;;) {
-        const I4 t = topo[k];
-        D2 x; x.x = x.y = 0.0;
-        if (k > 0) x = g.poolp[x_slot_of(t.w)];            // field 0 of its own slot, or of the parent's (see gfr_image.hpp)
-        v.x = fma(-m0.x, x.x, fma(-m0.y, x.y, v.x));
-        v.y = fma(-m1.x, x.x, fma(-m1.y, x.y, v.y));
-        {
-          int q = t.y;
-          if (t.w & FL_INHERIT) { g.poolp[pool_slot_of(t.w)] = v; ++q; }        // first child: same slot, no index load
-          if (!(t.w & FL_NO_SCATTER)) {
+    if (f0) { m0 = f0[2 * P + p]; m1 = f0[3 * P + p]; }
+    else { m0 = my[0]; m1 = my[LANES]; }
+    v = my[2 * LANES];
+    if (row + 2 < nrows) GFR_STAGE_MV(row + 2, my);    // the buffer is free again: row + 2 goes there
+    cp_async_commit();
+    if (t.z & FL_VALID) {
+      const int k = rec_bus(t);
+      D2 x = hx;
+      if (!(t.z & FL_P_REG)) x = g.poolp[pool_slot_of(t.z)];
+      v.x = fma(-m0.x, x.x, fma(-m0.y, x.y, v.x));
+      v.y = fma(-m1.x, x.x, fma(-m1.y, x.y, v.y));
+      {
+        const int q1 = t.y + rec_all_kids(t);
 #pragma unroll 1
-            for (; q < t.z; ++q) g.poolp[child_pool[q]] = v;
-          }
-        }
-        double sn, cs;
-        sincos_small(accel * v.x, &sn, &cs);
-        const double sc = fma(accel, v.y, 1.0);
-        const D2 e = g.ef(k);
-        D2 w;
-        w.x = sc * fma(e.x, cs, -e.y * sn);
-        w.y = sc * fma(e.x, sn, e.y * cs);
-        g.ef(k) = w;
-        k += LANES;
-        if (k >= k1) break;
-        GFR_LOAD_MV(k, m0, m1, v);                     // levels wider than the group: no prefetch
+        for (int q = q1 - rec_pool_kids(t); q < q1; ++q) g.poolp[child_slot[q]] = v;
       }
+      hx = v;
+      double sn, cs;
+      sincos_small(accel * v.x, &sn, &cs);
+      const double sc = fma(accel, v.y, 1.0);
+      const D2 e = g.ef(k);
+      D2 w;
+      w.x = sc * fma(e.x, cs, -e.y * sn);
+      w.y = sc * fma(e.x, sn, e.y * cs);
+      g.ef(k) = w;
     }
     g.sync();
   }
-  if (staged) cp_async_wait<0>();
-#undef GFR_LOAD_MV
+  cp_async_wait<0>();
 #undef GFR_STAGE_MV
 }
 
@@ -576,12 +580,11 @@ template <int LANES>
 GFR_HD void newton_solve(const NGrp<LANES>& g, const Layout& lay, const int* simg,
                          const double* dimg, double tol, int max_it, double accel,
                          SolveStat* out) {
-  const int n = lay.n, nl = lay.nl, np = lay.n_pool;
-  const I4* topo = reinterpret_cast<const I4*>(simg + lay.o_topo);
-  const int* level_ptr = simg + lay.o_level_ptr;
-  const int* child_pool = simg + lay.o_child_pool;   // pool slot of every child, indexed like child_idx
-  const D2* gb = reinterpret_cast<const D2*>(dimg + lay.o_gb);      // branch series g, b (0 for the root)
-  const D2* gbd = reinterpret_cast<const D2*>(dimg + lay.o_gbd);    // Re, Im of Y_kk
+  const int nrows = lay.nrows, np = lay.n_pool, P = lay.P;
+  const I4* sched = reinterpret_cast<const I4*>(simg + lay.o_sched);
+  const int* child_slot = simg + lay.o_child_slot;   // pool slot of every child, indexed like child_ent
+  const D2* gb = reinterpret_cast<const D2*>(dimg + lay.o_gb);      // branch series g, b by position (0 for the root)
+  const D2* gbd = reinterpret_cast<const D2*>(dimg + lay.o_gbd);    // Re, Im of Y_kk by position
   const D2* f0 = lay.o_f0 >= 0 ? reinterpret_cast<const D2*>(dimg + lay.o_f0) : nullptr;   // flat-start factors
 
   out->converged = 0;
@@ -594,17 +597,17 @@ GFR_HD void newton_solve(const NGrp<LANES>& g, const Layout& lay, const int* sim
     if (it == 0 && f0 != nullptr) {
       // ---- first iteration: every instance starts from the same flat profile, so its calculated
       //      injections, its Jacobian and the whole elimination of it are properties of the feeder.
-      //      The host factorised it once (image: D^-1, D^-1 U, J[p,k] and (P, Q) per bus); only the
+      //      The host factorised it once (image: D^-1, D^-1 U, J[p,k] and (P, Q) per position); only the
       //      right-hand side is instance data.
       mm = 0.0;
-      for (int k = g.lane; k < n; k += LANES) {
-        const int fl = topo[k].w;
-        const D2 pc = f0[5 * n + k];
-        double aP = fabs(g.pspec(k) - pc.x), aQ = fabs(pc.y);
+      for (int p = g.lane; p < P; p += LANES) {
+        const int fl = sched[p].z;
+        const D2 pc = f0[5 * P + p];
+        double aP = fabs(g.pspec(p) - pc.x), aQ = fabs(pc.y);
         if (!(fl & FL_THETA)) aP = 0.0;
         if (!(fl & FL_PQ)) aQ = 0.0;
         const double loc = (aQ > aP || aQ != aQ) ? aQ : aP;
-        mm = (loc > mm || loc != loc) ? loc : mm;
+        if (fl & FL_VALID) mm = (loc > mm || loc != loc) ? loc : mm;
       }
       mm = g.gmax_nan(mm);
       out->max_mismatch = mm;
@@ -613,32 +616,34 @@ GFR_HD void newton_solve(const NGrp<LANES>& g, const Layout& lay, const int* sim
         out->iterations = it + 1;
         break;
       }
-      for (int l = nl - 1; l >= 0; --l) {
-        const int k1 = level_ptr[l + 1];
-        for (int k = g.first(level_ptr[l]); k < k1; k += LANES) {
-          const I4 t = topo[k];
-          const D2 pc = f0[5 * n + k];
+      D2 hc; hc.x = hc.y = 0.0;                         // L v of the bus this lane eliminated in the previous row
+      for (int row = nrows - 1; row >= 0; --row) {
+        const int p = row * LANES + g.lane;
+        const I4 t = sched[p];
+        if (t.z & FL_VALID) {
+          const D2 pc = f0[5 * P + p];
+          const double ps = g.pspec(p);
           D2 sc; sc.x = sc.y = 0.0;
+          if (t.z & FL_C_REG) sc = hc;
           {
-            int q = t.y;
-            if (t.w & FL_INHERIT) { sc = g.poolp[2 * np + pool_slot_of(t.w)]; ++q; }
+            const int q1 = t.y + rec_all_kids(t);
 #pragma unroll 1
-            for (; q < t.z; ++q) {
-              const D2 cc = g.poolp[2 * np + child_pool[q]];
+            for (int q = q1 - rec_pool_kids(t); q < q1; ++q) {
+              const D2 cc = g.poolp[2 * np + child_slot[q]];
               sc.x += cc.x; sc.y += cc.y;
             }
           }
-          double r0 = g.pspec(k) - pc.x - sc.x, r1 = 0.0 - pc.y - sc.y;
-          if (!(t.w & FL_THETA)) r0 = 0.0;
-          if (!(t.w & FL_PQ)) r1 = 0.0;
-          const D2 i0 = f0[k], i1 = f0[n + k], lp = f0[4 * n + k];          // D^-1 rows, (ll, gl)
-          D2 v, cc;
+          double r0 = ps - pc.x - sc.x, r1 = 0.0 - pc.y - sc.y;
+          if (!(t.z & FL_THETA)) r0 = 0.0;
+          if (!(t.z & FL_PQ)) r1 = 0.0;
+          const D2 i0 = f0[p], i1 = f0[P + p], lp = f0[4 * P + p];          // D^-1 rows, (ll, gl)
+          D2 v;
           v.x = fma(i0.x, r0, i0.y * r1);
           v.y = fma(i1.x, r0, i1.y * r1);
-          cc.x = fma(lp.x, v.x, lp.y * v.y);
-          cc.y = fma(-lp.y, v.x, lp.x * v.y);
-          g.mg[2 * n + k] = v;
-          g.poolp[2 * np + pool_slot_of(t.w)] = cc;
+          hc.x = fma(lp.x, v.x, lp.y * v.y);
+          hc.y = fma(-lp.y, v.x, lp.x * v.y);
+          g.mg[2 * P + p] = v;
+          if (!(t.z & FL_P_REG)) g.poolp[2 * np + pool_slot_of(t.z)] = hc;
         }
         g.sync();
       }
@@ -662,47 +667,46 @@ GFR_HD void newton_solve(const NGrp<LANES>& g, const Layout& lay, const int* sim
       //      then the solve of :187)
       mm = 0.0;
       int singular = 0;
-      for (int l = nl - 1; l >= 0; --l) {
-        const int k1 = level_ptr[l + 1];
-        for (int k = g.first(level_ptr[l]); k < k1; k += LANES) {
-          const I4 t = topo[k];
-          const D2 vk = g.ef(k);
-          const D2 yd = gbd[k];
+      D2 h0, h1, hc, hf;                               // what the bus this lane eliminated in the previous row hands up
+      h0.x = h0.y = h1.x = h1.y = hc.x = hc.y = hf.x = hf.y = 0.0;
+      for (int row = nrows - 1; row >= 0; --row) {
+        const int p = row * LANES + g.lane;
+        const I4 t = sched[p];
+        if (t.z & FL_VALID) {
+          const D2 vk = g.ef(rec_bus(t));
+          const D2 yd = gbd[p];
+          const double ps = g.pspec(p);
           const double v2 = fma(vk.x, vk.x, vk.y * vk.y);
-          const BranchT bt = branch_terms(vk, g.ef(t.x), gb[k]);
-          D2 s0, s1, sc, sf;                               // children's contributions: plain sums
+          const BranchT bt = branch_terms(vk, g.ef(rec_parent(t)), gb[p]);
+          D2 s0, s1, sc, sf;                               // children's contributions: plain sums, the heir first
           s0.x = s0.y = s1.x = s1.y = sc.x = sc.y = sf.x = sf.y = 0.0;
-          D2* const own = g.poolp + pool_slot_of(t.w);
+          if (t.z & FL_C_REG) { s0 = h0; s1 = h1; sc = hc; sf = hf; }
           {
-            int q = t.y;
-            if (t.w & FL_INHERIT) {                        // first child: same slot, no index load
-              s0 = own[0]; s1 = own[np]; sc = own[2 * np]; sf = own[3 * np];
-              ++q;
-            }
+            const int q1 = t.y + rec_all_kids(t);
 #pragma unroll 1
-            for (; q < t.z; ++q) {
-              const D2* e = g.poolp + child_pool[q];
+            for (int q = q1 - rec_pool_kids(t); q < q1; ++q) {
+              const D2* e = g.poolp + child_slot[q];
               const D2 c0 = e[0], c1 = e[np], cc = e[2 * np], fl = e[3 * np];
               s0.x += c0.x; s0.y += c0.y; s1.x += c1.x; s1.y += c1.y; sc.x += cc.x; sc.y += cc.y;
               sf.x += fl.x; sf.y += fl.y;
             }
           }
-          const double P = fma(yd.x, v2, bt.ga) + sf.x, Q = fma(-yd.y, v2, bt.al) + sf.y;
+          const double Pk = fma(yd.x, v2, bt.ga) + sf.x, Q = fma(-yd.y, v2, bt.al) + sf.y;
           D2 d0, d1, r;
-          r.x = g.pspec(k) - P;
+          r.x = ps - Pk;
           r.y = 0.0 - Q;
           double aP = fabs(r.x), aQ = fabs(Q);
           r.x -= sc.x; r.y -= sc.y;
           d0.x = fma(-yd.y, v2, -Q) - s0.x;             // -Q - B v2
-          d0.y = fma(yd.x, v2, P) - s0.y;               //  P + G v2
-          d1.x = fma(-yd.x, v2, P) - s1.x;              //  P - G v2
+          d0.y = fma(yd.x, v2, Pk) - s0.y;              //  P + G v2
+          d1.x = fma(-yd.x, v2, Pk) - s1.x;             //  P - G v2
           d1.y = fma(-yd.y, v2, Q) - s1.y;              //  Q - B v2
           double u00 = bt.al, u01 = bt.ga, u10 = -bt.ga, u11 = bt.al;
-          if ((t.w & (FL_PQ | FL_THETA)) != (FL_PQ | FL_THETA)) {
+          if ((t.z & (FL_PQ | FL_THETA)) != (FL_PQ | FL_THETA)) {
             // a bus without the angle (slack) or magnitude (slack, PV) unknown: no equation, identity
             // row, no coupling
-            if (!(t.w & FL_THETA)) { aP = 0.0; d0.x = 1.0; d0.y = 0.0; r.x = 0.0; u00 = 0.0; u01 = 0.0; }
-            if (!(t.w & FL_PQ)) { aQ = 0.0; d1.x = 0.0; d1.y = 1.0; r.y = 0.0; u10 = 0.0; u11 = 0.0; }
+            if (!(t.z & FL_THETA)) { aP = 0.0; d0.x = 1.0; d0.y = 0.0; r.x = 0.0; u00 = 0.0; u01 = 0.0; }
+            if (!(t.z & FL_PQ)) { aQ = 0.0; d1.x = 0.0; d1.y = 1.0; r.y = 0.0; u10 = 0.0; u11 = 0.0; }
           }
           const double loc = (aQ > aP || aQ != aQ) ? aQ : aP;
           mm = (loc > mm || loc != loc) ? loc : mm;
@@ -717,18 +721,21 @@ GFR_HD void newton_solve(const NGrp<LANES>& g, const Layout& lay, const int* sim
           m1.y = fma(i10, u01, i11 * u11);
           v.x = fma(i00, r.x, i01 * r.y);
           v.y = fma(i10, r.x, i11 * r.y);
-          g.mg[k] = m0;                                  // needed again in the back-substitution only
-          g.mg[n + k] = m1;
-          g.mg[2 * n + k] = v;
-          D2 c0, c1, cc, fl;                             // handed to the parent: L M, L v, (gl, ll)
-          c0.x = fma(bt.ll, m0.x, bt.gl * m1.x);
-          c0.y = fma(bt.ll, m0.y, bt.gl * m1.y);
-          c1.x = fma(-bt.gl, m0.x, bt.ll * m1.x);
-          c1.y = fma(-bt.gl, m0.y, bt.ll * m1.y);
-          cc.x = fma(bt.ll, v.x, bt.gl * v.y);
-          cc.y = fma(-bt.gl, v.x, bt.ll * v.y);
-          fl.x = bt.gl; fl.y = bt.ll;
-          own[0] = c0; own[np] = c1; own[2 * np] = cc; own[3 * np] = fl;
+          g.mg[p] = m0;                                  // needed again in the back-substitution only
+          g.mg[P + p] = m1;
+          g.mg[2 * P + p] = v;
+          // handed to the parent: L M, L v, (gl, ll)
+          h0.x = fma(bt.ll, m0.x, bt.gl * m1.x);
+          h0.y = fma(bt.ll, m0.y, bt.gl * m1.y);
+          h1.x = fma(-bt.gl, m0.x, bt.ll * m1.x);
+          h1.y = fma(-bt.gl, m0.y, bt.ll * m1.y);
+          hc.x = fma(bt.ll, v.x, bt.gl * v.y);
+          hc.y = fma(-bt.gl, v.x, bt.ll * v.y);
+          hf.x = bt.gl; hf.y = bt.ll;
+          if (!(t.z & FL_P_REG)) {
+            D2* const own = g.poolp + pool_slot_of(t.z);
+            own[0] = h0; own[np] = h1; own[2 * np] = hc; own[3 * np] = hf;
+          }
         }
         g.sync();
       }
@@ -870,17 +877,17 @@ GFR_HD void sweep_solve(const SGrp<LANES>& g, const Layout& lay, const int* simg
   }
 }
 
-// From -> to flow of the branch above bus k (power_flow.py:329-358): P (pu), |S| (pu), series loss (pu)
+// From -> to flow of the branch above the bus at position p (power_flow.py:329-358): P (pu), |S| (pu), series loss (pu)
 template <class G>
 GFR_HD void branch_flow(const G& g, const Layout& lay, const int* simg, const double* dimg,
-                        int k, double* p_ft, double* s_abs, double* loss) {
-  const I4 t = reinterpret_cast<const I4*>(simg + lay.o_topo)[k];
-  const D2 vk = g.ef(k), vp = g.ef(t.x);
-  const D2 y = reinterpret_cast<const D2*>(dimg + lay.o_gb)[k];
+                        int p, double* p_ft, double* s_abs, double* loss) {
+  const I4 t = reinterpret_cast<const I4*>(simg + lay.o_sched)[p];
+  const D2 vk = g.ef(rec_bus(t)), vp = g.ef(rec_parent(t));
+  const D2 y = reinterpret_cast<const D2*>(dimg + lay.o_gb)[p];
   const double de = vp.x - vk.x, df = vp.y - vk.y;                 // V_parent - V_k
   const double ir = y.x * de - y.y * df, ii = y.x * df + y.y * de;   // current parent -> k
   double P, Q;
-  if (t.w & FL_FROM_IS_PARENT) {
+  if (t.z & FL_FROM_IS_PARENT) {
     P = vp.x * ir + vp.y * ii; Q = vp.y * ir - vp.x * ii;    // V_p conj(I)
   } else {
     P = -(vk.x * ir + vk.y * ii); Q = -(vk.y * ir - vk.x * ii);    // V_k conj(-I)
@@ -914,8 +921,10 @@ GFR_HD void solve_instance(const typename GroupOf<LANES, SOLVER>::type& g, const
                            const double* p_inj, const SolOut& o) {
   const int n = lay.n, m = lay.m;
   const int* rank = simg + lay.o_rank;
+  const int* rankp = simg + lay.o_rankp;
   const double* pin = p_inj + env * n;
-  for (int i = g.lane; i < n; i += LANES) g.pspec(rank[i]) = pin[i];
+  for (int i = g.lane; i < n; i += LANES) g.pspec(rankp[i]) = pin[i];
+  g.sync();          // a position's injection is read by the lane that owns the position, not the one that owns ref bus i
   flat_start(g, lay, simg, dimg);
   SolveStat st;
   run_solver(g, lay, simg, dimg, cfg, &st);
@@ -929,11 +938,11 @@ GFR_HD void solve_instance(const typename GroupOf<LANES, SOLVER>::type& g, const
   double loss = 0.0;
   const int* bol = simg + lay.o_branch_of_line;
   for (int li = g.lane; li < m; li += LANES) {
-    int k = bol[li];
+    int pb = bol[li];
     double P, S, ls;
-    branch_flow(g, lay, simg, dimg, k, &P, &S, &ls);
+    branch_flow(g, lay, simg, dimg, pb, &P, &S, &ls);
     loss += ls;
-    double rating = dimg[lay.o_rating + k];
+    double rating = dimg[lay.o_rating + pb];
     if (o.line_flows) o.line_flows[env * m + li] = P;
     if (o.line_loadings) o.line_loadings[env * m + li] = rating > 0.0 ? S * lay.s_base / rating : 0.0;
   }
@@ -1170,7 +1179,7 @@ GFR_HD void step_instance(const typename GroupOf<LANES, SOLVER>::type& g, const 
   {
     const int* inj_ptr = simg + lay.o_inj_ptr;
     const int* inj_idx = simg + lay.o_inj_idx;
-    for (int k = g.lane; k < n; k += LANES) {
+    for (int k = g.lane; k < lay.P; k += LANES) {        // by schedule position: lane k % LANES is the one that reads it back
       double ld = 0.0, gn = 0.0;
       for (int q = inj_ptr[k]; q < inj_ptr[k + 1]; ++q) {
         int j = inj_idx[q];
@@ -1213,12 +1222,12 @@ GFR_HD void step_instance(const typename GroupOf<LANES, SOLVER>::type& g, const 
   {
     const int* bol = simg + lay.o_branch_of_line;
     for (int li = g.lane; li < m; li += LANES) {
-      int k = bol[li];
+      int pb = bol[li];
       double P, S, ls;
-      branch_flow(g, lay, simg, dimg, k, &P, &S, &ls);
+      branch_flow(g, lay, simg, dimg, pb, &P, &S, &ls);
       loss_pu += ls;
       double pw = P * lay.s_base;
-      double rating = dimg[lay.o_rating + k];
+      double rating = dimg[lay.o_rating + pb];
       double loading = rating > 0.0 ? fabs(pw) * rcp_fast(rating) : 0.0;     // Line.update_state, base.py:261-264 (|P| / rating)
       st_stream(ob + o_line + 2 * li, pw);
       st_stream(ob + o_line + 2 * li + 1, loading);

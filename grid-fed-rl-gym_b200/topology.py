@@ -170,8 +170,10 @@ class FeederSoA:
     level_ptr: np.ndarray              # int32[n_levels+1]  level l = [ptr[l], ptr[l+1])
     child_ptr: np.ndarray              # int32[n+1] children of k = child_idx[child_ptr[k] : child_ptr[k+1]]
     child_idx: np.ndarray              # int32[n-1] level indices of the children, parent by parent
-    pool_slot: np.ndarray              # int32[n]  where bus k parks its Schur contribution until its parent is eliminated
-    n_pool: int                        # slots needed (max contributions alive at once)
+    pool_slot: Optional[np.ndarray]    # int32[n]  where bus k parks its Schur contribution until its parent is eliminated;
+                                       #           None (default): the native library plans the slots itself
+    n_pool: int                        # slots to provide at least (0: as few as the plan needs)
+    lane_of: Optional[np.ndarray]      # int32[n]  lane (< width) that eliminates bus k; None: position inside the level
     bus_type: np.ndarray               # int32[n]  BUS_*
     vm_set: np.ndarray                 # f64[n]   slack / pv magnitude (bus.voltage_magnitude)
     g: np.ndarray                      # f64[n]   series conductance of the branch parent[k]-k (k>=1)
@@ -315,6 +317,87 @@ def _schedule(n: int, root: int, adj, width: Optional[int], alap: bool = True):
     return order, parent_ref, level_of
 
 
+def _schedule_paths(n: int, root: int, adj, width: int):
+    """Order the buses for leaf -> root elimination on ``width`` lanes so that a lane FOLLOWS A PATH:
+    list scheduling in elimination time where a lane whose last bus's parent has become ready takes
+    that parent next (then Hu's rule, deepest first, for the lanes left).  A bus that is eliminated
+    right after one of its children on the same lane gets that child's Schur terms in registers
+    instead of through shared memory (and hands its correction back the same way on the way down);
+    every non-leaf bus can have one such child at most, and this rule reaches that bound on the
+    IEEE feeders (IEEE-123 on 8 lanes: 78 of 122 branches, in the same 17 steps as Hu's schedule).
+
+    Returns (order, parent_ref, level_of, lane_of): ``order`` lists ref bus indices level by level,
+    level 0 = {root}; a level is one elimination step (reversed), at most ``width`` buses."""
+    parent_ref = {root: (-1, -1)}
+    depth = {root: 0}
+    bfs = [root]
+    for u in bfs:
+        for v, k in adj[u]:
+            if v not in parent_ref:
+                parent_ref[v] = (u, k)
+                depth[v] = depth[u] + 1
+                bfs.append(v)
+    if len(bfs) != n:
+        raise TopologyError("feeder is not connected (run repair_topology first)")
+    pending = [0] * n
+    for v in bfs[1:]:
+        pending[parent_ref[v][0]] += 1
+    ready = set(v for v in bfs if pending[v] == 0)
+    last = [None] * width                 # the bus each lane eliminated in the previous step
+    steps = []                            # per step: {bus: lane}
+    while ready:
+        cont = {}
+        for lane in range(width):
+            b = last[lane]
+            if b is not None:
+                u = parent_ref[b][0]
+                if u >= 0 and u in ready and u not in cont:
+                    cont[u] = lane
+        take = sorted(ready, key=lambda v: (0 if v in cont else 1, -depth[v], v))[:width]
+        assign = {v: cont[v] for v in take if v in cont}
+        free = [lane for lane in range(width) if lane not in assign.values()]
+        for v in take:
+            if v not in assign:
+                assign[v] = free.pop(0)
+        last = [None] * width
+        for v, lane in assign.items():
+            last[lane] = v
+            ready.discard(v)
+        for v in assign:
+            u = parent_ref[v][0]
+            if u >= 0:
+                pending[u] -= 1
+                if pending[u] == 0:
+                    ready.add(u)
+        steps.append(assign)
+    steps.reverse()                       # level 0 = last eliminated = root
+    assert list(steps[0]) == [root]
+    # As-late-as-possible pass for the leaves that hand over through shared memory: a leaf eliminated long
+    # before its parent parks its contribution in a pool slot all that time; moved to a free lane of a row
+    # nearer the parent's, fewer slots are alive at once (IEEE-123 on 8 lanes: 17 -> fewer slots).
+    row_of = {v: l for l, assign in enumerate(steps) for v in assign}
+    has_kids = set(parent_ref[v][0] for v in bfs[1:])
+    for v in sorted((v for v in bfs[1:] if v not in has_kids), key=lambda v: -(row_of[v] - row_of[parent_ref[v][0]])):
+        u = parent_ref[v][0]
+        cur = row_of[v]
+        if cur == row_of[u] + 1 and steps[cur][v] == steps[row_of[u]].get(u):
+            continue                      # the heir of its parent: nothing parked
+        for r in range(row_of[u] + 1, cur):
+            if len(steps[r]) < width:
+                lane = min(set(range(width)) - set(steps[r].values()))
+                del steps[cur][v]
+                steps[r][v] = lane
+                row_of[v] = r
+                break
+    order, level_of, lane_of = [], {}, {}
+    for l, assign in enumerate(steps):
+        for v in sorted(assign, key=lambda v: assign[v]):
+            level_of[v] = l
+            lane_of[v] = assign[v]
+            order.append(v)
+    return order, parent_ref, level_of, lane_of
+
+
 def plan_pool(parent: np.ndarray, level_ptr: np.ndarray, contiguous: bool = False,
               width: Optional[int] = None, child_ptr: Optional[np.ndarray] = None,
               child_idx: Optional[np.ndarray] = None):
@@ -444,7 +527,8 @@ def tree_center(n: int, adj, fallback: int) -> int:
 
 def compile_feeder(feeder, renewable_sources: Optional[Sequence[str]] = None,
                    with_components: bool = True, root: str = "slack",
-                   width: Optional[int] = None, pool_contiguous: bool = False) -> FeederSoA:
+                   width: Optional[int] = None, pool_contiguous: bool = False,
+                   paths: bool = False, pool_plan: Optional[str] = None) -> FeederSoA:
     """Compile a *radial, connected* feeder (run ``repair_topology`` first if it is not).
 
     ``renewable_sources`` has the reference meaning (grid_env.py:167,273,282): a
@@ -456,7 +540,11 @@ def compile_feeder(feeder, renewable_sources: Optional[Sequence[str]] = None,
     ``root`` / ``width`` shape the device-side traversal only (never the bus / line numbering of
     the results): ``root="center"`` roots the elimination tree at the tree's center instead of
     the slack bus (Newton only; the sweep needs the slack at the root), ``width`` caps the buses
-    per level at the number of lanes that will cooperate on one instance.
+    per level at the number of lanes that will cooperate on one instance.  ``paths`` (needs a width)
+    lets lanes follow paths of the tree (``_schedule_paths``: register hand-off between a bus and the
+    child eliminated just before it on the same lane - what the Newton kernels want).  ``pool_plan``:
+    None = the native library places the shared-memory hand-off slots itself; "python" / "contiguous"
+    = this module's ``plan_pool`` (kept for experiments and tests).
     """
     buses, lines = list(feeder.buses), list(feeder.lines)
     n, m = len(buses), len(lines)
@@ -493,8 +581,15 @@ def compile_feeder(feeder, renewable_sources: Optional[Sequence[str]] = None,
     if width is not None and int(width) < 1:
         raise TopologyError("width must be >= 1")
     root_ref = slack if root == "slack" else tree_center(n, adj, slack)
+    if pool_contiguous:
+        pool_plan = "contiguous"
+
     def layout(alap: bool):
-        order, parent_ref, level_of = _schedule(n, root_ref, adj, None if width is None else int(width), alap)
+        lane_map = None
+        if paths and width is not None:
+            order, parent_ref, level_of, lane_map = _schedule_paths(n, root_ref, adj, int(width))
+        else:
+            order, parent_ref, level_of = _schedule(n, root_ref, adj, None if width is None else int(width), alap)
         rank = np.empty(n, dtype=np.int32)
         rank[np.array(order)] = np.arange(n, dtype=np.int32)
 
@@ -536,18 +631,23 @@ def compile_feeder(feeder, renewable_sources: Optional[Sequence[str]] = None,
             lead = next((c for c in kids_k if int(levels[c]) == deepest and child_ptr[c + 1] == child_ptr[c]), None)
             if lead is not None:
                 child_idx[q0:q1] = [lead] + [c for c in kids_k if c != lead]
-        pool_slot, n_pool = plan_pool(parent, level_ptr, contiguous=pool_contiguous, width=width,
-                                      child_ptr=child_ptr, child_idx=child_idx)
-        return dict(order=order, rank=rank, parent=parent, line_of=line_of, from_is_parent=from_is_parent,
+        if pool_plan is None:
+            pool_slot, n_pool = None, 0
+        else:
+            pool_slot, n_pool = plan_pool(parent, level_ptr, contiguous=pool_plan == "contiguous", width=width,
+                                          child_ptr=child_ptr, child_idx=child_idx)
+        lane_arr = None if lane_map is None else np.array([lane_map[v] for v in order], dtype=np.int32)
+        return dict(lane_of=lane_arr, order=order, rank=rank, parent=parent, line_of=line_of, from_is_parent=from_is_parent,
                     g=g, b=b, r=r, x=x, rating=rating, levels=levels, n_levels=n_levels, level_ptr=level_ptr,
                     child_ptr=child_ptr, child_idx=child_idx, pool_slot=pool_slot, n_pool=n_pool)
 
     # two valid schedules of the same length: keep the one that parks fewer contributions at once
-    lay = min((layout(True), layout(False)), key=lambda d: d["n_pool"])
+    lay = layout(True) if (paths and width is not None) or pool_plan is None else \
+        min((layout(True), layout(False)), key=lambda d: d["n_pool"])
     order, rank, parent, line_of, from_is_parent = (lay[k] for k in ("order", "rank", "parent", "line_of", "from_is_parent"))
     g, b, r, x, rating = (lay[k] for k in ("g", "b", "r", "x", "rating"))
     level_ptr, child_ptr, child_idx, pool_slot, n_pool = (lay[k] for k in ("level_ptr", "child_ptr", "child_idx", "pool_slot", "n_pool"))
-    if width is not None and 1 < int(width) <= 32 and os.environ.get("GFR_POOL_PAD", "1") == "1":
+    if pool_plan is not None and width is not None and 1 < int(width) <= 32 and os.environ.get("GFR_POOL_PAD", "1") == "1":
         # the Newton back-substitution stages its operands two levels ahead in the pool's idle fields,
         # which takes a pool of at least 2 x lanes slots; small feeders have shared memory to spare
         n_pool = min(max(n_pool, 2 * int(width)), max(n, n_pool))
@@ -561,7 +661,8 @@ def compile_feeder(feeder, renewable_sources: Optional[Sequence[str]] = None,
         s_base=float(feeder.parameters.base_power) * 1e6,
         bus_ids=[b_.id for b_ in buses], line_ids=[l_.id for l_ in lines],
         order=np.array(order, dtype=np.int32), rank=rank, parent=parent, level_ptr=level_ptr,
-        child_ptr=child_ptr, child_idx=child_idx, pool_slot=pool_slot, n_pool=n_pool, bus_type=bus_type, vm_set=vm_set, g=g, b=b,
+        child_ptr=child_ptr, child_idx=child_idx, pool_slot=pool_slot, n_pool=n_pool, lane_of=lay["lane_of"],
+        bus_type=bus_type, vm_set=vm_set, g=g, b=b,
         gdiag=ydiag.real[order].copy(), bdiag=ydiag.imag[order].copy(), r=r, x=x,
         line_of=line_of, from_is_parent=from_is_parent, rating=rating)
 
@@ -638,8 +739,9 @@ def compile_for_solver(feeder, solver: str = "newton", lanes: int = 0,
                                    with_components=False).n_levels
         lanes = auto_lanes(len(feeder.buses), solver, depth)
     lanes = int(lanes)
+    newton = solver != "sweep"
     kw = dict(renewable_sources=renewable_sources, with_components=with_components,
-              width=lanes if lanes > 1 else None)
+              width=lanes if (lanes > 1 or newton) else None, paths=newton)
     soa = compile_feeder(feeder, root="center", **kw)
     if solver == "sweep":
         # the sweep pays one extra bus-parallel pass per iteration when the slack is not the root:

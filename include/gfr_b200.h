@@ -60,8 +60,13 @@ typedef struct {
   const int32_t* level_ptr;         /* [n_levels+1] */
   const int32_t* child_ptr;         /* [n+1] children of k are child_idx[child_ptr[k] .. child_ptr[k+1]) */
   const int32_t* child_idx;         /* [n-1] level indices of the children, parent by parent */
-  const int32_t* pool_slot;         /* [n]  Newton: slot (< n_pool) where bus k parks its Schur contribution from
-                                            its own elimination until its parent's; NULL = one slot per bus */
+  const int32_t* pool_slot;         /* [n]  Newton, optional: slot (< n_pool) where bus k parks its Schur contribution from
+                                            its own elimination until its parent's (checked; buses whose hand-off stays in
+                                            registers ignore theirs).  NULL = the library plans the slots; n_pool is then
+                                            the least number of slots to provide (0 = as few as needed) */
+  const int32_t* lane_of;           /* [n]  Newton, optional: the lane (< lanes_hint) that eliminates bus k.  A bus
+                                            eliminated right after one of its children on the same lane takes that
+                                            child's contribution from registers.  NULL = position inside the level */
   const int32_t* bus_type;          /* [n]  GFR_BUS_* */
   const double* vm_set;             /* [n]  slack / pv voltage magnitude */
   const double* g;                  /* [n]  series conductance of branch (parent[k], k), k >= 1 */

@@ -74,3 +74,41 @@ def test_emu_philox_matches_oracle():
         a = emu.emu_noise(seeds, draws, n_slots)
         b = port.philox_noise(seeds, draws, n_slots)
         assert np.max(np.abs(a - b)) < 1e-13
+
+
+@pytest.mark.parametrize("lanes", [1, 2, 4, 8, 16])
+@pytest.mark.parametrize("name", ["trace_fixture3_s0", "trace_ieee13_s0", "trace_ieee34_s1", "trace_ieee123_s0"])
+def test_emu_newton_trace_on_every_lane_count(name, lanes):
+    """The path schedules (register hand-off along a lane, pool slots between lanes) on 1 - 16 emulated lanes."""
+    g = load_golden(name)
+
+    class _One(_factory("newton")):
+        def __init__(self, feeder, kw):
+            kw = dict(kw)
+            tol = kw.pop("tolerance")
+            self.env = emu.EmuEnv(feeder, 1, solver="newton", tolerance=tol, lanes=lanes, **kw)
+            assert self.env.emu_lanes == lanes
+    exact = replay_trace(_One, g, ctx=f"{name}/emu{lanes}")
+    assert exact >= 0.9 * g["obs"].shape[0]
+
+
+def test_schedule_hands_over_in_registers():
+    """IEEE-123 on 8 lanes: 17 rows (Hu's bound for 123 buses of depth 13), every non-leaf bus takes one
+    child's contribution in registers (78 of 122 branches), the rest fit a pool no larger than the staging
+    ring asks for; a schedule cut for another lane count is re-cut by the library and still solves."""
+    import grid_fed_rl_b200 as m
+    f = m.repair_topology(m.IEEE123Bus(seed=0))
+    e = emu.EmuEnv(f, 1, solver="newton", lanes=8, renewable_sources=["solar", "wind"])
+    assert e.schedule["rows"] == 17 and e.schedule["positions"] == 136
+    assert e.schedule["register_edges"] == 78
+    assert e.schedule["pool_slots"] <= 18
+    leaves = 123 - len({int(p) for p in e.soa.parent[1:]})
+    assert e.schedule["register_edges"] == 122 - (leaves - 1)          # the bound: one heir per non-leaf bus
+    e1 = emu.EmuEnv(f, 1, solver="newton", lanes=1, renewable_sources=["solar", "wind"])
+    assert e1.schedule["rows"] == 123 and e1.schedule["register_edges"] == 78
+    # compiled for 8 lanes, run on 4: rows are re-cut, results stay the same
+    g = load_golden("solve_ieee123")
+    a = emu.emu_solve(f, g["p_spec"], "newton", 1e-6, 50, lanes=8)
+    b = emu.emu_solve(f, g["p_spec"], "newton", 1e-6, 50, lanes=8, emu_lanes=4)
+    assert np.array_equal(a["iterations"], b["iterations"])
+    assert np.max(np.abs(a["bus_voltages"] - b["bus_voltages"])) < 1e-12
