@@ -16,7 +16,8 @@ import numpy as np
 from .topology import FeederSoA
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libgfr_b200.so")
+# GFR_B200_LIB: a tuning aid (tools/: kernels built with other compile-time settings under build_variants/)
+LIB_PATH = os.environ.get("GFR_B200_LIB") or os.path.join(HERE, "libgfr_b200.so")
 
 GFR_OK, GFR_E_ARG, GFR_E_CUDA, GFR_E_LIMIT = 0, -1, -2, -3
 SOLVER_SWEEP, SOLVER_NEWTON = 0, 1
@@ -32,7 +33,7 @@ class FeederDesc(C.Structure):
         ("n_bat", C.c_int32), ("n_pool", C.c_int32), ("lanes_hint", C.c_int32), ("reserved", C.c_int32),
         ("s_base", C.c_double),
         ("order", _i32p), ("parent", _i32p), ("level_ptr", _i32p), ("child_ptr", _i32p),
-        ("child_idx", _i32p), ("pool_slot", _i32p), ("lane_of", _i32p),
+        ("child_idx", _i32p), ("lane_of", _i32p),
         ("bus_type", _i32p), ("vm_set", _f64p), ("g", _f64p), ("b", _f64p), ("gdiag", _f64p),
         ("bdiag", _f64p), ("r", _f64p), ("x", _f64p), ("line_of", _i32p), ("from_is_parent", _i32p),
         ("rating", _f64p), ("load_bus", _i32p), ("load_base", _f64p), ("load_p", _f64p),
@@ -195,9 +196,8 @@ def make_feeder_desc(soa: FeederSoA):
     for name in ("order", "parent", "level_ptr", "child_ptr", "child_idx", "bus_type", "line_of", "from_is_parent",
                  "load_bus", "gen_type", "gen_bus", "bat_bus"):
         setattr(d, name, i32(name))
-    for name in ("pool_slot", "lane_of"):                # optional: NULL = the library decides
-        if getattr(soa, name, None) is not None:
-            setattr(d, name, i32(name))
+    if getattr(soa, "lane_of", None) is not None:        # optional: NULL = position inside the level
+        d.lane_of = i32("lane_of")
     for name in ("vm_set", "g", "b", "gdiag", "bdiag", "r", "x", "rating", "load_base", "load_p",
                  "load_q", "gen_cap", "gen_p0", "gen_p1", "gen_p2", "bat_cap", "bat_rating",
                  "bat_eff", "bat_soc0", "load_profile"):

@@ -36,7 +36,10 @@ constexpr int kSmemHeader = 16;   // the mbarrier, keeps the image 16-byte align
 #ifndef GFR_MAX_THREADS_16
 #define GFR_MAX_THREADS_16 512
 #endif
-constexpr int kMaxThreads = 512;
+#ifndef GFR_MAX_THREADS
+#define GFR_MAX_THREADS 512
+#endif
+constexpr int kMaxThreads = GFR_MAX_THREADS;
 #ifndef GFR_WIDE_LANES
 #define GFR_WIDE_LANES 0      // groups up to this many lanes are compiled for 768 threads per CTA (80 registers): measured, no gain (IEEE-34 237M -> 230M)
 #endif

@@ -44,8 +44,8 @@ enum { GEN_SOLAR = 0, GEN_WIND = 1 };
 //            children go through a pool slot (planned by the host: held from the child's row up to the
 //            parent's; field 0 carries the correction on the way down).  D^-1 U and D^-1 r, only needed
 //            again in the back-substitution, and the specified injections live in a per-slot scratch
-//            in global memory, by position, that stays L2 resident; the back-substitution stages them
-//            two rows ahead with cp.async into the pool's fields 1..3 (dead on the way down).
+//            in global memory, by position, that stays L2 resident; the back-substitution loads them
+//            two rows ahead into registers.
 //   sweep:   40 B per bus in three arrays: e + jf | Jr + jJi (branch current) | P
 // Before the solve the same space (Newton: ef + pool; sweep: the J fields) carries the load /
 // generator / battery powers into the per-position injection sums.
@@ -58,7 +58,9 @@ enum { FL_PQ = 1, FL_FROM_IS_PARENT = 2, FL_FIXED_VM = 4, FL_THETA = 8,     // P
        FL_C_REG = 32,                                                     // Newton: the bus eliminated just before on this lane is a child (the "heir"): its Schur terms are in registers
        FL_P_REG = 64,                                                     // Newton: this bus is its parent's heir: nothing goes through the pool, either way
        FL_VALID = 128,                                                    // the schedule position holds a bus
-       FL_POOL_SHIFT = 8, FL_POOL_MASK = 0xFFF };                         // bits 8..19: the bus's pool slot
+       FL_POOL_SHIFT = 8, FL_POOL_MASK = 0xFFF,                           // bits 8..19: the bus's pool slot
+       FL_XSLOT_SHIFT = 20,                                               // bits 20..31: the slot its parent's correction arrives in
+       REC_LIST_MASK = 0xFFFFF, REC_KIDX_SHIFT = 20 };                    // word y: child list begin | slot this bus puts ITS correction in << 20
 // record (persistent per-instance state) slots, in doubles
 enum { R_TIME = 0, R_FREQ, R_WIND, R_TEMP, R_CLOUD, R_TOTAL_LOSSES, R_EPISODE_REWARD, R_SEED,
        R_DRAWS, R_COUNTS, R_BAT };   // soc[Bt] then bpow[Bt] from R_BAT on
@@ -67,11 +69,16 @@ struct alignas(16) D2 { double x, y; };
 struct alignas(16) I4 { int x, y, z, w; };   // per-bus topology: parent, child list begin, end, flags
 GFR_HD int pool_slot_of(int w) { return (w >> FL_POOL_SHIFT) & FL_POOL_MASK; }
 // A schedule record (one per position p = row * lanes + lane, 16 bytes):
-//   x = bus k | parent's k << 16 (indices into ef)      y = first entry of the bus's child list
-//   z = flags | pool slot << 8                           w = children handed over through the pool | all children << 16
+//   x = bus k | parent's k << 16 (indices into ef)      y = first entry of the bus's child list | slot for its correction << 20
+//   z = flags | pool slot << 8 | correction slot << 20   w = children handed over through the pool | all children << 16
 // The child list (child_ent, child_slot) holds the heir first - if there is one - then the others.
+// On the way down a bus with children behind pool slots writes its correction ONCE, into the slot of the child
+// that holds its slot longest (the one eliminated first); every such child reads it there (z: correction slot).
 GFR_HD int rec_bus(const I4& t) { return (int)((unsigned)t.x & 0xFFFFu); }
 GFR_HD int rec_parent(const I4& t) { return (int)((unsigned)t.x >> 16); }
+GFR_HD int rec_list(const I4& t) { return t.y & REC_LIST_MASK; }
+GFR_HD int rec_kids_x_slot(const I4& t) { return (int)((unsigned)t.y >> REC_KIDX_SHIFT); }
+GFR_HD int x_slot_of(int z) { return (int)((unsigned)z >> FL_XSLOT_SHIFT); }
 GFR_HD int rec_pool_kids(const I4& t) { return (int)((unsigned)t.w & 0xFFFFu); }
 GFR_HD int rec_all_kids(const I4& t) { return (int)((unsigned)t.w >> 16); }
 
@@ -273,6 +280,20 @@ GFR_HD void st_stream(double* p, double v) {
 #endif
 }
 
+// 16-byte load of scratch this very thread wrote earlier in the launch: L2 only (the L1 left over beside the
+// shared-memory carve-out is a few KB)
+GFR_HD D2 ld_scratch(const D2* p) {
+#if defined(__CUDA_ARCH__)
+  D2 r;
+  // a plain (weak) load without L1 allocation; __ldcg would be a STRONG.GPU load here, ordered against every
+  // earlier store of the thread (measured: 3 x slower kernel)
+  asm volatile("ld.global.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p) : "memory");
+  return r;
+#else
+  return *p;
+#endif
+}
+
 // 1 / x for a normal, finite x: hardware seed + two Newton steps (~1 ulp), no slow-path call.
 GFR_HD double rcp_fast(double x) {
 #if defined(__CUDA_ARCH__)
@@ -468,9 +489,9 @@ GFR_HD double newton_mismatch(const NGrp<LANES>& g, const Layout& lay, const int
     const double v2 = fma(vk.x, vk.x, vk.y * vk.y);
     const BranchT bt = branch_terms(vk, g.ef(rec_parent(t)), gb[p]);
     D2 sf; sf.x = sf.y = 0.0;
-    const int q1 = t.y + rec_all_kids(t);
+    const int q0 = rec_list(t), q1 = q0 + rec_all_kids(t);
 #pragma unroll 1
-    for (int q = t.y; q < q1; ++q) {
+    for (int q = q0; q < q1; ++q) {
       const unsigned e = (unsigned)child_ent[q];
       const BranchT ct = branch_terms(g.ef((int)(e & 0xFFFFu)), vk, gb[e >> 16]);
       sf.x += ct.gl; sf.y += ct.ll;
@@ -487,93 +508,64 @@ GFR_HD double newton_mismatch(const NGrp<LANES>& g, const Layout& lay, const int
   return g.gmax_nan(mm);
 }
 
-// 16-byte asynchronous copy global -> shared (L2 only: the source was written by this very thread
-// moments ago), and the group bookkeeping around it.  The host build copies synchronously.
-GFR_HD void cp_async16(D2* dst_shared, const D2* src_global) {
-#if defined(__CUDA_ARCH__)
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_shared)),
-               "l"(src_global)
-               : "memory");
-#else
-  *dst_shared = *src_global;
-#endif
-}
-GFR_HD void cp_async_commit() {
-#if defined(__CUDA_ARCH__)
-  asm volatile("cp.async.commit_group;" ::: "memory");
-#endif
-}
-template <int N>
-GFR_HD void cp_async_wait() {
-#if defined(__CUDA_ARCH__)
-  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-#endif
-}
-
 // Back-substitution root -> leaf fused with the polar update (power_flow.py:297-327):
 //   x_k = v_k - M_k x_parent (the root's M is 0: it has no branch), then
 //   theta += a dtheta, |V| += a d|V|  <=>  V *= (1 + a x1) e^{j a x0}.
 // x_parent is in the lane's registers when the bus is its parent's heir (the lane handled the parent one
-// row earlier), else in field 0 of the bus's own pool slot (the parent put it there); x_k goes into the
-// slots of the children that are not the heir.  M and v come back from the global scratch (first
-// iteration: M from the image).  Their L2 round trip is taken off the critical path by staging them TWO
-// rows ahead with cp.async into the pool's fields 1..3, which are dead on the way down (a ring of two
-// row buffers, 48 B per lane each; the host sizes the pool for it: n_pool >= 2 LANES).
+// row earlier), else in field 0 of a pool slot (the parent put it there, once, for all such children).
+// M and v come back from the global scratch (first iteration: M from the image), position by position -
+// each lane reads back what it wrote itself.  Their L2 round trip is taken off the critical path by
+// loading them TWO rows ahead into registers (the row loop is unrolled by two: even rows use the A set,
+// odd rows the B set).
 template <int LANES>
 GFR_HD void newton_back_update(const NGrp<LANES>& g, const Layout& lay, const int* simg, const D2* f0,
                                double accel) {
-  const int nrows = lay.nrows, np = lay.n_pool, P = lay.P;
+  const int nrows = lay.nrows, P = lay.P;
   const I4* sched = reinterpret_cast<const I4*>(simg + lay.o_sched);
-  const int* child_slot = simg + lay.o_child_slot;
-  D2* const ring = g.poolp + np + g.lane;              // this lane's entries of row buffer 0 (field f at + f * LANES); buffer 1 is 3 * LANES further
-  // idle positions are staged too (their scratch entries exist): no record is needed this early
-#define GFR_STAGE_MV(row_, dst)                                            \
+  D2 a0, a1, av, b0, b1, bv;
+  a0.x = a0.y = a1.x = a1.y = b0.x = b0.y = b1.x = b1.y = bv.x = bv.y = 0.0;
+  // idle positions are loaded too (their scratch entries exist): no record is needed this early
+#define GFR_LOAD_MV(row_, m0_, m1_, v_)                                    \
   do {                                                                     \
     const int ps_ = (row_) * LANES + g.lane;                               \
-    if (!f0) { cp_async16((dst), g.mg + ps_); cp_async16((dst) + LANES, g.mg + P + ps_); } \
-    cp_async16((dst) + 2 * LANES, g.mg + 2 * P + ps_);                     \
+    if (!f0) { m0_ = ld_scratch(g.mg + ps_); m1_ = ld_scratch(g.mg + P + ps_); } \
+    v_ = ld_scratch(g.mg + 2 * P + ps_);                                   \
   } while (0)
-  GFR_STAGE_MV(0, ring);
-  cp_async_commit();
-  if (nrows > 1) GFR_STAGE_MV(1, ring + 3 * LANES);
-  cp_async_commit();
   D2 hx; hx.x = hx.y = 0.0;                            // the correction of the bus this lane handled in the previous row
-  for (int row = 0; row < nrows; ++row) {
-    const int p = row * LANES + g.lane;
-    const I4 t = sched[p];
-    cp_async_wait<1>();                               // the older of the two groups in flight: this row's
-    D2* const my = ring + (row & 1) * (3 * LANES);
-    D2 m0, m1, v;
-    if (f0) { m0 = f0[2 * P + p]; m1 = f0[3 * P + p]; }
-    else { m0 = my[0]; m1 = my[LANES]; }
-    v = my[2 * LANES];
-    if (row + 2 < nrows) GFR_STAGE_MV(row + 2, my);    // the buffer is free again: row + 2 goes there
-    cp_async_commit();
-    if (t.z & FL_VALID) {
-      const int k = rec_bus(t);
-      D2 x = hx;
-      if (!(t.z & FL_P_REG)) x = g.poolp[pool_slot_of(t.z)];
-      v.x = fma(-m0.x, x.x, fma(-m0.y, x.y, v.x));
-      v.y = fma(-m1.x, x.x, fma(-m1.y, x.y, v.y));
-      {
-        const int q1 = t.y + rec_all_kids(t);
-#pragma unroll 1
-        for (int q = q1 - rec_pool_kids(t); q < q1; ++q) g.poolp[child_slot[q]] = v;
-      }
-      hx = v;
-      double sn, cs;
-      sincos_small(accel * v.x, &sn, &cs);
-      const double sc = fma(accel, v.y, 1.0);
-      const D2 e = g.ef(k);
-      D2 w;
-      w.x = sc * fma(e.x, cs, -e.y * sn);
-      w.y = sc * fma(e.x, sn, e.y * cs);
-      g.ef(k) = w;
-    }
-    g.sync();
+#define GFR_BU_ROW(row_, m0_, m1_, v_)                                     \
+  do {                                                                     \
+    const int p = (row_) * LANES + g.lane;                                 \
+    const I4 t = sched[p];                                                 \
+    D2 m0 = m0_, m1 = m1_, v = v_;                                         \
+    if (f0) { m0 = f0[2 * P + p]; m1 = f0[3 * P + p]; }                    \
+    if ((row_) + 2 < nrows) GFR_LOAD_MV((row_) + 2, m0_, m1_, v_);         \
+    if (t.z & FL_VALID) {                                                  \
+      D2 x = hx;                                                           \
+      if (!(t.z & FL_P_REG)) x = g.poolp[x_slot_of(t.z)];                  \
+      v.x = fma(-m0.x, x.x, fma(-m0.y, x.y, v.x));                         \
+      v.y = fma(-m1.x, x.x, fma(-m1.y, x.y, v.y));                         \
+      if (rec_pool_kids(t)) g.poolp[rec_kids_x_slot(t)] = v;               \
+      hx = v;                                                              \
+      double sn, cs;                                                       \
+      sincos_small(accel * v.x, &sn, &cs);                                 \
+      const double sc = fma(accel, v.y, 1.0);                              \
+      D2* const ep = g.efp + rec_bus(t);                                   \
+      const D2 e = *ep;                                                    \
+      D2 w;                                                                \
+      w.x = sc * fma(e.x, cs, -e.y * sn);                                  \
+      w.y = sc * fma(e.x, sn, e.y * cs);                                   \
+      *ep = w;                                                             \
+    }                                                                      \
+    g.sync();                                                              \
+  } while (0)
+  GFR_LOAD_MV(0, a0, a1, av);
+  if (nrows > 1) GFR_LOAD_MV(1, b0, b1, bv);
+  for (int row = 0; row < nrows; row += 2) {
+    GFR_BU_ROW(row, a0, a1, av);
+    if (row + 1 < nrows) GFR_BU_ROW(row + 1, b0, b1, bv);
   }
-  cp_async_wait<0>();
-#undef GFR_STAGE_MV
+#undef GFR_BU_ROW
+#undef GFR_LOAD_MV
 }
 
 template <int LANES>
@@ -626,7 +618,7 @@ GFR_HD void newton_solve(const NGrp<LANES>& g, const Layout& lay, const int* sim
           D2 sc; sc.x = sc.y = 0.0;
           if (t.z & FL_C_REG) sc = hc;
           {
-            const int q1 = t.y + rec_all_kids(t);
+            const int q1 = rec_list(t) + rec_all_kids(t);
 #pragma unroll 1
             for (int q = q1 - rec_pool_kids(t); q < q1; ++q) {
               const D2 cc = g.poolp[2 * np + child_slot[q]];
@@ -682,7 +674,7 @@ GFR_HD void newton_solve(const NGrp<LANES>& g, const Layout& lay, const int* sim
           s0.x = s0.y = s1.x = s1.y = sc.x = sc.y = sf.x = sf.y = 0.0;
           if (t.z & FL_C_REG) { s0 = h0; s1 = h1; sc = hc; sf = hf; }
           {
-            const int q1 = t.y + rec_all_kids(t);
+            const int q1 = rec_list(t) + rec_all_kids(t);
 #pragma unroll 1
             for (int q = q1 - rec_pool_kids(t); q < q1; ++q) {
               const D2* e = g.poolp + child_slot[q];

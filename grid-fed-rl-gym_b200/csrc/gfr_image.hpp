@@ -71,7 +71,7 @@ struct DescCopy {
     iv.reserve(32); dv.reserve(32);                       // the inner vectors must not move once pointed at
     d.order = keep_i(s->order, n); d.parent = keep_i(s->parent, n); d.level_ptr = keep_i(s->level_ptr, nl + 1);
     d.child_ptr = keep_i(s->child_ptr, n + 1); d.child_idx = keep_i(s->child_idx, n ? n - 1 : 0);
-    d.pool_slot = keep_i(s->pool_slot, n); d.lane_of = keep_i(s->lane_of, n); d.bus_type = keep_i(s->bus_type, n);
+    d.lane_of = keep_i(s->lane_of, n); d.bus_type = keep_i(s->bus_type, n);
     d.vm_set = keep_d(s->vm_set, n); d.g = keep_d(s->g, n); d.b = keep_d(s->b, n); d.gdiag = keep_d(s->gdiag, n);
     d.bdiag = keep_d(s->bdiag, n); d.r = keep_d(s->r, n); d.x = keep_d(s->x, n); d.line_of = keep_i(s->line_of, n);
     d.from_is_parent = keep_i(s->from_is_parent, n); d.rating = keep_d(s->rating, n);
@@ -137,10 +137,7 @@ inline std::string check_feeder_desc(const gfr_feeder_desc* d) {
     if (d->gen_type[g] != GFR_GEN_SOLAR && d->gen_type[g] != GFR_GEN_WIND) return "unknown gen_type";
   }
   for (int b = 0; b < Bt; ++b) if (d->bat_bus[b] < 0 || d->bat_bus[b] >= n) return "bat_bus out of range";
-  if (d->pool_slot) {
-    if (d->n_pool < 1 || d->n_pool > n) return "n_pool must be in [1, n]";
-    for (int k = 0; k < n; ++k) if (d->pool_slot[k] < 0 || d->pool_slot[k] >= d->n_pool) return "pool_slot out of range";
-  }
+  if (d->n_pool < 0 || d->n_pool > n) return "n_pool must be in [0, n]";
   return std::string();
 }
 
@@ -279,64 +276,56 @@ inline std::string build_feeder_image(const gfr_feeder_desc* d, int lanes, int s
     flags[0] |= FL_P_REG;               // the root has no parent: its "correction from above" is the zero its lane starts with
   }
   // ---- pool plan (Newton): a slot for every bus whose hand-off goes through shared memory, held from its
-  //      own row up to its parent's.  The caller's plan is used when there is one (it covers every bus, so
-  //      it covers these); otherwise slots are handed out row by row, a slot read (released) in one row
-  //      being reused by later rows only.
+  //      own row up to its parent's.  Slots are handed out row by row; a slot read (released) in one row is
+  //      reused by LATER rows only, and a bus never takes over a slot of its own children - so on the way
+  //      down, when a parent's correction waits in a child's slot for all the children behind slots, nothing
+  //      can overwrite it before the last of them has read it.
   std::vector<int32_t> pool_slot(n, 0);
   lay.n_pool = 1;
   if (newton) {
     std::vector<std::vector<int>> by_row(sch.nrows);
     for (int k = 0; k < n; ++k) by_row[sch.row[k]].push_back(k);
-    if (d->pool_slot) {
-      // check by replaying the schedule: a slot may be taken over from one of the bus's own children
-      // (it reads them before it writes); any other slot must have been free before the row started
-      std::vector<int> owner(d->n_pool, -1);
-      for (int r = sch.nrows - 1; r >= 0; --r) {
-        std::vector<int> before(owner);
-        for (int k : by_row[r]) {
-          const int sl = d->pool_slot[k];
-          const int prev = before[sl];
-          if (prev >= 0 && d->parent[prev] != k) return "pool_slot reuses a slot that is still live";
-          if (owner[sl] >= 0 && owner[sl] != prev) return "two buses of one level share a pool slot";
-          owner[sl] = k;
-          pool_slot[k] = sl;
+    std::vector<int> free_slots;
+    int np = 0;
+    for (int r = sch.nrows - 1; r >= 0; --r) {
+      std::vector<int> released;
+      for (int k : by_row[r])
+        for (int q = d->child_ptr[k]; q < d->child_ptr[k + 1]; ++q) {
+          const int c = d->child_idx[q];
+          if (c != heir[k]) released.push_back(pool_slot[c]);
         }
-        for (int k : by_row[r])
-          for (int q = d->child_ptr[k]; q < d->child_ptr[k + 1]; ++q) {
-            const int cs = d->pool_slot[d->child_idx[q]];
-            if (owner[cs] == d->child_idx[q]) owner[cs] = -1;
-          }
-      }
-      lay.n_pool = d->n_pool;
-    } else {
-      std::vector<int> free_slots;
-      int np = 0;
-      for (int r = sch.nrows - 1; r >= 0; --r) {
-        std::vector<int> released;
-        for (int k : by_row[r])
-          for (int q = d->child_ptr[k]; q < d->child_ptr[k + 1]; ++q) {
-            const int c = d->child_idx[q];
-            if (c != heir[k]) released.push_back(pool_slot[c]);
-          }
-        for (int k : by_row[r]) {
-          if (flags[k] & FL_P_REG) continue;            // handed over in registers (or the root)
-          if (!free_slots.empty()) {
-            auto it = std::min_element(free_slots.begin(), free_slots.end());
-            pool_slot[k] = *it;
-            free_slots.erase(it);
-          } else {
-            pool_slot[k] = np++;
-          }
+      for (int k : by_row[r]) {
+        if (flags[k] & FL_P_REG) continue;            // handed over in registers (or the root)
+        if (!free_slots.empty()) {
+          auto it = std::min_element(free_slots.begin(), free_slots.end());
+          pool_slot[k] = *it;
+          free_slots.erase(it);
+        } else {
+          pool_slot[k] = np++;
         }
-        free_slots.insert(free_slots.end(), released.begin(), released.end());
       }
-      lay.n_pool = std::max(np, 1);
-      if (d->n_pool > lay.n_pool && d->n_pool <= n) lay.n_pool = d->n_pool;
+      free_slots.insert(free_slots.end(), released.begin(), released.end());
     }
+    lay.n_pool = std::max(np, 1);
+    if (d->n_pool > lay.n_pool) lay.n_pool = d->n_pool;      // the caller asks for more (padding experiments)
     if (lay.n_pool > FL_POOL_MASK) return "more than 4095 pool slots";
-    // the back-substitution stages its operands two rows ahead in the pool's fields 1..3 (a ring of two
-    // row buffers, 3 x lanes 16-byte entries each): the pool has at least 2 x lanes slots
-    lay.n_pool = std::max(lay.n_pool, 2 * lanes);
+  }
+  // the slot a bus's correction travels down in: that of the child (among those behind pool slots) eliminated
+  // first - it holds its slot from its own row up to the parent's, which covers its siblings' rows
+  std::vector<int32_t> kids_x_slot(n, 0), x_slot(n, 0);
+  if (newton) {
+    for (int k = 0; k < n; ++k) {
+      int best = -1;
+      for (int q = d->child_ptr[k]; q < d->child_ptr[k + 1]; ++q) {
+        const int c = d->child_idx[q];
+        if (c != heir[k] && (best < 0 || sch.row[c] > sch.row[best])) best = c;
+      }
+      if (best >= 0) {
+        kids_x_slot[k] = pool_slot[best];
+        for (int q = d->child_ptr[k]; q < d->child_ptr[k + 1]; ++q)
+          if (d->child_idx[q] != heir[k]) x_slot[d->child_idx[q]] = pool_slot[best];
+      }
+    }
   }
 
   ImageBuilder ib;
@@ -363,8 +352,9 @@ inline std::string build_feeder_image(const gfr_feeder_desc* d, int lanes, int s
       if (n_all > 65535) return "more than 65535 children on one bus";
     }
     sched[4 * p + 0] = (int32_t)((uint32_t)k | ((uint32_t)kp << 16));
-    sched[4 * p + 1] = begin;
-    sched[4 * p + 2] = flags[k] | (pool_slot[k] << FL_POOL_SHIFT);
+    if (begin > REC_LIST_MASK) return "child lists too long";
+    sched[4 * p + 1] = (int32_t)((uint32_t)begin | ((uint32_t)kids_x_slot[k] << REC_KIDX_SHIFT));
+    sched[4 * p + 2] = (int32_t)((uint32_t)flags[k] | ((uint32_t)pool_slot[k] << FL_POOL_SHIFT) | ((uint32_t)x_slot[k] << FL_XSLOT_SHIFT));
     sched[4 * p + 3] = (int32_t)((uint32_t)n_pool_kids | ((uint32_t)n_all << 16));
   }
   for (int k = 0; k < n; ++k) {

@@ -170,9 +170,7 @@ class FeederSoA:
     level_ptr: np.ndarray              # int32[n_levels+1]  level l = [ptr[l], ptr[l+1])
     child_ptr: np.ndarray              # int32[n+1] children of k = child_idx[child_ptr[k] : child_ptr[k+1]]
     child_idx: np.ndarray              # int32[n-1] level indices of the children, parent by parent
-    pool_slot: Optional[np.ndarray]    # int32[n]  where bus k parks its Schur contribution until its parent is eliminated;
-                                       #           None (default): the native library plans the slots itself
-    n_pool: int                        # slots to provide at least (0: as few as the plan needs)
+    n_pool: int                        # Newton: shared-memory hand-off slots to provide at least (0: as few as the library's plan needs)
     lane_of: Optional[np.ndarray]      # int32[n]  lane (< width) that eliminates bus k; None: position inside the level
     bus_type: np.ndarray               # int32[n]  BUS_*
     vm_set: np.ndarray                 # f64[n]   slack / pv magnitude (bus.voltage_magnitude)
@@ -398,108 +396,6 @@ def _schedule_paths(n: int, root: int, adj, width: int):
     return order, parent_ref, level_of, lane_of
 
 
-def plan_pool(parent: np.ndarray, level_ptr: np.ndarray, contiguous: bool = False,
-              width: Optional[int] = None, child_ptr: Optional[np.ndarray] = None,
-              child_idx: Optional[np.ndarray] = None):
-    """Slot of every bus's contribution to its parent.  A contribution is written when its bus is
-    eliminated (levels run last -> first) and read when the parent is; on the way back the same slot
-    carries the parent's correction to the bus.
-
-    ``contiguous`` (measured on B200: +1 % at 16 lanes on IEEE-123, -6 % at 8 lanes because fewer
-    instances stay resident, so it is off by default): the buses of one level get consecutive slots.
-    A level's block is free again once the last parent of its buses has been eliminated; blocks are
-    placed first-fit.
-
-    Otherwise (default) slots are handed out one by one: a parent inherits its first child's slot
-    (the kernels use that: no index load for the first child), slots released by a level are only
-    reused by later levels.  A bus without children starts a chain of buses that will carry its
-    slot (itself, then every ancestor reached through first-child links); it takes the free slot
-    whose 16-byte bank group (slot mod 8) clashes least, over the levels of that chain, with the
-    slots other buses of the same level and quarter-warp (``width`` lanes per instance, lane = bus
-    index mod width) already hold, or a new slot when that avoids clashes."""
-    n = parent.size
-    slot = np.zeros(n, dtype=np.int32)
-    nl = level_ptr.size - 1
-    if contiguous:
-        level = np.zeros(n, dtype=np.int64)
-        for l in range(nl):
-            level[int(level_ptr[l]):int(level_ptr[l + 1])] = l
-        live: List[Tuple[int, int, int]] = []          # (start, end, level after which the block is free)
-        n_pool = 0
-        for l in range(nl - 1, -1, -1):
-            k0, k1 = int(level_ptr[l]), int(level_ptr[l + 1])
-            release = min((int(level[parent[k]]) for k in range(k0, k1) if parent[k] >= 0), default=-1)
-            live = sorted(iv for iv in live if iv[2] <= l)     # blocks whose last reader is this level or later
-            pos = 0
-            for start, end, _ in live:
-                if start - pos >= k1 - k0:
-                    break
-                pos = max(pos, end)
-            slot[k0:k1] = np.arange(pos, pos + (k1 - k0))
-            n_pool = max(n_pool, pos + (k1 - k0))
-            live.append((pos, pos + (k1 - k0), release))
-        return slot, max(n_pool, 1)
-    free: List[int] = []
-    n_pool = 0
-    kids: List[List[int]] = [[] for _ in range(n)]
-    if child_ptr is not None and child_idx is not None:      # the caller's child order: the first one is inherited from
-        for k in range(n):
-            kids[k] = [int(c) for c in child_idx[int(child_ptr[k]):int(child_ptr[k + 1])]]
-    else:
-        for k in range(1, n):
-            kids[parent[k]].append(k)
-    w = int(width) if width else 0
-    level = np.zeros(n, dtype=np.int64)
-    for l in range(nl):
-        level[int(level_ptr[l]):int(level_ptr[l + 1])] = l
-
-    def where(k: int) -> Tuple[int, int]:      # (level, quarter-warp) a bus's pool accesses happen in
-        return int(level[k]), ((k % w) // 8 if w > 8 else 0)
-
-    taken: dict = {}                            # (level, quarter) -> bank groups in use there
-    # candidates for a NEW slot: only the next index.  Looking further (up to 8: any bank group) removes
-    # more clashes but costs slots - measured on B200, IEEE-123 at 8 lanes: 24 slots / 56 resident
-    # instances per SM 69.1 M env-steps/s against 22 slots / 60 instances 72.9 M
-    grow = int(os.environ.get('GFR_POOL_GROW', '1'))
-
-    def chain(k: int) -> List[int]:             # the buses that will carry k's slot: k, then every
-        out = [k]                               # ancestor reached through first-child links
-        while parent[out[-1]] >= 0 and kids[parent[out[-1]]][0] == out[-1]:
-            out.append(int(parent[out[-1]]))
-        return out
-
-    for l in range(nl - 1, -1, -1):
-        members = range(int(level_ptr[l]), int(level_ptr[l + 1]))
-        released: List[int] = []
-        for k in members:
-            if kids[k]:
-                # a parent reads its children's entries before it writes its own (same lane, program
-                # order), so it can take over its first child's slot; the others are released
-                slot[k] = slot[kids[k][0]]
-                released.extend(int(slot[c]) for c in kids[k][1:])
-        for k in members:
-            if kids[k]:
-                continue
-            path = [where(b) for b in chain(k)]
-
-            def clashes(s: int) -> int:
-                return sum(1 for at in path if s % 8 in taken.get(at, ()))
-            # the candidate with the fewest clashes: a free slot, or a new one (indices skipped on the
-            # way to a new one's bank group join the free list); ties go to the smaller pool
-            cands = [(clashes(s), 0, s) for s in free] + [(clashes(n_pool + j), j + 1, n_pool + j) for j in range(grow)]
-            _, _, best = min(cands)
-            if best >= n_pool:
-                free.extend(range(n_pool, best))
-                n_pool = best + 1
-            else:
-                free.remove(best)
-            slot[k] = best
-            for at in path:
-                taken.setdefault(at, set()).add(best % 8)
-        free.extend(released)                  # only later levels may reuse what this level read
-    return slot, max(n_pool, 1)
-
-
 def tree_center(n: int, adj, fallback: int) -> int:
     """A bus of minimum eccentricity (the middle of a longest path): rooting the elimination
     there halves the number of sequential levels of a feeder whose slack bus sits at one end."""
@@ -527,8 +423,7 @@ def tree_center(n: int, adj, fallback: int) -> int:
 
 def compile_feeder(feeder, renewable_sources: Optional[Sequence[str]] = None,
                    with_components: bool = True, root: str = "slack",
-                   width: Optional[int] = None, pool_contiguous: bool = False,
-                   paths: bool = False, pool_plan: Optional[str] = None) -> FeederSoA:
+                   width: Optional[int] = None, paths: bool = False) -> FeederSoA:
     """Compile a *radial, connected* feeder (run ``repair_topology`` first if it is not).
 
     ``renewable_sources`` has the reference meaning (grid_env.py:167,273,282): a
@@ -542,9 +437,8 @@ def compile_feeder(feeder, renewable_sources: Optional[Sequence[str]] = None,
     the slack bus (Newton only; the sweep needs the slack at the root), ``width`` caps the buses
     per level at the number of lanes that will cooperate on one instance.  ``paths`` (needs a width)
     lets lanes follow paths of the tree (``_schedule_paths``: register hand-off between a bus and the
-    child eliminated just before it on the same lane - what the Newton kernels want).  ``pool_plan``:
-    None = the native library places the shared-memory hand-off slots itself; "python" / "contiguous"
-    = this module's ``plan_pool`` (kept for experiments and tests).
+    child eliminated just before it on the same lane - what the Newton kernels want).  The hand-offs
+    that do go through shared memory get their slots from the native library.
     """
     buses, lines = list(feeder.buses), list(feeder.lines)
     n, m = len(buses), len(lines)
@@ -581,9 +475,6 @@ def compile_feeder(feeder, renewable_sources: Optional[Sequence[str]] = None,
     if width is not None and int(width) < 1:
         raise TopologyError("width must be >= 1")
     root_ref = slack if root == "slack" else tree_center(n, adj, slack)
-    if pool_contiguous:
-        pool_plan = "contiguous"
-
     def layout(alap: bool):
         lane_map = None
         if paths and width is not None:
@@ -619,38 +510,15 @@ def compile_feeder(feeder, renewable_sources: Optional[Sequence[str]] = None,
             fill[parent[k]] += 1
         for k in range(1, n):
             assert parent[k] < k and levels[parent[k]] < levels[k]
-        # The first child of a bus shares its pool slot.  When that child is a leaf handled no earlier
-        # (on the way down) than its siblings, all of them read the parent's correction from that
-        # one slot and the parent does not scatter it (gfr_image.hpp): put such a child first.
-        for k in range(n):
-            q0, q1 = int(child_ptr[k]), int(child_ptr[k + 1])
-            if q1 - q0 < 2:
-                continue
-            kids_k = [int(c) for c in child_idx[q0:q1]]
-            deepest = max(int(levels[c]) for c in kids_k)
-            lead = next((c for c in kids_k if int(levels[c]) == deepest and child_ptr[c + 1] == child_ptr[c]), None)
-            if lead is not None:
-                child_idx[q0:q1] = [lead] + [c for c in kids_k if c != lead]
-        if pool_plan is None:
-            pool_slot, n_pool = None, 0
-        else:
-            pool_slot, n_pool = plan_pool(parent, level_ptr, contiguous=pool_plan == "contiguous", width=width,
-                                          child_ptr=child_ptr, child_idx=child_idx)
         lane_arr = None if lane_map is None else np.array([lane_map[v] for v in order], dtype=np.int32)
         return dict(lane_of=lane_arr, order=order, rank=rank, parent=parent, line_of=line_of, from_is_parent=from_is_parent,
                     g=g, b=b, r=r, x=x, rating=rating, levels=levels, n_levels=n_levels, level_ptr=level_ptr,
-                    child_ptr=child_ptr, child_idx=child_idx, pool_slot=pool_slot, n_pool=n_pool)
+                    child_ptr=child_ptr, child_idx=child_idx)
 
-    # two valid schedules of the same length: keep the one that parks fewer contributions at once
-    lay = layout(True) if (paths and width is not None) or pool_plan is None else \
-        min((layout(True), layout(False)), key=lambda d: d["n_pool"])
+    lay = layout(True)
     order, rank, parent, line_of, from_is_parent = (lay[k] for k in ("order", "rank", "parent", "line_of", "from_is_parent"))
     g, b, r, x, rating = (lay[k] for k in ("g", "b", "r", "x", "rating"))
-    level_ptr, child_ptr, child_idx, pool_slot, n_pool = (lay[k] for k in ("level_ptr", "child_ptr", "child_idx", "pool_slot", "n_pool"))
-    if pool_plan is not None and width is not None and 1 < int(width) <= 32 and os.environ.get("GFR_POOL_PAD", "1") == "1":
-        # the Newton back-substitution stages its operands two levels ahead in the pool's idle fields,
-        # which takes a pool of at least 2 x lanes slots; small feeders have shared memory to spare
-        n_pool = min(max(n_pool, 2 * int(width)), max(n, n_pool))
+    level_ptr, child_ptr, child_idx = (lay[k] for k in ("level_ptr", "child_ptr", "child_idx"))
 
     tmap = {"slack": BUS_SLACK, "pv": BUS_PV}
     bus_type = np.array([tmap.get(buses[i].bus_type, BUS_PQ) for i in order], dtype=np.int32)
@@ -661,7 +529,7 @@ def compile_feeder(feeder, renewable_sources: Optional[Sequence[str]] = None,
         s_base=float(feeder.parameters.base_power) * 1e6,
         bus_ids=[b_.id for b_ in buses], line_ids=[l_.id for l_ in lines],
         order=np.array(order, dtype=np.int32), rank=rank, parent=parent, level_ptr=level_ptr,
-        child_ptr=child_ptr, child_idx=child_idx, pool_slot=pool_slot, n_pool=n_pool, lane_of=lay["lane_of"],
+        child_ptr=child_ptr, child_idx=child_idx, n_pool=0, lane_of=lay["lane_of"],
         bus_type=bus_type, vm_set=vm_set, g=g, b=b,
         gdiag=ydiag.real[order].copy(), bdiag=ydiag.imag[order].copy(), r=r, x=x,
         line_of=line_of, from_is_parent=from_is_parent, rating=rating)

@@ -50,7 +50,9 @@ typedef struct gfr_env gfr_env;         /* B environment instances on one device
  * Produced by grid_fed_rl_b200.topology.compile_feeder from feeder.buses / .lines / .loads /
  * .generators (reference feeders/base.py:30-52; Bus/Line/Load environments/base.py:197-295). */
 typedef struct {
-  int32_t n_bus, n_levels, n_load, n_gen, n_bat, n_pool;
+  int32_t n_bus, n_levels, n_load, n_gen, n_bat;
+  int32_t n_pool;                   /* Newton: least number of shared-memory hand-off slots to provide (0 = as few as the
+                                       library's own plan needs) */
   int32_t lanes_hint;               /* lanes the level schedule was capped for (levels hold at most this many buses);
                                        what `lanes = 0` resolves to.  0 = not said: gfr_auto_lanes decides */
   int32_t reserved;
@@ -60,10 +62,6 @@ typedef struct {
   const int32_t* level_ptr;         /* [n_levels+1] */
   const int32_t* child_ptr;         /* [n+1] children of k are child_idx[child_ptr[k] .. child_ptr[k+1]) */
   const int32_t* child_idx;         /* [n-1] level indices of the children, parent by parent */
-  const int32_t* pool_slot;         /* [n]  Newton, optional: slot (< n_pool) where bus k parks its Schur contribution from
-                                            its own elimination until its parent's (checked; buses whose hand-off stays in
-                                            registers ignore theirs).  NULL = the library plans the slots; n_pool is then
-                                            the least number of slots to provide (0 = as few as needed) */
   const int32_t* lane_of;           /* [n]  Newton, optional: the lane (< lanes_hint) that eliminates bus k.  A bus
                                             eliminated right after one of its children on the same lane takes that
                                             child's contribution from registers.  NULL = position inside the level */
