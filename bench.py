@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """bench.py - env-steps/s of the fused batched GridEnvironment.step on B200.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload ieee123|ieee13|ieee34] [--lanes L]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload ieee123|ieee13|ieee34|...] [--lanes L]
+                  [--scaling weak|strong] [--no-configs] [--no-cpu]
   python bench.py --impl reference ...      # the CPU oracle (port of the reference path) on host cores
 
 One JSON line on stdout (rank 0).  A "step" is one pass of the hot path over one batch of
@@ -245,6 +246,146 @@ def run_reference(args):
 
 # ----------------------------------------------------------------------------- GPU arm
 
+L2_BYTES = 126e6          # B200: 2 x 63 MB
+
+
+def load_profile_facts():
+    """Per-workload facts measured with ncu and kept under profiles/ (written by profiles/summarize_ncu.py
+    --json from the committed captures): DRAM bytes per launch, FP64 lane operations per env-step."""
+    facts = {}
+    pdir = os.path.join(ROOT, "profiles")
+    try:
+        names = sorted(n for n in os.listdir(pdir) if n.startswith("r02_ncu_") and n.endswith(".json"))
+    except OSError:
+        names = []
+    for n in names:
+        try:
+            with open(os.path.join(pdir, n)) as fh:
+                j = json.load(fh)
+            facts[(j["workload"], int(j["instances"]))] = dict(j, source="profiles/" + n)
+        except Exception:
+            pass
+    return facts
+
+
+def reference_cpu_rates():
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_reference_cpu_rates.json")) as fh:
+            return json.load(fh)
+    except Exception:
+        return None
+
+
+def bind_to_gpu_numa_node(index):
+    """Pin this rank to the CPUs next to its GPU before any pinned buffer is allocated (NUMA-local staging
+    buffers: with 8 ranks sharing one host the observation copies otherwise cross sockets)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, mk in enumerate(mask) for b in range(64) if (mk >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return 0
+
+
+def device_timed(dev, world, step_fn, k, max_over_ranks):
+    import torch
+    import torch.distributed as dist
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for i in range(k):
+        step_fn(i)
+    ev1.record()
+    barrier()
+    return max_over_ranks(ev0.elapsed_time(ev1), dev)     # a timed region counts as its slowest rank
+
+
+def make_envs(m, name, B, dev, rank, lanes, seed, obs_dtype=None, min_bytes=2 * L2_BYTES):
+    """The environment(s) of one workload: when one step's working set would sit in the 126 MB L2, several
+    environments are stepped round-robin so that every step streams from / to HBM."""
+    spec, _, solver, tol, max_it = WORKLOADS[name]
+    feeder = make_feeder(spec)
+    kw = dict(ENV_KW)
+    if obs_dtype is not None:
+        kw["obs_dtype"] = obs_dtype
+    envs = []
+    while True:
+        env = m.BatchedGridEnvironment(feeder, B, device=dev, solver=solver, tolerance=tol, max_iterations=max_it,
+                                       lanes=lanes, repair=False, start_time=START_TIME,
+                                       env_id_offset=(rank * 16 + len(envs)) * B, **kw)
+        env.reset(seed=seed)
+        envs.append(env)
+        if len(envs) * B * algorithmic_bytes(env.soa) >= min_bytes or len(envs) >= 8:
+            return envs
+
+
+def measure_device(m, lib, name, B, dev, world, rank, lanes, seed, K, W, max_over_ranks, peak, facts):
+    """Device-resident arm of one workload: actions in HBM, one kernel launch per step, CUDA events."""
+    import torch
+    import torch.distributed as dist
+    envs = make_envs(m, name, B, dev, rank, lanes, seed)
+    env = envs[0]
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1234 + rank)
+    R = 4
+    actions = [env.sample_actions(gen) for _ in range(R)]
+    E = len(envs)
+
+    def dev_step(i):
+        envs[i % E].step(actions[i % R])
+
+    for i in range(max(W, E)):
+        dev_step(i)
+    l0 = lib.gfr_launch_count()
+    ms = device_timed(dev, world, dev_step, K, max_over_ranks)
+    launches = lib.gfr_launch_count() - l0
+    info = env._info()
+    conv = float(info["power_flow_converged"].double().mean().item())
+    its = float(info["iterations"].double().mean().item())
+    if world > 1:
+        t = torch.tensor([conv, its], dtype=torch.float64, device=dev)
+        dist.all_reduce(t)
+        conv, its = (t / world).tolist()
+    soa, li = env.soa, env.launch_info()
+    abytes = algorithmic_bytes(soa)
+    solver = WORKLOADS[name][2]
+    value = B * world * K / (ms * 1e-3)
+    achieved = abytes * B / (ms / K * 1e-3) / 1e9          # GB/s of the one kernel a step launches
+    ws = B * abytes
+    fact = facts.get((name, B))
+    res = {
+        "value": value, "ms_per_step": ms / K, "steps": K, "converged_frac": conv, "mean_iterations": its,
+        "workload": f"{WORKLOADS[name][0]} fused GridEnvironment.step, {solver} load flow tol {WORKLOADS[name][3]:g}, "
+                    f"{B} instances per GPU, in-kernel Philox noise, random U(-1,1) policy",
+        "instances_per_gpu": B, "n_bus": soa.n_bus, "obs_dim": soa.obs_dim, "act_dim": soa.act_dim, "solver": solver,
+        "launch": li,
+        "l2": (f"per-step working set {ws / 1e6:.0f} MB > 2 x 126 MB L2: no flush needed" if E == 1 else
+               f"per-step working set {ws / 1e6:.0f} MB would sit in the 126 MB L2: {E} environments stepped "
+               f"round-robin ({E * ws / 1e6:.0f} MB between two visits of the same buffers)"),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak[0], "unit": "GB/s", "frac": achieved / peak[0],
+                     "traffic": fact.get("dram_bytes_per_launch") if fact else None,
+                     "traffic_source": fact.get("source") if fact else None,
+                     "peak_source": peak[1], "algorithmic_bytes_per_env_step": abytes,
+                     "kernel": f"step_kernel<{li['lanes']},{solver}>", "kernel_ms": ms / K},
+        "gpu_launches": int(launches),
+    }
+    return res, envs, actions
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -259,83 +400,57 @@ def run_gpu(args):
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU oracle")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_cpus = bind_to_gpu_numa_node(physical_gpu_index(local))
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     spec, B, solver, tol, max_it = WORKLOADS[args.workload]
+    if args.scaling == "strong":
+        # 1,048,576 instances in total, split evenly over the GPUs
+        total = args.total_envs or 1_048_576
+        B = total // world
     if args.envs:
         B = args.envs
     lib = _native.load_library()
-    feeder = make_feeder(spec)
-    env = m.BatchedGridEnvironment(feeder, B, device=dev, solver=solver, tolerance=tol,
-                                   max_iterations=max_it, lanes=args.lanes, repair=False,
-                                   start_time=START_TIME, env_id_offset=rank * B, **ENV_KW)
-    env.reset(seed=args.seed)
-    gen = torch.Generator(device=dev)
-    gen.manual_seed(1234 + rank)
-    R = 4
-    actions = [env.sample_actions(gen) for _ in range(R)]
-    A = env.act_dim
     K, W = args.steps, max(args.warmup, 3)
+    peak = hbm_peak()
+    facts = load_profile_facts()
+
+    sampler = ClockSampler(physical_gpu_index(local))
+    sampler.start()
+    main, envs, actions = measure_device(m, lib, args.workload, B, dev, world, rank, args.lanes, args.seed, K, W,
+                                         max_over_ranks, peak, facts)
+    env = envs[0]
+    value, ms = main["value"], main["ms_per_step"] * K
+    if args.kernel_only:                 # tuning aid (tools/): the device-resident arm only
+        sampler.stop()
+        if rank == 0:
+            print(json.dumps({"value": value, "ms_per_step": ms / K, "mean_iterations": main["mean_iterations"],
+                              "converged_frac": main["converged_frac"],
+                              "config": {"launch": main["launch"], "instances_per_gpu": B}}), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def timed(step_fn, k):
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
-        ev0.record()
-        for i in range(k):
-            step_fn(i)
-        ev1.record()
-        barrier()
-        return max_over_ranks(ev0.elapsed_time(ev1), dev)     # a timed region counts as its slowest rank
-
-    # ---- device-resident arm
-    conv_acc = torch.zeros((), dtype=torch.float64, device=dev)
-    it_acc = torch.zeros((), dtype=torch.float64, device=dev)
-
-    def dev_step(i):
-        env.step(actions[i % R])
-
-    for i in range(W):
-        dev_step(i)
-    sampler = ClockSampler(physical_gpu_index(local))
-    sampler.start()
-    l0 = lib.gfr_launch_count()
-    ms = timed(dev_step, K)
-    launches = lib.gfr_launch_count() - l0
-    info = env._info()
-    conv_frac = float(info["power_flow_converged"].double().mean().item())
-    mean_it = float(info["iterations"].double().mean().item())
-    if world > 1:
-        t = torch.tensor([conv_frac, mean_it], dtype=torch.float64, device=dev)
-        dist.all_reduce(t)
-        conv_frac, mean_it = (t / world).tolist()
-    value = B * world * K / (ms * 1e-3)
-    if args.kernel_only:                 # tuning aid (tools/): the device-resident arm only
-        sampler.stop()
-        if rank == 0:
-            print(json.dumps({"value": value, "ms_per_step": ms / K, "mean_iterations": mean_it,
-                              "converged_frac": conv_frac,
-                              "config": {"launch": env.launch_info(), "instances_per_gpu": B}}), flush=True)
-        env.close()
-        if world > 1:
-            dist.destroy_process_group()
-        return
-
-    # ---- end-to-end arm: every step copies ITS actions from pinned host memory (H2D) and its reward +
-    #      done flags back (D2H), and the host reads each step's result.  Measured twice through the
-    #      public API: serial (copy, step, copy, synchronise) and as HostStepper's depth-2 pipeline
-    #      (the next step's action copy overlaps the running kernel on a second stream).
+    # ---- end-to-end arm: every step copies ITS actions from pinned host memory (H2D) and its result back (D2H),
+    #      and the host reads each step's result.  Through the public API (HostStepper over
+    #      BatchedGridEnvironment.step): serial (copy, step, copy, synchronise), as a depth-2 pipeline (the next
+    #      step's action copy overlaps the running kernel on a second stream), and with every step's OBSERVATION
+    #      brought to the host too - what a host-side policy sees (fp64, and fp32 as the reference declares its
+    #      observation space, written by the kernel into alternating buffers so that the copy of step t overlaps
+    #      the kernel of step t + 1).
     from grid_fed_rl_b200.pipeline import HostStepper
+    R = len(actions)
     host_act = [a.cpu().pin_memory() for a in actions]
 
-    def e2e_run(depth, observations=False, k_steps=None):
-        stepper = HostStepper(env, depth=depth, observations=observations)
+    def e2e_run(e, depth, observations=False, k_steps=None):
+        stepper = HostStepper(e, depth=depth, observations=observations)
         checksum = [0.0]
-        K = k_steps or args.steps
+        k_run = k_steps or K
 
         def run(k):
             for i in range(k):
@@ -349,102 +464,129 @@ def run_gpu(args):
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         ev0.record()
-        run(K)
+        run(k_run)
         ev1.record()
         barrier()
         return max_over_ranks(ev0.elapsed_time(ev1), dev), stepper
 
-    # the same with every step's observation [B, D] copied to the host too (PCIe bound; fewer steps)
-    K_obs = max(2, min(K, 10))
-    ms_obs, stepper_obs = e2e_run(2, observations=True, k_steps=K_obs)
-    obs_value = B * world * K_obs / (ms_obs * 1e-3)
-    obs_d2h = stepper_obs.d2h_bytes_per_step
-    del stepper_obs
-    ms_serial, stepper = e2e_run(1)
-    ms_e2e, stepper = e2e_run(2)
-    clocks = sampler.stop()          # sampled across the timed regions
+    K_obs = max(2, min(K, 20))
+    ms_obs, st_obs = e2e_run(env, 2, observations=True, k_steps=K_obs)
+    obs64 = {"value": B * world * K_obs / (ms_obs * 1e-3), "d2h_bytes_per_step": st_obs.d2h_bytes_per_step, "steps": K_obs,
+             "gb_per_s_d2h": st_obs.d2h_bytes_per_step / (ms_obs / K_obs * 1e-3) / 1e9, "dtype": "f64"}
+    del st_obs
+    ms_serial, stepper = e2e_run(env, 1)
+    ms_e2e, stepper = e2e_run(env, 2)
     e2e_value = B * world * K / (ms_e2e * 1e-3)
     e2e_serial = B * world * K / (ms_serial * 1e-3)
+    h2d, d2h = stepper.h2d_bytes_per_step, stepper.d2h_bytes_per_step
+    del stepper
+    for e in envs:
+        e.close()
+    envs = []
+    # fp32 observations, alternating device buffers (a second environment: the option is fixed at construction)
+    env32 = make_envs(m, args.workload, B, dev, rank, args.lanes, args.seed, obs_dtype="float32", min_bytes=0)[0]
+    ms32, st32 = e2e_run(env32, 2, observations=True, k_steps=K_obs)
+    obs32 = {"value": B * world * K_obs / (ms32 * 1e-3), "d2h_bytes_per_step": st32.d2h_bytes_per_step, "steps": K_obs,
+             "gb_per_s_d2h": st32.d2h_bytes_per_step / (ms32 / K_obs * 1e-3) / 1e9, "dtype": "f32",
+             "note": "observation written as fp32 by the kernel (the reference declares float32, grid_env.py:346) into "
+                     "two alternating device buffers; the copy of step t runs on the copy stream under the kernel of "
+                     "step t + 1"}
+    del st32
+    env32.close()
+
+    # ---- the other BASELINE configurations, device-resident arm only, in the same JSON line
+    others = {}
+    if not args.no_configs and args.scaling == "weak":
+        for name in ("ieee13", "ieee34", "synthetic1000", "ieee13_newton", "ieee34_newton"):
+            if name == args.workload:
+                continue
+            Bn = WORKLOADS[name][1]
+            Kn = max(20, min(K, 200))
+            res, es, _ = measure_device(m, lib, name, Bn, dev, world, rank, 0, args.seed, Kn, W, max_over_ranks, peak, facts)
+            for e in es:
+                e.close()
+            others[name] = res
+        others["synthetic1000_rollout"] = measure_rollout(m, dev, world, rank, max_over_ranks, args)
+    clocks = sampler.stop()          # sampled across the timed regions
 
     fp64_peak = ctypes.c_double(0.0)
     if rank == 0:
         _native.check(lib, lib.gfr_fp64_peak(local, ctypes.byref(fp64_peak)))
-    if rank == 0:
-        soa = env.soa
-        abytes = algorithmic_bytes(soa)
-        peak, how = hbm_peak()
-        achieved = abytes * B / (ms / K * 1e-3) / 1e9          # GB/s of the one kernel a step launches
-        li = env.launch_info()
+        fact = facts.get((args.workload, B))
+        lane_ops = fact.get("fp64_lane_ops_per_env_step") if fact else None
         line = {
             "metric": "env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": world,
             "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{spec} fused GridEnvironment.step, {solver} load flow tol {tol:g}, "
-                                   f"{B} instances per GPU, in-kernel Philox noise, random U(-1,1) policy",
-                       "instances_per_gpu": B, "n_bus": soa.n_bus, "obs_dim": soa.obs_dim,
-                       "act_dim": soa.act_dim, "solver": solver, "parallelism": f"shard{world}",
-                       "l2": f"per-step working set {B * abytes / 1e6:.0f} MB > 126 MB L2, no flush needed",
-                       "launch": li},
-            "converged_frac": conv_frac, "converged_solves_per_s": value * conv_frac,
-            "mean_iterations": mean_it,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": TRAFFIC_BYTES.get((args.workload, B)),
-                         "peak_source": how, "algorithmic_bytes_per_env_step": abytes,
-                         "kernel": f"step_kernel<{li['lanes']},{solver}>", "kernel_ms": ms / K,
-                         "note": "not HBM bound: ncu shows the L1 / shared-memory data pipe at 70 %, issue slots 56 %, "
-                                 "FP64 pipe 28 %, DRAM 7.5 % (DESIGN.md section 5, profiles/); see also `fp64`"},
-            # FP64 side (the contract's roofline bounds are hbm | tensor; this kernel is neither): FP64 pipe
-            # operations per env-step (ncu, profiles/: executed DFMA / DMUL / DADD / DSETP thread
-            # instructions / instances) x env-steps/s, against the DFMA issue rate measured on this
-            # device just now (gfr_fp64_peak: TFLOP/s at 2 flop per DFMA, so ops/s = TFLOP/s / 2)
-            "fp64": {"lane_ops_per_env_step": FP64_LANE_OPS.get(args.workload),
-                     "achieved_gops": (FP64_LANE_OPS[args.workload] * value / world / 1e9)
-                                      if args.workload in FP64_LANE_OPS else None,
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": main["workload"], "instances_per_gpu": B, "total_instances": B * world,
+                       "n_bus": main["n_bus"], "obs_dim": main["obs_dim"], "act_dim": main["act_dim"], "solver": solver,
+                       "parallelism": f"shard{world}", "l2": main["l2"], "launch": main["launch"],
+                       "numa_bound_cpus": numa_cpus},
+            "converged_frac": main["converged_frac"], "converged_solves_per_s": value * main["converged_frac"],
+            "mean_iterations": main["mean_iterations"],
+            "roofline": dict(main["roofline"],
+                             note="not HBM bound: ncu shows issue slots and the L1 / shared-memory data pipe as the busiest "
+                                  "units (DESIGN.md section 5, profiles/r02_*); see also `fp64`"),
+            # FP64 side (the contract's roofline bounds are hbm | tensor; this kernel is neither): FP64 lane operations
+            # per env-step (ncu: executed DFMA / DMUL / DADD thread instructions / instances, profiles/) x env-steps/s,
+            # against the DFMA issue rate measured on this device just now (gfr_fp64_peak)
+            "fp64": {"lane_ops_per_env_step": lane_ops,
+                     "achieved_gops": (lane_ops * value / world / 1e9) if lane_ops else None,
                      "peak_gops": fp64_peak.value * 1e3 / 2.0, "peak_dfma_tflops": fp64_peak.value,
-                     "frac": (FP64_LANE_OPS[args.workload] * value / world / 1e9 / (fp64_peak.value * 1e3 / 2.0))
-                             if fp64_peak.value and args.workload in FP64_LANE_OPS else None},
-            "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": stepper.h2d_bytes_per_step,
-                    "d2h_bytes_per_step": stepper.d2h_bytes_per_step, "ms_per_step": ms_e2e / K,
+                     "frac": (lane_ops * value / world / 1e9 / (fp64_peak.value * 1e3 / 2.0))
+                             if fp64_peak.value and lane_ops else None,
+                     "source": fact.get("source") if fact else None},
+            "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / K,
                     "serial_value": e2e_serial, "serial_ms_per_step": ms_serial / K,
-                    "with_observations": {"value": obs_value, "d2h_bytes_per_step": obs_d2h, "steps": K_obs,
-                                          "gb_per_s_d2h": obs_d2h / (ms_obs / K_obs * 1e-3) / 1e9},
-                    "note": "HostStepper (public API): pinned host actions in, reward + terminated + truncated "
-                            "out, every step, each result read by the host; `value` = depth-2 pipeline (next "
-                            "step's H2D overlaps the kernel), `serial_value` = copy-step-copy-sync; "
-                            "observations stay in HBM for a device policy (`with_observations`: every "
-                            "observation row copied to pinned host memory too - PCIe bound)"},
-            "gpu_launches": int(launches), "clocks": clocks,
+                    "with_observations": obs64, "with_observations_f32": obs32,
+                    "note": "HostStepper (public API): pinned host actions in, reward + terminated + truncated out, every "
+                            "step, each result read by the host; `value` = depth-2 pipeline, `serial_value` = "
+                            "copy-step-copy-sync.  `value` is what a DEVICE-side policy sees (the observation stays in "
+                            "HBM); a HOST-side policy sees `with_observations_f32` (or `with_observations` in fp64): "
+                            "every observation row crosses PCIe"},
+            "gpu_launches": main["gpu_launches"], "clocks": clocks,
+            "configs": others,
         }
+        ref = reference_cpu_rates()
+        if ref:
+            line["reference_cpu_measured_in_build_container"] = ref
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline(spec, tol if solver == "newton" else 1e-8,
                                                 *{"ieee123": (256, 12), "ieee34": (2048, 12), "ieee13": (16384, 12), "synthetic1000": (2, 2)}[spec])
         print(json.dumps(line), flush=True)
-    env.close()
     if world > 1:
         dist.destroy_process_group()
 
 
-# FP64 lane operations per env-step: ncu smsp__sass_thread_inst_executed_op_{dfma,dmul,dadd}_pred_on summed over
-# the launch / instances (profiles/r01_ncu_ieee123_v8.txt: (990 + 526 + 302) per cycle x 3.196 M cycles / 131072)
-FP64_LANE_OPS = {"ieee123": 44300}
-
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of the step kernel, from the ncu --set full
-# capture summarised under profiles/ (keyed by workload and instances per launch)
-TRAFFIC_BYTES = {
-    # profiles/r01_ncu_ieee123_v8.txt: 37.3 MB read + 985.1 MB written per launch of step_kernel<8, newton>.
-    # The algorithmic bytes are 772.7 MB (of which the 2L static load columns of the observation, 199 MB, are
-    # never rewritten); the rest of the writes are the solver's scratch (D^-1 U, D^-1 r: 61 MB live, 2.1 GB
-    # written per launch) leaving the L2 under the observation stream
-    # (final binary of the round, profiles/r01_ncu_ieee123_v10.txt: 36.9 MB + 991.1 MB)
-    ("ieee123", 131072): 1028.0e6,
-}
+def measure_rollout(m, dev, world, rank, max_over_ranks, args):
+    """BASELINE configs[4]: synthetic 1,000-bus feeder, 2,048 instances per GPU (16,384 over 8), generating offline
+    rollout data: GraphedCollector replays chunks of steps (action sampling, fused step, copies into the
+    {observations, actions, rewards, next_observations, terminals} block, masked reset) as one CUDA graph."""
+    import torch
+    from grid_fed_rl_b200.compat import GraphedCollector
+    name = "synthetic1000"
+    B, chunk, chunks = WORKLOADS[name][1], 4, 6
+    env = make_envs(m, name, B, dev, rank, 0, args.seed, min_bytes=0)[0]
+    col = GraphedCollector(env, chunk=chunk, dtype=torch.float32)
+    col.run_chunk(); col.run_chunk()                       # eager + capture, then one replay
+    ms = device_timed(dev, world, lambda i: col.run_chunk(), chunks, max_over_ranks)
+    steps = chunks * chunk
+    bytes_per_step = B * 4 * (2 * env.obs_dim + env.act_dim + 2)
+    out = {"value": B * world * steps / (ms * 1e-3), "unit": "env-steps/s", "ms_per_step": ms / steps,
+           "instances_per_gpu": B, "steps": steps, "chunk": chunk,
+           "rollout_bytes_per_step": bytes_per_step, "rollout_gb_per_s_per_gpu": bytes_per_step / (ms / steps * 1e-3) / 1e9,
+           "note": "transitions land in a device-resident fp32 block with the reference's GridDataset field names "
+                   "(algorithms/base.py:180-298); nothing leaves the GPU"}
+    env.close()
+    return out
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="ieee123", choices=sorted(WORKLOADS))
     ap.add_argument("--lanes", type=int, default=0)
@@ -452,6 +594,10 @@ def main():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--kernel-only", action="store_true", help="tuning aid: time the device-resident arm only")
+    ap.add_argument("--no-configs", action="store_true", help="skip the sub-results of the other BASELINE configurations")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: the workload's per-GPU size on every GPU; strong: --total-envs (1,048,576) split over the GPUs")
+    ap.add_argument("--total-envs", type=int, default=0, help="instances in total for --scaling strong")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

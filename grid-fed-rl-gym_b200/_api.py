@@ -18,6 +18,7 @@ __all__ = [
     "NativeRuntimeError", "NetworkTopologyError", "PowerFlowError",
     "BatchedGridEnvironment", "B200PowerFlowSolver", "shard_range",
     "GridEnvironment", "VectorizedEnvironment", "RolloutBuffer", "collect_random_data", "GraphedCollector", "HostStepper",
+    "MultiAgentEnvironmentWrapper", "AgentConfig",
 ]
 
 
@@ -35,6 +36,9 @@ def __getattr__(name):
     if name in ("GridEnvironment", "VectorizedEnvironment", "RolloutBuffer", "collect_random_data", "GraphedCollector"):
         from . import compat
         return getattr(compat, name)
+    if name in ("MultiAgentEnvironmentWrapper", "AgentConfig"):
+        from . import multi_agent
+        return getattr(multi_agent, name)
     if name == "HostStepper":
         from .pipeline import HostStepper
         return HostStepper

@@ -23,6 +23,7 @@ GFR_OK, GFR_E_ARG, GFR_E_CUDA, GFR_E_LIMIT = 0, -1, -2, -3
 SOLVER_SWEEP, SOLVER_NEWTON = 0, 1
 SOLVERS = {"sweep": SOLVER_SWEEP, "newton": SOLVER_NEWTON, "newton_raphson": SOLVER_NEWTON}
 BUS_SLACK, BUS_PV, BUS_PQ = 0, 1, 2
+OBS_F64, OBS_F32 = 0, 1
 
 _i32p, _f64p, _u8p, _u64p = C.POINTER(C.c_int32), C.POINTER(C.c_double), C.POINTER(C.c_uint8), C.POINTER(C.c_uint64)
 
@@ -92,6 +93,8 @@ SIGNATURES: Dict[str, Tuple[object, List[object]]] = {
     "gfr_env_noise_dim": (C.c_int, [C.c_void_p]),
     "gfr_env_obs": (C.c_void_p, [C.c_void_p]),
     "gfr_env_bind_obs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "gfr_env_bind_obs_buffers": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "gfr_env_obs_current": (C.c_void_p, [C.c_void_p]),
     "gfr_env_launch_info": (C.c_int, [C.c_void_p, _i32p, _i32p, _i32p, C.POINTER(C.c_int64)]),
     "gfr_env_state_bytes": (C.c_int64, [C.c_void_p]),
     "gfr_env_state_get": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),

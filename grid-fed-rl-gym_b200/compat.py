@@ -219,8 +219,9 @@ class GraphedCollector:
     IEEE-13 instances) is shorter than the host-side launch work around it."""
 
     def __init__(self, env: BatchedGridEnvironment, chunk: int = 8, dtype=torch.float32) -> None:
-        if env.auto_reset or env.copy_outputs:
-            raise ValueError("GraphedCollector needs an environment with auto_reset=False, copy_outputs=False")
+        if env.auto_reset or env.copy_outputs or len(env._obs_bufs) != 1:
+            raise ValueError("GraphedCollector needs an environment with auto_reset=False, copy_outputs=False and one "
+                             "observation buffer (a captured graph replays fixed pointers)")
         self.env, self.chunk = env, int(chunk)
         B, D, A, dev = env.num_envs, env.obs_dim, env.act_dim, env.device
         z = dict(device=dev, dtype=dtype)

@@ -109,7 +109,8 @@ template <int LANES> __device__ __forceinline__ void use_local_injections(SGrp<L
 template <int LANES, int SOLVER, bool IMG_SMEM>
 __global__ void __launch_bounds__(max_threads_for(LANES))
 step_kernel(const Layout lay, const EnvCfg cfg, const void* __restrict__ img, const int slot_bytes,
-            D2* __restrict__ mscratch, double* __restrict__ state, double* __restrict__ obs,
+            D2* __restrict__ mscratch, double* __restrict__ state, void* __restrict__ obs,
+            const void* obs_prev, const int obs_f32,
             const double* __restrict__ actions, const double* __restrict__ noise, const StepOut o,
             const long long B) {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -122,7 +123,7 @@ step_kernel(const Layout lay, const EnvCfg cfg, const void* __restrict__ img, co
   use_local_injections(g, lay, p_local);
   const int E = blockDim.x / LANES;
   for (long long env = (long long)blockIdx.x * E + threadIdx.x / LANES; env < B; env += (long long)gridDim.x * E)
-    step_instance<LANES, SOLVER>(g, lay, simg, dimg, cfg, env, state, obs, actions, noise, o);
+    step_instance<LANES, SOLVER>(g, lay, simg, dimg, cfg, env, state, obs, obs_prev, obs_f32, actions, noise, o);
 }
 
 template <int LANES, int SOLVER, bool IMG_SMEM>
@@ -145,7 +146,7 @@ solve_kernel(const Layout lay, const EnvCfg cfg, const void* __restrict__ img, c
 // reset: 4 lanes per instance, image read through L2 (touched once per instance)
 __global__ void __launch_bounds__(128)
 reset_kernel(const Layout lay, const EnvCfg cfg, const void* __restrict__ img,
-             double* __restrict__ state, double* __restrict__ obs,
+             double* __restrict__ state, void* __restrict__ obs, const int obs_f32,
              const double* __restrict__ load_pq, const double* __restrict__ bat_soc0,
              const uint64_t* __restrict__ seeds, const uint8_t* __restrict__ mask,
              const double* __restrict__ noise, const double start_time, const int construct,
@@ -160,8 +161,16 @@ reset_kernel(const Layout lay, const EnvCfg cfg, const void* __restrict__ img,
   const int E = blockDim.x / LANES;
   for (long long env = (long long)blockIdx.x * E + threadIdx.x / LANES; env < B; env += (long long)gridDim.x * E) {
     if (mask && !mask[env]) continue;
-    reset_instance<LANES>(g, lay, simg, dimg, cfg, env, state, obs, load_pq, bat_soc0, seeds, noise,
+    reset_instance<LANES>(g, lay, simg, dimg, cfg, env, state, obs, obs_f32, load_pq, bat_soc0, seeds, noise,
                           start_time, construct != 0, env_id_offset);
+  }
+}
+
+// the observation the library holds (fp64) into a buffer the caller binds (fp64 or fp32)
+__global__ void obs_convert_kernel(const double* __restrict__ src, void* __restrict__ dst, const int f32, const long long count) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) {
+    if (f32) reinterpret_cast<float*>(dst)[i] = (float)src[i];
+    else reinterpret_cast<double*>(dst)[i] = src[i];
   }
 }
 
@@ -261,7 +270,9 @@ struct gfr_env {
   size_t smem = 0;
   const void* fn = nullptr;
   double* d_state = nullptr;
-  double* d_obs = nullptr;
+  void* d_obs = nullptr;         // the buffer holding the latest observation
+  void* d_obs_alt = nullptr;     // the other one of two alternating caller-owned buffers (nullptr: one buffer)
+  int obs_f32 = 0;               // caller-bound fp32 observation buffers
   D2* d_mscratch = nullptr;    // Newton: D^-1 U, D^-1 r, specified injections of every resident instance slot (L2 resident)
   int slot_bytes = 0;
   bool obs_external = false;   // bound by gfr_env_bind_obs: caller-owned
@@ -486,14 +497,18 @@ int launch_step(const gfr_env* e, const double* actions, const double* noise, co
                 cudaStream_t s) {
   const void* img = e->img->d_img;
   double* state = e->d_state;
-  double* obs = e->d_obs;
+  // two alternating buffers: this step writes the one that does not hold the latest observation
+  const void* obs_prev = e->d_obs;
+  void* obs = e->d_obs_alt ? e->d_obs_alt : e->d_obs;
+  int f32 = e->obs_f32;
   long long B = e->B;
   int slot = e->slot_bytes;
   D2* ms = e->d_mscratch;
   void* args[] = {(void*)&e->img->lay, (void*)&e->cfg, (void*)&img, (void*)&slot, (void*)&ms, (void*)&state,
-                  (void*)&obs, (void*)&actions, (void*)&noise, (void*)&o, (void*)&B};
+                  (void*)&obs, (void*)&obs_prev, (void*)&f32, (void*)&actions, (void*)&noise, (void*)&o, (void*)&B};
   GFR_CUDA(cudaLaunchKernel(e->fn, dim3(e->grid), dim3(e->threads), args, e->smem, s));
   g_launches.fetch_add(1);
+  if (e->d_obs_alt) std::swap(const_cast<gfr_env*>(e)->d_obs, const_cast<gfr_env*>(e)->d_obs_alt);
   return GFR_OK;
 }
 
@@ -602,7 +617,7 @@ static int launch_reset(gfr_env* e, const uint64_t* seeds, const uint8_t* mask, 
   long long grid = (e->B + per_cta - 1) / per_cta;
   const long long cap = (long long)e->f->sm_count * 16;
   if (grid > cap) grid = cap;
-  reset_kernel<<<(int)grid, threads, 0, s>>>(e->img->lay, e->cfg, e->img->d_img, e->d_state, e->d_obs,
+  reset_kernel<<<(int)grid, threads, 0, s>>>(e->img->lay, e->cfg, e->img->d_img, e->d_state, e->d_obs, e->obs_f32,
                                             e->f->d_load_pq, e->f->d_bat_soc0, seeds, mask, noise,
                                             start_time, construct, e->env_id_offset, e->B);
   g_launches.fetch_add(1);
@@ -655,19 +670,43 @@ int64_t gfr_env_num_envs(const gfr_env* e) { return e ? e->B : 0; }
 int gfr_env_obs_dim(const gfr_env* e) { return e ? e->f->lay.D : 0; }
 int gfr_env_act_dim(const gfr_env* e) { return e ? e->f->lay.A : 0; }
 int gfr_env_noise_dim(const gfr_env* e) { return e ? e->f->lay.n_noise : 0; }
-double* gfr_env_obs(gfr_env* e) { return e ? e->d_obs : nullptr; }
+double* gfr_env_obs(gfr_env* e) { return e && !e->obs_f32 ? (double*)e->d_obs : nullptr; }
+void* gfr_env_obs_current(gfr_env* e) { return e ? e->d_obs : nullptr; }
 int64_t gfr_env_state_bytes(const gfr_env* e) { return e ? (int64_t)e->B * e->f->lay.R * 8 : 0; }
 
-int gfr_env_bind_obs(gfr_env* e, double* obs, void* stream) {
-  if (!e || !obs) return fail(GFR_E_ARG, "null argument");
+int gfr_env_bind_obs_buffers(gfr_env* e, void* obs_a, void* obs_b, int dtype, void* stream) {
+  if (!e || !obs_a) return fail(GFR_E_ARG, "null argument");
+  if (dtype != GFR_OBS_F64 && dtype != GFR_OBS_F32) return fail(GFR_E_ARG, "dtype must be GFR_OBS_F64 or GFR_OBS_F32");
+  if (obs_a == obs_b) return fail(GFR_E_ARG, "the two observation buffers must differ");
   DeviceGuard guard(e->f->device);
   cudaStream_t s = (cudaStream_t)stream;
-  GFR_CUDA(cudaMemcpyAsync(obs, e->d_obs, (size_t)e->B * e->f->lay.D * 8, cudaMemcpyDeviceToDevice, s));
+  const long long count = (long long)e->B * e->f->lay.D;
+  // the observation so far (fp64 if the library still owns it, else the bound type) moves into the new buffers
+  void* bufs[2] = {obs_a, obs_b};
+  for (int i = 0; i < 2; ++i) {
+    if (!bufs[i]) continue;
+    if (!e->obs_f32) {
+      long long grid = (count + 255) / 256;
+      if (grid > (long long)e->f->sm_count * 16) grid = (long long)e->f->sm_count * 16;
+      obs_convert_kernel<<<(int)grid, 256, 0, s>>>((const double*)e->d_obs, bufs[i], dtype == GFR_OBS_F32, count);
+      g_launches.fetch_add(1);
+      GFR_CUDA(cudaGetLastError());
+    } else {
+      if (dtype != GFR_OBS_F32) return fail(GFR_E_ARG, "an environment bound to fp32 observations stays fp32");
+      GFR_CUDA(cudaMemcpyAsync(bufs[i], e->d_obs, (size_t)count * 4, cudaMemcpyDeviceToDevice, s));
+    }
+  }
   GFR_CUDA(cudaStreamSynchronize(s));
   if (!e->obs_external) cudaFree(e->d_obs);
-  e->d_obs = obs;
+  e->d_obs = obs_a;
+  e->d_obs_alt = obs_b;
+  e->obs_f32 = dtype == GFR_OBS_F32;
   e->obs_external = true;
   return GFR_OK;
+}
+
+int gfr_env_bind_obs(gfr_env* e, double* obs, void* stream) {
+  return gfr_env_bind_obs_buffers(e, obs, nullptr, GFR_OBS_F64, stream);
 }
 
 int gfr_env_launch_info(const gfr_env* e, int32_t* lanes, int32_t* threads, int32_t* grid, int64_t* smem_bytes) {

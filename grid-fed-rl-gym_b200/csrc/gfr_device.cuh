@@ -140,8 +140,17 @@ struct Lanes {
 
   GFR_HD void sync() const {
 #if defined(__CUDA_ARCH__)
+#ifdef GFR_STRESS
+    // race hunting build (tests only): every lane dawdles a pseudo-random while before AND after each group
+    // barrier, so an access that relies on lanes happening to run in step - instead of on the barrier - shows
+    // up as a result that differs from the plain build's
+    { unsigned h_ = (unsigned)clock() * 2654435761u + (unsigned)threadIdx.x * 40503u; __nanosleep((h_ >> 20) & 1023u); }
+#endif
     if (LANES > 32) __syncthreads();
     else if (LANES > 1) __syncwarp(mask);
+#ifdef GFR_STRESS
+    { unsigned h_ = (unsigned)clock() * 2246822519u + (unsigned)threadIdx.x * 7919u; __nanosleep((h_ >> 21) & 511u); }
+#endif
 #elif !defined(__CUDACC__)
     if (LANES > 1 && team) team->barrier(team->ctx);
 #endif
@@ -270,14 +279,45 @@ GFR_HD void bind_slot(SGrp<LANES>& g, unsigned char* slot, const Layout& lay, D2
 }
 
 
-// Store of a value nobody on the chip reads again this launch (observation, outputs): evict-first,
-// so that the stream does not push the solver's L2-resident scratch out.
-GFR_HD void st_stream(double* p, double v) {
+// Observation stores are evict-first (st.global.cs): nobody on the chip reads them again this launch, and the
+// stream must not push the solver's L2-resident scratch out.
+// One instance's row of the observation [B, D]: fp64 (default) or fp32 (opt-in; the reference declares float32,
+// grid_env.py:346), in this step's buffer; `prev` reads the previous observation (another buffer when the caller
+// bound two alternating ones).  Pairs (2i, 2i + 1) go out as one 16-byte (8-byte) store when the row starts on an
+// even element.
+struct ObsRow {
+  double* o64; float* o32;
+  const double* p64; const float* p32;
+  bool pair_ok;
+  GFR_HD void put(int i, double v) const {
 #if defined(__CUDA_ARCH__)
-  __stcs(p, v);
+    if (o32) __stcs(o32 + i, (float)v); else __stcs(o64 + i, v);
 #else
-  *p = v;
+    if (o32) o32[i] = (float)v; else o64[i] = v;
 #endif
+  }
+  GFR_HD void put2(int i, double a, double b) const {     // i even
+#if defined(__CUDA_ARCH__)
+    if (pair_ok) {
+      if (o32) __stcs(reinterpret_cast<float2*>(o32 + i), make_float2((float)a, (float)b));
+      else __stcs(reinterpret_cast<double2*>(o64 + i), make_double2(a, b));
+      return;
+    }
+#endif
+    put(i, a); put(i + 1, b);
+  }
+  GFR_HD double prev(int i) const { return p32 ? (double)p32[i] : p64[i]; }
+  GFR_HD bool same_buffer() const { return o32 ? (const float*)o32 == p32 : (const double*)o64 == p64; }
+};
+GFR_HD ObsRow obs_row(void* obs, const void* obs_prev, int f32, long long env, int D) {
+  ObsRow r;
+  const long long off = env * (long long)D;
+  r.o64 = f32 ? nullptr : reinterpret_cast<double*>(obs) + off;
+  r.o32 = f32 ? reinterpret_cast<float*>(obs) + off : nullptr;
+  r.p64 = f32 ? nullptr : reinterpret_cast<const double*>(obs_prev) + off;
+  r.p32 = f32 ? reinterpret_cast<const float*>(obs_prev) + off : nullptr;
+  r.pair_ok = (off & 1LL) == 0;
+  return r;
 }
 
 // 16-byte load of scratch this very thread wrote earlier in the launch: L2 only (the L1 left over beside the
@@ -1001,11 +1041,11 @@ GFR_HD void update_weather(double hour, double u, double z1, double z2, double z
 template <int LANES, int SOLVER>
 GFR_HD void step_instance(const typename GroupOf<LANES, SOLVER>::type& g, const Layout& lay,
                           const int* simg, const double* dimg, const EnvCfg& cfg, long long env,
-                          double* state, double* obs, const double* actions, const double* noise,
-                          const StepOut& o) {
+                          double* state, void* obs, const void* obs_prev, int obs_f32, const double* actions,
+                          const double* noise, const StepOut& o) {
   const int n = lay.n, m = lay.m, L = lay.L, G = lay.G, Bt = lay.Bt, A = lay.A, D = lay.D;
   double* rec = state + env * lay.R;
-  double* ob = obs + env * D;
+  const ObsRow ob = obs_row(obs, obs_prev, obs_f32, env, D);
   const double* act = actions + env * A;
   const int o_line = 2 * n, o_freq = 2 * n + 2 * m, o_gen = o_freq + 1 + 2 * L, o_bat = o_gen + G;
 
@@ -1024,16 +1064,19 @@ GFR_HD void step_instance(const typename GroupOf<LANES, SOLVER>::type& g, const 
   if (bad) {
     double vmax = -INFINITY, vmin = INFINITY;
     for (int i = g.lane; i < n; i += LANES) {
-      double v = ob[2 * i];
+      double v = ob.prev(2 * i);
       vmax = fmax(vmax, v); vmin = fmin(vmin, v);
     }
     vmax = g.gmax(vmax); vmin = g.gmin(vmin);
+    if (!ob.same_buffer())                               // alternating buffers: the unchanged state moves along
+      for (int i = g.lane; i < D; i += LANES) ob.put(i, ob.prev(i));
+    g.sync();
     {
       // get_observation() recomputes the renewable outputs from the clock and the weather
       // (grid_env.py:772-776); every other entry is state this path leaves alone
       const double hour = hour_of(rec[R_TIME]);
       for (int gi = g.lane; gi < G; gi += LANES)
-        ob[o_gen + gi] = renewable_power(lay, simg, dimg, gi, hour, rec[R_WIND], rec[R_TEMP], rec[R_CLOUD]);
+        ob.put(o_gen + gi, renewable_power(lay, simg, dimg, gi, hour, rec[R_WIND], rec[R_TEMP], rec[R_CLOUD]));
     }
     if (g.lane == 0) {
       if (o.reward) o.reward[env] = -cfg.penalty * 2.0;
@@ -1084,7 +1127,7 @@ GFR_HD void step_instance(const typename GroupOf<LANES, SOLVER>::type& g, const 
       soc = soc + en * eff / cap;
     }
     rec[R_BAT + b] = soc; rec[R_BAT + Bt + b] = cur;
-    st_stream(ob + o_bat + 2 * b, soc); st_stream(ob + o_bat + 2 * b + 1, cur);
+    ob.put(o_bat + 2 * b, soc); ob.put(o_bat + 2 * b + 1, cur);
     g.scr(L + G + b) = cur;
     soc_reward += (soc >= 0.2 && soc <= 0.8) ? 1.0 : -5.0;
   }
@@ -1121,7 +1164,7 @@ GFR_HD void step_instance(const typename GroupOf<LANES, SOLVER>::type& g, const 
   for (int gi = g.lane; gi < G; gi += LANES) {
     double p = renewable_power(lay, simg, dimg, gi, hour, wind, temp, cloud);
     double curtail = ((zero_action ? 0.0 : act[Bt + gi]) + 1.0) / 2.0;
-    st_stream(ob + o_gen + gi, p);
+    ob.put(o_gen + gi, p);
     g.scr(L + gi) = p * curtail;
     tot_ren += p;
     tot_used += p - p * (1.0 - curtail);
@@ -1200,8 +1243,7 @@ GFR_HD void step_instance(const typename GroupOf<LANES, SOLVER>::type& g, const 
       const D2 vv = g.ef(k);
       double e = vv.x, f = vv.y;
       double vm = sqrt(e * e + f * f);
-      st_stream(ob + 2 * i, vm);
-      st_stream(ob + 2 * i + 1, atan2_bus(f, e));
+      ob.put2(2 * i, vm, atan2_bus(f, e));
       dev += fabs(vm - 1.0);
       vmax = (vm > vmax || vm != vm) ? vm : vmax;
       vmin = (vm < vmin || vm != vm) ? vm : vmin;
@@ -1221,8 +1263,7 @@ GFR_HD void step_instance(const typename GroupOf<LANES, SOLVER>::type& g, const 
       double pw = P * lay.s_base;
       double rating = dimg[lay.o_rating + pb];
       double loading = rating > 0.0 ? fabs(pw) * rcp_fast(rating) : 0.0;     // Line.update_state, base.py:261-264 (|P| / rating)
-      st_stream(ob + o_line + 2 * li, pw);
-      st_stream(ob + o_line + 2 * li + 1, loading);
+      ob.put2(o_line + 2 * li, pw, loading);
       over80 += loading > 0.8;
     }
   }
@@ -1260,7 +1301,7 @@ GFR_HD void step_instance(const typename GroupOf<LANES, SOLVER>::type& g, const 
   episode_reward += reward;
 
   if (g.lane == 0) {
-    st_stream(ob + o_freq, freq);
+    ob.put(o_freq, freq);
     rec[R_TIME] = t; rec[R_FREQ] = freq; rec[R_WIND] = wind; rec[R_TEMP] = temp; rec[R_CLOUD] = cloud;
     rec[R_TOTAL_LOSSES] = total_losses; rec[R_EPISODE_REWARD] = episode_reward;
     ((uint64_t*)rec)[R_DRAWS] = draw + 1ull;
@@ -1292,12 +1333,12 @@ GFR_HD void step_instance(const typename GroupOf<LANES, SOLVER>::type& g, const 
 template <int LANES>
 GFR_HD void reset_instance(const Lanes<LANES>& g, const Layout& lay, const int* simg,
                            const double* dimg, const EnvCfg& cfg, long long env, double* state,
-                           double* obs, const double* load_pq, const double* bat_soc0,
+                           void* obs, int obs_f32, const double* load_pq, const double* bat_soc0,
                            const uint64_t* seeds, const double* noise, double start_time,
                            bool construct, long long env_id_offset) {
   const int n = lay.n, m = lay.m, L = lay.L, G = lay.G, Bt = lay.Bt, D = lay.D;
   double* rec = state + env * lay.R;
-  double* ob = obs + env * D;
+  const ObsRow ob = obs_row(obs, obs, obs_f32, env, D);
   const int o_line = 2 * n, o_freq = 2 * n + 2 * m, o_load = o_freq + 1, o_gen = o_load + 2 * L,
             o_bat = o_gen + G;
   uint64_t seed = seeds ? seeds[env] : ((const uint64_t*)rec)[R_SEED];
@@ -1321,17 +1362,17 @@ GFR_HD void reset_instance(const Lanes<LANES>& g, const Layout& lay, const int* 
     update_weather(hour_of(0.0), u, z1, z2, z3, &wind, &temp, &cloud);
   }
   g.sync();   // every lane has read the record (weather, seed, draw counter) before lane 0 rewrites it
-  for (int i = g.lane; i < n; i += LANES) { ob[2 * i] = 1.0; ob[2 * i + 1] = 0.0; }
-  for (int li = g.lane; li < m; li += LANES) { ob[o_line + 2 * li] = 0.0; ob[o_line + 2 * li + 1] = 0.0; }
-  for (int l = g.lane; l < 2 * L; l += LANES) ob[o_load + l] = load_pq[l];
+  for (int i = g.lane; i < n; i += LANES) { ob.put(2 * i, 1.0); ob.put(2 * i + 1, 0.0); }
+  for (int li = g.lane; li < m; li += LANES) { ob.put(o_line + 2 * li, 0.0); ob.put(o_line + 2 * li + 1, 0.0); }
+  for (int l = g.lane; l < 2 * L; l += LANES) ob.put(o_load + l, load_pq[l]);
   for (int gi = g.lane; gi < G; gi += LANES)
-    ob[o_gen + gi] = renewable_power(lay, simg, dimg, gi, hour_of(0.0), wind, temp, cloud);
+    ob.put(o_gen + gi, renewable_power(lay, simg, dimg, gi, hour_of(0.0), wind, temp, cloud));
   for (int b = g.lane; b < Bt; b += LANES) {
     rec[R_BAT + b] = bat_soc0[b]; rec[R_BAT + Bt + b] = 0.0;
-    ob[o_bat + 2 * b] = bat_soc0[b]; ob[o_bat + 2 * b + 1] = 0.0;
+    ob.put(o_bat + 2 * b, bat_soc0[b]); ob.put(o_bat + 2 * b + 1, 0.0);
   }
   if (g.lane == 0) {
-    ob[o_freq] = 60.0;
+    ob.put(o_freq, 60.0);
     rec[R_TIME] = start_time; rec[R_FREQ] = 60.0; rec[R_WIND] = wind; rec[R_TEMP] = temp;
     rec[R_CLOUD] = cloud; rec[R_TOTAL_LOSSES] = 0.0; rec[R_EPISODE_REWARD] = 0.0;
     ((uint64_t*)rec)[R_SEED] = seed;

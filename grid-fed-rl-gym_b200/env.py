@@ -101,7 +101,13 @@ class BatchedGridEnvironment:
                  solver: str = "newton", tolerance: float = 1e-6, max_iterations: int = 50,
                  acceleration: float = 1.0, lanes: int = 0, load_noise: float = 0.1, repair="auto",
                  start_time: float = 0.0, env_id_offset: int = 0, auto_reset: bool = False,
-                 copy_outputs: bool = False, record_noise: bool = False, **kwargs) -> None:
+                 copy_outputs: bool = False, record_noise: bool = False, obs_dtype=torch.float64,
+                 obs_buffers: int = 0, **kwargs) -> None:
+        # ``obs_dtype=torch.float32``: the kernels write the observation as fp32 (the type the reference
+        # declares for its observation space, grid_env.py:346; every other output stays fp64).
+        # ``obs_buffers=2``: two alternating observation buffers - step t writes the one that does not hold
+        # observation t - 1, so observation t - 1 can be copied out on another stream while step t runs
+        # (pipeline.HostStepper does).  Default: two for fp32, one for fp64.
         # **kwargs are accepted and ignored, as the reference constructor does (base.py:84)
         if int(num_envs) < 1:
             raise InvalidConfigurationError("num_envs must be >= 1")
@@ -143,14 +149,28 @@ class BatchedGridEnvironment:
         self.act_dim = self.lib.gfr_env_act_dim(h)
         self.noise_dim = self.lib.gfr_env_noise_dim(h)
         # reference spaces (grid_env.py:300-358): obs bounds are +-inf placeholders there too
-        self.observation_space = Box(low=-np.inf, high=np.inf, shape=(self.obs_dim,), dtype=np.float64)
+        if isinstance(obs_dtype, str):
+            obs_dtype = {"float64": torch.float64, "float32": torch.float32}.get(obs_dtype)
+        if obs_dtype not in (torch.float64, torch.float32):
+            raise InvalidConfigurationError("obs_dtype must be torch.float64 or torch.float32")
+        self.obs_dtype = obs_dtype
+        obs_buffers = int(obs_buffers) or (2 if obs_dtype == torch.float32 else 1)
+        if obs_buffers not in (1, 2):
+            raise InvalidConfigurationError("obs_buffers must be 1 or 2")
+        if obs_buffers == 2 and (auto_reset or copy_outputs):
+            obs_buffers = 1           # those modes hand out clones anyway
+        self.observation_space = Box(low=-np.inf, high=np.inf, shape=(self.obs_dim,),
+                                     dtype=np.float32 if obs_dtype == torch.float32 else np.float64)
         self.action_space = Box(low=-1.0, high=1.0, shape=(self.act_dim,), dtype=np.float64)
 
         dev = self.device
         f64 = dict(dtype=torch.float64, device=dev)
-        # the observation buffer is a torch tensor the library writes into (gfr_env_bind_obs)
-        self._obs = torch.empty(B, self.obs_dim, **f64)
-        nat.check(self.lib, self.lib.gfr_env_bind_obs(h, self._obs.data_ptr(), self._stream()))
+        # the observation buffers are torch tensors the library writes into (gfr_env_bind_obs_buffers)
+        self._obs_bufs = [torch.empty(B, self.obs_dim, dtype=obs_dtype, device=dev) for _ in range(obs_buffers)]
+        nat.check(self.lib, self.lib.gfr_env_bind_obs_buffers(
+            h, self._obs_bufs[0].data_ptr(), self._obs_bufs[1].data_ptr() if obs_buffers == 2 else None,
+            nat.OBS_F32 if obs_dtype == torch.float32 else nat.OBS_F64, self._stream()))
+        self._obs_ptr = {t.data_ptr(): t for t in self._obs_bufs}
         u8 = dict(dtype=torch.uint8, device=dev)
         i32 = dict(dtype=torch.int32, device=dev)
         self._out = dict(
@@ -169,6 +189,13 @@ class BatchedGridEnvironment:
         self._seeds = None
 
     # ------------------------------------------------------------------ plumbing
+    @property
+    def _obs(self) -> torch.Tensor:
+        """The buffer holding the latest observation (the library alternates between the bound ones)."""
+        if len(self._obs_bufs) == 1:
+            return self._obs_bufs[0]
+        return self._obs_ptr[self.lib.gfr_env_obs_current(self._h)]
+
     def _stream(self) -> int:
         return torch.cuda.current_stream(self.device).cuda_stream
 
@@ -328,7 +355,8 @@ class BatchedGridEnvironment:
         rec = self._as_device(sd["records"], (self.lib.gfr_env_state_bytes(self._h) // 8,),
                               torch.float64, "records")
         nat.check(self.lib, self.lib.gfr_env_state_set(self._h, rec.data_ptr(), self._stream()))
-        self._obs.copy_(sd["observation"])
+        for t in self._obs_bufs:
+            t.copy_(sd["observation"])
         for k, v in self._out.items():
             if v is not None and k in sd:
                 v.copy_(sd[k])

@@ -33,9 +33,13 @@ class HostStepper:
                            terminated=torch.empty(B, dtype=torch.bool).pin_memory(),
                            truncated=torch.empty(B, dtype=torch.bool).pin_memory())
                       for _ in range(depth)]
+        # with two alternating observation buffers in the environment (obs_buffers=2, the default for fp32
+        # observations) the observation of step t is copied on the copy stream while step t + 1 runs
+        self._overlap_obs = self.observations and len(getattr(env, "_obs_bufs", [])) == 2
         if self.observations:
             for h in self._host:
-                h["observations"] = torch.empty(B, env.obs_dim, dtype=torch.float64).pin_memory()
+                h["observations"] = torch.empty(B, env.obs_dim, dtype=env.obs_dtype).pin_memory()
+        self._stepped = [torch.cuda.Event() for _ in range(depth)]
         self._copied = [torch.cuda.Event() for _ in range(depth)]
         self._done = [torch.cuda.Event() for _ in range(depth)]
         self._busy = [False] * depth
@@ -48,7 +52,8 @@ class HostStepper:
 
     @property
     def d2h_bytes_per_step(self) -> int:
-        return self.env.num_envs * (8 + 1 + 1 + (8 * self.env.obs_dim if self.observations else 0))
+        item = 4 if self.env.obs_dtype == torch.float32 else 8
+        return self.env.num_envs * (8 + 1 + 1 + (item * self.env.obs_dim if self.observations else 0))
 
     def submit(self, host_actions: torch.Tensor) -> None:
         """Queue one step.  ``host_actions``: pinned fp64 ``[B, A]`` (a pageable tensor works but
@@ -65,11 +70,22 @@ class HostStepper:
         compute.wait_event(self._copied[j])
         obs, reward, term, trunc, _ = self.env.step(self._act[j])
         h = self._host[j]
-        if self.observations:
+        if self.observations and not self._overlap_obs:
             h["observations"].copy_(obs, non_blocking=True)
         h["reward"].copy_(reward, non_blocking=True)
         h["terminated"].copy_(term, non_blocking=True)
         h["truncated"].copy_(trunc, non_blocking=True)
+        if self._overlap_obs:
+            # the step after next writes this observation buffer again: by then result() has waited for this copy
+            self._stepped[j].record(compute)
+            with torch.cuda.stream(self.copy_stream):
+                self.copy_stream.wait_event(self._stepped[j])
+                h["observations"].copy_(obs, non_blocking=True)
+                self._done[j].record(self.copy_stream)
+            self._busy[j] = True
+            self._pending.append(j)
+            self._n += 1
+            return
         self._done[j].record(compute)
         self._busy[j] = True
         self._pending.append(j)

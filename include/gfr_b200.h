@@ -178,6 +178,15 @@ double* gfr_env_obs(gfr_env* e);
  * current contents are copied over, the library's own buffer is released).  This is how a host
  * framework gets the observation as one of its own tensors without a copy per step. */
 int gfr_env_bind_obs(gfr_env* e, double* obs, void* stream);
+/* The same with a choice of type and, optionally, TWO alternating buffers: step t writes the buffer that does not
+ * hold observation t - 1, so a caller can copy observation t - 1 out (to the host, to a replay block) on another
+ * stream while step t runs.  dtype GFR_OBS_F32 makes the kernels write the observation as fp32 - the type the
+ * reference declares for its observation space (grid_env.py:346) - halving what a host-side policy pulls over
+ * PCIe; every other output stays fp64.  obs_b = NULL binds one buffer.  gfr_env_obs_current() is the buffer
+ * holding the latest observation (reset writes into it, the next step into the other one). */
+enum { GFR_OBS_F64 = 0, GFR_OBS_F32 = 1 };
+int gfr_env_bind_obs_buffers(gfr_env* e, void* obs_a, void* obs_b, int dtype, void* stream);
+void* gfr_env_obs_current(gfr_env* e);
 /* How the step kernel is launched for this env (for benchmarks / profiles): threads cooperating
  * on one instance, threads per CTA, CTAs, dynamic shared memory per CTA. */
 int gfr_env_launch_info(const gfr_env* e, int32_t* lanes, int32_t* threads, int32_t* grid,

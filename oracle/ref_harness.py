@@ -490,6 +490,63 @@ def freeze_dataset(ns, out_dir: str) -> None:
     print("dataset", sorted(out), flush=True)
 
 
+def freeze_multi_agent(ns, out_dir: str) -> None:
+    """tests/golden/multi_agent_wrapper.npz: the reference's MultiAgentEnvironmentWrapper
+    (algorithms/multi_agent.py:37-135) around a scripted base environment - observation slices (incl. one agent
+    whose slice runs past the end and is zero-padded), joint actions (scalar action, missing agent), reward
+    split with a per-agent bonus in info, done flags."""
+    from grid_fed_rl.algorithms.multi_agent import AgentConfig, MultiAgentEnvironmentWrapper
+    rs = np.random.RandomState(11)
+    D, steps = 19, 6
+    cfgs = [("battery", 7, 1), ("solar", 5, 1), ("wind", 4, 1), ("observer", 6, 2)]     # 7 + 5 + 4 + 6 = 22 > 19
+    obs_script = rs.normal(size=(steps + 1, D))
+    rew_script = rs.normal(size=steps) * 10
+    done_script = [(False, False), (False, False), (False, True), (False, False), (True, False), (False, False)]
+    bonus_script = rs.normal(size=steps)
+
+    class Scripted:
+        def __init__(self):
+            self.t = 0
+            self.joint = []
+
+        def reset(self):
+            self.t = 0
+            return obs_script[0], {}
+
+        def step(self, joint):
+            self.joint.append(np.array(joint, dtype=float))
+            t = self.t
+            self.t += 1
+            info = {"solar_reward_bonus": float(bonus_script[t]), "t": t}
+            return obs_script[t + 1], float(rew_script[t]), done_script[t][0], done_script[t][1], info
+
+    base = Scripted()
+    w = MultiAgentEnvironmentWrapper(base, [AgentConfig(a, o, d) for a, o, d in cfgs])
+    out = {"obs_script": obs_script, "rew_script": rew_script, "bonus_script": bonus_script,
+           "done_script": np.array(done_script), "agents": np.array([c[0] for c in cfgs]),
+           "obs_dims": np.array([c[1] for c in cfgs]), "act_dims": np.array([c[2] for c in cfgs])}
+    first = w.reset()
+    for a in first:
+        out[f"reset_obs_{a}"] = np.asarray(first[a], dtype=float)
+    act_script = []
+    for t in range(steps):
+        acts = {"battery": rs.uniform(-1, 1, size=1), "solar": float(rs.uniform(-1, 1)),      # a scalar action
+                "observer": rs.uniform(-1, 1, size=2)}
+        if t % 2 == 0:
+            acts["wind"] = rs.uniform(-1, 1, size=1)                                            # else: missing -> zeros
+        act_script.append({k: np.atleast_1d(np.asarray(v, dtype=float)) for k, v in acts.items()})
+        obs, rew, done, info = w.step(acts)
+        for a in obs:
+            out[f"step{t}_obs_{a}"] = np.asarray(obs[a], dtype=float)
+            out[f"step{t}_rew_{a}"] = np.array(float(rew[a]))
+            out[f"step{t}_done_{a}"] = np.array(bool(done[a]))
+        for k, v in act_script[-1].items():
+            out[f"step{t}_act_{k}"] = v
+    out["joint_actions"] = np.array(base.joint)
+    np.savez_compressed(os.path.join(out_dir, "multi_agent_wrapper.npz"), **out)
+    print("multi-agent wrapper golden:", out["joint_actions"].shape, flush=True)
+
+
 def main() -> None:
     ns = build()
     out_dir = os.path.join(REPO_ROOT, "tests", "golden")
@@ -499,6 +556,8 @@ def main() -> None:
         freeze_feeders(ns, out_dir)
     if not only or "dataset" in only:
         freeze_dataset(ns, out_dir)
+    if not only or "multi_agent" in only:
+        freeze_multi_agent(ns, out_dir)
     for name, (spec, seed, count, tol, scale) in SOLVE_CASES.items():
         if only and name not in only:
             continue

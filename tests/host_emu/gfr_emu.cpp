@@ -69,10 +69,10 @@ void step_all(emu_env* e, const double* actions, const double* noise, const Step
     for (long long i = 0; i < e->B; ++i) {
       if (e->solver == SOLVER_NEWTON)
         step_instance<LANES, SOLVER_NEWTON>(slot.group<NGrp<LANES>>(lay, lane, team), lay, simg, dimg, e->cfg, i,
-                                            e->state.data(), e->obs.data(), actions, noise, o);
+                                            e->state.data(), e->obs.data(), e->obs.data(), 0, actions, noise, o);
       else
         step_instance<LANES, SOLVER_SWEEP>(slot.group<SGrp<LANES>>(lay, lane, team), lay, simg, dimg, e->cfg, i,
-                                           e->state.data(), e->obs.data(), actions, noise, o);
+                                           e->state.data(), e->obs.data(), e->obs.data(), 0, actions, noise, o);
     }
   });
 }
@@ -120,7 +120,7 @@ emu_env* emu_create(const gfr_feeder_desc* d, long long B, const gfr_env_cfg* c)
   Lanes<1> g; g.lane = 0; g.mask = 1u;
   for (long long i = 0; i < B; ++i)
     reset_instance<1>(g, lay, (const int*)e->fi.img.data(), (const double*)e->fi.img.data(), k, i,
-                      e->state.data(), e->obs.data(), e->fi.load_pq.data(), e->bat_soc0.data(),
+                      e->state.data(), e->obs.data(), 0, e->fi.load_pq.data(), e->bat_soc0.data(),
                       nullptr, nullptr, 0.0, true, (long long)c->env_id_offset);
   return e;
 }
@@ -140,7 +140,7 @@ void emu_reset(emu_env* e, const uint64_t* seeds, const uint8_t* mask, const dou
   for (long long i = 0; i < e->B; ++i) {
     if (mask && !mask[i]) continue;
     reset_instance<1>(g, lay, (const int*)e->fi.img.data(), (const double*)e->fi.img.data(), e->cfg, i,
-                      e->state.data(), e->obs.data(), e->fi.load_pq.data(), e->bat_soc0.data(), seeds,
+                      e->state.data(), e->obs.data(), 0, e->fi.load_pq.data(), e->bat_soc0.data(), seeds,
                       noise, start_time, false, 0);
   }
 }

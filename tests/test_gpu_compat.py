@@ -194,3 +194,117 @@ def test_graphed_collection_is_consistent_and_faster_to_launch():
     torch.cuda.synchronize(); t_graph = time.perf_counter() - t0
     print(f"64 steps x {B} instances: eager loop {t_eager * 1e3:.1f} ms, graph replay {t_graph * 1e3:.1f} ms")
     assert t_graph < t_eager
+
+
+@pytest.mark.parametrize("spec", ["ieee13", "ieee34"])
+def test_fp32_and_alternating_observation_buffers(spec):
+    """obs_dtype=float32: the kernels write the observation rounded to fp32 (the reference declares float32,
+    grid_env.py:346) - bit for bit the fp64 observation cast to float, every other output untouched; two
+    alternating buffers (so that observation t - 1 can be copied out under step t) change nothing either, incl.
+    the rejected-action path, which carries the unchanged state over from the previous buffer, and masked resets."""
+    import grid_fed_rl_b200 as m
+    from oracle.ref_harness import make_feeder
+    f = make_feeder(None, spec, use_reference_classes=False)
+    kw = dict(renewable_sources=["solar", "wind"], timestep=60.0, repair=False, start_time=11 * 3600.0, tolerance=1e-8)
+    B = 203
+    ref = m.BatchedGridEnvironment(f, B, **kw)                                   # fp64, one buffer
+    alt = m.BatchedGridEnvironment(f, B, obs_buffers=2, **kw)                    # fp64, alternating
+    f32 = m.BatchedGridEnvironment(f, B, obs_dtype=torch.float32, **kw)          # fp32, alternating (default)
+    one = m.BatchedGridEnvironment(f, B, obs_dtype="float32", obs_buffers=1, **kw)
+    assert len(f32._obs_bufs) == 2 and f32.observation_space.dtype == np.float32
+    envs = (ref, alt, f32, one)
+    for e in envs:
+        o, _ = e.reset(seed=9)
+    assert torch.equal(f32.get_observation(), ref.get_observation().float()) and f32.get_observation().dtype == torch.float32
+    g = torch.Generator(device="cuda"); g.manual_seed(4)
+    prev32 = None
+    for t in range(7):
+        act = ref.sample_actions(g)
+        if t in (2, 3) and ref.act_dim > 1:
+            act[5, 0] = float("nan")                     # rejected twice in a row: the row travels through both buffers
+            act[77, 1] = float("inf")
+        outs = [e.step(act) for e in envs]
+        o64, r64, t64, u64, i64 = outs[0]
+        for (o, r, te, tr, info), e in zip(outs[1:], envs[1:]):
+            assert torch.equal(r, r64) and torch.equal(te, t64) and torch.equal(tr, u64)
+            assert torch.equal(info["iterations"], i64["iterations"]) and torch.equal(info["error"], i64["error"])
+            assert torch.equal(info["max_voltage"], i64["max_voltage"])
+            if e.obs_dtype == torch.float32:
+                assert o.dtype == torch.float32 and torch.equal(o, o64.float())
+            else:
+                assert torch.equal(o, o64)
+        if prev32 is not None:
+            # the previous step's observation is still intact in the other buffer (what the overlapped copy reads)
+            assert torch.equal(prev32[0], prev32[1])
+        prev32 = (outs[2][0], outs[2][0].clone())
+        if t == 4:
+            mask = torch.zeros(B, dtype=torch.bool, device="cuda"); mask[::3] = True
+            rs = [e.reset(mask=mask)[0] for e in envs]
+            assert torch.equal(rs[1], rs[0]) and torch.equal(rs[2], rs[0].float()) and torch.equal(rs[3], rs[0].float())
+            prev32 = None
+    sd = f32.state_dict()
+    clone = m.BatchedGridEnvironment(f, B, obs_dtype=torch.float32, **kw)
+    clone.load_state_dict(sd)
+    act = ref.sample_actions(g)
+    assert torch.equal(clone.step(act)[0], f32.step(act)[0])
+    for e in envs + (clone,):
+        e.close()
+
+
+def test_host_stepper_overlaps_fp32_observation_copies():
+    import grid_fed_rl_b200 as m
+    from grid_fed_rl_b200.pipeline import HostStepper
+    f = m.repair_topology(m.IEEE13Bus())
+    kw = dict(renewable_sources=["solar", "wind"], timestep=60.0, repair=False, start_time=10 * 3600.0)
+    B = 4096
+    a = m.BatchedGridEnvironment(f, B, **kw)
+    b = m.BatchedGridEnvironment(f, B, obs_dtype=torch.float32, **kw)
+    a.reset(seed=2); b.reset(seed=2)
+    g = torch.Generator(device="cuda"); g.manual_seed(1)
+    acts = [a.sample_actions(g).cpu().pin_memory() for _ in range(6)]
+    st = HostStepper(b, depth=2, observations=True)
+    assert st._overlap_obs and st.d2h_bytes_per_step == B * (10 + 4 * b.obs_dim)
+    got = []
+    for i, act in enumerate(acts):
+        st.submit(act)
+        if i >= 1:
+            r = st.result()
+            got.append((r["observations"].clone(), r["reward"].clone()))
+    while st._pending:
+        r = st.result()
+        got.append((r["observations"].clone(), r["reward"].clone()))
+    assert len(got) == len(acts)
+    for act, (o, r) in zip(acts, got):
+        o64, r64, _, _, _ = a.step(act)
+        assert torch.equal(o, o64.float().cpu()) and torch.equal(r, r64.cpu())
+    with pytest.raises(ValueError):
+        from grid_fed_rl_b200.compat import GraphedCollector
+        GraphedCollector(b)
+
+
+def test_multi_agent_wrapper_on_the_batched_environment():
+    """Three agents (battery, solar, wind) over IEEE-13: the joint action drives the same step, every agent gets
+    its slice of the observation as a view, the shared reward is split evenly (multi_agent.py:37-135)."""
+    import grid_fed_rl_b200 as m
+    f = m.repair_topology(m.IEEE13Bus())
+    kw = dict(renewable_sources=["solar", "wind"], timestep=60.0, repair=False, start_time=10 * 3600.0)
+    B = 64
+    base, plain = m.BatchedGridEnvironment(f, B, **kw), m.BatchedGridEnvironment(f, B, **kw)
+    D = base.obs_dim
+    cfgs = [m.AgentConfig("battery", 26, 1), m.AgentConfig("solar", 30, 1), m.AgentConfig("wind", D - 56 + 4, 1)]
+    w = m.MultiAgentEnvironmentWrapper(base, cfgs)
+    base.reset(seed=4); plain.reset(seed=4)
+    first = w.reset(seed=4)
+    assert first["battery"].shape == (B, 26) and first["wind"].shape == (B, D - 52)
+    g = torch.Generator(device="cuda"); g.manual_seed(8)
+    for t in range(3):
+        act = plain.sample_actions(g)
+        obs, rew, done, info = w.step({"battery": act[:, 0:1], "solar": act[:, 1], "wind": act[:, 2:3]})
+        o, r, te, tr, _ = plain.step(act)
+        assert torch.equal(obs["battery"], o[:, :26]) and torch.equal(obs["solar"], o[:, 26:56])
+        assert torch.equal(obs["wind"][:, :D - 56], o[:, 56:]) and torch.equal(obs["wind"][:, D - 56:], torch.zeros(B, 4, dtype=o.dtype, device=o.device))
+        for a in ("battery", "solar", "wind"):
+            assert torch.equal(rew[a], r / 3) and torch.equal(done[a], te | tr)
+    obs, rew, done, info = w.step({"battery": torch.zeros(B, 1)})          # the others send nothing: zeros
+    o, r, _, _, _ = plain.step(torch.zeros(B, 3, dtype=torch.float64))
+    assert torch.equal(obs["solar"], o[:, 26:56]) and torch.equal(rew["wind"], r / 3)
