@@ -59,30 +59,39 @@ def global_seeds(seed: int, start: int, count: int, device=None) -> torch.Tensor
 
 
 def fedavg_all_reduce(parameters: Dict[str, torch.Tensor], num_samples: float,
-                      group=None) -> Dict[str, torch.Tensor]:
+                      group=None, bucket_dtype=None) -> Dict[str, torch.Tensor]:
     """Sample-weighted average of per-rank client parameters - the reference's
     ``FedAvgAggregator.aggregate`` (federated/core.py:233-258: ``sum_i (n_i / N) p_i``) with the
     list of clients replaced by the ranks of a process group.  Every tensor is packed into one
-    flat bucket (plus the sample count), one all-reduce (NCCL over NVLink / NVSwitch on GPUs)
-    moves it, and the result is unpacked into new tensors of the original shapes and dtypes.
-    A rank with ``num_samples == 0`` contributes nothing; if no rank has samples the result is
-    empty, as upstream."""
+    flat bucket (one ``cat``), scaled by the rank's sample count, moved by ONE all-reduce (NCCL over
+    NVLink / NVSwitch on GPUs; the sample counts ride along as the bucket's last element) and handed
+    back as views of the reduced bucket in the original shapes - a handful of kernels whatever the
+    number of tensors.  The bucket has the parameters' own floating type when they all share one
+    (fp32 for the reference's torch learners; its numpy arithmetic keeps float32 too), else fp64;
+    ``bucket_dtype`` overrides.  A rank with ``num_samples == 0`` contributes nothing; if no rank
+    has samples the result is empty, as upstream."""
     names = list(parameters)
     if not names:
         return {}
-    ref = parameters[names[0]]
-    flat = torch.cat([parameters[k].reshape(-1).to(torch.float64) for k in names]
-                     + [torch.zeros(1, dtype=torch.float64, device=ref.device)])
-    flat[:-1] *= float(num_samples)
-    flat[-1] = float(num_samples)
+    tensors = [parameters[k] for k in names]
+    dtypes = {t.dtype for t in tensors}
+    if bucket_dtype is None:
+        only = next(iter(dtypes)) if len(dtypes) == 1 else None
+        bucket_dtype = only if only in (torch.float32, torch.float64) else torch.float64
+    dev = tensors[0].device
+    count = torch.full((1,), 1.0, dtype=bucket_dtype, device=dev)
+    flat = torch.cat([t.reshape(-1).to(bucket_dtype) for t in tensors] + [count])
+    flat *= float(num_samples)
     if is_distributed():
         dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
     total = float(flat[-1].item())
     if total == 0.0:
         return {}
+    flat /= total
     out, o = {}, 0
-    for k in names:
-        n = parameters[k].numel()
-        out[k] = (flat[o:o + n] / total).reshape(parameters[k].shape).to(parameters[k].dtype)
+    for k, t in zip(names, tensors):
+        n = t.numel()
+        v = flat[o:o + n].reshape(t.shape)
+        out[k] = v if v.dtype == t.dtype else v.to(t.dtype)
         o += n
     return out

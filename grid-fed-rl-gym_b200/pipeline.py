@@ -37,8 +37,17 @@ class HostStepper:
         # observations) the observation of step t is copied on the copy stream while step t + 1 runs
         self._overlap_obs = self.observations and len(getattr(env, "_obs_bufs", [])) == 2
         if self.observations:
+            # The 2L static load columns of the observation never change after construction (the reference reads
+            # them as constants, grid_env.py:766-770): the host rows get them once, here, and every step copies
+            # only the columns around them (IEEE-123: 502 of 692 entries).
+            soa = env.soa
+            c0 = 2 * soa.n_bus + 2 * soa.n_line + 1
+            c1 = c0 + 2 * soa.n_load
+            self._dyn_cols = [(0, c0), (c1, env.obs_dim)] if c1 > c0 else [(0, env.obs_dim)]
+            first = env.get_observation().cpu()
             for h in self._host:
                 h["observations"] = torch.empty(B, env.obs_dim, dtype=env.obs_dtype).pin_memory()
+                h["observations"].copy_(first)
         self._stepped = [torch.cuda.Event() for _ in range(depth)]
         self._copied = [torch.cuda.Event() for _ in range(depth)]
         self._done = [torch.cuda.Event() for _ in range(depth)]
@@ -53,7 +62,13 @@ class HostStepper:
     @property
     def d2h_bytes_per_step(self) -> int:
         item = 4 if self.env.obs_dtype == torch.float32 else 8
-        return self.env.num_envs * (8 + 1 + 1 + (item * self.env.obs_dim if self.observations else 0))
+        cols = sum(b - a for a, b in self._dyn_cols) if self.observations else 0
+        return self.env.num_envs * (8 + 1 + 1 + item * cols)
+
+    def _copy_obs(self, dst: torch.Tensor, obs: torch.Tensor) -> None:
+        for a, b in self._dyn_cols:
+            if b > a:
+                dst[:, a:b].copy_(obs[:, a:b], non_blocking=True)
 
     def submit(self, host_actions: torch.Tensor) -> None:
         """Queue one step.  ``host_actions``: pinned fp64 ``[B, A]`` (a pageable tensor works but
@@ -71,7 +86,7 @@ class HostStepper:
         obs, reward, term, trunc, _ = self.env.step(self._act[j])
         h = self._host[j]
         if self.observations and not self._overlap_obs:
-            h["observations"].copy_(obs, non_blocking=True)
+            self._copy_obs(h["observations"], obs)
         h["reward"].copy_(reward, non_blocking=True)
         h["terminated"].copy_(term, non_blocking=True)
         h["truncated"].copy_(trunc, non_blocking=True)
@@ -80,7 +95,7 @@ class HostStepper:
             self._stepped[j].record(compute)
             with torch.cuda.stream(self.copy_stream):
                 self.copy_stream.wait_event(self._stepped[j])
-                h["observations"].copy_(obs, non_blocking=True)
+                self._copy_obs(h["observations"], obs)
                 self._done[j].record(self.copy_stream)
             self._busy[j] = True
             self._pending.append(j)

@@ -263,7 +263,7 @@ def test_host_stepper_overlaps_fp32_observation_copies():
     g = torch.Generator(device="cuda"); g.manual_seed(1)
     acts = [a.sample_actions(g).cpu().pin_memory() for _ in range(6)]
     st = HostStepper(b, depth=2, observations=True)
-    assert st._overlap_obs and st.d2h_bytes_per_step == B * (10 + 4 * b.obs_dim)
+    assert st._overlap_obs and st.d2h_bytes_per_step == B * (10 + 4 * (b.obs_dim - 2 * b.soa.n_load))
     got = []
     for i, act in enumerate(acts):
         st.submit(act)

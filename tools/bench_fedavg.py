@@ -51,7 +51,7 @@ def main():
     res = {}
     for name, params in cases.items():
         nbytes32 = sum(v.numel() * 4 for v in params.values())
-        wire = sum(v.numel() for v in params.values()) * 8 + 8            # the bucket travels as fp64
+        wire = (sum(v.numel() for v in params.values()) + 1) * 4          # the bucket travels in the parameters' fp32
         out = fedavg_all_reduce(params, n_samples)                        # warm-up + correctness
         if name.startswith("flat"):
             tot = sum(1000.0 * (r + 1) for r in range(world))
@@ -72,7 +72,7 @@ def main():
         ms = max_over_ranks(ev0.elapsed_time(ev1), dev) / K
         alg = wire / (ms * 1e-3) / 1e9
         res[name] = {"parameters": sum(v.numel() for v in params.values()), "tensors": len(params),
-                     "param_bytes_fp32": nbytes32, "bucket_bytes_fp64": wire, "ms_per_aggregation": ms,
+                     "param_bytes_fp32": nbytes32, "bucket_bytes": wire, "ms_per_aggregation": ms,
                      "algbw_gb_s": alg, "busbw_gb_s": alg * 2 * (world - 1) / world if world > 1 else None}
     if rank == 0:
         print(json.dumps({"what": "fedavg_all_reduce (weighted FedAvg as one NCCL all-reduce, pack + reduce + unpack timed)",
