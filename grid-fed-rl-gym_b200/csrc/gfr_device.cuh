@@ -110,6 +110,62 @@ struct SolveStat {
   int converged;
 };
 
+// The Newton scratch in global memory (D^-1 U, D^-1 r, specified injections: written and read back within the
+// launch, every Newton iteration) must stay in L2 while the observation - four to five times as many bytes,
+// written once - streams past it.  The observation goes out evict-first (__stcs); the scratch carries an L2
+// evict-last policy (a 64-bit descriptor made once per thread with createpolicy) on its stores and loads.
+// Loads are plain (weak) loads without L1 allocation: __ldcg would be a STRONG.GPU load here, ordered against
+// every earlier store of the thread (measured: 3 x slower kernel).
+GFR_HD uint64_t scratch_policy() {
+#if defined(__CUDA_ARCH__) && !defined(GFR_NO_L2_POLICY)
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+#else
+  return 0;
+#endif
+}
+GFR_HD D2 ld_scratch(const D2* p, uint64_t pol) {
+#if defined(__CUDA_ARCH__) && !defined(GFR_NO_L2_POLICY)
+  D2 r;
+  asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(r.x), "=d"(r.y) : "l"(p), "l"(pol) : "memory");
+  return r;
+#elif defined(__CUDA_ARCH__)
+  D2 r;
+  asm volatile("ld.global.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p) : "memory");
+  return r;
+#else
+  (void)pol;
+  return *p;
+#endif
+}
+GFR_HD void st_scratch(D2* p, const D2 v, uint64_t pol) {
+#if defined(__CUDA_ARCH__) && !defined(GFR_NO_L2_POLICY)
+  asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(p), "d"(v.x), "d"(v.y), "l"(pol) : "memory");
+#else
+  (void)pol;
+  *p = v;
+#endif
+}
+GFR_HD double ld_scratch1(const double* p, uint64_t pol) {
+#if defined(__CUDA_ARCH__) && !defined(GFR_NO_L2_POLICY)
+  double r;
+  asm volatile("ld.global.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(r) : "l"(p), "l"(pol) : "memory");
+  return r;
+#else
+  (void)pol;
+  return *p;
+#endif
+}
+GFR_HD void st_scratch1(double* p, double v, uint64_t pol) {
+#if defined(__CUDA_ARCH__) && !defined(GFR_NO_L2_POLICY)
+  asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(pol) : "memory");
+#else
+  (void)pol;
+  *p = v;
+#endif
+}
+
 // ----------------------------------------------------------------------------- group ops
 
 struct OpMaxNan { GFR_HD double operator()(double v, double w) const { return (w > v || w != w) ? w : v; } };
@@ -222,7 +278,8 @@ struct SGrp : Lanes<LANES> {
   GFR_HD double& at(int, int k) const { return pp[k]; }                                   // S_P
   GFR_HD D2& at2(int field, int k) const { return field == F_E ? efp[k] : jrp[k]; }       // F_E | S_JR
   GFR_HD D2& ef(int k) const { return efp[k]; }
-  GFR_HD double& pspec(int k) const { return pp[k]; }
+  GFR_HD double pspec(int k) const { return pp[k]; }
+  GFR_HD void set_pspec(int k, double v) const { pp[k] = v; }
   GFR_HD double& scr(int j) const { return reinterpret_cast<double*>(jrp)[j]; }           // sources: the J array, flat (2 n doubles)
 };
 
@@ -237,8 +294,10 @@ struct NGrp : Lanes<LANES> {
   int np;         // n_pool
   double* pp;     // [P]      specified injections by position (global scratch, right after mg)
   D2* mg;         // [3][P]   GLOBAL scratch of this instance slot: rows of D^-1 U (2) and D^-1 r (1), field-major, by position
+  uint64_t pol;   // L2 evict-last policy of the scratch
   GFR_HD D2& ef(int k) const { return efp[k]; }
-  GFR_HD double& pspec(int p) const { return pp[p]; }
+  GFR_HD double pspec(int p) const { return ld_scratch1(pp + p, pol); }
+  GFR_HD void set_pspec(int p, double v) const { st_scratch1(pp + p, v, pol); }
   GFR_HD double& scr(int j) const { return reinterpret_cast<double*>(efp)[j]; }   // ef + pool, flat
 };
 
@@ -268,6 +327,7 @@ GFR_HD void bind_slot(NGrp<LANES>& g, unsigned char* slot, const Layout& lay, D2
   g.poolp = g.efp + lay.n;
   g.pp = reinterpret_cast<double*>(mg + 3 * (size_t)lay.P);
   g.mg = mg;
+  g.pol = scratch_policy();
 }
 template <int LANES>
 GFR_HD void bind_slot(SGrp<LANES>& g, unsigned char* slot, const Layout& lay, D2*) {
@@ -318,20 +378,6 @@ GFR_HD ObsRow obs_row(void* obs, const void* obs_prev, int f32, long long env, i
   r.p32 = f32 ? reinterpret_cast<const float*>(obs_prev) + off : nullptr;
   r.pair_ok = (off & 1LL) == 0;
   return r;
-}
-
-// 16-byte load of scratch this very thread wrote earlier in the launch: L2 only (the L1 left over beside the
-// shared-memory carve-out is a few KB)
-GFR_HD D2 ld_scratch(const D2* p) {
-#if defined(__CUDA_ARCH__)
-  D2 r;
-  // a plain (weak) load without L1 allocation; __ldcg would be a STRONG.GPU load here, ordered against every
-  // earlier store of the thread (measured: 3 x slower kernel)
-  asm volatile("ld.global.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p) : "memory");
-  return r;
-#else
-  return *p;
-#endif
 }
 
 // 1 / x for a normal, finite x: hardware seed + two Newton steps (~1 ulp), no slow-path call.
@@ -568,8 +614,8 @@ GFR_HD void newton_back_update(const NGrp<LANES>& g, const Layout& lay, const in
 #define GFR_LOAD_MV(row_, m0_, m1_, v_)                                    \
   do {                                                                     \
     const int ps_ = (row_) * LANES + g.lane;                               \
-    if (!f0) { m0_ = ld_scratch(g.mg + ps_); m1_ = ld_scratch(g.mg + P + ps_); } \
-    v_ = ld_scratch(g.mg + 2 * P + ps_);                                   \
+    if (!f0) { m0_ = ld_scratch(g.mg + ps_, g.pol); m1_ = ld_scratch(g.mg + P + ps_, g.pol); } \
+    v_ = ld_scratch(g.mg + 2 * P + ps_, g.pol);                                   \
   } while (0)
   D2 hx; hx.x = hx.y = 0.0;                            // the correction of the bus this lane handled in the previous row
 #define GFR_BU_ROW(row_, m0_, m1_, v_)                                     \
@@ -674,7 +720,7 @@ GFR_HD void newton_solve(const NGrp<LANES>& g, const Layout& lay, const int* sim
           v.y = fma(i1.x, r0, i1.y * r1);
           hc.x = fma(lp.x, v.x, lp.y * v.y);
           hc.y = fma(-lp.y, v.x, lp.x * v.y);
-          g.mg[2 * P + p] = v;
+          st_scratch(g.mg + 2 * P + p, v, g.pol);
           if (!(t.z & FL_P_REG)) g.poolp[2 * np + pool_slot_of(t.z)] = hc;
         }
         g.sync();
@@ -753,9 +799,9 @@ GFR_HD void newton_solve(const NGrp<LANES>& g, const Layout& lay, const int* sim
           m1.y = fma(i10, u01, i11 * u11);
           v.x = fma(i00, r.x, i01 * r.y);
           v.y = fma(i10, r.x, i11 * r.y);
-          g.mg[p] = m0;                                  // needed again in the back-substitution only
-          g.mg[P + p] = m1;
-          g.mg[2 * P + p] = v;
+          st_scratch(g.mg + p, m0, g.pol);               // needed again in the back-substitution only
+          st_scratch(g.mg + P + p, m1, g.pol);
+          st_scratch(g.mg + 2 * P + p, v, g.pol);
           // handed to the parent: L M, L v, (gl, ll)
           h0.x = fma(bt.ll, m0.x, bt.gl * m1.x);
           h0.y = fma(bt.ll, m0.y, bt.gl * m1.y);
@@ -955,7 +1001,7 @@ GFR_HD void solve_instance(const typename GroupOf<LANES, SOLVER>::type& g, const
   const int* rank = simg + lay.o_rank;
   const int* rankp = simg + lay.o_rankp;
   const double* pin = p_inj + env * n;
-  for (int i = g.lane; i < n; i += LANES) g.pspec(rankp[i]) = pin[i];
+  for (int i = g.lane; i < n; i += LANES) g.set_pspec(rankp[i], pin[i]);
   g.sync();          // a position's injection is read by the lane that owns the position, not the one that owns ref bus i
   flat_start(g, lay, simg, dimg);
   SolveStat st;
@@ -1225,7 +1271,7 @@ GFR_HD void step_instance(const typename GroupOf<LANES, SOLVER>::type& g, const 
         else if (v < 0.0) ld += fabs(v);
       }
       // write after every lane has read its sources: F_P is not part of the scratch region
-      g.pspec(k) = fma(gn, lay.inv_s_base, -ld * lay.inv_s_base);
+      g.set_pspec(k, fma(gn, lay.inv_s_base, -ld * lay.inv_s_base));
     }
   }
   g.sync();
