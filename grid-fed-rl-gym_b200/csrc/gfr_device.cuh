@@ -397,6 +397,13 @@ GFR_HD double rcp_fast(double x) {
 // < 1 ulp of 1.0 for |x| <= 0.25 (next terms x^17/17! < 2e-25, x^18/18! < 1e-26).  Larger steps
 // (a diverging solve) are halved first and doubled back; nothing here calls a library slow path.
 GFR_HD void sincos_small(double x, double* s, double* c) {
+  if (fabs(x) <= 0.0078125) {
+    // every update after the first: |x| <= 2^-7, the next terms x^9 / 9! and x^8 / 8! are below 1e-24
+    const double x2 = x * x;
+    *s = fma(x * x2, fma(x2, fma(x2, -1.0 / 5040.0, 1.0 / 120.0), -1.0 / 6.0), x);
+    *c = fma(x2, fma(x2, fma(x2, -1.0 / 720.0, 1.0 / 24.0), -0.5), 1.0);
+    return;
+  }
   int halvings = 0;
   if (fabs(x) > 0.25) {
     if (!(fabs(x) <= 64.0)) x -= 6.283185307179586 * rint(x * 0.15915494309189535);   // garbage in, bounded out
@@ -701,16 +708,16 @@ GFR_HD void newton_solve(const NGrp<LANES>& g, const Layout& lay, const int* sim
         if (t.z & FL_VALID) {
           const D2 pc = f0[5 * P + p];
           const double ps = g.pspec(p);
-          D2 sc; sc.x = sc.y = 0.0;
-          if (t.z & FL_C_REG) sc = hc;
+          if (!(t.z & FL_C_REG)) { hc.x = hc.y = 0.0; }
           {
             const int q1 = rec_list(t) + rec_all_kids(t);
 #pragma unroll 1
             for (int q = q1 - rec_pool_kids(t); q < q1; ++q) {
               const D2 cc = g.poolp[2 * np + child_slot[q]];
-              sc.x += cc.x; sc.y += cc.y;
+              hc.x += cc.x; hc.y += cc.y;
             }
           }
+          const D2 sc = hc;
           double r0 = ps - pc.x - sc.x, r1 = 0.0 - pc.y - sc.y;
           if (!(t.z & FL_THETA)) r0 = 0.0;
           if (!(t.z & FL_PQ)) r1 = 0.0;
@@ -756,19 +763,19 @@ GFR_HD void newton_solve(const NGrp<LANES>& g, const Layout& lay, const int* sim
           const double ps = g.pspec(p);
           const double v2 = fma(vk.x, vk.x, vk.y * vk.y);
           const BranchT bt = branch_terms(vk, g.ef(rec_parent(t)), gb[p]);
-          D2 s0, s1, sc, sf;                               // children's contributions: plain sums, the heir first
-          s0.x = s0.y = s1.x = s1.y = sc.x = sc.y = sf.x = sf.y = 0.0;
-          if (t.z & FL_C_REG) { s0 = h0; s1 = h1; sc = hc; sf = hf; }
+          // children's contributions: plain sums, the heir first - it is what the lane still holds in h*
+          if (!(t.z & FL_C_REG)) { h0.x = h0.y = h1.x = h1.y = hc.x = hc.y = hf.x = hf.y = 0.0; }
           {
             const int q1 = rec_list(t) + rec_all_kids(t);
 #pragma unroll 1
             for (int q = q1 - rec_pool_kids(t); q < q1; ++q) {
               const D2* e = g.poolp + child_slot[q];
               const D2 c0 = e[0], c1 = e[np], cc = e[2 * np], fl = e[3 * np];
-              s0.x += c0.x; s0.y += c0.y; s1.x += c1.x; s1.y += c1.y; sc.x += cc.x; sc.y += cc.y;
-              sf.x += fl.x; sf.y += fl.y;
+              h0.x += c0.x; h0.y += c0.y; h1.x += c1.x; h1.y += c1.y; hc.x += cc.x; hc.y += cc.y;
+              hf.x += fl.x; hf.y += fl.y;
             }
           }
+          const D2 s0 = h0, s1 = h1, sc = hc, sf = hf;
           const double Pk = fma(yd.x, v2, bt.ga) + sf.x, Q = fma(-yd.y, v2, bt.al) + sf.y;
           D2 d0, d1, r;
           r.x = ps - Pk;

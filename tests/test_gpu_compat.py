@@ -140,7 +140,7 @@ def test_host_stepper_pipeline_matches_plain_stepping():
     a2 = m.BatchedGridEnvironment(f, 512, **kw); a2.reset(seed=3)
     b = m.BatchedGridEnvironment(f, 512, **kw); b.reset(seed=3)
     st = m.HostStepper(b, depth=2, observations=True)
-    assert st.d2h_bytes_per_step == 512 * (10 + 8 * b.obs_dim)
+    assert st.d2h_bytes_per_step == 512 * (10 + 8 * (b.obs_dim - 2 * b.soa.n_load))      # the static load columns stay put
     want = []
     for x in acts[:4]:
         o, _, _, _, _ = a2.step(x)
