@@ -702,12 +702,14 @@ GFR_HD void newton_solve(const NGrp<LANES>& g, const Layout& lay, const int* sim
         break;
       }
       D2 hc; hc.x = hc.y = 0.0;                         // L v of the bus this lane eliminated in the previous row
+      double ps_next = g.pspec((nrows - 1) * LANES + g.lane);     // the specified injection, one row ahead (an L2 round trip)
       for (int row = nrows - 1; row >= 0; --row) {
         const int p = row * LANES + g.lane;
         const I4 t = sched[p];
+        const double ps = ps_next;
+        if (row > 0) ps_next = g.pspec(p - LANES);
         if (t.z & FL_VALID) {
           const D2 pc = f0[5 * P + p];
-          const double ps = g.pspec(p);
           if (!(t.z & FL_C_REG)) { hc.x = hc.y = 0.0; }
           {
             const int q1 = rec_list(t) + rec_all_kids(t);
@@ -754,13 +756,15 @@ GFR_HD void newton_solve(const NGrp<LANES>& g, const Layout& lay, const int* sim
       int singular = 0;
       D2 h0, h1, hc, hf;                               // what the bus this lane eliminated in the previous row hands up
       h0.x = h0.y = h1.x = h1.y = hc.x = hc.y = hf.x = hf.y = 0.0;
+      double ps_next = g.pspec((nrows - 1) * LANES + g.lane);     // the specified injection, one row ahead (an L2 round trip)
       for (int row = nrows - 1; row >= 0; --row) {
         const int p = row * LANES + g.lane;
         const I4 t = sched[p];
+        const double ps = ps_next;
+        if (row > 0) ps_next = g.pspec(p - LANES);
         if (t.z & FL_VALID) {
           const D2 vk = g.ef(rec_bus(t));
           const D2 yd = gbd[p];
-          const double ps = g.pspec(p);
           const double v2 = fma(vk.x, vk.x, vk.y * vk.y);
           const BranchT bt = branch_terms(vk, g.ef(rec_parent(t)), gb[p]);
           // children's contributions: plain sums, the heir first - it is what the lane still holds in h*
