@@ -628,7 +628,9 @@ GFR_HD void newton_back_update(const NGrp<LANES>& g, const Layout& lay, const in
 #define GFR_BU_ROW(row_, m0_, m1_, v_)                                     \
   do {                                                                     \
     const int p = (row_) * LANES + g.lane;                                 \
-    const I4 t = sched[p];                                                 \
+    I4 t;                                                                  \
+    if (LANES > 32) { t = t_next; if ((row_) + 1 < nrows) t_next = sched[p + LANES]; } \
+    else t = sched[p];                                                     \
     D2 m0 = m0_, m1 = m1_, v = v_;                                         \
     if (f0) { m0 = f0[2 * P + p]; m1 = f0[3 * P + p]; }                    \
     if ((row_) + 2 < nrows) GFR_LOAD_MV((row_) + 2, m0_, m1_, v_);         \
@@ -653,6 +655,9 @@ GFR_HD void newton_back_update(const NGrp<LANES>& g, const Layout& lay, const in
   } while (0)
   GFR_LOAD_MV(0, a0, a1, av);
   if (nrows > 1) GFR_LOAD_MV(1, b0, b1, bv);
+  I4 t_next;                                           // CTA-wide groups (image in global memory): the record one row ahead
+  t_next.x = t_next.y = t_next.z = t_next.w = 0;
+  if (LANES > 32) t_next = sched[g.lane];
   for (int row = 0; row < nrows; row += 2) {
     GFR_BU_ROW(row, a0, a1, av);
     if (row + 1 < nrows) GFR_BU_ROW(row + 1, b0, b1, bv);
@@ -703,13 +708,21 @@ GFR_HD void newton_solve(const NGrp<LANES>& g, const Layout& lay, const int* sim
       }
       D2 hc; hc.x = hc.y = 0.0;                         // L v of the bus this lane eliminated in the previous row
       double ps_next = g.pspec((nrows - 1) * LANES + g.lane);     // the specified injection, one row ahead (an L2 round trip)
+      I4 t_next; D2 pc_next;                              // CTA-wide groups: record and flat-profile injections one row ahead
+      t_next.x = t_next.y = t_next.z = t_next.w = 0; pc_next.x = pc_next.y = 0.0;
+      if (LANES > 32) { const int p0 = (nrows - 1) * LANES + g.lane; t_next = sched[p0]; pc_next = f0[5 * P + p0]; }
       for (int row = nrows - 1; row >= 0; --row) {
         const int p = row * LANES + g.lane;
-        const I4 t = sched[p];
+        I4 t; D2 pc;
+        if (LANES > 32) {
+          t = t_next; pc = pc_next;
+          if (row > 0) { t_next = sched[p - LANES]; pc_next = f0[5 * P + p - LANES]; }
+        } else {
+          t = sched[p]; pc = f0[5 * P + p];
+        }
         const double ps = ps_next;
         if (row > 0) ps_next = g.pspec(p - LANES);
         if (t.z & FL_VALID) {
-          const D2 pc = f0[5 * P + p];
           if (!(t.z & FL_C_REG)) { hc.x = hc.y = 0.0; }
           {
             const int q1 = rec_list(t) + rec_all_kids(t);
@@ -757,16 +770,25 @@ GFR_HD void newton_solve(const NGrp<LANES>& g, const Layout& lay, const int* sim
       D2 h0, h1, hc, hf;                               // what the bus this lane eliminated in the previous row hands up
       h0.x = h0.y = h1.x = h1.y = hc.x = hc.y = hf.x = hf.y = 0.0;
       double ps_next = g.pspec((nrows - 1) * LANES + g.lane);     // the specified injection, one row ahead (an L2 round trip)
+      // CTA-wide groups read the feeder image from global memory: record and admittances come one row ahead too
+      I4 t_next; D2 y_next, yd_next;
+      t_next.x = t_next.y = t_next.z = t_next.w = 0; y_next.x = y_next.y = yd_next.x = yd_next.y = 0.0;
+      if (LANES > 32) { const int p0 = (nrows - 1) * LANES + g.lane; t_next = sched[p0]; y_next = gb[p0]; yd_next = gbd[p0]; }
       for (int row = nrows - 1; row >= 0; --row) {
         const int p = row * LANES + g.lane;
-        const I4 t = sched[p];
+        I4 t; D2 yb, yd;
+        if (LANES > 32) {
+          t = t_next; yb = y_next; yd = yd_next;
+          if (row > 0) { t_next = sched[p - LANES]; y_next = gb[p - LANES]; yd_next = gbd[p - LANES]; }
+        } else {
+          t = sched[p]; yb = gb[p]; yd = gbd[p];
+        }
         const double ps = ps_next;
         if (row > 0) ps_next = g.pspec(p - LANES);
         if (t.z & FL_VALID) {
           const D2 vk = g.ef(rec_bus(t));
-          const D2 yd = gbd[p];
           const double v2 = fma(vk.x, vk.x, vk.y * vk.y);
-          const BranchT bt = branch_terms(vk, g.ef(rec_parent(t)), gb[p]);
+          const BranchT bt = branch_terms(vk, g.ef(rec_parent(t)), yb);
           // children's contributions: plain sums, the heir first - it is what the lane still holds in h*
           if (!(t.z & FL_C_REG)) { h0.x = h0.y = h1.x = h1.y = hc.x = hc.y = hf.x = hf.y = 0.0; }
           {
