@@ -564,39 +564,51 @@ GFR_HD BranchT branch_terms(const D2 vk, const D2 vp, const D2 y) {
   return t;
 }
 
-// max |mismatch| of the present voltages, every bus independently (power_flow.py:150-166); same
-// arithmetic, term by term and in the same order, as the elimination pass below
+// max |mismatch| of the present voltages (power_flow.py:150-166), as a leaf -> root row pass on the elimination
+// schedule: every branch is evaluated ONCE, by the bus below it, which keeps its own share (ga, al) and hands the
+// parent's share (gl, ll) up - in registers to an heir's parent, through field 3 of its pool slot otherwise.
+// Same arithmetic, term by term and in the same order, as the elimination pass.
 template <int LANES>
 GFR_HD double newton_mismatch(const NGrp<LANES>& g, const Layout& lay, const int* simg, const double* dimg) {
+  const int nrows = lay.nrows, np = lay.n_pool;
   const I4* sched = reinterpret_cast<const I4*>(simg + lay.o_sched);
-  const int* child_ent = simg + lay.o_child_ent;
+  const int* child_slot = simg + lay.o_child_slot;
   const D2* gb = reinterpret_cast<const D2*>(dimg + lay.o_gb);
   const D2* gbd = reinterpret_cast<const D2*>(dimg + lay.o_gbd);
   double mm = 0.0;
-  for (int p = g.lane; p < lay.P; p += LANES) {
+  D2 hf; hf.x = hf.y = 0.0;                             // (gl, ll) of the bus this lane handled in the previous row
+  double ps_next = g.pspec((nrows - 1) * LANES + g.lane);
+  for (int row = nrows - 1; row >= 0; --row) {
+    const int p = row * LANES + g.lane;
     const I4 t = sched[p];
-    if (!(t.z & FL_VALID)) continue;
-    const D2 vk = g.ef(rec_bus(t));
-    const D2 yd = gbd[p];
-    const double ps = g.pspec(p);
-    const double v2 = fma(vk.x, vk.x, vk.y * vk.y);
-    const BranchT bt = branch_terms(vk, g.ef(rec_parent(t)), gb[p]);
-    D2 sf; sf.x = sf.y = 0.0;
-    const int q0 = rec_list(t), q1 = q0 + rec_all_kids(t);
+    const double ps = ps_next;
+    if (row > 0) ps_next = g.pspec(p - LANES);
+    if (t.z & FL_VALID) {
+      const D2 vk = g.ef(rec_bus(t));
+      const D2 yd = gbd[p];
+      const double v2 = fma(vk.x, vk.x, vk.y * vk.y);
+      const BranchT bt = branch_terms(vk, g.ef(rec_parent(t)), gb[p]);
+      if (!(t.z & FL_C_REG)) { hf.x = hf.y = 0.0; }
+      {
+        const int q1 = rec_list(t) + rec_all_kids(t);
 #pragma unroll 1
-    for (int q = q0; q < q1; ++q) {
-      const unsigned e = (unsigned)child_ent[q];
-      const BranchT ct = branch_terms(g.ef((int)(e & 0xFFFFu)), vk, gb[e >> 16]);
-      sf.x += ct.gl; sf.y += ct.ll;
+        for (int q = q1 - rec_pool_kids(t); q < q1; ++q) {
+          const D2 fl = g.poolp[3 * np + child_slot[q]];
+          hf.x += fl.x; hf.y += fl.y;
+        }
+      }
+      const double P = fma(yd.x, v2, bt.ga) + hf.x, Q = fma(-yd.y, v2, bt.al) + hf.y;
+      double aP = fabs(ps - P), aQ = fabs(Q);
+      if ((t.z & (FL_PQ | FL_THETA)) != (FL_PQ | FL_THETA)) {   // slack: no equations; PV: no Q equation
+        if (!(t.z & FL_THETA)) aP = 0.0;
+        if (!(t.z & FL_PQ)) aQ = 0.0;
+      }
+      const double loc = (aQ > aP || aQ != aQ) ? aQ : aP;
+      mm = (loc > mm || loc != loc) ? loc : mm;
+      hf.x = bt.gl; hf.y = bt.ll;
+      if (!(t.z & FL_P_REG)) g.poolp[3 * np + pool_slot_of(t.z)] = hf;
     }
-    const double P = fma(yd.x, v2, bt.ga) + sf.x, Q = fma(-yd.y, v2, bt.al) + sf.y;
-    double aP = fabs(ps - P), aQ = fabs(Q);
-    if ((t.z & (FL_PQ | FL_THETA)) != (FL_PQ | FL_THETA)) {   // slack: no equations; PV: no Q equation
-      if (!(t.z & FL_THETA)) aP = 0.0;
-      if (!(t.z & FL_PQ)) aQ = 0.0;
-    }
-    const double loc = (aQ > aP || aQ != aQ) ? aQ : aP;
-    mm = (loc > mm || loc != loc) ? loc : mm;
+    g.sync();
   }
   return g.gmax_nan(mm);
 }

@@ -385,8 +385,7 @@ inline std::string build_feeder_image(const gfr_feeder_desc* d, int lanes, int s
   lay.o_gen_type = ib.add_i(d->gen_type, G);
   lay.o_child_ent = lay.o_child_slot = lay.o_topo = lay.o_child_idx = lay.o_level_ptr = -1;
   if (newton) {
-    lay.o_child_ent = ib.add_i(child_ent.data(), (int)child_ent.size());
-    lay.o_child_slot = ib.add_i(child_slot.data(), (int)child_slot.size());
+    lay.o_child_slot = ib.add_i(child_slot.data(), (int)child_slot.size());   // (child_ent: no kernel reads it any more)
   } else {
     lay.o_topo = ib.add_i(topo.data(), 4 * n);
     lay.o_child_idx = ib.add_i(d->child_idx, n - 1);
