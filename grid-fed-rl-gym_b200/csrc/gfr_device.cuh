@@ -578,16 +578,24 @@ GFR_HD double newton_mismatch(const NGrp<LANES>& g, const Layout& lay, const int
   double mm = 0.0;
   D2 hf; hf.x = hf.y = 0.0;                             // (gl, ll) of the bus this lane handled in the previous row
   double ps_next = g.pspec((nrows - 1) * LANES + g.lane);
+  I4 t_next; D2 y_next, yd_next;                        // CTA-wide groups (image in global memory): one row ahead
+  t_next.x = t_next.y = t_next.z = t_next.w = 0; y_next.x = y_next.y = yd_next.x = yd_next.y = 0.0;
+  if (LANES > 32) { const int p0 = (nrows - 1) * LANES + g.lane; t_next = sched[p0]; y_next = gb[p0]; yd_next = gbd[p0]; }
   for (int row = nrows - 1; row >= 0; --row) {
     const int p = row * LANES + g.lane;
-    const I4 t = sched[p];
+    I4 t; D2 yb, yd;
+    if (LANES > 32) {
+      t = t_next; yb = y_next; yd = yd_next;
+      if (row > 0) { t_next = sched[p - LANES]; y_next = gb[p - LANES]; yd_next = gbd[p - LANES]; }
+    } else {
+      t = sched[p]; yb = gb[p]; yd = gbd[p];
+    }
     const double ps = ps_next;
     if (row > 0) ps_next = g.pspec(p - LANES);
     if (t.z & FL_VALID) {
       const D2 vk = g.ef(rec_bus(t));
-      const D2 yd = gbd[p];
       const double v2 = fma(vk.x, vk.x, vk.y * vk.y);
-      const BranchT bt = branch_terms(vk, g.ef(rec_parent(t)), gb[p]);
+      const BranchT bt = branch_terms(vk, g.ef(rec_parent(t)), yb);
       if (!(t.z & FL_C_REG)) { hf.x = hf.y = 0.0; }
       {
         const int q1 = rec_list(t) + rec_all_kids(t);
@@ -644,7 +652,12 @@ GFR_HD void newton_back_update(const NGrp<LANES>& g, const Layout& lay, const in
     if (LANES > 32) { t = t_next; if ((row_) + 1 < nrows) t_next = sched[p + LANES]; } \
     else t = sched[p];                                                     \
     D2 m0 = m0_, m1 = m1_, v = v_;                                         \
-    if (f0) { m0 = f0[2 * P + p]; m1 = f0[3 * P + p]; }                    \
+    if (f0) {                                                              \
+      if (LANES > 32) {                                                    \
+        m0 = f0m0_next; m1 = f0m1_next;                                    \
+        if ((row_) + 1 < nrows) { f0m0_next = f0[2 * P + p + LANES]; f0m1_next = f0[3 * P + p + LANES]; } \
+      } else { m0 = f0[2 * P + p]; m1 = f0[3 * P + p]; }                   \
+    }                                                                      \
     if ((row_) + 2 < nrows) GFR_LOAD_MV((row_) + 2, m0_, m1_, v_);         \
     if (t.z & FL_VALID) {                                                  \
       D2 x = hx;                                                           \
@@ -669,7 +682,9 @@ GFR_HD void newton_back_update(const NGrp<LANES>& g, const Layout& lay, const in
   if (nrows > 1) GFR_LOAD_MV(1, b0, b1, bv);
   I4 t_next;                                           // CTA-wide groups (image in global memory): the record one row ahead
   t_next.x = t_next.y = t_next.z = t_next.w = 0;
-  if (LANES > 32) t_next = sched[g.lane];
+  D2 f0m0_next, f0m1_next;                             // ... and the flat-start D^-1 U rows in the first iteration
+  f0m0_next.x = f0m0_next.y = f0m1_next.x = f0m1_next.y = 0.0;
+  if (LANES > 32) { t_next = sched[g.lane]; if (f0) { f0m0_next = f0[2 * P + g.lane]; f0m1_next = f0[3 * P + g.lane]; } }
   for (int row = 0; row < nrows; row += 2) {
     GFR_BU_ROW(row, a0, a1, av);
     if (row + 1 < nrows) GFR_BU_ROW(row + 1, b0, b1, bv);
@@ -720,17 +735,24 @@ GFR_HD void newton_solve(const NGrp<LANES>& g, const Layout& lay, const int* sim
       }
       D2 hc; hc.x = hc.y = 0.0;                         // L v of the bus this lane eliminated in the previous row
       double ps_next = g.pspec((nrows - 1) * LANES + g.lane);     // the specified injection, one row ahead (an L2 round trip)
-      I4 t_next; D2 pc_next;                              // CTA-wide groups: record and flat-profile injections one row ahead
-      t_next.x = t_next.y = t_next.z = t_next.w = 0; pc_next.x = pc_next.y = 0.0;
-      if (LANES > 32) { const int p0 = (nrows - 1) * LANES + g.lane; t_next = sched[p0]; pc_next = f0[5 * P + p0]; }
+      I4 t_next; D2 pc_next, i0_next, i1_next, lp_next;   // CTA-wide groups: record and flat-start factors one row ahead
+      t_next.x = t_next.y = t_next.z = t_next.w = 0;
+      pc_next.x = pc_next.y = i0_next.x = i0_next.y = i1_next.x = i1_next.y = lp_next.x = lp_next.y = 0.0;
+      if (LANES > 32) {
+        const int p0 = (nrows - 1) * LANES + g.lane;
+        t_next = sched[p0]; pc_next = f0[5 * P + p0]; i0_next = f0[p0]; i1_next = f0[P + p0]; lp_next = f0[4 * P + p0];
+      }
       for (int row = nrows - 1; row >= 0; --row) {
         const int p = row * LANES + g.lane;
-        I4 t; D2 pc;
+        I4 t; D2 pc, i0, i1, lp;                        // record, flat-profile (P, Q), D^-1 rows, (ll, gl)
         if (LANES > 32) {
-          t = t_next; pc = pc_next;
-          if (row > 0) { t_next = sched[p - LANES]; pc_next = f0[5 * P + p - LANES]; }
+          t = t_next; pc = pc_next; i0 = i0_next; i1 = i1_next; lp = lp_next;
+          if (row > 0) {
+            t_next = sched[p - LANES]; pc_next = f0[5 * P + p - LANES];
+            i0_next = f0[p - LANES]; i1_next = f0[P + p - LANES]; lp_next = f0[4 * P + p - LANES];
+          }
         } else {
-          t = sched[p]; pc = f0[5 * P + p];
+          t = sched[p]; pc = f0[5 * P + p]; i0 = f0[p]; i1 = f0[P + p]; lp = f0[4 * P + p];
         }
         const double ps = ps_next;
         if (row > 0) ps_next = g.pspec(p - LANES);
@@ -748,7 +770,6 @@ GFR_HD void newton_solve(const NGrp<LANES>& g, const Layout& lay, const int* sim
           double r0 = ps - pc.x - sc.x, r1 = 0.0 - pc.y - sc.y;
           if (!(t.z & FL_THETA)) r0 = 0.0;
           if (!(t.z & FL_PQ)) r1 = 0.0;
-          const D2 i0 = f0[p], i1 = f0[P + p], lp = f0[4 * P + p];          // D^-1 rows, (ll, gl)
           D2 v;
           v.x = fma(i0.x, r0, i0.y * r1);
           v.y = fma(i1.x, r0, i1.y * r1);
