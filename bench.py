@@ -33,6 +33,8 @@ WORKLOADS = {
     "ieee13_newton": ("ieee13", 65536, "newton", 1e-6, 50),
     "ieee34_newton": ("ieee34", 262144, "newton", 1e-6, 50),
     "ieee123_sweep": ("ieee123", 131072, "sweep", 1e-8, 50),
+    # IEEE-123 with its 26 loop-closing tie lines KEPT (148 lines): sweep on the spanning tree + compensation
+    "ieee123_mesh": ("ieee123mesh", 131072, "sweep", 1e-8, 100),
     # configs[4]: synthetic 1,000-bus radial feeder, 16,384 instances over 8 GPUs
     "synthetic1000": ("synthetic1000", 2048, "newton", 1e-6, 50),
 }
@@ -52,6 +54,8 @@ def make_feeder(spec):
         for ld in f.loads:
             ld.base_power *= 0.03; ld.active_power *= 0.03; ld.reactive_power *= 0.03
         return f
+    if spec == "ieee123mesh":
+        return m.repair_topology(m.IEEE123Bus(seed=0), keep_cycles=True)
     f = {"ieee13": m.IEEE13Bus, "ieee34": lambda: m.IEEE34Bus(seed=0),
          "ieee123": lambda: m.IEEE123Bus(seed=0)}[spec]()
     return m.repair_topology(f)
@@ -198,7 +202,7 @@ def run_reference(args):
     if int(os.environ.get("RANK", "0")) != 0:
         return
     cores = os.cpu_count() or 1
-    per_proc = {"ieee123": 48, "ieee34": 384, "ieee13": 2048, "synthetic1000": 1}[spec]
+    per_proc = {"ieee123": 48, "ieee123mesh": 48, "ieee34": 384, "ieee13": 2048, "synthetic1000": 1}[spec]
     ptol = tol if solver == "newton" else 1e-8
     steps, warm = max(1, args.steps), max(0, args.warmup)
     ctx = mp.get_context("spawn")
@@ -497,7 +501,7 @@ def run_gpu(args):
     # ---- the other BASELINE configurations, device-resident arm only, in the same JSON line
     others = {}
     if not args.no_configs and args.scaling == "weak":
-        for name in ("ieee13", "ieee34", "synthetic1000", "ieee13_newton", "ieee34_newton"):
+        for name in ("ieee13", "ieee34", "synthetic1000", "ieee13_newton", "ieee34_newton", "ieee123_mesh"):
             if name == args.workload:
                 continue
             Bn = WORKLOADS[name][1]
@@ -553,7 +557,7 @@ def run_gpu(args):
             line["reference_cpu_measured_in_build_container"] = ref
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline(spec, tol if solver == "newton" else 1e-8,
-                                                *{"ieee123": (256, 12), "ieee34": (2048, 12), "ieee13": (16384, 12), "synthetic1000": (2, 2)}[spec])
+                                                *{"ieee123": (256, 12), "ieee123mesh": (256, 12), "ieee34": (2048, 12), "ieee13": (16384, 12), "synthetic1000": (2, 2)}[spec])
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -31,7 +31,7 @@ _i32p, _f64p, _u8p, _u64p = C.POINTER(C.c_int32), C.POINTER(C.c_double), C.POINT
 class FeederDesc(C.Structure):
     _fields_ = [
         ("n_bus", C.c_int32), ("n_levels", C.c_int32), ("n_load", C.c_int32), ("n_gen", C.c_int32),
-        ("n_bat", C.c_int32), ("n_pool", C.c_int32), ("lanes_hint", C.c_int32), ("reserved", C.c_int32),
+        ("n_bat", C.c_int32), ("n_pool", C.c_int32), ("lanes_hint", C.c_int32), ("n_tie", C.c_int32),
         ("s_base", C.c_double),
         ("order", _i32p), ("parent", _i32p), ("level_ptr", _i32p), ("child_ptr", _i32p),
         ("child_idx", _i32p), ("lane_of", _i32p),
@@ -42,6 +42,8 @@ class FeederDesc(C.Structure):
         ("gen_p0", _f64p), ("gen_p1", _f64p), ("gen_p2", _f64p), ("bat_bus", _i32p),
         ("bat_cap", _f64p), ("bat_rating", _f64p), ("bat_eff", _f64p), ("bat_soc0", _f64p),
         ("load_profile", _f64p),
+        ("tie_line", _i32p), ("tie_from", _i32p), ("tie_to", _i32p), ("tie_r", _f64p), ("tie_x", _f64p),
+        ("tie_rating", _f64p), ("tie_zinv", _f64p),
     ]
 
 
@@ -201,6 +203,12 @@ def make_feeder_desc(soa: FeederSoA):
         setattr(d, name, i32(name))
     if getattr(soa, "lane_of", None) is not None:        # optional: NULL = position inside the level
         d.lane_of = i32("lane_of")
+    d.n_tie = int(getattr(soa, "n_tie", 0))
+    if d.n_tie:
+        for name in ("tie_line", "tie_from", "tie_to"):
+            setattr(d, name, i32(name))
+        for name in ("tie_r", "tie_x", "tie_rating", "tie_zinv"):
+            setattr(d, name, f64(name))
     for name in ("vm_set", "g", "b", "gdiag", "bdiag", "r", "x", "rating", "load_base", "load_p",
                  "load_q", "gen_cap", "gen_p0", "gen_p1", "gen_p2", "bat_cap", "bat_rating",
                  "bat_eff", "bat_soc0", "load_profile"):

@@ -314,7 +314,7 @@ int image_for(const gfr_feeder* f, int solver, int lanes, const ImageDev** out) 
 // shared memory of one instance slot; 0 if the scratch it doubles as cannot hold the sources
 size_t slot_bytes(const Layout& lay, int solver, int lanes) {
   return solver == GFR_SOLVER_NEWTON ? newton_slot_bytes(lay.n, lay.n_pool, lay.n_src)
-                                     : sweep_slot_bytes(lay.n, lay.n_src, sweep_p_local(lanes, lay.n));
+                                     : sweep_slot_bytes(lay.n, lay.n_src, sweep_p_local(lanes, lay.n), lay.n_tie);
 }
 
 // Threads cooperating on one instance when the caller does not say: THE rule (exported as gfr_auto_lanes; the
@@ -553,7 +553,8 @@ int gfr_feeder_create(const gfr_feeder_desc* d, int device, gfr_feeder** out) {
   FeederImage fi;
   {
     const int lanes0 = d->lanes_hint > 0 && d->lanes_hint <= 256 ? d->lanes_hint : 1;
-    std::string complaint = build_feeder_image(d, lanes0, GFR_SOLVER_NEWTON, &fi);
+    // (a feeder with ties only has sweep images)
+    std::string complaint = build_feeder_image(d, lanes0, d->n_tie > 0 ? GFR_SOLVER_SWEEP : GFR_SOLVER_NEWTON, &fi);
     if (!complaint.empty()) return fail(GFR_E_ARG, complaint);
   }
   DeviceGuard guard(device);

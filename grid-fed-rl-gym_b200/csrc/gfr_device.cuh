@@ -87,6 +87,8 @@ GFR_HD int rec_all_kids(const I4& t) { return (int)((unsigned)t.w >> 16); }
 struct Layout {
   int n, nl, L, G, Bt, A, D, m, n_src, R, img_bytes, n_noise, n_pool, k_slack;
   int nrows, P;                  // schedule: rows and positions (Newton: rows x lanes; sweep: P = n, position = bus)
+  int n_tie;                     // loop-closing lines (sweep only): m = n - 1 + n_tie
+  int o_tie_ends, o_tie_ptr, o_tie_inc, o_tie_y, o_tie_z, o_tie_rating, o_tie_zinv;
   // by position, every image
   int o_sched, o_rank, o_rankp, o_branch_of_line, o_inj_ptr, o_inj_idx, o_gen_type;
   int o_gb, o_rating, o_vm_set;
@@ -274,6 +276,7 @@ struct SGrp : Lanes<LANES> {
   D2* efp;        // [n]
   D2* jrp;        // [n]
   double* pp;     // [n] specified injections
+  D2* jt;         // [n_tie] tie currents (from -> to) of a weakly meshed feeder, then [n_tie] their loop mismatches
   int n;
   GFR_HD double& at(int, int k) const { return pp[k]; }                                   // S_P
   GFR_HD D2& at2(int field, int k) const { return field == F_E ? efp[k] : jrp[k]; }       // F_E | S_JR
@@ -315,9 +318,9 @@ GFR_HD size_t newton_scratch_doubles(int P) { return (size_t)P * 6 + (((size_t)P
 // interleaved by thread), 32 B per bus stay in shared memory - 40 % more resident instances per SM
 enum { SWEEP_P_LOCAL_MAX = 20 };
 GFR_HD bool sweep_p_local(int lanes, int n) { return lanes == 1 && n <= SWEEP_P_LOCAL_MAX; }
-GFR_HD size_t sweep_slot_bytes(int n, int n_src, bool p_local = false) {
+GFR_HD size_t sweep_slot_bytes(int n, int n_src, bool p_local = false, int n_tie = 0) {
   if (n_src > SCRATCH_FIELDS_SWEEP * n) return 0;
-  const size_t units = ((size_t)n * (p_local ? 32 : 40) + 15) / 16;   // 16-byte units, made odd: neighbouring instances'
+  const size_t units = ((size_t)n * (p_local ? 32 : 40) + 15) / 16 + 2 * (size_t)n_tie;   // 16-byte units, made odd: neighbouring instances'
   return (units | 1) * 16;                                // slots then start 4 banks apart (conflict-free 128-bit accesses)
 }
 template <int LANES>
@@ -335,6 +338,7 @@ GFR_HD void bind_slot(SGrp<LANES>& g, unsigned char* slot, const Layout& lay, D2
   g.efp = reinterpret_cast<D2*>(slot);
   g.jrp = g.efp + n;
   g.pp = reinterpret_cast<double*>(g.jrp + n);
+  g.jt = g.jrp + n + (sweep_p_local(LANES, n) ? 0 : (n + 1) / 2);      // after the injections, when they live here
   g.n = n;
 }
 
@@ -918,18 +922,43 @@ GFR_HD void newton_solve(const NGrp<LANES>& g, const Layout& lay, const int* sim
 //                        (what leaves subtree(k) through its branch; the slack's own injection is
 //                        -A(root) by Kirchhoff), W = voltage relative to the root
 //   fix  (every bus)     V(k) = V_slack - W(slack) + W(k)
+//
+// Weakly meshed feeders (lay.n_tie loop-closing lines, "ties"): the compensation method.  Every tie carries a
+// current J (from -> to) that enters the sweep as a pair of bus injections (-J at the from-end, +J at the to-end);
+// after the down pass the loop equations e = V_from - V_to - z_tie J are evaluated and J += Z_loop^-1 e, with the
+// inverse loop-impedance matrix (constant: tree-path impedances shared by the loops + the ties' own) computed once
+// by the host.  Convergence then needs max |dV| AND max |e| below the tolerance.
 template <int LANES>
 GFR_HD void sweep_solve(const SGrp<LANES>& g, const Layout& lay, const int* simg,
                         const double* dimg, double tol, int max_it, SolveStat* out) {
-  const int n = lay.n, nl = lay.nl, ks = lay.k_slack;
+  const int n = lay.n, nl = lay.nl, ks = lay.k_slack, nt = lay.n_tie;
   const I4* topo = reinterpret_cast<const I4*>(simg + lay.o_topo);
   const int* level_ptr = simg + lay.o_level_ptr;
   const int* child_idx = simg + lay.o_child_idx;
+  const int* tie_ptr = simg + lay.o_tie_ptr;
+  const int* tie_inc = simg + lay.o_tie_inc;
   const D2* rx = reinterpret_cast<const D2*>(dimg + lay.o_rx);
   const double vslack = dimg[lay.o_vm_set + ks];
   out->converged = 0;
   out->iterations = max_it;
   out->max_mismatch = INFINITY;
+  if (nt) {
+    D2 z0; z0.x = z0.y = 0.0;
+    for (int i = g.lane; i < nt; i += LANES) g.jt[i] = z0;
+    g.sync();
+  }
+  // current the ties feed into bus k: + J at a to-end, - J at a from-end
+#define GFR_TIE_CURRENT(k_, a_)                                            \
+  do {                                                                     \
+    if (nt) {                                                              \
+      for (int q_ = tie_ptr[(k_)]; q_ < tie_ptr[(k_) + 1]; ++q_) {         \
+        const int e_ = tie_inc[q_];                                        \
+        const D2 j_ = g.jt[e_ >> 1];                                       \
+        if (e_ & 1) { (a_).x += j_.x; (a_).y += j_.y; }                    \
+        else { (a_).x -= j_.x; (a_).y -= j_.y; }                           \
+      }                                                                    \
+    }                                                                      \
+  } while (0)
   for (int it = 0; it < max_it; ++it) {
     if (LANES == 1) {
       // one thread per instance: buses are numbered parent before child, so a plain descending loop that
@@ -945,6 +974,7 @@ GFR_HD void sweep_solve(const SGrp<LANES>& g, const Layout& lay, const int* simg
         const double w = (t.w & FL_THETA) ? p_k * rcp_fast(fma(v.x, v.x, v.y * v.y)) : 0.0;
         D2 a = g.at2(S_JR, k);
         a.x = fma(w, v.x, a.x); a.y = fma(w, v.y, a.y);
+        GFR_TIE_CURRENT(k, a);
         g.at2(S_JR, k) = a;
         if (k > 0) { D2& ap = g.at2(S_JR, t.x); ap.x += a.x; ap.y += a.y; }
       }
@@ -957,6 +987,7 @@ GFR_HD void sweep_solve(const SGrp<LANES>& g, const Layout& lay, const int* simg
         const double w = (t.w & FL_THETA) ? g.at(S_P, k) * rcp_fast(fma(v.x, v.x, v.y * v.y)) : 0.0;   // conj(S / V) = P V / |V|^2
         D2 a;
         a.x = w * v.x; a.y = w * v.y;
+        GFR_TIE_CURRENT(k, a);
 #pragma unroll 1
         for (int q = t.y; q < t.z; ++q) {
           const D2 ac = g.at2(S_JR, child_idx[q]);
@@ -1010,6 +1041,36 @@ GFR_HD void sweep_solve(const SGrp<LANES>& g, const Layout& lay, const int* simg
       mm = (loc > mm || loc != loc) ? loc : mm;
       g.at2(F_E, k) = vn;
     }
+    if (nt) {
+      // loop equations of the ties with the new voltages, then the compensation step J += Z_loop^-1 e
+      const int* ends = simg + lay.o_tie_ends;
+      const D2* tz = reinterpret_cast<const D2*>(dimg + lay.o_tie_z);
+      const D2* zinv = reinterpret_cast<const D2*>(dimg + lay.o_tie_zinv);
+      D2* const et = g.jt + nt;
+      g.sync();
+      for (int i = g.lane; i < nt; i += LANES) {
+        const D2 va = g.at2(F_E, ends[2 * i]), vb = g.at2(F_E, ends[2 * i + 1]), z = tz[i], j = g.jt[i];
+        D2 e;
+        e.x = (va.x - vb.x) - fma(z.x, j.x, -z.y * j.y);
+        e.y = (va.y - vb.y) - fma(z.x, j.y, z.y * j.x);
+        et[i] = e;
+        const double de = fabs(e.x), df = fabs(e.y);
+        const double loc = (df > de || df != df) ? df : de;
+        mm = (loc > mm || loc != loc) ? loc : mm;
+      }
+      g.sync();
+      for (int i = g.lane; i < nt; i += LANES) {
+        D2 dj; dj.x = dj.y = 0.0;
+        for (int q = 0; q < nt; ++q) {
+          const D2 a = zinv[(size_t)i * nt + q], e = et[q];
+          dj.x += fma(a.x, e.x, -a.y * e.y);
+          dj.y += fma(a.x, e.y, a.y * e.x);
+        }
+        D2 j = g.jt[i];
+        j.x += dj.x; j.y += dj.y;
+        g.jt[i] = j;
+      }
+    }
     mm = g.gmax_nan(mm);
     g.sync();
     out->max_mismatch = mm;
@@ -1019,6 +1080,7 @@ GFR_HD void sweep_solve(const SGrp<LANES>& g, const Layout& lay, const int* simg
       break;
     }
   }
+#undef GFR_TIE_CURRENT
 }
 
 // From -> to flow of the branch above the bus at position p (power_flow.py:329-358): P (pu), |S| (pu), series loss (pu)
@@ -1039,6 +1101,30 @@ GFR_HD void branch_flow(const G& g, const Layout& lay, const int* simg, const do
   *p_ft = P;
   *s_abs = sqrt(P * P + Q * Q);
   *loss = y.x * (de * de + df * df);                 // Re sum_i V_i conj((YV)_i), branch by branch
+}
+
+// From -> to flow of line `li` (ref order): a tree branch, or a tie of a weakly meshed feeder (I = y (V_from - V_to),
+// S = V_from conj(I), power_flow.py:329-358).  Also gives the line's rating.
+template <class G>
+GFR_HD void line_flow(const G& g, const Layout& lay, const int* simg, const double* dimg,
+                      int li, double* p_ft, double* s_abs, double* loss, double* rating) {
+  const int pb = (simg + lay.o_branch_of_line)[li];
+  if (pb >= 0) {
+    branch_flow(g, lay, simg, dimg, pb, p_ft, s_abs, loss);
+    *rating = dimg[lay.o_rating + pb];
+    return;
+  }
+  const int i = -1 - pb;
+  const int* ends = simg + lay.o_tie_ends;
+  const D2 va = g.ef(ends[2 * i]), vb = g.ef(ends[2 * i + 1]);
+  const D2 y = reinterpret_cast<const D2*>(dimg + lay.o_tie_y)[i];
+  const double de = va.x - vb.x, df = va.y - vb.y;
+  const double ir = y.x * de - y.y * df, ii = y.x * df + y.y * de;
+  const double P = va.x * ir + va.y * ii, Q = va.y * ir - va.x * ii;
+  *p_ft = P;
+  *s_abs = sqrt(P * P + Q * Q);
+  *loss = y.x * (de * de + df * df);
+  *rating = dimg[lay.o_tie_rating + i];
 }
 
 // ----------------------------------------------------------------------------- solver entry (gfr_solve)
@@ -1080,13 +1166,10 @@ GFR_HD void solve_instance(const typename GroupOf<LANES, SOLVER>::type& g, const
     if (o.bus_angles) o.bus_angles[env * n + i] = atan2_bus(f, e);
   }
   double loss = 0.0;
-  const int* bol = simg + lay.o_branch_of_line;
   for (int li = g.lane; li < m; li += LANES) {
-    int pb = bol[li];
-    double P, S, ls;
-    branch_flow(g, lay, simg, dimg, pb, &P, &S, &ls);
+    double P, S, ls, rating;
+    line_flow(g, lay, simg, dimg, li, &P, &S, &ls, &rating);
     loss += ls;
-    double rating = dimg[lay.o_rating + pb];
     if (o.line_flows) o.line_flows[env * m + li] = P;
     if (o.line_loadings) o.line_loadings[env * m + li] = rating > 0.0 ? S * lay.s_base / rating : 0.0;
   }
@@ -1366,14 +1449,11 @@ GFR_HD void step_instance(const typename GroupOf<LANES, SOLVER>::type& g, const 
   double loss_pu = 0.0;
   int over80 = 0;
   {
-    const int* bol = simg + lay.o_branch_of_line;
     for (int li = g.lane; li < m; li += LANES) {
-      int pb = bol[li];
-      double P, S, ls;
-      branch_flow(g, lay, simg, dimg, pb, &P, &S, &ls);
+      double P, S, ls, rating;
+      line_flow(g, lay, simg, dimg, li, &P, &S, &ls, &rating);
       loss_pu += ls;
       double pw = P * lay.s_base;
-      double rating = dimg[lay.o_rating + pb];
       double loading = rating > 0.0 ? fabs(pw) * rcp_fast(rating) : 0.0;     // Line.update_state, base.py:261-264 (|P| / rating)
       ob.put2(o_line + 2 * li, pw, loading);
       over80 += loading > 0.8;

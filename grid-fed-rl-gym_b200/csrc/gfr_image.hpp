@@ -81,6 +81,10 @@ struct DescCopy {
     d.gen_p2 = keep_d(s->gen_p2, G); d.bat_bus = keep_i(s->bat_bus, Bt); d.bat_cap = keep_d(s->bat_cap, Bt);
     d.bat_rating = keep_d(s->bat_rating, Bt); d.bat_eff = keep_d(s->bat_eff, Bt); d.bat_soc0 = keep_d(s->bat_soc0, Bt);
     d.load_profile = keep_d(s->load_profile, 24);
+    const size_t t = s->n_tie > 0 ? s->n_tie : 0;
+    d.tie_line = keep_i(s->tie_line, t); d.tie_from = keep_i(s->tie_from, t); d.tie_to = keep_i(s->tie_to, t);
+    d.tie_r = keep_d(s->tie_r, t); d.tie_x = keep_d(s->tie_x, t); d.tie_rating = keep_d(s->tie_rating, t);
+    d.tie_zinv = keep_d(s->tie_zinv, 2 * t * t);
   }
 };
 
@@ -101,7 +105,12 @@ inline std::string check_feeder_desc(const gfr_feeder_desc* d) {
   if (d->parent[0] != -1) return "k = 0 must be the root (parent -1)";
   if (d->level_ptr[0] != 0 || d->level_ptr[nl] != n) return "level_ptr must span [0, n]";
   if (d->level_ptr[1] != 1) return "level 0 must hold the root only";
-  std::vector<int32_t> seen_ref(n, 0), seen_line(n > 1 ? n - 1 : 0, 0), seen_child(n, 0);
+  const int nt = d->n_tie;
+  if (nt < 0 || nt > 4095) return "n_tie out of range";
+  if (nt && (!d->tie_line || !d->tie_from || !d->tie_to || !d->tie_r || !d->tie_x || !d->tie_rating || !d->tie_zinv))
+    return "missing tie array";
+  const int m_all = n - 1 + nt;
+  std::vector<int32_t> seen_ref(n, 0), seen_line(m_all > 0 ? m_all : 0, 0), seen_child(n, 0);
   std::vector<int> level(n, 0);
   for (int l = 0; l < nl; ++l) {
     if (d->level_ptr[l + 1] <= d->level_ptr[l]) return "empty level";
@@ -124,12 +133,20 @@ inline std::string check_feeder_desc(const gfr_feeder_desc* d) {
       if (p < 0 || p >= k) return "parent must precede its child in level order";
       if (level[p] >= level[k]) return "a bus must sit in a later level than its parent";
       const int li = d->line_of[k];
-      if (li < 0 || li >= n - 1 || seen_line[li]++) return "line_of is not a permutation of the lines";
+      if (li < 0 || li >= m_all || seen_line[li]++) return "line_of is not a permutation of the lines";
       if (!(d->g[k] == d->g[k]) || !(d->b[k] == d->b[k]) || (d->g[k] == 0.0 && d->b[k] == 0.0))
         return "branch with zero / NaN admittance";
     }
   }
   for (int k = 1; k < n; ++k) if (!seen_child[k]) return "child_idx does not list every bus";
+  for (int i = 0; i < nt; ++i) {
+    const int li = d->tie_line[i];
+    if (li < 0 || li >= m_all || seen_line[li]++) return "tie_line and line_of do not partition the lines";
+    if (d->tie_from[i] < 0 || d->tie_from[i] >= n || d->tie_to[i] < 0 || d->tie_to[i] >= n || d->tie_from[i] == d->tie_to[i])
+      return "tie end out of range";
+    if (!(d->tie_r[i] == d->tie_r[i]) || !(d->tie_x[i] == d->tie_x[i]) || (d->tie_r[i] == 0.0 && d->tie_x[i] == 0.0))
+      return "tie with zero / NaN impedance";
+  }
   if (n_slack != 1) return "exactly one slack bus is required";
   for (int l = 0; l < L; ++l) if (d->load_bus[l] < 0 || d->load_bus[l] >= n) return "load_bus out of range";
   for (int g = 0; g < G; ++g) {
@@ -196,7 +213,10 @@ inline std::string build_feeder_image(const gfr_feeder_desc* d, int lanes, int s
   }
   if (lanes < 1 || lanes > 256) return "lanes out of range";
   const bool newton = solver == GFR_SOLVER_NEWTON;
-  const int n = d->n_bus, nl = d->n_levels, L = d->n_load, G = d->n_gen, Bt = d->n_bat;
+  const int n = d->n_bus, nl = d->n_levels, L = d->n_load, G = d->n_gen, Bt = d->n_bat, nt = d->n_tie;
+  if (newton && nt)
+    return "the feeder has loop-closing lines: the tree-ordered Newton-Raphson takes radial feeders "
+           "(GFR_SOLVER_SWEEP restores the loops by compensation)";
   FeederImage* f = out;
   f->lanes = lanes; f->solver = solver; f->n_reg_edges = 0; f->has_pv = false;
   {
@@ -213,8 +233,8 @@ inline std::string build_feeder_image(const gfr_feeder_desc* d, int lanes, int s
   }
   Layout& lay = f->lay;
   lay = Layout{};
-  lay.n = n; lay.nl = nl; lay.L = L; lay.G = G; lay.Bt = Bt; lay.A = Bt + G; lay.m = n - 1;
-  lay.D = 2 * n + 2 * (n - 1) + 1 + 2 * L + G + 2 * Bt;
+  lay.n = n; lay.nl = nl; lay.L = L; lay.G = G; lay.Bt = Bt; lay.A = Bt + G; lay.m = n - 1 + nt; lay.n_tie = nt;
+  lay.D = 2 * n + 2 * lay.m + 1 + 2 * L + G + 2 * Bt;
   lay.n_src = L + G + Bt; lay.R = R_BAT + 2 * Bt; lay.n_noise = 4 + L;
   lay.s_base = d->s_base;
   lay.inv_s_base = 1.0 / d->s_base;
@@ -240,7 +260,8 @@ inline std::string build_feeder_image(const gfr_feeder_desc* d, int lanes, int s
   std::vector<int> bus_at(P, -1);
   for (int k = 0; k < n; ++k) bus_at[pos[k]] = k;
 
-  std::vector<int32_t> flags(n), rank(n), rankp(n), bol(n > 1 ? n - 1 : 0);
+  std::vector<int32_t> flags(n), rank(n), rankp(n), bol(lay.m > 0 ? lay.m : 0);
+  for (int i = 0; i < nt; ++i) bol[d->tie_line[i]] = -1 - i;          // a tie: its index, negated
   for (int k = 0; k < n; ++k) {
     int fl = FL_VALID;
     if (d->bus_type[k] == GFR_BUS_PQ) fl |= FL_PQ;
@@ -379,7 +400,7 @@ inline std::string build_feeder_image(const gfr_feeder_desc* d, int lanes, int s
   }
   lay.o_rank = ib.add_i(rank.data(), n);
   lay.o_rankp = newton ? ib.add_i(rankp.data(), n) : lay.o_rank;
-  lay.o_branch_of_line = ib.add_i(bol.data(), n - 1);
+  lay.o_branch_of_line = ib.add_i(bol.data(), lay.m);
   lay.o_inj_ptr = ib.add_i(inj_ptr.data(), P + 1);
   lay.o_inj_idx = ib.add_i(inj_idx.data(), lay.n_src);
   lay.o_gen_type = ib.add_i(d->gen_type, G);
@@ -390,6 +411,19 @@ inline std::string build_feeder_image(const gfr_feeder_desc* d, int lanes, int s
     lay.o_topo = ib.add_i(topo.data(), 4 * n);
     lay.o_child_idx = ib.add_i(d->child_idx, n - 1);
     lay.o_level_ptr = ib.add_i(d->level_ptr, nl + 1);
+  }
+  lay.o_tie_ends = lay.o_tie_ptr = lay.o_tie_inc = lay.o_tie_y = lay.o_tie_z = lay.o_tie_rating = lay.o_tie_zinv = -1;
+  if (nt) {
+    // tie ends (from, to) as ef indices, and per bus the ties that meet it: entry = tie << 1 | (1 if the bus is the to-end)
+    std::vector<int32_t> ends(2 * (size_t)nt), tptr(n + 1, 0), tinc(2 * (size_t)nt);
+    std::vector<int> cnt(n, 0);
+    for (int i = 0; i < nt; ++i) { ends[2 * i] = d->tie_from[i]; ends[2 * i + 1] = d->tie_to[i]; cnt[d->tie_from[i]]++; cnt[d->tie_to[i]]++; }
+    for (int k = 0; k < n; ++k) tptr[k + 1] = tptr[k] + cnt[k];
+    std::vector<int> fill(tptr.begin(), tptr.end() - 1);
+    for (int i = 0; i < nt; ++i) { tinc[fill[d->tie_from[i]]++] = i << 1; tinc[fill[d->tie_to[i]]++] = (i << 1) | 1; }
+    lay.o_tie_ends = ib.add_i(ends.data(), 2 * nt);
+    lay.o_tie_ptr = ib.add_i(tptr.data(), n + 1);
+    lay.o_tie_inc = ib.add_i(tinc.data(), 2 * nt);
   }
   const int n_int_padded = ((int)ib.ints.size() + 3) / 4 * 4;      // keep the doubles 16-byte aligned
   const int dbase = n_int_padded / 2;
@@ -457,6 +491,18 @@ inline std::string build_feeder_image(const gfr_feeder_desc* d, int lanes, int s
       cc[2] = -gl * m00 + ll * m10; cc[3] = -gl * m01 + ll * m11;
     }
     lay.o_f0 = ok ? dbase + ib.add_d(f0.data(), 12 * P) : -1;     // singular at the flat start: no shortcut
+  }
+  if (nt) {
+    std::vector<double> ty(2 * (size_t)nt), tz(2 * (size_t)nt);
+    for (int i = 0; i < nt; ++i) {
+      const double r = d->tie_r[i], x = d->tie_x[i], z2 = r * r + x * x;
+      ty[2 * i] = r / z2; ty[2 * i + 1] = -x / z2;            // y = 1 / (r + jx), as power_flow.py:62
+      tz[2 * i] = r; tz[2 * i + 1] = x;
+    }
+    lay.o_tie_y = dbase + ib.add_d(ty.data(), 2 * nt);
+    lay.o_tie_z = dbase + ib.add_d(tz.data(), 2 * nt);
+    lay.o_tie_zinv = dbase + ib.add_d(d->tie_zinv, 2 * nt * nt);
+    lay.o_tie_rating = dbase + ib.add_d(d->tie_rating, nt);
   }
   lay.o_rating = dbase + ib.add_d(rating.data(), P);
   lay.o_vm_set = dbase + ib.add_d(vm_set.data(), P);

@@ -29,18 +29,18 @@ from .errors import InvalidActionError, InvalidConfigurationError, NetworkTopolo
 from .topology import FeederSoA, TopologyError, compile_for_solver, repair_topology
 
 
-def _compile(feeder, renewable_sources, repair, solver, lanes) -> Tuple[FeederSoA, Any, int]:
+def _compile(feeder, renewable_sources, repair, solver, lanes, keep_cycles=False) -> Tuple[FeederSoA, Any, int]:
     if isinstance(feeder, FeederSoA):
         # a precompiled feeder runs on the lane count its level schedule was capped for
         return feeder, None, int(lanes) or int(getattr(feeder, "lanes_hint", 0) or 0)
     try:
         if repair is True:
-            feeder = repair_topology(feeder)
+            feeder = repair_topology(feeder, keep_cycles=keep_cycles)
         soa, lanes = compile_for_solver(feeder, solver, lanes, renewable_sources=renewable_sources)
         return soa, feeder, lanes
     except TopologyError as exc:
         if repair == "auto":
-            fixed = repair_topology(feeder)
+            fixed = repair_topology(feeder, keep_cycles=keep_cycles)
             soa, lanes = compile_for_solver(fixed, solver, lanes, renewable_sources=renewable_sources)
             return soa, fixed, lanes
         raise NetworkTopologyError(str(exc)) from exc
@@ -102,12 +102,15 @@ class BatchedGridEnvironment:
                  acceleration: float = 1.0, lanes: int = 0, load_noise: float = 0.1, repair="auto",
                  start_time: float = 0.0, env_id_offset: int = 0, auto_reset: bool = False,
                  copy_outputs: bool = False, record_noise: bool = False, obs_dtype=torch.float64,
-                 obs_buffers: int = 0, **kwargs) -> None:
+                 obs_buffers: int = 0, keep_cycles: bool = False, **kwargs) -> None:
         # ``obs_dtype=torch.float32``: the kernels write the observation as fp32 (the type the reference
         # declares for its observation space, grid_env.py:346; every other output stays fp64).
         # ``obs_buffers=2``: two alternating observation buffers - step t writes the one that does not hold
         # observation t - 1, so observation t - 1 can be copied out on another stream while step t runs
         # (pipeline.HostStepper does).  Default: two for fp32, one for fp64.
+        # ``keep_cycles=True`` (sweep solver): a repair keeps the lines that close a cycle (the shipped IEEE-34 /
+        # IEEE-123 ties, SyntheticFeeder(connectivity > 0)) and the sweep restores the loops by compensation,
+        # instead of dropping them (deviation D4-iii).  A meshed connected feeder passed with repair=False works too.
         # **kwargs are accepted and ignored, as the reference constructor does (base.py:84)
         if int(num_envs) < 1:
             raise InvalidConfigurationError("num_envs must be >= 1")
@@ -121,7 +124,10 @@ class BatchedGridEnvironment:
         self.renewable_sources = list(renewable_sources or [])
         if solver not in nat.SOLVERS:
             raise InvalidConfigurationError(f"solver must be one of {sorted(nat.SOLVERS)}, got {solver!r}")
-        self.soa, self.feeder, lanes = _compile(feeder, self.renewable_sources, repair, solver, lanes)
+        if keep_cycles and solver != "sweep":
+            raise InvalidConfigurationError("keep_cycles=True needs solver='sweep' (the tree-ordered Newton-Raphson takes "
+                                            "radial feeders; the dense Newton-Raphson lives on the solver surface)")
+        self.soa, self.feeder, lanes = _compile(feeder, self.renewable_sources, repair, solver, lanes, keep_cycles)
         self.timestep, self.episode_length = float(timestep), int(episode_length)
         self.stochastic_loads, self.weather_variation = bool(stochastic_loads), bool(weather_variation)
         self.safety_penalty = float(safety_penalty)

@@ -24,7 +24,7 @@ import torch
 from . import _native as nat
 from .components import FeederParameters, PowerFlowSolution
 from .env import NativeFeeder, _cuda_device
-from .errors import InvalidConfigurationError, NetworkTopologyError
+from .errors import GridLimitError, InvalidConfigurationError, NetworkTopologyError
 from .topology import FeederSoA, TopologyError, auto_lanes, compile_for_solver
 
 
@@ -92,11 +92,12 @@ def is_radial(buses, lines) -> bool:
 class B200PowerFlowSolver:
     """Batched load flow on one GPU.  ``method`` is "newton" (the reference's polar Newton-Raphson
     iterates, solved by tree-ordered block elimination; radial feeders of any size), "sweep"
-    (backward / forward sweep; radial), "dense" (the same Newton-Raphson on the dense Jacobian,
+    (backward / forward sweep; radial, or weakly meshed with the loops restored by the compensation
+    method: one current per loop-closing line, corrected every iteration), "dense" (the same Newton-Raphson on the dense Jacobian,
     eliminated with partial pivoting by one CTA per instance: any connected network, cycles
     included, up to ~80 buses; ``dense_kernel`` = "auto" | "shared" | "registers" picks where the
     system lives during the elimination) or "auto" ("newton" on a radial network, "dense" on a
-    meshed one)."""
+    meshed one that fits, the compensation sweep - run tight - on one that does not)."""
 
     METHODS = tuple(sorted(set(nat.SOLVERS) | {"dense", "auto"}))
     DENSE_KERNELS = {"auto": 0, "shared": 1, "registers": 2}
@@ -117,8 +118,8 @@ class B200PowerFlowSolver:
         self.last: Optional[PowerFlowSolution] = None
 
     # -- compiled topologies ------------------------------------------------------
-    def _compile(self, feeder) -> FeederSoA:
-        method = "newton" if self.method in ("auto", "dense") else self.method
+    def _compile(self, feeder, method: Optional[str] = None) -> FeederSoA:
+        method = method or ("newton" if self.method in ("auto", "dense") else self.method)
         soa, self._lanes_used = compile_for_solver(feeder, method, self.lanes, with_components=False)
         return soa
 
@@ -177,13 +178,24 @@ class B200PowerFlowSolver:
         returns a ``PowerFlowSolution`` of tensors with a leading B axis."""
         if isinstance(feeder, NativeNetwork):
             return self.solve_network_batch(feeder, p_inj)
+        sweep_ties = False
         if not isinstance(feeder, (NativeFeeder, FeederSoA)) and self._use_dense(feeder.buses, feeder.lines):
             s_base = float(feeder.parameters.base_power) * 1e6
-            return self.solve_network_batch(self._network(feeder.buses, feeder.lines, s_base), p_inj)
+            try:
+                return self.solve_network_batch(self._network(feeder.buses, feeder.lines, s_base), p_inj)
+            except GridLimitError:
+                # the dense Jacobian does not fit an SM (e.g. IEEE-123 with its 26 tie lines: 244 unknowns):
+                # "auto" falls back to the sweep on the spanning tree with the loops restored by compensation
+                if self.method != "auto":
+                    raise
+                sweep_ties = True
         if isinstance(feeder, NativeFeeder):
             nf = feeder
         elif isinstance(feeder, FeederSoA):
             nf = self._native(("soa", id(feeder)), lambda: feeder)
+        elif sweep_ties:
+            nf = self._native(("feeder-sweep", id(feeder), _signature(feeder.buses, feeder.lines)),
+                              lambda: self._compile(feeder, "sweep"))
         else:
             nf = self._native(("feeder", id(feeder), _signature(feeder.buses, feeder.lines)),
                               lambda: self._compile(feeder))
@@ -203,7 +215,9 @@ class B200PowerFlowSolver:
                    losses=torch.empty(B, **f64), max_mismatch=torch.empty(B, **f64))
         so = nat.SolOut(*[out[k].data_ptr() for k, _ in nat.SolOut._fields_])
         method = "newton" if self.method in ("auto", "dense") else self.method
-        cfg = nat.make_solver_cfg(method, self.tolerance, self.max_iterations,
+        if soa.n_tie:
+            method = "sweep"                 # a tree with ties compiled for the compensation sweep
+        cfg = nat.make_solver_cfg(method, self.tolerance if not sweep_ties else min(self.tolerance, 1e-9), self.max_iterations if not sweep_ties else max(self.max_iterations, 200),
                                   self.acceleration_factor,
                                   self.lanes or getattr(soa, "lanes_hint", 0) or auto_lanes(soa.n_bus, method))
         nat.check(lib, lib.gfr_solve(nf.handle, B, p.data_ptr(), C.byref(cfg), C.byref(so),

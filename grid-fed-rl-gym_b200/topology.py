@@ -202,6 +202,18 @@ class FeederSoA:
     bat_eff: np.ndarray                # f64[Bt]
     bat_soc0: np.ndarray               # f64[Bt]
     load_profile: np.ndarray = field(default_factory=lambda: np.array(DEFAULT_LOAD_PROFILE))
+    # loop-closing lines of a weakly meshed feeder (sweep solver only; empty for a radial feeder) ------------
+    tie_line: np.ndarray = field(default_factory=lambda: np.zeros(0, dtype=np.int32))    # int32[t] ref line index
+    tie_from: np.ndarray = field(default_factory=lambda: np.zeros(0, dtype=np.int32))    # int32[t] level index of line.from_bus
+    tie_to: np.ndarray = field(default_factory=lambda: np.zeros(0, dtype=np.int32))      # int32[t] level index of line.to_bus
+    tie_r: np.ndarray = field(default_factory=lambda: np.zeros(0))                       # f64[t] pu
+    tie_x: np.ndarray = field(default_factory=lambda: np.zeros(0))                       # f64[t] pu
+    tie_rating: np.ndarray = field(default_factory=lambda: np.zeros(0))                  # f64[t] VA
+    tie_zinv: np.ndarray = field(default_factory=lambda: np.zeros(0))                    # f64[t, t, 2] inverse loop-impedance matrix (re, im)
+
+    @property
+    def n_tie(self) -> int:
+        return int(self.tie_line.size)
 
     @property
     def n_load(self) -> int:
@@ -424,7 +436,11 @@ def tree_center(n: int, adj, fallback: int) -> int:
 def compile_feeder(feeder, renewable_sources: Optional[Sequence[str]] = None,
                    with_components: bool = True, root: str = "slack",
                    width: Optional[int] = None, paths: bool = False) -> FeederSoA:
-    """Compile a *radial, connected* feeder (run ``repair_topology`` first if it is not).
+    """Compile a *connected* feeder (run ``repair_topology`` first if it is not): radial, or weakly
+    meshed - lines that close a cycle (in list order, as ``repair_topology(keep_cycles=True)`` keeps them)
+    become *ties*: the traversal tree is the rest, and the sweep solver restores the loops with the
+    compensation method (one current per tie, corrected every iteration through the inverse
+    loop-impedance matrix computed here).  The tree-ordered Newton kernels take radial feeders only.
 
     ``renewable_sources`` has the reference meaning (grid_env.py:167,273,282): a
     generator of type "solar"/"wind" becomes an environment generator only if
@@ -444,8 +460,8 @@ def compile_feeder(feeder, renewable_sources: Optional[Sequence[str]] = None,
     n, m = len(buses), len(lines)
     if n < 1:
         raise TopologyError("feeder has no buses")
-    if m != n - 1:
-        raise TopologyError(f"radial solver needs n-1 lines, feeder has {n} buses and {m} lines "
+    if m < n - 1:
+        raise TopologyError(f"a connected feeder needs at least n-1 lines, this one has {n} buses and {m} lines "
                             "(run repair_topology first)")
     index = {b.id: i for i, b in enumerate(buses)}
     if len(index) != n:
@@ -455,6 +471,15 @@ def compile_feeder(feeder, renewable_sources: Optional[Sequence[str]] = None,
     adj: List[List[Tuple[int, int]]] = [[] for _ in range(n)]
     ydiag = np.zeros(n, dtype=complex)
     ys: List[complex] = []
+    uf = list(range(n))                   # spanning tree = the lines that do not close a cycle, in list order
+    ties: List[int] = []
+
+    def _find(a: int) -> int:
+        while uf[a] != a:
+            uf[a] = uf[uf[a]]
+            a = uf[a]
+        return a
+
     for k, ln in enumerate(lines):
         if ln.from_bus not in index or ln.to_bus not in index:
             raise TopologyError(f"line {ln.id} references an unknown bus")
@@ -467,8 +492,15 @@ def compile_feeder(feeder, renewable_sources: Optional[Sequence[str]] = None,
         ys.append(y)
         ydiag[i] += y          # accumulation order = line order, as the reference Ybus
         ydiag[j] += y
+        a, b = _find(i), _find(j)
+        if a == b:
+            ties.append(k)     # closes a cycle: a tie, restored by the sweep's compensation step
+            continue
+        uf[a] = b
         adj[i].append((j, k))
         adj[j].append((i, k))
+    if m - len(ties) != n - 1:
+        raise TopologyError("feeder is not connected (run repair_topology first)")
 
     if root not in ("slack", "center"):
         raise TopologyError("root must be 'slack' or 'center'")
@@ -520,6 +552,31 @@ def compile_feeder(feeder, renewable_sources: Optional[Sequence[str]] = None,
     g, b, r, x, rating = (lay[k] for k in ("g", "b", "r", "x", "rating"))
     level_ptr, child_ptr, child_idx = (lay[k] for k in ("level_ptr", "child_ptr", "child_idx"))
 
+    # ---- ties: end points in level order and the inverse of the loop-impedance matrix
+    #      Z_loop[i][j] = sum over tree branches e of z_e s_i(e) s_j(e) + [i == j] z_tie_i, where
+    #      s_i(e) = [to-end of tie i below e] - [from-end of tie i below e] (non-zero on the tree path between
+    #      the two ends): d(V_from - V_to - z_tie J)_i / dJ_j = -Z_loop[i][j] for tie currents J (from -> to)
+    tie_soa = {}
+    if ties:
+        t = len(ties)
+        tf = np.array([rank[index[lines[k].from_bus]] for k in ties], dtype=np.int32)
+        tt = np.array([rank[index[lines[k].to_bus]] for k in ties], dtype=np.int32)
+        S = np.zeros((t, n))
+        for i in range(t):
+            for end, sign in ((tt[i], 1.0), (tf[i], -1.0)):
+                k = int(end)
+                while k > 0:
+                    S[i, k] += sign
+                    k = int(parent[k])
+        zb = r + 1j * x                                       # branch above bus k (0 for the root)
+        zt = np.array([complex(lines[k].resistance, lines[k].reactance) for k in ties])
+        zloop = (S * zb[None, :]) @ S.T + np.diag(zt)
+        zinv = np.linalg.inv(zloop)
+        tie_soa = dict(tie_line=np.array(ties, dtype=np.int32), tie_from=tf, tie_to=tt,
+                       tie_r=zt.real.copy(), tie_x=zt.imag.copy(),
+                       tie_rating=np.array([float(lines[k].rating) for k in ties]),
+                       tie_zinv=np.stack([zinv.real, zinv.imag], axis=-1).copy())
+
     tmap = {"slack": BUS_SLACK, "pv": BUS_PV}
     bus_type = np.array([tmap.get(buses[i].bus_type, BUS_PQ) for i in order], dtype=np.int32)
     vm_set = np.array([float(buses[i].voltage_magnitude) for i in order])
@@ -532,7 +589,7 @@ def compile_feeder(feeder, renewable_sources: Optional[Sequence[str]] = None,
         child_ptr=child_ptr, child_idx=child_idx, n_pool=0, lane_of=lay["lane_of"],
         bus_type=bus_type, vm_set=vm_set, g=g, b=b,
         gdiag=ydiag.real[order].copy(), bdiag=ydiag.imag[order].copy(), r=r, x=x,
-        line_of=line_of, from_is_parent=from_is_parent, rating=rating)
+        line_of=line_of, from_is_parent=from_is_parent, rating=rating, **tie_soa)
 
     # ---- components -------------------------------------------------------
     loads = list(feeder.loads) if with_components else []
@@ -617,5 +674,8 @@ def compile_for_solver(feeder, solver: str = "newton", lanes: int = 0,
         alt = compile_feeder(feeder, root="slack", **kw)
         if soa.n_levels > 0.75 * alt.n_levels:
             soa = alt
+    if soa.n_tie and solver != "sweep":
+        raise TopologyError(f"the feeder has {soa.n_tie} loop-closing lines: the tree-ordered Newton-Raphson takes radial "
+                            "feeders (solver='sweep' restores the loops by compensation; repair_topology() drops them)")
     soa.lanes_hint = lanes             # the lane count the level schedule was capped for
     return soa, lanes

@@ -55,7 +55,8 @@ typedef struct {
                                        library's own plan needs) */
   int32_t lanes_hint;               /* lanes the level schedule was capped for (levels hold at most this many buses);
                                        what `lanes = 0` resolves to.  0 = not said: gfr_auto_lanes decides */
-  int32_t reserved;
+  int32_t n_tie;                    /* loop-closing lines of a weakly meshed feeder (0: radial).  The feeder then has
+                                       n - 1 + n_tie lines; sweep solver only */
   double s_base;                    /* VA; feeder.parameters.base_power * 1e6 */
   const int32_t* order;             /* [n]  level k -> ref bus index */
   const int32_t* parent;            /* [n]  level index of the parent, -1 for k = 0 */
@@ -73,7 +74,7 @@ typedef struct {
   const double* bdiag;              /* [n]  Im Y_kk */
   const double* r;                  /* [n]  branch resistance, pu */
   const double* x;                  /* [n]  branch reactance, pu */
-  const int32_t* line_of;           /* [n]  ref line index of branch k (-1 for k = 0) */
+  const int32_t* line_of;           /* [n]  ref line index of branch k (-1 for k = 0); with tie_line a permutation of the lines */
   const int32_t* from_is_parent;    /* [n]  1 if line.from_bus is the parent end */
   const double* rating;             /* [n]  line rating, VA */
   const int32_t* load_bus;          /* [L]  level index */
@@ -92,6 +93,18 @@ typedef struct {
   const double* bat_eff;            /* [Bt] BatteryModel.efficiency */
   const double* bat_soc0;           /* [Bt] state of charge after reset (0.5) */
   const double* load_profile;       /* [24] TimeVaryingLoadModel.daily_profile (dynamics.py:43-48) */
+  /* Ties: the lines that close a cycle (feeder.lines in list order, every line that joins two buses already
+   * connected).  The traversal tree is the rest; the sweep restores the loops by compensation: one current per
+   * tie (from -> to), corrected every iteration by tie_zinv x (V_from - V_to - z_tie J).  The reference takes
+   * such networks through its dense Ybus (power_flow.py:48-73). */
+  const int32_t* tie_line;          /* [t]  ref line index */
+  const int32_t* tie_from;          /* [t]  level index of line.from_bus */
+  const int32_t* tie_to;            /* [t]  level index of line.to_bus */
+  const double* tie_r;              /* [t]  pu */
+  const double* tie_x;              /* [t]  pu */
+  const double* tie_rating;         /* [t]  VA */
+  const double* tie_zinv;           /* [t, t, 2] inverse of the loop-impedance matrix, row-major (re, im):
+                                            Z[i][j] = sum over tree branches on both loops of +-z + [i == j] z_tie */
 } gfr_feeder_desc;
 
 /* Solver settings: PowerFlowSolver.__init__(tolerance, max_iterations) + NewtonRaphsonSolver's

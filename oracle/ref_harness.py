@@ -204,11 +204,12 @@ def make_feeder(ns, spec: str, use_reference_classes: bool = True):
     elif spec.startswith("mesh"):
         # meshed: 'mesh<N>:<seed>:<connectivity>' (SyntheticFeeder with extra ties), 'meshieee34' (the
         # shipped IEEE-34 with its loop-closing line kept); repaired with keep_cycles=True
-        if spec == "meshieee34":
+        if spec in ("meshieee34", "meshieee123"):
+            cls = "IEEE34Bus" if spec == "meshieee34" else "IEEE123Bus"
             if use_reference_classes:
-                st = np.random.get_state(); np.random.seed(0); f = ns.feeders.IEEE34Bus(); np.random.set_state(st)
+                st = np.random.get_state(); np.random.seed(0); f = getattr(ns.feeders, cls)(); np.random.set_state(st)
             else:
-                f = mine.IEEE34Bus(seed=0)
+                f = getattr(mine, cls)(seed=0)
         else:
             n, seed, conn = spec[4:].split(":")
             cfg = dict(num_buses=int(n), connectivity=float(conn), load_probability=0.9, dg_probability=0.4,
@@ -368,6 +369,14 @@ TRACE_CASES = {
     "trace_ieee123_long_s11": ("ieee123", 150, 11, dict(start_time=13 * 3600.0, timestep=30.0, episode_length=60)),
     "trace_ieee123_long_s12": ("ieee123", 150, 12, dict(start_time=18.5 * 3600.0, timestep=60.0, tolerance=1e-8)),
 }
+# environments on MESHED feeders (loop-closing lines kept): the reference's step with its dense Newton-Raphson;
+# the CUDA path takes these through the sweep with compensation (a different algorithm: compared tight)
+MESH_TRACE_CASES = {
+    "meshtrace_ieee34_s0": ("meshieee34", 60, 0, dict(start_time=9 * 3600.0, timestep=30.0, tolerance=1e-8)),
+    "meshtrace_synthetic40_s1": ("mesh40:3:0.05", 40, 1, dict(start_time=13 * 3600.0, timestep=60.0, tolerance=1e-8,
+                                                            load_scale=0.05)),
+    "meshtrace_ieee123_s2": ("meshieee123", 10, 2, dict(start_time=11 * 3600.0, timestep=60.0, tolerance=1e-8)),
+}
 SOLVE_CASES = {
     "solve_fixture3": ("fixture3", 0, 4, 1e-10, 0.025),
     "solve_radial34": ("radial34", 1, 6, 1e-8, 0.02),
@@ -385,6 +394,8 @@ SOLVE_CASES = {
     "meshsolve_synthetic40": ("mesh40:3:0.05", 8, 5, 1e-8, 0.05),
     "meshsolve_synthetic72": ("mesh72:5:0.02", 9, 3, 1e-8, 0.03),
     "meshsolve_synthetic24_overload": ("mesh24:2:0.1", 10, 2, 1e-6, 200.0),
+    # IEEE-123 with its 26 tie lines kept: 244 unknowns - too large for the dense CUDA kernels, taken by the sweep
+    "meshsolve_ieee123": ("meshieee123", 12, 2, 1e-8, 1.0),
 }
 
 
@@ -565,7 +576,7 @@ def main() -> None:
         data = solve_cases(ns, f, seed, count, tol, scale=scale, max_iterations=30 if "overload" in name else 50)
         np.savez_compressed(os.path.join(out_dir, name + ".npz"), spec=np.array(spec), **data)
         print(name, "iters", data["iterations"], "conv", data["converged"], flush=True)
-    for name, (spec, steps, seed, kw) in TRACE_CASES.items():
+    for name, (spec, steps, seed, kw) in list(TRACE_CASES.items()) + list(MESH_TRACE_CASES.items()):
         if only and name not in only:
             continue
         f = make_feeder(ns, spec)

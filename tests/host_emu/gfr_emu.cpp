@@ -35,13 +35,19 @@ void team_barrier(void* ctx) { pthread_barrier_wait((pthread_barrier_t*)ctx); }
 struct EmuSlot {
   std::vector<double> work;    // shared-memory slot
   std::vector<D2> mg;          // the global scratch of the slot
+  std::vector<double> plocal;  // the per-thread injection array of a one-thread sweep on a small feeder
   explicit EmuSlot(const Layout& lay)
-      : work(8 + (newton_slot_bytes(lay.n, lay.n_pool, 0) + sweep_slot_bytes(lay.n, 0)) / 8, 0.0),
-        mg(newton_scratch_doubles(lay.P) / 2 + 1) {}
+      : work(8 + (newton_slot_bytes(lay.n, lay.n_pool, 0) + sweep_slot_bytes(lay.n, 0, false, lay.n_tie)) / 8, 0.0),
+        mg(newton_scratch_doubles(lay.P) / 2 + 1), plocal(SWEEP_P_LOCAL_MAX + 1, 0.0) {}
+  template <int LANES> void local_injections(NGrp<LANES>&, const Layout&) {}
+  template <int LANES> void local_injections(SGrp<LANES>& g, const Layout& lay) {
+    if (sweep_p_local(LANES, lay.n)) g.pp = plocal.data();          // as use_local_injections in gfr_b200.cu
+  }
   template <class G> G group(const Layout& lay, int lane, EmuTeam* team) {
     G g;
     g.lane = lane; g.mask = 1u; g.red = nullptr; g.team = team;
     bind_slot(g, reinterpret_cast<unsigned char*>(work.data()), lay, mg.data());
+    local_injections(g, lay);
     return g;
   }
 };

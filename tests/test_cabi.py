@@ -40,7 +40,7 @@ def test_binding_covers_header(lib):
 def test_struct_layouts():
     from grid_fed_rl_b200 import _native as nat
     # sizes of the C structs on LP64 (int32 x5 + pad, double, 32 pointers)
-    assert C.sizeof(nat.FeederDesc) == 32 + 8 + 33 * 8
+    assert C.sizeof(nat.FeederDesc) == 32 + 8 + 40 * 8
     assert C.sizeof(nat.SolverCfg) == 32
     assert C.sizeof(nat.EnvCfg) == 8 + 16 + 6 * 8 + 32 + 8
     assert C.sizeof(nat.StepOut) == 15 * 8

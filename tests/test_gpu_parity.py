@@ -642,6 +642,8 @@ def test_dense_solver_matches_reference_on_meshed_networks(name):
     assert not is_radial(f.buses, f.lines)
     tol, max_it = float(g["meta"][0]), int(g["meta"][1])
     unknowns = 2 * (len(f.buses) - 1)
+    if unknowns > 165:
+        pytest.skip("too large for the dense kernels: see test_sweep_takes_meshed_networks")
     for method, where in (("dense", "auto"), ("auto", "auto"), ("dense", "shared"), ("dense", "registers")):
         if where == "registers" and unknowns > 127:
             continue
@@ -740,3 +742,60 @@ def test_dense_solver_limits_and_singular_network():
     for where in ("shared", "registers"):
         sol = m.B200PowerFlowSolver(method="dense", dense_kernel=where).solve_batch(g, p)
         assert not bool(sol.converged[0]) and int(sol.iterations[0]) == 1
+
+
+# ----------------------------------------------------------------------------- weakly meshed feeders (sweep + compensation)
+
+@pytest.mark.parametrize("lanes", (1, 8, 32, 64))
+@pytest.mark.parametrize("name", golden_names("meshtrace_"))
+def test_sweep_steps_meshed_feeders(name, lanes):
+    """Environments on feeders with their loop-closing lines kept (the shipped IEEE-34 loop, IEEE-123's 26 ties, a
+    synthetic mesh with 37): the reference steps them with its dense Newton-Raphson (frozen traces, pinned to the
+    oracle at their own tolerance by test_oracle_golden); the kernels walk the spanning tree and restore the loops
+    by compensation - one current per tie, corrected every iteration through the inverse loop-impedance matrix."""
+    g = port_trace(load_golden(name), tolerance=1e-10)
+    exact = replay_trace(_factory("sweep", lanes, 1e-11), g, ctx=f"{name}/sweep/lanes{lanes}", check_iterations=False)
+    assert exact >= 0.9 * g["obs"].shape[0]
+
+
+@pytest.mark.parametrize("name", [n for n in golden_names("meshsolve_") if "overload" not in n])
+def test_sweep_takes_meshed_networks(name):
+    """The solver surface on meshed networks through the sweep (any size the tree kernels take - IEEE-123 with its 26
+    ties is beyond the dense kernels; method="auto" falls back to this path there), against the frozen reference."""
+    import grid_fed_rl_b200 as m
+    g = load_golden(name)
+    f = feeder_for(g)
+    conv = g["converged"]
+    net = port.DenseNetwork(f.buses, f.lines)
+    ref = port.newton_raphson(net, g["p_spec"], 1e-10, 50)
+    methods = [("sweep", 1e-11, 300)]
+    if 2 * (len(f.buses) - 1) > 165:
+        methods.append(("auto", 1e-8, 50))
+        with pytest.raises(m.GridLimitError):
+            m.B200PowerFlowSolver(method="dense").solve_batch(f, g["p_spec"])
+    for method, tol, max_it in methods:
+        for lanes in (0, 8, 32):
+            sol = m.B200PowerFlowSolver(tolerance=tol, max_iterations=max_it, method=method, lanes=lanes).solve_batch(f, g["p_spec"])
+            assert bool(sol.converged.all()) and conv.all()
+            for k in ("bus_voltages", "bus_angles", "line_flows", "losses"):
+                assert np.max(np.abs(getattr(sol, k).cpu().numpy() - ref[k])) <= TOL_PU, (method, k)
+            # and against the frozen reference run itself (its own tolerance: 1e-8 or looser)
+            assert np.max(np.abs(sol.bus_voltages.cpu().numpy() - g["bus_voltages"])) <= 1e-6
+    with pytest.raises(m.NetworkTopologyError):
+        m.B200PowerFlowSolver(method="newton").solve_batch(f, g["p_spec"])
+
+
+def test_meshed_environment_options():
+    """keep_cycles=True: a repair keeps the loop-closing lines (sweep only); the default repair drops them (D4-iii)."""
+    import grid_fed_rl_b200 as m
+    raw = m.IEEE123Bus(seed=0)
+    a = m.BatchedGridEnvironment(raw, 8, solver="sweep", tolerance=1e-10, renewable_sources=["solar", "wind"])
+    b = m.BatchedGridEnvironment(raw, 8, solver="sweep", tolerance=1e-10, renewable_sources=["solar", "wind"], keep_cycles=True)
+    assert a.soa.n_tie == 0 and a.soa.n_line == 122 and b.soa.n_tie == 26 and b.soa.n_line == 148
+    assert b.obs_dim == a.obs_dim + 2 * 26
+    with pytest.raises(m.InvalidConfigurationError):
+        m.BatchedGridEnvironment(raw, 8, solver="newton", keep_cycles=True)
+    b.reset(seed=1)
+    g = torch.Generator(device="cuda"); g.manual_seed(0)
+    obs, reward, term, trunc, info = b.step(b.sample_actions(g))
+    assert bool(info["power_flow_converged"].all()) and torch.isfinite(obs).all()

@@ -19,7 +19,7 @@ class _OneEnv:
         return {k: v[0] for k, v in out.items()}
 
 
-@pytest.mark.parametrize("name", golden_names("trace_"))
+@pytest.mark.parametrize("name", golden_names("trace_") + golden_names("meshtrace_"))
 def test_port_env_matches_reference_trace(name):
     g = load_golden(name)
     exact = replay_trace(_OneEnv, g, ctx=name)
