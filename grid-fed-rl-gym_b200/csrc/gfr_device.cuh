@@ -519,6 +519,20 @@ GFR_HD double noise_slot(uint64_t seed, uint64_t draw, int s) {
 
 // ----------------------------------------------------------------------------- solvers
 
+// Row passes of CTA-wide groups fetch what the NEXT row needs (its record, its branch / diagonal admittances) while
+// the present row computes: their feeder image is in global memory, an L2 round trip per row otherwise
+// (synthetic-1000: +8 %).  Measured and left off: the same for warp-sized groups, whose image is in shared memory
+// (GFR_PIPE_SMEM: IEEE-123 99.0 M -> 94.3 M, IEEE-34 306 M -> 284 M env-steps/s - the registers and moves cost more
+// than the shared-memory latency they hide), and fetching the branch's two voltages ahead as well (GFR_PIPE_EF:
+// synthetic-1000 5.91 M -> 5.64 M).
+#ifndef GFR_PIPE_SMEM
+#define GFR_PIPE_SMEM 0
+#endif
+#ifndef GFR_PIPE_EF
+#define GFR_PIPE_EF 0
+#endif
+template <int LANES> GFR_HD constexpr bool pipe_rows() { return LANES > 32 || GFR_PIPE_SMEM; }
+
 // Flat start (power_flow.py:103, :131): 1.0 at 0 rad, slack / PV buses at their set magnitude.
 template <class G, int LANES>
 GFR_HD void flat_start_t(const G& g, const Lanes<LANES>&, const Layout& lay, const int* simg,
@@ -568,6 +582,31 @@ GFR_HD BranchT branch_terms(const D2 vk, const D2 vp, const D2 y) {
   return t;
 }
 
+// What a leaf -> root row pass (mismatch, elimination) needs of a row besides the children's hand-offs: its record,
+// branch / diagonal admittances and the voltages at both ends of its branch (fixed during the pass).  With the
+// pipe on they are fetched one row ahead into registers.
+#define GFR_ROW_PIPE_DECL                                                                                          \
+  I4 t_next; D2 y_next, yd_next, vk_next, vp_next;                                                                 \
+  t_next.x = t_next.y = t_next.z = t_next.w = 0;                                                                   \
+  y_next.x = y_next.y = yd_next.x = yd_next.y = vk_next.x = vk_next.y = vp_next.x = vp_next.y = 0.0
+#define GFR_ROW_PIPE_LOAD(pos_)                                                                                    \
+  do {                                                                                                             \
+    t_next = sched[(pos_)]; y_next = gb[(pos_)]; yd_next = gbd[(pos_)];                                            \
+    if (GFR_PIPE_EF) { vk_next = g.ef(rec_bus(t_next)); vp_next = g.ef(rec_parent(t_next)); }                      \
+  } while (0)
+#define GFR_ROW_PIPE_FIRST(pos_)                                                                                   \
+  do { if (pipe_rows<LANES>()) GFR_ROW_PIPE_LOAD(pos_); } while (0)
+// defines t, yb, yd, vk, vp of position p_ (idle positions: record 0 -> bus 0, harmless) and starts the next row's fetch
+#define GFR_ROW_PIPE_TAKE(p_, more_, next_)                                                                        \
+  I4 t; D2 yb, yd, vk, vp;                                                                                         \
+  if (pipe_rows<LANES>()) {                                                                                        \
+    t = t_next; yb = y_next; yd = yd_next;                                                                         \
+    if (GFR_PIPE_EF) { vk = vk_next; vp = vp_next; } else { vk = g.ef(rec_bus(t)); vp = g.ef(rec_parent(t)); }     \
+    if (more_) GFR_ROW_PIPE_LOAD(next_);                                                                           \
+  } else {                                                                                                         \
+    t = sched[(p_)]; yb = gb[(p_)]; yd = gbd[(p_)]; vk = g.ef(rec_bus(t)); vp = g.ef(rec_parent(t));               \
+  }
+
 // max |mismatch| of the present voltages (power_flow.py:150-166), as a leaf -> root row pass on the elimination
 // schedule: every branch is evaluated ONCE, by the bus below it, which keeps its own share (ga, al) and hands the
 // parent's share (gl, ll) up - in registers to an heir's parent, through field 3 of its pool slot otherwise.
@@ -582,24 +621,16 @@ GFR_HD double newton_mismatch(const NGrp<LANES>& g, const Layout& lay, const int
   double mm = 0.0;
   D2 hf; hf.x = hf.y = 0.0;                             // (gl, ll) of the bus this lane handled in the previous row
   double ps_next = g.pspec((nrows - 1) * LANES + g.lane);
-  I4 t_next; D2 y_next, yd_next;                        // CTA-wide groups (image in global memory): one row ahead
-  t_next.x = t_next.y = t_next.z = t_next.w = 0; y_next.x = y_next.y = yd_next.x = yd_next.y = 0.0;
-  if (LANES > 32) { const int p0 = (nrows - 1) * LANES + g.lane; t_next = sched[p0]; y_next = gb[p0]; yd_next = gbd[p0]; }
+  GFR_ROW_PIPE_DECL;
+  GFR_ROW_PIPE_FIRST((nrows - 1) * LANES + g.lane);
   for (int row = nrows - 1; row >= 0; --row) {
     const int p = row * LANES + g.lane;
-    I4 t; D2 yb, yd;
-    if (LANES > 32) {
-      t = t_next; yb = y_next; yd = yd_next;
-      if (row > 0) { t_next = sched[p - LANES]; y_next = gb[p - LANES]; yd_next = gbd[p - LANES]; }
-    } else {
-      t = sched[p]; yb = gb[p]; yd = gbd[p];
-    }
+    GFR_ROW_PIPE_TAKE(p, row > 0, p - LANES);
     const double ps = ps_next;
     if (row > 0) ps_next = g.pspec(p - LANES);
     if (t.z & FL_VALID) {
-      const D2 vk = g.ef(rec_bus(t));
       const double v2 = fma(vk.x, vk.x, vk.y * vk.y);
-      const BranchT bt = branch_terms(vk, g.ef(rec_parent(t)), yb);
+      const BranchT bt = branch_terms(vk, vp, yb);
       if (!(t.z & FL_C_REG)) { hf.x = hf.y = 0.0; }
       {
         const int q1 = rec_list(t) + rec_all_kids(t);
@@ -653,8 +684,12 @@ GFR_HD void newton_back_update(const NGrp<LANES>& g, const Layout& lay, const in
   do {                                                                     \
     const int p = (row_) * LANES + g.lane;                                 \
     I4 t;                                                                  \
-    if (LANES > 32) { t = t_next; if ((row_) + 1 < nrows) t_next = sched[p + LANES]; } \
-    else t = sched[p];                                                     \
+    D2 e_now;                                                              \
+    if (pipe_rows<LANES>()) {                                              \
+      t = t_next; e_now = e_next;                                          \
+      if ((row_) + 1 < nrows) { t_next = sched[p + LANES]; if (GFR_PIPE_EF) e_next = g.efp[rec_bus(t_next)]; } \
+      if (!GFR_PIPE_EF) e_now = g.efp[rec_bus(t)];                         \
+    } else { t = sched[p]; e_now = g.efp[rec_bus(t)]; }                    \
     D2 m0 = m0_, m1 = m1_, v = v_;                                         \
     if (f0) {                                                              \
       if (LANES > 32) {                                                    \
@@ -674,7 +709,7 @@ GFR_HD void newton_back_update(const NGrp<LANES>& g, const Layout& lay, const in
       sincos_small(accel * v.x, &sn, &cs);                                 \
       const double sc = fma(accel, v.y, 1.0);                              \
       D2* const ep = g.efp + rec_bus(t);                                   \
-      const D2 e = *ep;                                                    \
+      const D2 e = e_now;                                                  \
       D2 w;                                                                \
       w.x = sc * fma(e.x, cs, -e.y * sn);                                  \
       w.y = sc * fma(e.x, sn, e.y * cs);                                   \
@@ -688,7 +723,9 @@ GFR_HD void newton_back_update(const NGrp<LANES>& g, const Layout& lay, const in
   t_next.x = t_next.y = t_next.z = t_next.w = 0;
   D2 f0m0_next, f0m1_next;                             // ... and the flat-start D^-1 U rows in the first iteration
   f0m0_next.x = f0m0_next.y = f0m1_next.x = f0m1_next.y = 0.0;
-  if (LANES > 32) { t_next = sched[g.lane]; if (f0) { f0m0_next = f0[2 * P + g.lane]; f0m1_next = f0[3 * P + g.lane]; } }
+  D2 e_next; e_next.x = e_next.y = 0.0;                // ... and the voltage of its bus (only its own lane ever rewrites it)
+  if (pipe_rows<LANES>()) { t_next = sched[g.lane]; if (GFR_PIPE_EF) e_next = g.efp[rec_bus(t_next)]; }
+  if (LANES > 32 && f0) { f0m0_next = f0[2 * P + g.lane]; f0m1_next = f0[3 * P + g.lane]; }
   for (int row = 0; row < nrows; row += 2) {
     GFR_BU_ROW(row, a0, a1, av);
     if (row + 1 < nrows) GFR_BU_ROW(row + 1, b0, b1, bv);
@@ -742,14 +779,14 @@ GFR_HD void newton_solve(const NGrp<LANES>& g, const Layout& lay, const int* sim
       I4 t_next; D2 pc_next, i0_next, i1_next, lp_next;   // CTA-wide groups: record and flat-start factors one row ahead
       t_next.x = t_next.y = t_next.z = t_next.w = 0;
       pc_next.x = pc_next.y = i0_next.x = i0_next.y = i1_next.x = i1_next.y = lp_next.x = lp_next.y = 0.0;
-      if (LANES > 32) {
+      if (pipe_rows<LANES>()) {
         const int p0 = (nrows - 1) * LANES + g.lane;
         t_next = sched[p0]; pc_next = f0[5 * P + p0]; i0_next = f0[p0]; i1_next = f0[P + p0]; lp_next = f0[4 * P + p0];
       }
       for (int row = nrows - 1; row >= 0; --row) {
         const int p = row * LANES + g.lane;
         I4 t; D2 pc, i0, i1, lp;                        // record, flat-profile (P, Q), D^-1 rows, (ll, gl)
-        if (LANES > 32) {
+        if (pipe_rows<LANES>()) {
           t = t_next; pc = pc_next; i0 = i0_next; i1 = i1_next; lp = lp_next;
           if (row > 0) {
             t_next = sched[p - LANES]; pc_next = f0[5 * P + p - LANES];
@@ -807,25 +844,16 @@ GFR_HD void newton_solve(const NGrp<LANES>& g, const Layout& lay, const int* sim
       D2 h0, h1, hc, hf;                               // what the bus this lane eliminated in the previous row hands up
       h0.x = h0.y = h1.x = h1.y = hc.x = hc.y = hf.x = hf.y = 0.0;
       double ps_next = g.pspec((nrows - 1) * LANES + g.lane);     // the specified injection, one row ahead (an L2 round trip)
-      // CTA-wide groups read the feeder image from global memory: record and admittances come one row ahead too
-      I4 t_next; D2 y_next, yd_next;
-      t_next.x = t_next.y = t_next.z = t_next.w = 0; y_next.x = y_next.y = yd_next.x = yd_next.y = 0.0;
-      if (LANES > 32) { const int p0 = (nrows - 1) * LANES + g.lane; t_next = sched[p0]; y_next = gb[p0]; yd_next = gbd[p0]; }
+      GFR_ROW_PIPE_DECL;
+      GFR_ROW_PIPE_FIRST((nrows - 1) * LANES + g.lane);
       for (int row = nrows - 1; row >= 0; --row) {
         const int p = row * LANES + g.lane;
-        I4 t; D2 yb, yd;
-        if (LANES > 32) {
-          t = t_next; yb = y_next; yd = yd_next;
-          if (row > 0) { t_next = sched[p - LANES]; y_next = gb[p - LANES]; yd_next = gbd[p - LANES]; }
-        } else {
-          t = sched[p]; yb = gb[p]; yd = gbd[p];
-        }
+        GFR_ROW_PIPE_TAKE(p, row > 0, p - LANES);
         const double ps = ps_next;
         if (row > 0) ps_next = g.pspec(p - LANES);
         if (t.z & FL_VALID) {
-          const D2 vk = g.ef(rec_bus(t));
           const double v2 = fma(vk.x, vk.x, vk.y * vk.y);
-          const BranchT bt = branch_terms(vk, g.ef(rec_parent(t)), yb);
+          const BranchT bt = branch_terms(vk, vp, yb);
           // children's contributions: plain sums, the heir first - it is what the lane still holds in h*
           if (!(t.z & FL_C_REG)) { h0.x = h0.y = h1.x = h1.y = hc.x = hc.y = hf.x = hf.y = 0.0; }
           {
