@@ -97,6 +97,7 @@ SIGNATURES: Dict[str, Tuple[object, List[object]]] = {
     "gfr_env_bind_obs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "gfr_env_bind_obs_buffers": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "gfr_env_obs_current": (C.c_void_p, [C.c_void_p]),
+    "gfr_env_obs_to_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "gfr_env_launch_info": (C.c_int, [C.c_void_p, _i32p, _i32p, _i32p, C.POINTER(C.c_int64)]),
     "gfr_env_state_bytes": (C.c_int64, [C.c_void_p]),
     "gfr_env_state_get": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),

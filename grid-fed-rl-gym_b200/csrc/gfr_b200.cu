@@ -119,7 +119,7 @@ step_kernel(const Layout lay, const EnvCfg cfg, const void* __restrict__ img, co
   const double* dimg = IMG_SMEM ? (const double*)(smem + kSmemHeader) : (const double*)img;
   auto g = make_group<LANES, SOLVER>(lay, smem + kSmemHeader + (IMG_SMEM ? lay.img_bytes : 0),
                                      slot_bytes, mscratch);
-  double p_local[LANES == 1 && SOLVER == SOLVER_SWEEP ? SWEEP_P_LOCAL_MAX : 1];
+  double p_local[LANES == 1 && SOLVER != SOLVER_NEWTON ? SWEEP_P_LOCAL_MAX : 1];
   use_local_injections(g, lay, p_local);
   const int E = blockDim.x / LANES;
   for (long long env = (long long)blockIdx.x * E + threadIdx.x / LANES; env < B; env += (long long)gridDim.x * E)
@@ -136,7 +136,7 @@ solve_kernel(const Layout lay, const EnvCfg cfg, const void* __restrict__ img, c
   const double* dimg = IMG_SMEM ? (const double*)(smem + kSmemHeader) : (const double*)img;
   auto g = make_group<LANES, SOLVER>(lay, smem + kSmemHeader + (IMG_SMEM ? lay.img_bytes : 0),
                                      slot_bytes, mscratch);
-  double p_local[LANES == 1 && SOLVER == SOLVER_SWEEP ? SWEEP_P_LOCAL_MAX : 1];
+  double p_local[LANES == 1 && SOLVER != SOLVER_NEWTON ? SWEEP_P_LOCAL_MAX : 1];
   use_local_injections(g, lay, p_local);
   const int E = blockDim.x / LANES;
   for (long long env = (long long)blockIdx.x * E + threadIdx.x / LANES; env < B; env += (long long)gridDim.x * E)
@@ -382,9 +382,10 @@ const void* solve_fn(int lanes, bool img_smem) {
   }
   return nullptr;
 }
-const void* kernel_fn(bool step, int solver, int lanes, bool img_smem) {
-  if (step) return solver == GFR_SOLVER_NEWTON ? step_fn<SOLVER_NEWTON>(lanes, img_smem) : step_fn<SOLVER_SWEEP>(lanes, img_smem);
-  return solver == GFR_SOLVER_NEWTON ? solve_fn<SOLVER_NEWTON>(lanes, img_smem) : solve_fn<SOLVER_SWEEP>(lanes, img_smem);
+const void* kernel_fn(bool step, int solver, int lanes, bool img_smem, bool ties) {
+  if (solver == GFR_SOLVER_NEWTON) return step ? step_fn<SOLVER_NEWTON>(lanes, img_smem) : solve_fn<SOLVER_NEWTON>(lanes, img_smem);
+  if (ties) return step ? step_fn<SOLVER_SWEEP_TIES>(lanes, img_smem) : solve_fn<SOLVER_SWEEP_TIES>(lanes, img_smem);
+  return step ? step_fn<SOLVER_SWEEP>(lanes, img_smem) : solve_fn<SOLVER_SWEEP>(lanes, img_smem);
 }
 
 // One candidate split of an SM: `c` CTAs of E instance slots each.
@@ -453,9 +454,9 @@ int plan_launch(const gfr_feeder* f, bool step, int solver, int lanes, long long
     return fail(GFR_E_LIMIT, "more loads + generators + batteries than the solver's working set can stage "
                              "(sweep: 2 per bus on average)");
   PlanTry best;
-  if (lanes <= 32) best = plan_mode(f, lay, kernel_fn(step, solver, lanes, true), lanes, true, per_env, B);
+  if (lanes <= 32) best = plan_mode(f, lay, kernel_fn(step, solver, lanes, true, lay.n_tie > 0), lanes, true, per_env, B);
   if (lanes > 32 || (lanes == 32 && best.resident < 4)) {
-    PlanTry alt = plan_mode(f, lay, kernel_fn(step, solver, lanes, false), lanes, false, per_env, B);
+    PlanTry alt = plan_mode(f, lay, kernel_fn(step, solver, lanes, false, lay.n_tie > 0), lanes, false, per_env, B);
     if (alt.resident > best.resident) best = alt;
   }
   if (!best.resident)
@@ -489,7 +490,7 @@ int plan_launch(const gfr_feeder* f, bool step, int solver, int lanes, long long
   // Newton spills D^-1 U (32 B per bus) of every resident instance slot to global memory
   plan.mscratch_bytes = solver == GFR_SOLVER_NEWTON ? (size_t)grid * E * newton_scratch_doubles(lay.P) * 8 : 0;
   *out = plan;
-  *fn_out = kernel_fn(step, solver, lanes, plan.img_smem);
+  *fn_out = kernel_fn(step, solver, lanes, plan.img_smem, lay.n_tie > 0);
   return GFR_OK;
 }
 
@@ -708,6 +709,19 @@ int gfr_env_bind_obs_buffers(gfr_env* e, void* obs_a, void* obs_b, int dtype, vo
 
 int gfr_env_bind_obs(gfr_env* e, double* obs, void* stream) {
   return gfr_env_bind_obs_buffers(e, obs, nullptr, GFR_OBS_F64, stream);
+}
+
+int gfr_env_obs_to_host(gfr_env* e, const void* obs_device, void* host_dst, int32_t col0, int32_t ncols, void* stream) {
+  if (!e || !obs_device || !host_dst) return fail(GFR_E_ARG, "null argument");
+  const int D = e->f->lay.D;
+  if (col0 < 0 || ncols < 1 || col0 + ncols > D) return fail(GFR_E_ARG, "column range outside the observation");
+  if (obs_device != e->d_obs && obs_device != e->d_obs_alt) return fail(GFR_E_ARG, "not one of this environment's observation buffers");
+  DeviceGuard guard(e->f->device);
+  const size_t item = e->obs_f32 ? 4 : 8, pitch = (size_t)D * item;
+  // one strided DMA: rows of `ncols` entries, both sides with the full row pitch
+  GFR_CUDA(cudaMemcpy2DAsync((char*)host_dst + (size_t)col0 * item, pitch, (const char*)obs_device + (size_t)col0 * item, pitch,
+                             (size_t)ncols * item, (size_t)e->B, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  return GFR_OK;
 }
 
 int gfr_env_launch_info(const gfr_env* e, int32_t* lanes, int32_t* threads, int32_t* grid, int64_t* smem_bytes) {

@@ -31,7 +31,7 @@
 
 namespace gfr {
 
-enum { SOLVER_SWEEP = 0, SOLVER_NEWTON = 1 };
+enum { SOLVER_SWEEP = 0, SOLVER_NEWTON = 1, SOLVER_SWEEP_TIES = 2 };   // TIES: the sweep with the compensation step compiled in
 enum { BUS_SLACK = 0, BUS_PV = 1, BUS_PQ = 2 };
 enum { GEN_SOLAR = 0, GEN_WIND = 1 };
 // An instance's working set in shared memory:
@@ -306,6 +306,7 @@ struct NGrp : Lanes<LANES> {
 
 template <int LANES, int SOLVER> struct GroupOf { typedef NGrp<LANES> type; };
 template <int LANES> struct GroupOf<LANES, SOLVER_SWEEP> { typedef SGrp<LANES> type; };
+template <int LANES> struct GroupOf<LANES, SOLVER_SWEEP_TIES> { typedef SGrp<LANES> type; };
 
 // bytes of shared memory one instance slot needs (0 if the sources do not fit the scratch)
 GFR_HD size_t newton_slot_bytes(int n, int n_pool, int n_src) {
@@ -956,10 +957,12 @@ GFR_HD void newton_solve(const NGrp<LANES>& g, const Layout& lay, const int* sim
 // after the down pass the loop equations e = V_from - V_to - z_tie J are evaluated and J += Z_loop^-1 e, with the
 // inverse loop-impedance matrix (constant: tree-path impedances shared by the loops + the ties' own) computed once
 // by the host.  Convergence then needs max |dV| AND max |e| below the tolerance.
-template <int LANES>
+// TIES is a compile-time switch: the radial kernels do not carry the compensation code (4 more registers cost the
+// IEEE-34 sweep its second CTA per SM: 270 M -> 238 M env-steps/s).
+template <int LANES, bool TIES>
 GFR_HD void sweep_solve(const SGrp<LANES>& g, const Layout& lay, const int* simg,
                         const double* dimg, double tol, int max_it, SolveStat* out) {
-  const int n = lay.n, nl = lay.nl, ks = lay.k_slack, nt = lay.n_tie;
+  const int n = lay.n, nl = lay.nl, ks = lay.k_slack, nt = TIES ? lay.n_tie : 0;
   const I4* topo = reinterpret_cast<const I4*>(simg + lay.o_topo);
   const int* level_ptr = simg + lay.o_level_ptr;
   const int* child_idx = simg + lay.o_child_idx;
@@ -1162,15 +1165,15 @@ struct SolOut {
   double* line_flows; double* line_loadings; double* losses; double* max_mismatch;
 };
 
-template <int LANES>
+template <int SOLVER, int LANES>
 GFR_HD void run_solver(const NGrp<LANES>& g, const Layout& lay, const int* simg, const double* dimg,
                        const EnvCfg& cfg, SolveStat* st) {
   newton_solve(g, lay, simg, dimg, cfg.tol, cfg.max_it, cfg.accel, st);
 }
-template <int LANES>
+template <int SOLVER, int LANES>
 GFR_HD void run_solver(const SGrp<LANES>& g, const Layout& lay, const int* simg, const double* dimg,
                        const EnvCfg& cfg, SolveStat* st) {
-  sweep_solve(g, lay, simg, dimg, cfg.tol, cfg.max_it, st);
+  sweep_solve<LANES, SOLVER == SOLVER_SWEEP_TIES>(g, lay, simg, dimg, cfg.tol, cfg.max_it, st);
 }
 
 template <int LANES, int SOLVER>
@@ -1185,7 +1188,7 @@ GFR_HD void solve_instance(const typename GroupOf<LANES, SOLVER>::type& g, const
   g.sync();          // a position's injection is read by the lane that owns the position, not the one that owns ref bus i
   flat_start(g, lay, simg, dimg);
   SolveStat st;
-  run_solver(g, lay, simg, dimg, cfg, &st);
+  run_solver<SOLVER>(g, lay, simg, dimg, cfg, &st);
   for (int i = g.lane; i < n; i += LANES) {
     int k = rank[i];
     const D2 vv = g.ef(k);
@@ -1454,7 +1457,7 @@ GFR_HD void step_instance(const typename GroupOf<LANES, SOLVER>::type& g, const 
   g.sync();
   flat_start(g, lay, simg, dimg);
   SolveStat st;
-  run_solver(g, lay, simg, dimg, cfg, &st);
+  run_solver<SOLVER>(g, lay, simg, dimg, cfg, &st);
 
   // ---- bus state -> observation (grid_env.py:722-731, 753-765), reductions for reward / constraints
   double dev = 0.0, vmax = -INFINITY, vmin = INFINITY;

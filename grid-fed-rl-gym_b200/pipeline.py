@@ -15,6 +15,7 @@ from typing import Deque, Dict, Tuple
 
 import torch
 
+from . import _native as nat
 from .env import BatchedGridEnvironment
 
 
@@ -66,9 +67,13 @@ class HostStepper:
         return self.env.num_envs * (8 + 1 + 1 + item * cols)
 
     def _copy_obs(self, dst: torch.Tensor, obs: torch.Tensor) -> None:
+        # one strided DMA per column block on the current stream (a sliced tensor.copy_ would stage the block
+        # through a temporary and finish it with a synchronous host-side scatter)
+        env = self.env
+        stream = torch.cuda.current_stream(env.device).cuda_stream
         for a, b in self._dyn_cols:
             if b > a:
-                dst[:, a:b].copy_(obs[:, a:b], non_blocking=True)
+                nat.check(env.lib, env.lib.gfr_env_obs_to_host(env._h, obs.data_ptr(), dst.data_ptr(), a, b - a, stream))
 
     def submit(self, host_actions: torch.Tensor) -> None:
         """Queue one step.  ``host_actions``: pinned fp64 ``[B, A]`` (a pageable tensor works but

@@ -200,6 +200,11 @@ int gfr_env_bind_obs(gfr_env* e, double* obs, void* stream);
 enum { GFR_OBS_F64 = 0, GFR_OBS_F32 = 1 };
 int gfr_env_bind_obs_buffers(gfr_env* e, void* obs_a, void* obs_b, int dtype, void* stream);
 void* gfr_env_obs_current(gfr_env* e);
+/* Columns [col0, col0 + ncols) of every row of one of the bound observation buffers to a HOST buffer laid out
+ * like the observation ([B, D], same item type; pinned memory for an asynchronous copy): one strided DMA on
+ * `stream`.  A host-side policy uses it to leave the 2L static load columns (constants after construction,
+ * grid_env.py:766-770) where they are and pull only what a step rewrote. */
+int gfr_env_obs_to_host(gfr_env* e, const void* obs_device, void* host_dst, int32_t col0, int32_t ncols, void* stream);
 /* How the step kernel is launched for this env (for benchmarks / profiles): threads cooperating
  * on one instance, threads per CTA, CTAs, dynamic shared memory per CTA. */
 int gfr_env_launch_info(const gfr_env* e, int32_t* lanes, int32_t* threads, int32_t* grid,

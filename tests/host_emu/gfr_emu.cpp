@@ -76,6 +76,9 @@ void step_all(emu_env* e, const double* actions, const double* noise, const Step
       if (e->solver == SOLVER_NEWTON)
         step_instance<LANES, SOLVER_NEWTON>(slot.group<NGrp<LANES>>(lay, lane, team), lay, simg, dimg, e->cfg, i,
                                             e->state.data(), e->obs.data(), e->obs.data(), 0, actions, noise, o);
+      else if (lay.n_tie)
+        step_instance<LANES, SOLVER_SWEEP_TIES>(slot.group<SGrp<LANES>>(lay, lane, team), lay, simg, dimg, e->cfg, i,
+                                                e->state.data(), e->obs.data(), e->obs.data(), 0, actions, noise, o);
       else
         step_instance<LANES, SOLVER_SWEEP>(slot.group<SGrp<LANES>>(lay, lane, team), lay, simg, dimg, e->cfg, i,
                                            e->state.data(), e->obs.data(), e->obs.data(), 0, actions, noise, o);
@@ -93,6 +96,8 @@ void solve_all(const FeederImage& fi, int solver, const EnvCfg& k, long long B, 
     for (long long i = 0; i < B; ++i) {
       if (solver == SOLVER_NEWTON)
         solve_instance<LANES, SOLVER_NEWTON>(slot.group<NGrp<LANES>>(lay, lane, team), lay, simg, dimg, k, i, p_inj, o);
+      else if (lay.n_tie)
+        solve_instance<LANES, SOLVER_SWEEP_TIES>(slot.group<SGrp<LANES>>(lay, lane, team), lay, simg, dimg, k, i, p_inj, o);
       else
         solve_instance<LANES, SOLVER_SWEEP>(slot.group<SGrp<LANES>>(lay, lane, team), lay, simg, dimg, k, i, p_inj, o);
     }
