@@ -42,6 +42,8 @@ def facts(rep, workload, instances):
         u = units[i].lower()
         if scale:
             v *= {"gbyte": 1e9, "mbyte": 1e6, "kbyte": 1e3, "byte": 1.0}.get(u, 1.0)
+        if name == "gpu__time_duration.sum":
+            v *= {"us": 1e-3, "ns": 1e-6, "ms": 1.0, "s": 1e3}.get(u, 1.0)      # always ms
         return v
     # executed DFMA + DMUL + DADD thread instructions: per elapsed cycle (summed over SMSPs) x elapsed cycles
     per_cycle = sum(val(n, False) or 0.0 for n in
