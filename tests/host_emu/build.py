@@ -16,7 +16,10 @@ def build() -> str:
     os.makedirs(OUT_DIR, exist_ok=True)
     if os.path.exists(OUT) and all(os.path.getmtime(d) <= os.path.getmtime(OUT) for d in DEPENDS):
         return OUT
-    cmd = ["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=fast", "-pthread", "-o", OUT,
+    cmd = ["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=fast", "-pthread",
+           # the header-only builder is also compiled into libgfr_b200.so, which loads with RTLD_GLOBAL: without these
+           # the emulation would bind to THAT copy of the inline functions (stale whenever the two are built apart)
+           "-fvisibility-inlines-hidden", "-Wl,-Bsymbolic", "-o", OUT,
            os.path.join(HERE, "gfr_emu.cpp"), "-lm"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
