@@ -484,6 +484,12 @@ int plan_launch(const gfr_feeder* f, bool step, int solver, int lanes, long long
   long long tiles = (B + E - 1) / E;
   long long grid = (long long)f->sm_count * plan.ctas_per_sm;
   if (grid > tiles) grid = tiles;
+  if (lanes > 32 && grid > 0) {
+    // one instance per CTA: the same number of rounds for every CTA (2 048 instances on 8 x 148 resident CTAs made
+    // 864 CTAs with two instances and 320 with one; 1 024 with two each leave every SM a CTA less to interleave)
+    const long long rounds = (tiles + grid - 1) / grid;
+    if (rounds <= 8) grid = (tiles + rounds - 1) / rounds;
+  }
   if (grid < 1) grid = 1;
   plan.grid = (int)grid;
   plan.slot_bytes = (int)per_env;

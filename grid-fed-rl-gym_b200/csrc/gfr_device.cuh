@@ -94,6 +94,7 @@ struct Layout {
   int o_gb, o_rating, o_vm_set;
   // Newton
   int o_child_ent, o_child_slot, o_gbd, o_f0;
+  int o_kids;                    // CTA-wide groups: the pool slots of a position's first 8 pool children, 16 bits each (one I4)
   // sweep (compact per-bus arrays)
   int o_topo, o_child_idx, o_level_ptr, o_rx;
   // components
@@ -532,6 +533,12 @@ GFR_HD double noise_slot(uint64_t seed, uint64_t draw, int s) {
 #ifndef GFR_PIPE_EF
 #define GFR_PIPE_EF 0
 #endif
+// Groups this wide read the feeder image from global memory (one CTA per instance): they take the variants that
+// fetch index chains several positions at a time and the packed pool-child records.
+#ifndef GFR_WIDE_GROUP_MIN_LANES
+#define GFR_WIDE_GROUP_MIN_LANES 64      // (the host emulation builds with 8 to walk this path on its 8- and 16-lane teams)
+#endif
+template <int LANES> GFR_HD constexpr bool wide_group() { return LANES >= GFR_WIDE_GROUP_MIN_LANES; }
 template <int LANES> GFR_HD constexpr bool pipe_rows() { return LANES > 32 || GFR_PIPE_SMEM; }
 
 // Flat start (power_flow.py:103, :131): 1.0 at 0 rad, slack / PV buses at their set magnitude.
@@ -539,6 +546,26 @@ template <class G, int LANES>
 GFR_HD void flat_start_t(const G& g, const Lanes<LANES>&, const Layout& lay, const int* simg,
                          const double* dimg) {
   const I4* sched = reinterpret_cast<const I4*>(simg + lay.o_sched);
+  if (wide_group<LANES>()) {
+    // image in global memory: four positions' records (and set points) per L2 round trip
+    for (int p0 = g.lane; p0 < lay.P; p0 += 4 * LANES) {
+      I4 t[4]; double vs[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int p = p0 + u * LANES;
+        t[u].x = t[u].y = t[u].z = t[u].w = 0; vs[u] = 1.0;
+        if (p < lay.P) { t[u] = sched[p]; vs[u] = dimg[lay.o_vm_set + p]; }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (!(t[u].z & FL_VALID)) continue;
+        D2 v;
+        v.x = (t[u].z & FL_FIXED_VM) ? vs[u] : 1.0;
+        v.y = 0.0;
+        g.ef(rec_bus(t[u])) = v;
+      }
+    }
+  } else
   for (int p = g.lane; p < lay.P; p += LANES) {
     const I4 t = sched[p];
     if (!(t.z & FL_VALID)) continue;
@@ -583,29 +610,58 @@ GFR_HD BranchT branch_terms(const D2 vk, const D2 vp, const D2 y) {
   return t;
 }
 
+// The pool slots of a position's children behind pool slots, one after the other in `slot` for the body given last.  CTA-wide groups
+// read their image from global memory: there the first 8 slots come packed in a record (kq_) that travels one row
+// ahead with the position's own record, which takes the list's L2 round trip off every row's critical path.
+GFR_HD unsigned shr16_pair(unsigned lo, unsigned hi) { return (lo >> 16) | (hi << 16); }
+#define GFR_POOL_GATHER(t_, kq_, ...)                                                                              \
+  do {                                                                                                             \
+    const int npk_ = rec_pool_kids(t_);                                                                            \
+    if (wide_group<LANES>() && npk_ <= 8) {                                                                       \
+      unsigned w0_ = (unsigned)(kq_).x, w1_ = (unsigned)(kq_).y, w2_ = (unsigned)(kq_).z, w3_ = (unsigned)(kq_).w; \
+      _Pragma("unroll 1")                                                                                          \
+      for (int j_ = 0; j_ < npk_; ++j_) {                                                                          \
+        const int slot = (int)(w0_ & 0xffffu);                                                                     \
+        w0_ = shr16_pair(w0_, w1_); w1_ = shr16_pair(w1_, w2_); w2_ = shr16_pair(w2_, w3_); w3_ >>= 16;            \
+        __VA_ARGS__                                                                                                \
+      }                                                                                                            \
+    } else {                                                                                                       \
+      const int q1_ = rec_list(t_) + rec_all_kids(t_);                                                             \
+      _Pragma("unroll 1")                                                                                          \
+      for (int q_ = q1_ - npk_; q_ < q1_; ++q_) {                                                                  \
+        const int slot = child_slot[q_];                                                                           \
+        __VA_ARGS__                                                                                                \
+      }                                                                                                            \
+    }                                                                                                              \
+  } while (0)
+
 // What a leaf -> root row pass (mismatch, elimination) needs of a row besides the children's hand-offs: its record,
 // branch / diagonal admittances and the voltages at both ends of its branch (fixed during the pass).  With the
 // pipe on they are fetched one row ahead into registers.
 #define GFR_ROW_PIPE_DECL                                                                                          \
-  I4 t_next; D2 y_next, yd_next, vk_next, vp_next;                                                                 \
+  I4 t_next, kq_next; D2 y_next, yd_next, vk_next, vp_next;                                                        \
   t_next.x = t_next.y = t_next.z = t_next.w = 0;                                                                   \
+  kq_next = t_next;                                                                                                \
   y_next.x = y_next.y = yd_next.x = yd_next.y = vk_next.x = vk_next.y = vp_next.x = vp_next.y = 0.0
 #define GFR_ROW_PIPE_LOAD(pos_)                                                                                    \
   do {                                                                                                             \
     t_next = sched[(pos_)]; y_next = gb[(pos_)]; yd_next = gbd[(pos_)];                                            \
+    if (wide_group<LANES>()) kq_next = kids[(pos_)];                                                              \
     if (GFR_PIPE_EF) { vk_next = g.ef(rec_bus(t_next)); vp_next = g.ef(rec_parent(t_next)); }                      \
   } while (0)
 #define GFR_ROW_PIPE_FIRST(pos_)                                                                                   \
   do { if (pipe_rows<LANES>()) GFR_ROW_PIPE_LOAD(pos_); } while (0)
 // defines t, yb, yd, vk, vp of position p_ (idle positions: record 0 -> bus 0, harmless) and starts the next row's fetch
 #define GFR_ROW_PIPE_TAKE(p_, more_, next_)                                                                        \
-  I4 t; D2 yb, yd, vk, vp;                                                                                         \
+  I4 t, kq; D2 yb, yd, vk, vp;                                                                                     \
+  kq.x = kq.y = kq.z = kq.w = 0;                                                                                   \
   if (pipe_rows<LANES>()) {                                                                                        \
-    t = t_next; yb = y_next; yd = yd_next;                                                                         \
+    t = t_next; yb = y_next; yd = yd_next; kq = kq_next;                                                           \
     if (GFR_PIPE_EF) { vk = vk_next; vp = vp_next; } else { vk = g.ef(rec_bus(t)); vp = g.ef(rec_parent(t)); }     \
     if (more_) GFR_ROW_PIPE_LOAD(next_);                                                                           \
   } else {                                                                                                         \
     t = sched[(p_)]; yb = gb[(p_)]; yd = gbd[(p_)]; vk = g.ef(rec_bus(t)); vp = g.ef(rec_parent(t));               \
+    if (wide_group<LANES>()) kq = kids[(p_)];                                                                     \
   }
 
 // max |mismatch| of the present voltages (power_flow.py:150-166), as a leaf -> root row pass on the elimination
@@ -619,6 +675,7 @@ GFR_HD double newton_mismatch(const NGrp<LANES>& g, const Layout& lay, const int
   const int* child_slot = simg + lay.o_child_slot;
   const D2* gb = reinterpret_cast<const D2*>(dimg + lay.o_gb);
   const D2* gbd = reinterpret_cast<const D2*>(dimg + lay.o_gbd);
+  const I4* kids = reinterpret_cast<const I4*>(simg + (wide_group<LANES>() ? lay.o_kids : 0));
   double mm = 0.0;
   D2 hf; hf.x = hf.y = 0.0;                             // (gl, ll) of the bus this lane handled in the previous row
   double ps_next = g.pspec((nrows - 1) * LANES + g.lane);
@@ -633,14 +690,10 @@ GFR_HD double newton_mismatch(const NGrp<LANES>& g, const Layout& lay, const int
       const double v2 = fma(vk.x, vk.x, vk.y * vk.y);
       const BranchT bt = branch_terms(vk, vp, yb);
       if (!(t.z & FL_C_REG)) { hf.x = hf.y = 0.0; }
-      {
-        const int q1 = rec_list(t) + rec_all_kids(t);
-#pragma unroll 1
-        for (int q = q1 - rec_pool_kids(t); q < q1; ++q) {
-          const D2 fl = g.poolp[3 * np + child_slot[q]];
-          hf.x += fl.x; hf.y += fl.y;
-        }
-      }
+      GFR_POOL_GATHER(t, kq, {
+        const D2 fl = g.poolp[3 * np + slot];
+        hf.x += fl.x; hf.y += fl.y;
+      });
       const double P = fma(yd.x, v2, bt.ga) + hf.x, Q = fma(-yd.y, v2, bt.al) + hf.y;
       double aP = fabs(ps - P), aQ = fabs(Q);
       if ((t.z & (FL_PQ | FL_THETA)) != (FL_PQ | FL_THETA)) {   // slack: no equations; PV: no Q equation
@@ -745,6 +798,7 @@ GFR_HD void newton_solve(const NGrp<LANES>& g, const Layout& lay, const int* sim
   const D2* gb = reinterpret_cast<const D2*>(dimg + lay.o_gb);      // branch series g, b by position (0 for the root)
   const D2* gbd = reinterpret_cast<const D2*>(dimg + lay.o_gbd);    // Re, Im of Y_kk by position
   const D2* f0 = lay.o_f0 >= 0 ? reinterpret_cast<const D2*>(dimg + lay.o_f0) : nullptr;   // flat-start factors
+  const I4* kids = reinterpret_cast<const I4*>(simg + (wide_group<LANES>() ? lay.o_kids : 0));
 
   out->converged = 0;
   out->iterations = max_it;
@@ -777,37 +831,38 @@ GFR_HD void newton_solve(const NGrp<LANES>& g, const Layout& lay, const int* sim
       }
       D2 hc; hc.x = hc.y = 0.0;                         // L v of the bus this lane eliminated in the previous row
       double ps_next = g.pspec((nrows - 1) * LANES + g.lane);     // the specified injection, one row ahead (an L2 round trip)
-      I4 t_next; D2 pc_next, i0_next, i1_next, lp_next;   // CTA-wide groups: record and flat-start factors one row ahead
+      I4 t_next, kq_next; D2 pc_next, i0_next, i1_next, lp_next;   // CTA-wide groups: records and flat-start factors one row ahead
       t_next.x = t_next.y = t_next.z = t_next.w = 0;
+      kq_next = t_next;
       pc_next.x = pc_next.y = i0_next.x = i0_next.y = i1_next.x = i1_next.y = lp_next.x = lp_next.y = 0.0;
       if (pipe_rows<LANES>()) {
         const int p0 = (nrows - 1) * LANES + g.lane;
         t_next = sched[p0]; pc_next = f0[5 * P + p0]; i0_next = f0[p0]; i1_next = f0[P + p0]; lp_next = f0[4 * P + p0];
+        if (wide_group<LANES>()) kq_next = kids[p0];
       }
       for (int row = nrows - 1; row >= 0; --row) {
         const int p = row * LANES + g.lane;
-        I4 t; D2 pc, i0, i1, lp;                        // record, flat-profile (P, Q), D^-1 rows, (ll, gl)
+        I4 t, kq; D2 pc, i0, i1, lp;                    // record, flat-profile (P, Q), D^-1 rows, (ll, gl)
+        kq.x = kq.y = kq.z = kq.w = 0;
         if (pipe_rows<LANES>()) {
-          t = t_next; pc = pc_next; i0 = i0_next; i1 = i1_next; lp = lp_next;
+          t = t_next; pc = pc_next; i0 = i0_next; i1 = i1_next; lp = lp_next; kq = kq_next;
           if (row > 0) {
+            if (wide_group<LANES>()) kq_next = kids[p - LANES];
             t_next = sched[p - LANES]; pc_next = f0[5 * P + p - LANES];
             i0_next = f0[p - LANES]; i1_next = f0[P + p - LANES]; lp_next = f0[4 * P + p - LANES];
           }
         } else {
           t = sched[p]; pc = f0[5 * P + p]; i0 = f0[p]; i1 = f0[P + p]; lp = f0[4 * P + p];
+          if (wide_group<LANES>()) kq = kids[p];
         }
         const double ps = ps_next;
         if (row > 0) ps_next = g.pspec(p - LANES);
         if (t.z & FL_VALID) {
           if (!(t.z & FL_C_REG)) { hc.x = hc.y = 0.0; }
-          {
-            const int q1 = rec_list(t) + rec_all_kids(t);
-#pragma unroll 1
-            for (int q = q1 - rec_pool_kids(t); q < q1; ++q) {
-              const D2 cc = g.poolp[2 * np + child_slot[q]];
-              hc.x += cc.x; hc.y += cc.y;
-            }
-          }
+          GFR_POOL_GATHER(t, kq, {
+            const D2 cc = g.poolp[2 * np + slot];
+            hc.x += cc.x; hc.y += cc.y;
+          });
           const D2 sc = hc;
           double r0 = ps - pc.x - sc.x, r1 = 0.0 - pc.y - sc.y;
           if (!(t.z & FL_THETA)) r0 = 0.0;
@@ -857,16 +912,12 @@ GFR_HD void newton_solve(const NGrp<LANES>& g, const Layout& lay, const int* sim
           const BranchT bt = branch_terms(vk, vp, yb);
           // children's contributions: plain sums, the heir first - it is what the lane still holds in h*
           if (!(t.z & FL_C_REG)) { h0.x = h0.y = h1.x = h1.y = hc.x = hc.y = hf.x = hf.y = 0.0; }
-          {
-            const int q1 = rec_list(t) + rec_all_kids(t);
-#pragma unroll 1
-            for (int q = q1 - rec_pool_kids(t); q < q1; ++q) {
-              const D2* e = g.poolp + child_slot[q];
-              const D2 c0 = e[0], c1 = e[np], cc = e[2 * np], fl = e[3 * np];
-              h0.x += c0.x; h0.y += c0.y; h1.x += c1.x; h1.y += c1.y; hc.x += cc.x; hc.y += cc.y;
-              hf.x += fl.x; hf.y += fl.y;
-            }
-          }
+          GFR_POOL_GATHER(t, kq, {
+            const D2* e = g.poolp + slot;
+            const D2 c0 = e[0], c1 = e[np], cc = e[2 * np], fl = e[3 * np];
+            h0.x += c0.x; h0.y += c0.y; h1.x += c1.x; h1.y += c1.y; hc.x += cc.x; hc.y += cc.y;
+            hf.x += fl.x; hf.y += fl.y;
+          });
           const D2 s0 = h0, s1 = h1, sc = hc, sf = hf;
           const double Pk = fma(yd.x, v2, bt.ga) + sf.x, Q = fma(-yd.y, v2, bt.al) + sf.y;
           D2 d0, d1, r;
@@ -1029,9 +1080,11 @@ GFR_HD void sweep_solve(const SGrp<LANES>& g, const Layout& lay, const int* simg
       g.sync();
     }
     const D2 atot = g.at2(S_JR, 0);
-    g.sync();                                          // everyone has A(root) before the root's slot is reused
     double mm = 0.0;
-    for (int l = 0; l < (LANES == 1 ? 1 : nl); ++l) {      // one thread per instance: a single ascending loop over the buses
+    // Several lanes: the root (level 0) is skipped - its W is 0 by definition, its voltage (the slack's set point when
+    // the slack is the root, else rewritten by the fix-up pass) does not move, and its field keeps A(root) until the
+    // next up pass, so no lane can find it overwritten before it has read it: two barriers less per iteration.
+    for (int l = LANES == 1 ? 0 : 1; l < (LANES == 1 ? 1 : nl); ++l) {      // one thread per instance: a single ascending loop over the buses
       const int k1 = LANES == 1 ? n : level_ptr[l + 1];
       for (int k = LANES == 1 ? 0 : g.first(level_ptr[l]); k < k1; k += LANES) {
         const I4 t = topo[k];
@@ -1040,7 +1093,8 @@ GFR_HD void sweep_solve(const SGrp<LANES>& g, const Layout& lay, const int* simg
         if (k > 0) {
           D2 a = g.at2(S_JR, k);
           if (t.w & FL_SLACK_PATH) { a.x -= atot.x; a.y -= atot.y; }
-          const D2 wp = g.at2(S_JR, t.x);
+          D2 wp = g.at2(S_JR, t.x);
+          if (LANES > 1 && t.x == 0) { wp.x = 0.0; wp.y = 0.0; }
           const D2 z = rx[k];
           w.x = wp.x + fma(z.x, a.x, -z.y * a.y);
           w.y = wp.y + fma(z.x, a.y, z.y * a.x);
@@ -1061,7 +1115,8 @@ GFR_HD void sweep_solve(const SGrp<LANES>& g, const Layout& lay, const int* simg
     const D2 ws = g.at2(S_JR, ks);
     if (ks != 0)
     for (int k = g.lane; k < n; k += LANES) {
-      const D2 w = g.at2(S_JR, k);
+      D2 w = g.at2(S_JR, k);
+      if (LANES > 1 && k == 0) { w.x = 0.0; w.y = 0.0; }
       const D2 vo = g.at2(F_E, k);
       D2 vn;
       vn.x = (vslack - ws.x) + w.x;
@@ -1115,12 +1170,10 @@ GFR_HD void sweep_solve(const SGrp<LANES>& g, const Layout& lay, const int* simg
 }
 
 // From -> to flow of the branch above the bus at position p (power_flow.py:329-358): P (pu), |S| (pu), series loss (pu)
+// (the branch's record t and series admittance y already loaded)
 template <class G>
-GFR_HD void branch_flow(const G& g, const Layout& lay, const int* simg, const double* dimg,
-                        int p, double* p_ft, double* s_abs, double* loss) {
-  const I4 t = reinterpret_cast<const I4*>(simg + lay.o_sched)[p];
+GFR_HD void branch_flow_rec(const G& g, const I4 t, const D2 y, double* p_ft, double* s_abs, double* loss) {
   const D2 vk = g.ef(rec_bus(t)), vp = g.ef(rec_parent(t));
-  const D2 y = reinterpret_cast<const D2*>(dimg + lay.o_gb)[p];
   const double de = vp.x - vk.x, df = vp.y - vk.y;                 // V_parent - V_k
   const double ir = y.x * de - y.y * df, ii = y.x * df + y.y * de;   // current parent -> k
   double P, Q;
@@ -1132,6 +1185,13 @@ GFR_HD void branch_flow(const G& g, const Layout& lay, const int* simg, const do
   *p_ft = P;
   *s_abs = sqrt(P * P + Q * Q);
   *loss = y.x * (de * de + df * df);                 // Re sum_i V_i conj((YV)_i), branch by branch
+}
+
+template <class G>
+GFR_HD void branch_flow(const G& g, const Layout& lay, const int* simg, const double* dimg,
+                        int p, double* p_ft, double* s_abs, double* loss) {
+  branch_flow_rec(g, reinterpret_cast<const I4*>(simg + lay.o_sched)[p],
+                  reinterpret_cast<const D2*>(dimg + lay.o_gb)[p], p_ft, s_abs, loss);
 }
 
 // From -> to flow of line `li` (ref order): a tree branch, or a tie of a weakly meshed feeder (I = y (V_from - V_to),
@@ -1440,6 +1500,37 @@ GFR_HD void step_instance(const typename GroupOf<LANES, SOLVER>::type& g, const 
   {
     const int* inj_ptr = simg + lay.o_inj_ptr;
     const int* inj_idx = simg + lay.o_inj_idx;
+    if (wide_group<LANES>()) {
+      // CTA-wide groups read the image from global memory: the list bounds and the first source of FOUR positions
+      // are fetched together, so a lane waits for two L2 round trips per four positions instead of eight
+      for (int k0 = g.lane; k0 < lay.P; k0 += 4 * LANES) {
+        int qb[4], qe[4], j0[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int k = k0 + u * LANES;
+          const bool in = k < lay.P;
+          qb[u] = in ? inj_ptr[k] : 0;
+          qe[u] = in ? inj_ptr[k + 1] : 0;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) j0[u] = qb[u] < qe[u] ? inj_idx[qb[u]] : 0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int k = k0 + u * LANES;
+          if (k >= lay.P) break;
+          double ld = 0.0, gn = 0.0;
+          for (int q = qb[u]; q < qe[u]; ++q) {
+            const int j = q == qb[u] ? j0[u] : inj_idx[q];
+            const double v = g.scr(j);
+            if (j < L) ld += v;
+            else if (j < L + G) gn += v;
+            else if (v > 0.0) gn += v;
+            else if (v < 0.0) ld += fabs(v);
+          }
+          g.set_pspec(k, fma(gn, lay.inv_s_base, -ld * lay.inv_s_base));
+        }
+      }
+    } else
     for (int k = g.lane; k < lay.P; k += LANES) {        // by schedule position: lane k % LANES is the one that reads it back
       double ld = 0.0, gn = 0.0;
       for (int q = inj_ptr[k]; q < inj_ptr[k + 1]; ++q) {
@@ -1464,22 +1555,59 @@ GFR_HD void step_instance(const typename GroupOf<LANES, SOLVER>::type& g, const 
   int v_hi = 0, v_lo = 0;
   {
     const int* rank = simg + lay.o_rank;
-    for (int i = g.lane; i < n; i += LANES) {
-      int k = rank[i];
-      const D2 vv = g.ef(k);
-      double e = vv.x, f = vv.y;
-      double vm = sqrt(e * e + f * f);
-      ob.put2(2 * i, vm, atan2_bus(f, e));
-      dev += fabs(vm - 1.0);
-      vmax = (vm > vmax || vm != vm) ? vm : vmax;
-      vmin = (vm < vmin || vm != vm) ? vm : vmin;
-      v_hi |= vm > cfg.v_max;
-      v_lo |= vm < cfg.v_min;
+    constexpr int UB = wide_group<LANES>() ? 4 : 1;     // image in global memory: four indices per L2 round trip
+    for (int i0 = g.lane; i0 < n; i0 += UB * LANES) {
+      int kk[UB];
+#pragma unroll
+      for (int u = 0; u < UB; ++u) kk[u] = i0 + u * LANES < n ? rank[i0 + u * LANES] : 0;
+#pragma unroll
+      for (int u = 0; u < UB; ++u) {
+        const int i = i0 + u * LANES;
+        if (i >= n) break;
+        const D2 vv = g.ef(kk[u]);
+        double e = vv.x, f = vv.y;
+        double vm = sqrt(e * e + f * f);
+        ob.put2(2 * i, vm, atan2_bus(f, e));
+        dev += fabs(vm - 1.0);
+        vmax = (vm > vmax || vm != vm) ? vm : vmax;
+        vmin = (vm < vmin || vm != vm) ? vm : vmin;
+        v_hi |= vm > cfg.v_max;
+        v_lo |= vm < cfg.v_min;
+      }
     }
   }
   double loss_pu = 0.0;
   int over80 = 0;
   {
+    if (wide_group<LANES>()) {
+      // image in global memory: branch positions, then records / admittances / ratings, of four lines at a time
+      const int* bol = simg + lay.o_branch_of_line;
+      const I4* sched = reinterpret_cast<const I4*>(simg + lay.o_sched);
+      const D2* gb = reinterpret_cast<const D2*>(dimg + lay.o_gb);
+      for (int l0 = g.lane; l0 < m; l0 += 4 * LANES) {
+        int pb[4]; I4 tt[4]; D2 yy[4]; double rt[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) pb[u] = l0 + u * LANES < m ? bol[l0 + u * LANES] : -1;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          tt[u].x = tt[u].y = tt[u].z = tt[u].w = 0; yy[u].x = yy[u].y = 0.0; rt[u] = 0.0;
+          if (pb[u] >= 0) { tt[u] = sched[pb[u]]; yy[u] = gb[pb[u]]; rt[u] = dimg[lay.o_rating + pb[u]]; }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int li = l0 + u * LANES;
+          if (li >= m) break;
+          double P, S, ls, rating;
+          if (pb[u] >= 0) { branch_flow_rec(g, tt[u], yy[u], &P, &S, &ls); rating = rt[u]; }
+          else line_flow(g, lay, simg, dimg, li, &P, &S, &ls, &rating);          // a tie
+          loss_pu += ls;
+          double pw = P * lay.s_base;
+          double loading = rating > 0.0 ? fabs(pw) * rcp_fast(rating) : 0.0;
+          ob.put2(o_line + 2 * li, pw, loading);
+          over80 += loading > 0.8;
+        }
+      }
+    } else
     for (int li = g.lane; li < m; li += LANES) {
       double P, S, ls, rating;
       line_flow(g, lay, simg, dimg, li, &P, &S, &ls, &rating);

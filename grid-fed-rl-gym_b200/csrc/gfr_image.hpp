@@ -405,8 +405,22 @@ inline std::string build_feeder_image(const gfr_feeder_desc* d, int lanes, int s
   lay.o_inj_idx = ib.add_i(inj_idx.data(), lay.n_src);
   lay.o_gen_type = ib.add_i(d->gen_type, G);
   lay.o_child_ent = lay.o_child_slot = lay.o_topo = lay.o_child_idx = lay.o_level_ptr = -1;
+  lay.o_kids = -1;
   if (newton) {
     lay.o_child_slot = ib.add_i(child_slot.data(), (int)child_slot.size());   // (child_ent: no kernel reads it any more)
+    if (lanes >= GFR_WIDE_GROUP_MIN_LANES) {
+      // CTA-wide groups: the first 8 pool children's slots of every position, 16 bits each, in list order
+      std::vector<int32_t> kids(4 * (size_t)P, 0);
+      for (int p = 0; p < P; ++p) {
+        const uint32_t begin = (uint32_t)sched[4 * p + 1] & (uint32_t)REC_LIST_MASK;
+        const uint32_t npk = (uint32_t)sched[4 * p + 3] & 0xffffu, nall = (uint32_t)sched[4 * p + 3] >> 16;
+        for (uint32_t j = 0; j < npk && j < 8; ++j) {
+          const uint32_t slot = (uint32_t)child_slot[begin + nall - npk + j];
+          kids[4 * p + (j >> 1)] = (int32_t)((uint32_t)kids[4 * p + (j >> 1)] | (slot << (16 * (j & 1))));
+        }
+      }
+      lay.o_kids = ib.add_i(kids.data(), 4 * P);
+    }
   } else {
     lay.o_topo = ib.add_i(topo.data(), 4 * n);
     lay.o_child_idx = ib.add_i(d->child_idx, n - 1);

@@ -19,7 +19,10 @@ def build() -> str:
     cmd = ["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=fast", "-pthread",
            # the header-only builder is also compiled into libgfr_b200.so, which loads with RTLD_GLOBAL: without these
            # the emulation would bind to THAT copy of the inline functions (stale whenever the two are built apart)
-           "-fvisibility-inlines-hidden", "-Wl,-Bsymbolic", "-o", OUT,
+           "-fvisibility-inlines-hidden", "-Wl,-Bsymbolic",
+           # packed pool-child records (the kernels use them for CTA-wide groups) on the 8- and 16-lane teams, the
+           # child lists on the 2- and 4-lane ones
+           "-DGFR_WIDE_GROUP_MIN_LANES=8", "-o", OUT,
            os.path.join(HERE, "gfr_emu.cpp"), "-lm"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
