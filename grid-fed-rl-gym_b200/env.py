@@ -287,15 +287,32 @@ class BatchedGridEnvironment:
         obs = self._obs.clone() if self.copy_outputs else self._obs
         return obs, self._info()
 
-    def step(self, actions, noise=None):
+    def step_outputs_into(self, reward: torch.Tensor, terminated: torch.Tensor, truncated: torch.Tensor):
+        """A copy of the step's output table with reward (fp64 [B]) and the two done flags (uint8 [B]) pointed
+        at the caller's device buffers: ``step(actions, _step_out=...)`` then writes THOSE instead of the
+        environment's own (``gfr_env_step`` takes the output table per call).  ``pipeline.HostStepper`` alternates
+        two such sets, so a step's results can leave for the host while the next step already runs."""
+        B = self.num_envs
+        for t, dt in ((reward, torch.float64), (terminated, torch.uint8), (truncated, torch.uint8)):
+            if t.dtype != dt or t.numel() != B or not t.is_contiguous() or t.device != self.device:
+                raise ValueError("reward: fp64 [B], terminated / truncated: uint8 [B], contiguous, on the environment's device")
+        out = nat.StepOut(*[getattr(self._step_out, k) for k, _ in nat.StepOut._fields_])
+        out.reward, out.terminated, out.truncated = reward.data_ptr(), terminated.data_ptr(), truncated.data_ptr()
+        return out
+
+    def step(self, actions, noise=None, _step_out=None):
         """``actions`` [B, A] float64 (any device / dtype is converted; a host array costs one
-        H2D copy).  ``noise`` [B, 4 + L] replays the reference's random draws (parity mode)."""
+        H2D copy).  ``noise`` [B, 4 + L] replays the reference's random draws (parity mode).
+        ``_step_out`` (from ``step_outputs_into``): this step's reward / done flags go to the caller's buffers and
+        the returned reward / flag tensors are NOT updated (not with ``auto_reset`` / ``copy_outputs``)."""
         B = self.num_envs
         act = self._as_device(actions, (B, self.act_dim), torch.float64, "actions")
         noise_t = self._as_device(noise, (B, self.noise_dim), torch.float64, "noise")
+        if _step_out is not None and (self.auto_reset or self.copy_outputs):
+            raise ValueError("_step_out cannot be combined with auto_reset / copy_outputs")
         nat.check(self.lib, self.lib.gfr_env_step(
             self._h, act.data_ptr(), noise_t.data_ptr() if noise_t is not None else None,
-            C.byref(self._step_out), self._stream()))
+            C.byref(self._step_out if _step_out is None else _step_out), self._stream()))
         o, b = self._out, self._bool
         reward, terminated, truncated = o["reward"], b["terminated"], b["truncated"]
         info = self._info()

@@ -4,8 +4,10 @@
 action log, the reference's own loops): every step still copies that step's actions host ->
 device and its reward / done flags device -> host, but the copy of step t+1's actions runs on a
 second stream while step t's kernel executes, and the results come back through pinned buffers
-one step behind the submissions (depth-2 software pipeline).  ``depth=1`` degenerates to the
-plain copy - step - copy - synchronise sequence.
+one step behind the submissions (depth-2 software pipeline).  The step writes its reward / done flags
+into one of ``depth`` alternating device buffers, so their copy to the host runs on a third stream
+under the next step's kernel and the kernels follow each other without a gap.  ``depth=1`` degenerates
+to the plain copy - step - copy - synchronise sequence.
 """
 
 from __future__ import annotations
@@ -28,7 +30,8 @@ class HostStepper:
             raise ValueError("depth must be >= 1")
         self.env, self.depth, self.observations = env, depth, bool(observations)
         dev, B, A = env.device, env.num_envs, env.act_dim
-        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.copy_stream = torch.cuda.Stream(device=dev)      # host -> device: actions
+        self.out_stream = torch.cuda.Stream(device=dev)       # device -> host: results
         self._act = [torch.empty(B, A, dtype=torch.float64, device=dev) for _ in range(depth)]
         self._host = [dict(reward=torch.empty(B, dtype=torch.float64).pin_memory(),
                            terminated=torch.empty(B, dtype=torch.bool).pin_memory(),
@@ -49,6 +52,16 @@ class HostStepper:
             for h in self._host:
                 h["observations"] = torch.empty(B, env.obs_dim, dtype=env.obs_dtype).pin_memory()
                 h["observations"].copy_(first)
+        # The step's reward / done flags in alternating device buffers of the stepper's own (the environment's
+        # single set would have to be copied out before the next kernel may start).  Not with auto_reset /
+        # copy_outputs (the environment post-processes its own outputs there) and not when a single observation
+        # buffer has to be copied out between two kernels anyway.
+        self._own_out = (not (env.auto_reset or env.copy_outputs)) and (not self.observations or self._overlap_obs)
+        if self._own_out:
+            self._dev_out = [dict(reward=torch.zeros(B, dtype=torch.float64, device=dev),
+                                  terminated=torch.zeros(B, dtype=torch.uint8, device=dev),
+                                  truncated=torch.zeros(B, dtype=torch.uint8, device=dev)) for _ in range(depth)]
+            self._step_outs = [env.step_outputs_into(d["reward"], d["terminated"], d["truncated"]) for d in self._dev_out]
         self._stepped = [torch.cuda.Event() for _ in range(depth)]
         self._copied = [torch.cuda.Event() for _ in range(depth)]
         self._done = [torch.cuda.Event() for _ in range(depth)]
@@ -82,6 +95,33 @@ class HostStepper:
         if len(self._pending) >= self.depth:
             raise RuntimeError("pipeline full: call result() first")
         compute = torch.cuda.current_stream(self.env.device)
+        h = self._host[j]
+        if self._own_out:
+            with torch.cuda.stream(self.copy_stream):
+                if self._busy[j]:
+                    self.copy_stream.wait_event(self._stepped[j])   # the kernel that last read this action buffer
+                self._act[j].copy_(host_actions, non_blocking=True)
+                self._copied[j].record(self.copy_stream)
+            compute.wait_event(self._copied[j])
+            if self._busy[j]:
+                compute.wait_event(self._done[j])                   # the results last written to this set have left
+            if self._overlap_obs and self.depth > 2 and self._n >= 2 and self._busy[(self._n - 2) % self.depth]:
+                compute.wait_event(self._done[(self._n - 2) % self.depth])   # ... and the observation buffer written two steps ago
+            obs = self.env.step(self._act[j], _step_out=self._step_outs[j])[0]
+            self._stepped[j].record(compute)
+            d = self._dev_out[j]
+            with torch.cuda.stream(self.out_stream):
+                self.out_stream.wait_event(self._stepped[j])
+                h["reward"].copy_(d["reward"], non_blocking=True)
+                h["terminated"].copy_(d["terminated"].view(torch.bool), non_blocking=True)
+                h["truncated"].copy_(d["truncated"].view(torch.bool), non_blocking=True)
+                if self.observations:
+                    self._copy_obs(h["observations"], obs)
+                self._done[j].record(self.out_stream)
+            self._busy[j] = True
+            self._pending.append(j)
+            self._n += 1
+            return
         with torch.cuda.stream(self.copy_stream):
             if self._busy[j]:
                 self.copy_stream.wait_event(self._done[j])      # the step that last read this buffer
@@ -89,7 +129,6 @@ class HostStepper:
             self._copied[j].record(self.copy_stream)
         compute.wait_event(self._copied[j])
         obs, reward, term, trunc, _ = self.env.step(self._act[j])
-        h = self._host[j]
         if self.observations and not self._overlap_obs:
             self._copy_obs(h["observations"], obs)
         h["reward"].copy_(reward, non_blocking=True)

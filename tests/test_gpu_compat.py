@@ -251,7 +251,8 @@ def test_fp32_and_alternating_observation_buffers(spec):
         e.close()
 
 
-def test_host_stepper_overlaps_fp32_observation_copies():
+@pytest.mark.parametrize("depth", [2, 3])
+def test_host_stepper_overlaps_fp32_observation_copies(depth):
     import grid_fed_rl_b200 as m
     from grid_fed_rl_b200.pipeline import HostStepper
     f = m.repair_topology(m.IEEE13Bus())
@@ -262,12 +263,12 @@ def test_host_stepper_overlaps_fp32_observation_copies():
     a.reset(seed=2); b.reset(seed=2)
     g = torch.Generator(device="cuda"); g.manual_seed(1)
     acts = [a.sample_actions(g).cpu().pin_memory() for _ in range(6)]
-    st = HostStepper(b, depth=2, observations=True)
-    assert st._overlap_obs and st.d2h_bytes_per_step == B * (10 + 4 * (b.obs_dim - 2 * b.soa.n_load))
+    st = HostStepper(b, depth=depth, observations=True)
+    assert st._overlap_obs and st._own_out and st.d2h_bytes_per_step == B * (10 + 4 * (b.obs_dim - 2 * b.soa.n_load))
     got = []
     for i, act in enumerate(acts):
         st.submit(act)
-        if i >= 1:
+        if i + 1 >= depth:
             r = st.result()
             got.append((r["observations"].clone(), r["reward"].clone()))
     while st._pending:
@@ -280,6 +281,39 @@ def test_host_stepper_overlaps_fp32_observation_copies():
     with pytest.raises(ValueError):
         from grid_fed_rl_b200.compat import GraphedCollector
         GraphedCollector(b)
+
+
+def test_host_stepper_with_auto_reset_keeps_the_environments_own_outputs():
+    """auto_reset post-processes the environment's own output buffers: the stepper must not redirect them."""
+    import grid_fed_rl_b200 as m
+    from grid_fed_rl_b200.pipeline import HostStepper
+    f = m.repair_topology(m.IEEE13Bus())
+    kw = dict(renewable_sources=["solar", "wind"], timestep=60.0, repair=False, start_time=10 * 3600.0,
+              episode_length=3, auto_reset=True)
+    a = m.BatchedGridEnvironment(f, 256, **kw); a.reset(seed=4)
+    b = m.BatchedGridEnvironment(f, 256, **kw); b.reset(seed=4)
+    g = torch.Generator(device="cuda"); g.manual_seed(9)
+    acts = [a.sample_actions(g).cpu().pin_memory() for _ in range(7)]
+    st = HostStepper(b, depth=2)
+    assert not st._own_out
+    got = []
+    for i, x in enumerate(acts):
+        st.submit(x)
+        if i >= 1:
+            h = st.result(); got.append((h["reward"].clone(), h["terminated"].clone(), h["truncated"].clone()))
+    while st._pending:
+        h = st.result(); got.append((h["reward"].clone(), h["terminated"].clone(), h["truncated"].clone()))
+    seen_done = False
+    for x, (r1, t1, u1) in zip(acts, got):
+        _, r0, t0, u0, _ = a.step(x)
+        assert torch.equal(r0.cpu(), r1) and torch.equal(t0.cpu(), t1) and torch.equal(u0.cpu(), u1)
+        seen_done |= bool(t1.any())
+    assert seen_done
+    with pytest.raises(ValueError):
+        b.step(acts[0], _step_out=a.step_outputs_into(torch.zeros(256, dtype=torch.float64, device="cuda"),
+                                                      torch.zeros(256, dtype=torch.uint8, device="cuda"),
+                                                      torch.zeros(256, dtype=torch.uint8, device="cuda")))
+    a.close(); b.close()
 
 
 def test_multi_agent_wrapper_on_the_batched_environment():
