@@ -97,6 +97,7 @@ struct Layout {
   int o_kids;                    // CTA-wide groups: the pool slots of a position's first 8 pool children, 16 bits each (one I4)
   // sweep (compact per-bus arrays)
   int o_topo, o_child_idx, o_level_ptr, o_rx;
+  int o_rowrec, sw_rows;         // several lanes: one record per (row, lane) = (bus | parent << 16, child list begin, end, flags)
   // components
   int o_load_base, o_gen_cap, o_gen_p0, o_gen_p1, o_gen_p2, o_bat_cap, o_bat_rating, o_bat_eff, o_profile;
   double s_base, inv_s_base, load_p_sum;
@@ -1013,9 +1014,9 @@ GFR_HD void newton_solve(const NGrp<LANES>& g, const Layout& lay, const int* sim
 template <int LANES, bool TIES>
 GFR_HD void sweep_solve(const SGrp<LANES>& g, const Layout& lay, const int* simg,
                         const double* dimg, double tol, int max_it, SolveStat* out) {
-  const int n = lay.n, nl = lay.nl, ks = lay.k_slack, nt = TIES ? lay.n_tie : 0;
+  const int n = lay.n, nrows = lay.sw_rows, ks = lay.k_slack, nt = TIES ? lay.n_tie : 0;
   const I4* topo = reinterpret_cast<const I4*>(simg + lay.o_topo);
-  const int* level_ptr = simg + lay.o_level_ptr;
+  const I4* rowrec = reinterpret_cast<const I4*>(simg + (LANES > 1 ? lay.o_rowrec : 0));
   const int* child_idx = simg + lay.o_child_idx;
   const int* tie_ptr = simg + lay.o_tie_ptr;
   const int* tie_inc = simg + lay.o_tie_inc;
@@ -1060,41 +1061,44 @@ GFR_HD void sweep_solve(const SGrp<LANES>& g, const Layout& lay, const int* simg
         g.at2(S_JR, k) = a;
         if (k > 0) { D2& ap = g.at2(S_JR, t.x); ap.x += a.x; ap.y += a.y; }
       }
-    } else
-    for (int l = nl - 1; l >= 0; --l) {
-      const int k1 = level_ptr[l + 1];
-      for (int k = g.first(level_ptr[l]); k < k1; k += LANES) {
-        const I4 t = topo[k];
-        const D2 v = g.at2(F_E, k);
-        const double w = (t.w & FL_THETA) ? g.at(S_P, k) * rcp_fast(fma(v.x, v.x, v.y * v.y)) : 0.0;   // conj(S / V) = P V / |V|^2
-        D2 a;
-        a.x = w * v.x; a.y = w * v.y;
-        GFR_TIE_CURRENT(k, a);
+    } else {
+      // several lanes: rows of at most LANES buses; a lane's record of the NEXT row (its bus, the parent, the child
+      // list) is already in registers when the barrier falls - its position is known in advance
+      I4 t_next = rowrec[(nrows - 1) * LANES + g.lane];
+      for (int row = nrows - 1; row >= 0; --row) {
+        const I4 t = t_next;
+        if (row > 0) t_next = rowrec[(row - 1) * LANES + g.lane];
+        if (t.w & FL_VALID) {
+          const int k = t.x & 0xffff;
+          const D2 v = g.at2(F_E, k);
+          const double w = (t.w & FL_THETA) ? g.at(S_P, k) * rcp_fast(fma(v.x, v.x, v.y * v.y)) : 0.0;   // conj(S / V) = P V / |V|^2
+          D2 a;
+          a.x = w * v.x; a.y = w * v.y;
+          GFR_TIE_CURRENT(k, a);
 #pragma unroll 1
-        for (int q = t.y; q < t.z; ++q) {
-          const D2 ac = g.at2(S_JR, child_idx[q]);
-          a.x += ac.x; a.y += ac.y;
+          for (int q = t.y; q < t.z; ++q) {
+            const D2 ac = g.at2(S_JR, child_idx[q]);
+            a.x += ac.x; a.y += ac.y;
+          }
+          g.at2(S_JR, k) = a;
         }
-        g.at2(S_JR, k) = a;
+        g.sync();
       }
-      g.sync();
     }
     const D2 atot = g.at2(S_JR, 0);
     double mm = 0.0;
     // Several lanes: the root (level 0) is skipped - its W is 0 by definition, its voltage (the slack's set point when
     // the slack is the root, else rewritten by the fix-up pass) does not move, and its field keeps A(root) until the
     // next up pass, so no lane can find it overwritten before it has read it: two barriers less per iteration.
-    for (int l = LANES == 1 ? 0 : 1; l < (LANES == 1 ? 1 : nl); ++l) {      // one thread per instance: a single ascending loop over the buses
-      const int k1 = LANES == 1 ? n : level_ptr[l + 1];
-      for (int k = LANES == 1 ? 0 : g.first(level_ptr[l]); k < k1; k += LANES) {
+    if (LANES == 1) {
+      for (int k = 0; k < n; ++k) {                    // one thread per instance: a single ascending loop over the buses
         const I4 t = topo[k];
         D2 w;
         w.x = 0.0; w.y = 0.0;
         if (k > 0) {
           D2 a = g.at2(S_JR, k);
           if (t.w & FL_SLACK_PATH) { a.x -= atot.x; a.y -= atot.y; }
-          D2 wp = g.at2(S_JR, t.x);
-          if (LANES > 1 && t.x == 0) { wp.x = 0.0; wp.y = 0.0; }
+          const D2 wp = g.at2(S_JR, t.x);
           const D2 z = rx[k];
           w.x = wp.x + fma(z.x, a.x, -z.y * a.y);
           w.y = wp.y + fma(z.x, a.y, z.y * a.x);
@@ -1110,7 +1114,34 @@ GFR_HD void sweep_solve(const SGrp<LANES>& g, const Layout& lay, const int* simg
           g.at2(F_E, k) = vn;
         }
       }
-      g.sync();
+    } else {
+      I4 t_next = rowrec[(nrows > 1 ? 1 : 0) * LANES + g.lane];
+      for (int row = 1; row < nrows; ++row) {
+        const I4 t = t_next;
+        if (row + 1 < nrows) t_next = rowrec[(row + 1) * LANES + g.lane];
+        if (t.w & FL_VALID) {
+          const int k = t.x & 0xffff, kp = (int)((unsigned)t.x >> 16);
+          D2 a = g.at2(S_JR, k);
+          if (t.w & FL_SLACK_PATH) { a.x -= atot.x; a.y -= atot.y; }
+          D2 wp = g.at2(S_JR, kp);
+          if (kp == 0) { wp.x = 0.0; wp.y = 0.0; }      // the root's field still holds A(root)
+          const D2 z = rx[k];
+          D2 w;
+          w.x = wp.x + fma(z.x, a.x, -z.y * a.y);
+          w.y = wp.y + fma(z.x, a.y, z.y * a.x);
+          g.at2(S_JR, k) = w;
+          if (ks == 0) {                               // slack at the root: W is already V - V_slack
+            const D2 vo = g.at2(F_E, k);
+            D2 vn;
+            vn.x = vslack + w.x; vn.y = w.y;
+            const double de = fabs(vn.x - vo.x), df = fabs(vn.y - vo.y);
+            const double loc = (df > de || df != df) ? df : de;
+            mm = (loc > mm || loc != loc) ? loc : mm;
+            g.at2(F_E, k) = vn;
+          }
+        }
+        g.sync();
+      }
     }
     const D2 ws = g.at2(S_JR, ks);
     if (ks != 0)

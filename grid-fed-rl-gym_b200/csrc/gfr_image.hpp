@@ -406,6 +406,7 @@ inline std::string build_feeder_image(const gfr_feeder_desc* d, int lanes, int s
   lay.o_gen_type = ib.add_i(d->gen_type, G);
   lay.o_child_ent = lay.o_child_slot = lay.o_topo = lay.o_child_idx = lay.o_level_ptr = -1;
   lay.o_kids = -1;
+  lay.o_rowrec = -1; lay.sw_rows = 0;
   if (newton) {
     lay.o_child_slot = ib.add_i(child_slot.data(), (int)child_slot.size());   // (child_ent: no kernel reads it any more)
     if (lanes >= GFR_WIDE_GROUP_MIN_LANES) {
@@ -425,6 +426,20 @@ inline std::string build_feeder_image(const gfr_feeder_desc* d, int lanes, int s
     lay.o_topo = ib.add_i(topo.data(), 4 * n);
     lay.o_child_idx = ib.add_i(d->child_idx, n - 1);
     lay.o_level_ptr = ib.add_i(d->level_ptr, nl + 1);
+    if (lanes > 1) {
+      // several lanes: the levels cut into rows of at most `lanes` buses, one record per (row, lane)
+      const Schedule sw = make_schedule(d, lanes);
+      std::vector<int32_t> rowrec(4 * (size_t)sw.nrows * lanes, 0);
+      for (int k = 0; k < n; ++k) {
+        int32_t* r = &rowrec[4 * ((size_t)sw.row[k] * lanes + sw.lane[k])];
+        r[0] = (int32_t)((uint32_t)k | ((uint32_t)(k > 0 ? d->parent[k] : 0) << 16));
+        r[1] = d->child_ptr[k];
+        r[2] = d->child_ptr[k + 1];
+        r[3] = flags[k];
+      }
+      lay.sw_rows = sw.nrows;
+      lay.o_rowrec = ib.add_i(rowrec.data(), (int)rowrec.size());
+    }
   }
   lay.o_tie_ends = lay.o_tie_ptr = lay.o_tie_inc = lay.o_tie_y = lay.o_tie_z = lay.o_tie_rating = lay.o_tie_zinv = -1;
   if (nt) {
