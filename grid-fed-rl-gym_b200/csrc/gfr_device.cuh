@@ -531,9 +531,6 @@ GFR_HD double noise_slot(uint64_t seed, uint64_t draw, int s) {
 #ifndef GFR_PIPE_SMEM
 #define GFR_PIPE_SMEM 0
 #endif
-#ifndef GFR_SWEEP_PIPE_V
-#define GFR_SWEEP_PIPE_V 0      // multi-lane sweep: also the next row's voltage / injection (up) and A / z (down) a row ahead
-#endif
 #ifndef GFR_PIPE_EF
 #define GFR_PIPE_EF 0
 #endif
@@ -1068,30 +1065,13 @@ GFR_HD void sweep_solve(const SGrp<LANES>& g, const Layout& lay, const int* simg
       // several lanes: rows of at most LANES buses; a lane's record of the NEXT row (its bus, the parent, the child
       // list) is already in registers when the barrier falls - its position is known in advance
       I4 t_next = rowrec[(nrows - 1) * LANES + g.lane];
-#if GFR_SWEEP_PIPE_V
-      D2 v_next = g.at2(F_E, t_next.x & 0xffff);        // voltages and injections do not move during the up pass
-      double p_next = g.at(S_P, t_next.x & 0xffff);
-#endif
       for (int row = nrows - 1; row >= 0; --row) {
         const I4 t = t_next;
-#if GFR_SWEEP_PIPE_V
-        const D2 v_now = v_next; const double p_now = p_next;
-#endif
-        if (row > 0) {
-          t_next = rowrec[(row - 1) * LANES + g.lane];
-#if GFR_SWEEP_PIPE_V
-          v_next = g.at2(F_E, t_next.x & 0xffff); p_next = g.at(S_P, t_next.x & 0xffff);
-#endif
-        }
+        if (row > 0) t_next = rowrec[(row - 1) * LANES + g.lane];
         if (t.w & FL_VALID) {
           const int k = t.x & 0xffff;
-#if GFR_SWEEP_PIPE_V
-          const D2 v = v_now;
-          const double w = (t.w & FL_THETA) ? p_now * rcp_fast(fma(v.x, v.x, v.y * v.y)) : 0.0;
-#else
           const D2 v = g.at2(F_E, k);
           const double w = (t.w & FL_THETA) ? g.at(S_P, k) * rcp_fast(fma(v.x, v.x, v.y * v.y)) : 0.0;   // conj(S / V) = P V / |V|^2
-#endif
           D2 a;
           a.x = w * v.x; a.y = w * v.y;
           GFR_TIE_CURRENT(k, a);
@@ -1136,36 +1116,16 @@ GFR_HD void sweep_solve(const SGrp<LANES>& g, const Layout& lay, const int* simg
       }
     } else {
       I4 t_next = rowrec[(nrows > 1 ? 1 : 0) * LANES + g.lane];
-#if GFR_SWEEP_PIPE_V
-      D2 a_next = g.at2(S_JR, t_next.x & 0xffff);       // A(k) stays until its own row rewrites the field with W(k)
-      D2 z_next = rx[t_next.x & 0xffff];
-#endif
       for (int row = 1; row < nrows; ++row) {
         const I4 t = t_next;
-#if GFR_SWEEP_PIPE_V
-        const D2 a_now = a_next, z_now = z_next;
-#endif
-        if (row + 1 < nrows) {
-          t_next = rowrec[(row + 1) * LANES + g.lane];
-#if GFR_SWEEP_PIPE_V
-          a_next = g.at2(S_JR, t_next.x & 0xffff); z_next = rx[t_next.x & 0xffff];
-#endif
-        }
+        if (row + 1 < nrows) t_next = rowrec[(row + 1) * LANES + g.lane];
         if (t.w & FL_VALID) {
           const int k = t.x & 0xffff, kp = (int)((unsigned)t.x >> 16);
-#if GFR_SWEEP_PIPE_V
-          D2 a = a_now;
-#else
           D2 a = g.at2(S_JR, k);
-#endif
           if (t.w & FL_SLACK_PATH) { a.x -= atot.x; a.y -= atot.y; }
           D2 wp = g.at2(S_JR, kp);
           if (kp == 0) { wp.x = 0.0; wp.y = 0.0; }      // the root's field still holds A(root)
-#if GFR_SWEEP_PIPE_V
-          const D2 z = z_now;
-#else
           const D2 z = rx[k];
-#endif
           D2 w;
           w.x = wp.x + fma(z.x, a.x, -z.y * a.y);
           w.y = wp.y + fma(z.x, a.y, z.y * a.x);
