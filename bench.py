@@ -318,7 +318,7 @@ def device_timed(dev, world, step_fn, k, max_over_ranks):
     return max_over_ranks(ev0.elapsed_time(ev1), dev)     # a timed region counts as its slowest rank
 
 
-def make_envs(m, name, B, dev, rank, lanes, seed, obs_dtype=None, min_bytes=2 * L2_BYTES):
+def make_envs(m, name, B, dev, rank, lanes, seed, obs_dtype=None, min_bytes=2 * L2_BYTES, obs_buffers=0):
     """The environment(s) of one workload: when one step's working set would sit in the 126 MB L2, several
     environments are stepped round-robin so that every step streams from / to HBM."""
     spec, _, solver, tol, max_it = WORKLOADS[name]
@@ -326,6 +326,8 @@ def make_envs(m, name, B, dev, rank, lanes, seed, obs_dtype=None, min_bytes=2 * 
     kw = dict(ENV_KW)
     if obs_dtype is not None:
         kw["obs_dtype"] = obs_dtype
+    if obs_buffers:
+        kw["obs_buffers"] = obs_buffers
     envs = []
     while True:
         env = m.BatchedGridEnvironment(feeder, B, device=dev, solver=solver, tolerance=tol, max_iterations=max_it,
@@ -571,7 +573,9 @@ def measure_rollout(m, dev, world, rank, max_over_ranks, args):
     from grid_fed_rl_b200.compat import GraphedCollector
     name = "synthetic1000"
     B, chunk, chunks = WORKLOADS[name][1], 4, 6
-    env = make_envs(m, name, B, dev, rank, 0, args.seed, min_bytes=0)[0]
+    # the block is fp32 like the reference's GridDataset arrays: the kernel writes its observation in fp32 too (one
+    # buffer: a captured graph replays fixed pointers), so the copies into the block are plain copies
+    env = make_envs(m, name, B, dev, rank, 0, args.seed, obs_dtype="float32", min_bytes=0, obs_buffers=1)[0]
     col = GraphedCollector(env, chunk=chunk, dtype=torch.float32)
     col.run_chunk(); col.run_chunk()                       # eager + capture, then one replay
     ms = device_timed(dev, world, lambda i: col.run_chunk(), chunks, max_over_ranks)
@@ -580,6 +584,7 @@ def measure_rollout(m, dev, world, rank, max_over_ranks, args):
     out = {"value": B * world * steps / (ms * 1e-3), "unit": "env-steps/s", "ms_per_step": ms / steps,
            "instances_per_gpu": B, "steps": steps, "chunk": chunk,
            "rollout_bytes_per_step": bytes_per_step, "rollout_gb_per_s_per_gpu": bytes_per_step / (ms / steps * 1e-3) / 1e9,
+           "obs_dtype": "f32",
            "note": "transitions land in a device-resident fp32 block with the reference's GridDataset field names "
                    "(algorithms/base.py:180-298); nothing leaves the GPU"}
     env.close()

@@ -228,22 +228,22 @@ class GraphedCollector:
         self.stage = dict(observations=torch.empty(chunk, B, D, **z), actions=torch.empty(chunk, B, A, **z),
                           rewards=torch.empty(chunk, B, **z), next_observations=torch.empty(chunk, B, D, **z),
                           terminals=torch.empty(chunk, B, **z))
-        self._obs = env.get_observation().clone()
         self._graph = None
 
     def _body(self) -> None:
         env, st = self.env, self.stage
         for k in range(self.chunk):
-            act = torch.rand(env.num_envs, env.act_dim, dtype=torch.float64, device=env.device) * 2.0 - 1.0
+            act = torch.empty(env.num_envs, env.act_dim, dtype=torch.float64, device=env.device).uniform_(-1.0, 1.0)
+            # the environment's single observation buffer holds the state the step starts from (after the masked
+            # reset of the previous step): it goes to the block before the kernel overwrites it in place
+            st["observations"][k].copy_(env.get_observation())
             nxt, reward, term, trunc, _ = env.step(act)
             done = term | trunc
-            st["observations"][k].copy_(self._obs)
             st["actions"][k].copy_(act)
             st["rewards"][k].copy_(reward)
             st["next_observations"][k].copy_(nxt)
             st["terminals"][k].copy_(done)
             env.reset(mask=done)                     # rewrites the observation rows of finished instances only
-            self._obs.copy_(env.get_observation())
 
     def run_chunk(self) -> Dict[str, torch.Tensor]:
         """Advance ``chunk`` steps; returns the staging block (overwritten by the next call)."""
@@ -253,13 +253,11 @@ class GraphedCollector:
             torch.cuda.synchronize(self.env.device)
             graph = torch.cuda.CUDAGraph()
             snapshot = self.env.state_dict()
-            obs_snapshot = self._obs.clone()
             first = {k: v.clone() for k, v in self.stage.items()}
             with torch.cuda.graph(graph):
                 self._body()
             # capturing records launches without running them, but be explicit that nothing moved
             self.env.load_state_dict(snapshot)
-            self._obs.copy_(obs_snapshot)
             for k, v in first.items():
                 self.stage[k].copy_(v)
             self._graph = graph

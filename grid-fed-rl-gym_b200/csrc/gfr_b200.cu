@@ -176,6 +176,29 @@ __global__ void obs_convert_kernel(const double* __restrict__ src, void* __restr
 
 // FP64 pipe microbenchmark: 8 independent DFMA chains per thread (the roofline denominator that
 // MEASURED_PEAKS.json does not carry)
+// The info rows of the instances a reset touched (grid_env.py:360-408: counters and episode sums to zero, voltages
+// at 1.0): one launch instead of one masked fill per output array
+__global__ void __launch_bounds__(256) reset_outputs_kernel(const StepOut o, const uint8_t* __restrict__ mask,
+                                                            const long long B) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < B; i += (long long)gridDim.x * blockDim.x) {
+    if (mask && !mask[i]) continue;
+    if (o.reward) o.reward[i] = 0.0;
+    if (o.terminated) o.terminated[i] = 0;
+    if (o.truncated) o.truncated[i] = 0;
+    if (o.error) o.error[i] = 0;
+    if (o.converged) o.converged[i] = 0;
+    if (o.iterations) o.iterations[i] = 0;
+    if (o.max_voltage) o.max_voltage[i] = 1.0;
+    if (o.min_voltage) o.min_voltage[i] = 1.0;
+    if (o.losses) o.losses[i] = 0.0;
+    if (o.max_mismatch) o.max_mismatch[i] = 0.0;
+    if (o.violations) { for (int q = 0; q < 4; ++q) o.violations[i * 4 + q] = 0; }
+    if (o.violation_count) o.violation_count[i] = 0;
+    if (o.current_step) o.current_step[i] = 0;
+    if (o.episode_reward) o.episode_reward[i] = 0.0;
+  }
+}
+
 __global__ void __launch_bounds__(256) dfma_peak_kernel(double* __restrict__ out, const int iters, const double seed) {
   double a0 = seed + threadIdx.x, a1 = a0 + 1.0, a2 = a0 + 2.0, a3 = a0 + 3.0, a4 = a0 + 4.0, a5 = a0 + 5.0,
          a6 = a0 + 6.0, a7 = a0 + 7.0;
@@ -761,9 +784,7 @@ int gfr_env_reset(gfr_env* e, const uint64_t* seeds, const uint8_t* mask, const 
   return launch_reset(e, seeds, mask, noise, start_time, 0, (cudaStream_t)stream);
 }
 
-int gfr_env_step(gfr_env* e, const double* actions, const double* noise, const gfr_step_out* out,
-                 void* stream) {
-  if (!e || !actions) return fail(GFR_E_ARG, "null argument");
+static StepOut step_out_of(const gfr_step_out* out) {
   StepOut o{};
   if (out) {
     o.reward = out->reward; o.terminated = out->terminated; o.truncated = out->truncated;
@@ -773,8 +794,29 @@ int gfr_env_step(gfr_env* e, const double* actions, const double* noise, const g
     o.violation_count = out->violation_count; o.current_step = out->current_step;
     o.episode_reward = out->episode_reward; o.noise_used = out->noise_used;
   }
+  return o;
+}
+
+int gfr_env_step(gfr_env* e, const double* actions, const double* noise, const gfr_step_out* out,
+                 void* stream) {
+  if (!e || !actions) return fail(GFR_E_ARG, "null argument");
+  const StepOut o = step_out_of(out);
   DeviceGuard guard(e->f->device);
   return launch_step(e, actions, noise, o, (cudaStream_t)stream);
+}
+
+int gfr_env_reset_outputs(gfr_env* e, const uint8_t* mask, const gfr_step_out* out, void* stream) {
+  if (!e || !out) return fail(GFR_E_ARG, "null argument");
+  const StepOut o = step_out_of(out);
+  DeviceGuard guard(e->f->device);
+  const long long B = e->B;
+  const int threads = 256;
+  long long blocks = (B + threads - 1) / threads;
+  if (blocks > 4LL * e->f->sm_count) blocks = 4LL * e->f->sm_count;
+  reset_outputs_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(o, mask, B);
+  GFR_CUDA(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return GFR_OK;
 }
 
 int gfr_solve(const gfr_feeder* f, int64_t B, const double* p_inj, const gfr_solver_cfg* cfg,

@@ -268,22 +268,9 @@ class BatchedGridEnvironment:
             self._h, seeds.data_ptr() if seeds is not None else None,
             mask_t.data_ptr() if mask_t is not None else None,
             noise_t.data_ptr() if noise_t is not None else None, start, self._stream()))
-        # info of the instances that were reset
-        o = self._out
-        if mask_t is None:
-            for k in ("reward", "losses", "max_mismatch", "episode_reward"):
-                o[k].zero_()
-            for k in ("terminated", "truncated", "error", "converged", "iterations", "violations",
-                      "violation_count", "current_step"):
-                o[k].zero_()
-            o["max_voltage"].fill_(1.0); o["min_voltage"].fill_(1.0)
-        else:
-            sel = mask_t.bool()
-            for k in ("reward", "losses", "max_mismatch", "episode_reward", "terminated", "truncated",
-                      "error", "converged", "iterations", "violation_count", "current_step"):
-                o[k].masked_fill_(sel, 0)
-            o["violations"].masked_fill_(sel[:, None], 0)
-            o["max_voltage"].masked_fill_(sel, 1.0); o["min_voltage"].masked_fill_(sel, 1.0)
+        # info of the instances that were reset: zeros, voltages at 1.0 (one launch for all the output arrays)
+        nat.check(self.lib, self.lib.gfr_env_reset_outputs(
+            self._h, mask_t.data_ptr() if mask_t is not None else None, C.byref(self._step_out), self._stream()))
         obs = self._obs.clone() if self.copy_outputs else self._obs
         return obs, self._info()
 

@@ -221,6 +221,11 @@ int gfr_env_state_set(gfr_env* e, const void* src_device, void* stream);
 int gfr_env_reset(gfr_env* e, const uint64_t* seeds, const uint8_t* mask, const double* noise,
                   double start_time, void* stream);
 
+/* The info of the instances a reset touched (reference grid_env.py:360-408: step and violation counters, episode
+ * reward, losses back to zero, voltages at 1.0), written into the caller's output table `out` (the one gfr_env_step
+ * fills; noise_used is left alone) for the instances with mask != 0 (mask NULL = all).  One launch. */
+int gfr_env_reset_outputs(gfr_env* e, const uint8_t* mask, const gfr_step_out* out, void* stream);
+
 /* GridEnvironment.step(action) (reference grid_env.py:410-619) for all B instances.
  * actions [B,A].  noise [B,4+L] (u_irradiance, z_wind, z_temperature, z_cloud, z_load_0..)
  * replays the reference's random.random / random.gauss / np.random.normal draws; NULL =
