@@ -299,11 +299,22 @@ def test_reset_mask_autoreset_and_checkpoint():
     assert torch.equal(oa, ob) and torch.equal(ra, rb) and torch.equal(ia["current_step"], ib["current_step"])
     # masked reset touches only the selected instances
     before = a.get_observation().clone()
+    info_before = {k: v.clone() for k, v in ia.items() if isinstance(v, torch.Tensor)}
     mask = torch.zeros(64, dtype=torch.bool, device="cuda"); mask[::4] = True
     obs, info = a.reset(mask=mask)
     assert torch.equal(obs[~mask], before[~mask])
     assert torch.all(obs[mask][:, 0] == 1.0) and torch.all(info["current_step"][mask] == 0)
     assert torch.all(info["current_step"][~mask] == 4)
+    # ... and so do the info arrays (one launch, gfr_env_reset_outputs): zeros / 1.0 pu where reset, untouched elsewhere
+    for k, v in info_before.items():
+        assert torch.equal(info[k][~mask], v[~mask]), k
+        want = 1.0 if k in ("max_voltage", "min_voltage") else 0
+        assert torch.all(info[k][mask] == want), k
+    assert torch.all(a._out["reward"][mask] == 0) and torch.equal(a._out["reward"][~mask], ra[~mask])
+    # an unmasked reset clears every row
+    _, info = a.reset()
+    assert all(torch.all(info[k] == (1.0 if k in ("max_voltage", "min_voltage") else 0))
+               for k in info_before)
     # auto-reset: instances that terminate come back at step 0 with the initial observation
     c = m.BatchedGridEnvironment(f, 32, auto_reset=True, **kw)
     c.reset(seed=5)
