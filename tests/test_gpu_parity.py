@@ -300,6 +300,7 @@ def test_reset_mask_autoreset_and_checkpoint():
     # masked reset touches only the selected instances
     before = a.get_observation().clone()
     info_before = {k: v.clone() for k, v in ia.items() if isinstance(v, torch.Tensor)}
+    r_before = ra.clone()                      # (the step's return values are the live output buffers)
     mask = torch.zeros(64, dtype=torch.bool, device="cuda"); mask[::4] = True
     obs, info = a.reset(mask=mask)
     assert torch.equal(obs[~mask], before[~mask])
@@ -310,7 +311,7 @@ def test_reset_mask_autoreset_and_checkpoint():
         assert torch.equal(info[k][~mask], v[~mask]), k
         want = 1.0 if k in ("max_voltage", "min_voltage") else 0
         assert torch.all(info[k][mask] == want), k
-    assert torch.all(a._out["reward"][mask] == 0) and torch.equal(a._out["reward"][~mask], ra[~mask])
+    assert torch.all(a._out["reward"][mask] == 0) and torch.equal(a._out["reward"][~mask], r_before[~mask])
     # an unmasked reset clears every row
     _, info = a.reset()
     assert all(torch.all(info[k] == (1.0 if k in ("max_voltage", "min_voltage") else 0))
