@@ -316,7 +316,8 @@ GFR_HD size_t newton_slot_bytes(int n, int n_pool, int n_src) {
   return (size_t)n * 16 + (size_t)n_pool * (16 * POOL_D2);
 }
 // doubles of global scratch per instance slot (Newton): D^-1 U, D^-1 r (48 B per position) + specified injections
-GFR_HD size_t newton_scratch_doubles(int P) { return (size_t)P * 6 + (((size_t)P + 1) / 2) * 2; }
+// (a whole number of 128-byte lines per slot: a slot's lines can be dropped from L2 without touching a neighbour's)
+GFR_HD size_t newton_scratch_doubles(int P) { return (((size_t)P * 6 + (((size_t)P + 1) / 2) * 2) + 15) & ~(size_t)15; }
 // One thread per instance on a small feeder: the specified injections move to a per-thread local array (L1,
 // interleaved by thread), 32 B per bus stay in shared memory - 40 % more resident instances per SM
 enum { SWEEP_P_LOCAL_MAX = 20 };
@@ -530,6 +531,14 @@ GFR_HD double noise_slot(uint64_t seed, uint64_t draw, int s) {
 // synthetic-1000 5.91 M -> 5.64 M).
 #ifndef GFR_PIPE_SMEM
 #define GFR_PIPE_SMEM 0
+#endif
+// After a solve the Newton scratch of the slot is dead, but L2 cannot know: its dirty lines were written back to HBM
+// whenever the observation stream pushed them out (IEEE-123, 131 072 instances: 1.02 GB written per launch for 0.59 GB
+// of observation + state + outputs; the evict-last hint alone changed nothing).  2 = drop the D^-1 U / D^-1 r lines
+// with discard.global.L2 when the solve ends (581 MB written, 98.1 M env-steps/s), 1 = the injections' lines too
+// (565 MB, 97.8 M), 0 = keep them (1.02 GB, 99.2 M).
+#ifndef GFR_SCRATCH_DISCARD
+#define GFR_SCRATCH_DISCARD 2
 #endif
 #ifndef GFR_PIPE_EF
 #define GFR_PIPE_EF 0
@@ -991,6 +1000,21 @@ GFR_HD void newton_solve(const NGrp<LANES>& g, const Layout& lay, const int* sim
       mm_prev = mm;
     }
   }
+#if defined(__CUDA_ARCH__) && GFR_SCRATCH_DISCARD
+  // The scratch of this solve is dead (the next instance of the slot rewrites it before reading): tell L2, so that
+  // the dirty lines need not be written back to HBM when the observation stream pushes them out.  Every exit of the
+  // loop above comes after a group-wide reduction, and every scratch read before that.
+  {
+    char* const base = reinterpret_cast<char*>(g.mg);
+#if GFR_SCRATCH_DISCARD == 2
+    const size_t bytes = ((size_t)P * 48) & ~(size_t)127;         // D^-1 U, D^-1 r only (whole lines), not the injections
+#else
+    const size_t bytes = newton_scratch_doubles(P) * 8;
+#endif
+    for (size_t off = (size_t)g.lane * 128; off < bytes; off += (size_t)LANES * 128)
+      asm volatile("discard.global.L2 [%0], 128;" ::"l"(base + off) : "memory");
+  }
+#endif
 }
 
 // Backward / forward sweep (no counterpart in the reference; compared with the
