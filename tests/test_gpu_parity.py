@@ -240,6 +240,44 @@ def test_pv_bus_feeder_vs_oracle():
         m.B200PowerFlowSolver(method="sweep").solve_batch(f, p)
 
 
+@pytest.mark.parametrize("lanes", [8, 64, 128])
+def test_hub_with_more_pool_children_than_a_packed_record_holds(lanes):
+    """A hub with 13 children on CTA-wide groups (64 / 128 lanes): 12 pool children, the packed pool-child record of
+    the hub's position holds 8, so that position walks the child list instead; the others take the record.  Both
+    solvers and one environment step against the oracle."""
+    import grid_fed_rl_b200 as m
+    f = m.SimpleRadialFeeder(18)
+    for ln in f.lines[3:16]:
+        ln.from_bus = 4
+    for ld in f.loads:
+        ld.base_power *= 0.2; ld.active_power *= 0.2; ld.reactive_power *= 0.2
+    f = m.repair_topology(f)
+    n = len(f.buses)
+    rs = np.random.RandomState(5)
+    p = -np.abs(rs.uniform(0.002, 0.01, size=(37, n))); p[:, 0] = 0.0
+    ref = port.newton_raphson(port.DenseNetwork(f.buses, f.lines), p, 1e-10, 50)
+    assert ref["converged"].all()
+    for method, tol, it in (("newton", 1e-10, 50), ("sweep", 1e-11, 200)):
+        sol = m.B200PowerFlowSolver(tolerance=tol, max_iterations=it, method=method, lanes=lanes).solve_batch(f, p)
+        assert bool(sol.converged.all()), method
+        assert np.max(np.abs(sol.bus_voltages.cpu().numpy() - ref["bus_voltages"])) <= TOL_PU
+        assert np.max(np.abs(sol.bus_angles.cpu().numpy() - ref["bus_angles"])) <= TOL_PU
+        assert np.max(np.abs(sol.line_flows.cpu().numpy() - ref["line_flows"])) <= TOL_PU
+    # one step of the environment on the same lanes: the batched loops around the solve (injections, flat start,
+    # observation) against a one-lane run
+    kw = dict(timestep=60.0, repair=False, tolerance=1e-10, start_time=12 * 3600.0)
+    a = m.BatchedGridEnvironment(f, 33, lanes=1, **kw); a.reset(seed=2)
+    b = m.BatchedGridEnvironment(f, 33, lanes=lanes, **kw); b.reset(seed=2)
+    g = torch.Generator(device="cuda"); g.manual_seed(3)
+    for _ in range(3):
+        act = a.sample_actions(g)
+        oa, ra, _, _, ia = a.step(act)
+        ob, rb, _, _, ib = b.step(act)
+        assert torch.allclose(oa, ob, rtol=1e-11, atol=1e-6) and torch.allclose(ra, rb, rtol=1e-11, atol=1e-9)
+        assert torch.equal(ia["iterations"], ib["iterations"])
+    a.close(); b.close()
+
+
 def test_philox_noise_matches_oracle_and_replays():
     import ctypes as C
     import grid_fed_rl_b200 as m

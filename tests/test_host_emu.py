@@ -169,3 +169,35 @@ def test_newton_refuses_ties_and_zinv_is_the_loop_inverse():
     assert np.allclose(z, z.T, atol=1e-12)
     zt = soa.tie_r + 1j * soa.tie_x
     assert np.all(np.abs(np.diag(z)) >= np.abs(zt) - 1e-12)
+
+
+# ----------------------------------------------------------------------------- more pool children than a packed record holds
+
+@pytest.mark.parametrize("lanes", [2, 8, 16])
+def test_emu_hub_with_many_children(lanes):
+    """A hub bus with 13 children: 12 of them hand over through pool slots - more than the 8 a packed pool-child
+    record holds (the wide-group path of the emulation build, 8 and 16 lanes, must fall back to the child list for
+    that position; 2 lanes walk the list anyway).  Newton and sweep against the oracle's dense Newton-Raphson."""
+    import grid_fed_rl_b200 as m
+    f = m.SimpleRadialFeeder(18)
+    for ln in f.lines[3:16]:                     # buses 5 .. 17 all hang off bus 4; bus 18 stays behind 17
+        ln.from_bus = 4
+    for ld in f.loads:
+        ld.base_power *= 0.2; ld.active_power *= 0.2; ld.reactive_power *= 0.2
+    f = m.repair_topology(f)
+    net = port.DenseNetwork(f.buses, f.lines)
+    rs = np.random.RandomState(5)
+    n = len(f.buses)
+    p_spec = -np.abs(rs.uniform(0.002, 0.01, size=(6, n))); p_spec[:, 0] = 0.0
+    ref = port.newton_raphson(net, p_spec, 1e-10, 50)
+    assert ref["converged"].all()
+    for solver, tol, it in (("newton", 1e-10, 50), ("sweep", 1e-11, 200)):
+        sol = emu.emu_solve(f, p_spec, solver, tol, it, lanes=lanes)
+        assert sol["converged"].all(), solver
+        for k in ("bus_voltages", "bus_angles", "line_flows", "losses"):
+            assert np.max(np.abs(sol[k] - ref[k])) <= TOL_PU, (solver, k)
+    if lanes > 1:
+        from grid_fed_rl_b200.topology import compile_for_solver
+        soa, _ = compile_for_solver(f, "newton", lanes, with_components=False)
+        kids = np.bincount(np.asarray(soa.parent)[1:], minlength=n)
+        assert kids.max() >= 10                   # the hub survived the center rooting with > 9 children
