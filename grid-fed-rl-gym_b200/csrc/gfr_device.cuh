@@ -96,7 +96,7 @@ struct Layout {
   int o_child_ent, o_child_slot, o_gbd, o_f0;
   int o_kids;                    // CTA-wide groups: the pool slots of a position's first 8 pool children, 16 bits each (one I4)
   // sweep (compact per-bus arrays)
-  int o_topo, o_child_idx, o_level_ptr, o_rx;
+  int o_topo, o_child_idx, o_rx;
   int o_rowrec, sw_rows;         // several lanes: one record per (row, lane) = (bus | parent << 16, child list begin, end, flags)
   // components
   int o_load_base, o_gen_cap, o_gen_p0, o_gen_p1, o_gen_p2, o_bat_cap, o_bat_rating, o_bat_eff, o_profile;
@@ -195,9 +195,6 @@ struct Lanes {
 #if !defined(__CUDACC__)
   EmuTeam* team = nullptr;
 #endif
-  // first index >= k0 owned by this lane (lane k % LANES owns bus k in every phase)
-  GFR_HD int first(int k0) const { return k0 + ((lane - k0) & (LANES - 1)); }
-
   GFR_HD void sync() const {
 #if defined(__CUDA_ARCH__)
 #ifdef GFR_STRESS

@@ -404,7 +404,7 @@ inline std::string build_feeder_image(const gfr_feeder_desc* d, int lanes, int s
   lay.o_inj_ptr = ib.add_i(inj_ptr.data(), P + 1);
   lay.o_inj_idx = ib.add_i(inj_idx.data(), lay.n_src);
   lay.o_gen_type = ib.add_i(d->gen_type, G);
-  lay.o_child_ent = lay.o_child_slot = lay.o_topo = lay.o_child_idx = lay.o_level_ptr = -1;
+  lay.o_child_ent = lay.o_child_slot = lay.o_topo = lay.o_child_idx = -1;
   lay.o_kids = -1;
   lay.o_rowrec = -1; lay.sw_rows = 0;
   if (newton) {
@@ -425,7 +425,6 @@ inline std::string build_feeder_image(const gfr_feeder_desc* d, int lanes, int s
   } else {
     lay.o_topo = ib.add_i(topo.data(), 4 * n);
     lay.o_child_idx = ib.add_i(d->child_idx, n - 1);
-    lay.o_level_ptr = ib.add_i(d->level_ptr, nl + 1);
     if (lanes > 1) {
       // several lanes: the levels cut into rows of at most `lanes` buses, one record per (row, lane)
       const Schedule sw = make_schedule(d, lanes);
