@@ -6,12 +6,15 @@
 // "image") is staged next to it once per CTA with one bulk (TMA) copy, or read from global memory
 // when the group is CTA-wide.  Buses are numbered in LEVEL order: the host's leaf -> root
 // elimination schedule (topology.compile_feeder), k = 0 being the root of the elimination tree.
-// Lane `k % LANES` owns bus k in every phase, so a lane only needs a group barrier when it reads
-// another bus's data.
+// The passes over the tree run ROW by row: lane l takes schedule position row * LANES + l (Newton:
+// a lane follows a path of the tree and hands a child's terms to its parent in registers; sweep:
+// the (row, lane) record names the bus), so a lane only needs a group barrier when it reads what
+// another lane wrote.
 //
-// The functions are __host__ __device__ so that tests/host_emu can run the LANES = 1
-// instantiation on a CPU to debug control flow without a GPU.  That harness is test
-// infrastructure; the shipped library only launches the __global__ kernels.
+// The functions are __host__ __device__ so that tests/host_emu can run them on a CPU - a group of
+// 1 - 16 lanes as that many host threads meeting at a barrier wherever the kernels synchronise -
+// without a GPU.  That harness is test infrastructure; the shipped library only launches the
+// __global__ kernels.
 //
 // Reference (paths under /root/reference/grid_fed_rl/):
 //   Newton-Raphson        environments/power_flow.py:89-211  (polar; flat start; check-then-update)
@@ -1583,7 +1586,7 @@ GFR_HD void step_instance(const typename GroupOf<LANES, SOLVER>::type& g, const 
         }
       }
     } else
-    for (int k = g.lane; k < lay.P; k += LANES) {        // by schedule position: lane k % LANES is the one that reads it back
+    for (int k = g.lane; k < lay.P; k += LANES) {        // by schedule position: lane k % LANES is the one that reads position k back
       double ld = 0.0, gn = 0.0;
       for (int q = inj_ptr[k]; q < inj_ptr[k + 1]; ++q) {
         int j = inj_idx[q];
